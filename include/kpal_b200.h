@@ -1,0 +1,232 @@
+/*
+ * kpal_b200.h -- C ABI of libkpal_b200.so: the B200 (sm_100a) implementation of
+ * kPAL's data-parallel hot path (k-mer counting + reverse-complement balance,
+ * and the N x N profile distance matrix).
+ *
+ * kPAL (LUMC/kPAL) is pure Python and has no FFI of its own; the boundary this
+ * library replaces is the body of a handful of Python functions.  Each entry
+ * point below names the reference function (file:line, relative to the
+ * reference tree) whose arithmetic it replaces.  INTEGRATION.md shows the
+ * ctypes stub a kPAL maintainer would add to call them from kpal/klib.py and
+ * kpal/kdistlib.py.
+ *
+ * Conventions
+ *   - plain C types only; the caller owns every buffer; the library never
+ *     keeps a host pointer after a call returns;
+ *   - every function returns 0 on success or a KPAL_E* code; the message is
+ *     available (per thread) from kpal_last_error();
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with KPAL_ECUDA;
+ *   - "host" entry points take host pointers and do their own H2D/D2H copies;
+ *     "dev" entry points take CUDA device pointers plus a cudaStream_t (passed
+ *     as void*) and never synchronise unless stated.
+ *
+ * Profile layout (kpal/klib.py:160-170): int64[4^k], index = base-4 number of
+ * the k-mer, first base most significant, A=0 C=1 G=2 T=3.
+ */
+#ifndef KPAL_B200_H
+#define KPAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KPAL_B200_ABI_VERSION 1
+
+/* error codes */
+#define KPAL_OK        0
+#define KPAL_EINVAL    1   /* bad argument (Python wrapper raises ValueError)   */
+#define KPAL_ECUDA     2   /* CUDA runtime / no device (RuntimeError)           */
+#define KPAL_ENOMEM    3   /* host or device allocation failed (MemoryError)    */
+#define KPAL_EOVERFLOW 4   /* a 32-bit device counter would overflow            */
+
+/* metric / pairwise selectors (kpal/metrics.py:151-162) */
+#define KPAL_METRIC_MULTISET  0   /* metrics.multiset, kpal/metrics.py:101-123  */
+#define KPAL_METRIC_EUCLIDEAN 1   /* metrics.euclidean, kpal/metrics.py:126-135 */
+#define KPAL_METRIC_COSINE    2   /* metrics.cosine_similarity, 138-147         */
+#define KPAL_PAIRWISE_PROD    0   /* |x-y| / ((x+1)(y+1)), kpal/metrics.py:160  */
+#define KPAL_PAIRWISE_SUM     1   /* |x-y| / (x+y+1),      kpal/metrics.py:161  */
+
+#define KPAL_MAX_K 15
+
+/* ------------------------------------------------------------------ misc */
+
+int         kpal_abi_version(void);
+const char *kpal_last_error(void);
+/* number of visible CUDA devices (0 when there is none; never fails) */
+int         kpal_device_count(void);
+/* bind the calling thread's library context to `device` (default 0) */
+int         kpal_set_device(int device);
+/* pinned (page-locked) host memory for fast H2D/D2H; caller frees */
+void       *kpal_host_alloc(size_t bytes);
+void        kpal_host_free(void *p);
+/* device memory helpers for hosts that do not link the CUDA runtime */
+void       *kpal_dev_alloc(size_t bytes);
+void        kpal_dev_free(void *p);
+int         kpal_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, void *stream);
+int         kpal_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes, void *stream);
+int         kpal_stream_sync(void *stream);
+
+/* ------------------------------------------------- packed sequence format
+ *
+ * The device kernels read sequence as two bit streams over a single run of
+ * "bases" in which records are separated by ONE invalid base:
+ *   codes: 2 bits per base, 16 bases per uint32, first base in the MOST
+ *          significant bits (so a k-mer index is a funnel shift of 2 words);
+ *   valid: 1 bit per base, 32 bases per uint32, same order; 0 for every byte
+ *          that is not ACGTacgt (kpal/klib.py:152) and for record separators.
+ * "window valid <=> its k valid bits are all 1" then reproduces both the
+ * N-split (kpal/klib.py:152-156) and the no-window-across-records rule
+ * (kpal/klib.py:154) in one predicate.  Buffers are padded with zero words:
+ * kpal_packed_words() gives the required uint32 counts.
+ */
+void kpal_packed_words(uint64_t n_bases, uint64_t *code_words, uint64_t *valid_words);
+
+/*
+ * Host packer for a list of sequences (the iterable handed to
+ * Profile.from_sequences, kpal/klib.py:135): record r is
+ * text[offsets[r] .. offsets[r+1]).  Emits n_bases = sum(len) + n_records.
+ * rec_starts (optional, n_records+1 entries) receives the base index at which
+ * each record starts in the packed stream.
+ */
+int kpal_pack_sequences(const char *text, const uint64_t *offsets, uint64_t n_records,
+                        uint32_t *codes, uint32_t *valid, uint64_t *rec_starts,
+                        uint64_t *n_bases_out);
+
+/*
+ * Host FASTA scanner + packer, replacing Bio.SeqIO.parse + str(record.seq)
+ * at kpal/klib.py:111 / 131 (FastaIterator rules: text before the first '>'
+ * skipped; sequence lines right-stripped, spaces and '\r' removed, joined).
+ * Call kpal_fasta_scan first to size the buffers.
+ *   n_records   number of '>' records
+ *   n_bases     packed length (sequence bytes + one separator per record)
+ *   name_bytes  bytes needed for the '\0'-separated record names
+ */
+int kpal_fasta_scan(const char *fasta, uint64_t n_bytes, uint64_t *n_records,
+                    uint64_t *n_bases, uint64_t *name_bytes);
+int kpal_fasta_pack(const char *fasta, uint64_t n_bytes, uint32_t *codes, uint32_t *valid,
+                    uint64_t *rec_starts /* n_records+1 */, char *names /* name_bytes */);
+
+/* ------------------------------------------------------ counting: host API */
+
+/*
+ * Replaces Profile.from_sequences (kpal/klib.py:135-170) [+ Profile.balance,
+ * kpal/klib.py:285-298, when balance != 0]: counts_out[4^k] int64.
+ */
+int kpal_count_sequences(const char *text, const uint64_t *offsets, uint64_t n_records,
+                         int k, int balance, int64_t *counts_out);
+
+/* Replaces Profile.from_fasta (kpal/klib.py:97-112) [+ balance]. */
+int kpal_count_fasta(const char *fasta, uint64_t n_bytes, int k, int balance,
+                     int64_t *counts_out);
+
+/*
+ * Replaces the per-record loop of Profile.from_fasta_by_record
+ * (kpal/klib.py:114-133) for records [first, first+n) of an already packed
+ * stream: rows_out is row-major [n][4^k] int64.
+ */
+int kpal_count_by_record(const uint32_t *codes, const uint32_t *valid, uint64_t n_bases,
+                         const uint64_t *rec_starts, uint64_t first, uint64_t n,
+                         int k, int balance, int64_t *rows_out);
+
+/* Replaces Profile.balance (kpal/klib.py:285-298) on a host vector, in place. */
+int kpal_balance(int64_t *counts_inout, int k);
+
+/* ----------------------------------------------------- distances: host API */
+
+/*
+ * Replaces kdistlib.distance_matrix's pair loop (kpal/kdistlib.py:179-184) with
+ * ProfileDistance.distance (kpal/kdistlib.py:126-161) restricted to the
+ * device fast path (do_positive = do_smooth = False, built-in pairwise):
+ * profiles is row-major [n_profiles][4^k] int64; out is row-major
+ * [n_profiles][n_profiles] float64, symmetric, diagonal = d(p,p).
+ */
+int kpal_distance_matrix(const int64_t *profiles, uint64_t n_profiles, int k,
+                         int metric, int pairwise, int do_balance, int do_scale, int down,
+                         double *out);
+
+/* ProfileDistance.distance for one pair (kpal/kdistlib.py:126-161). */
+int kpal_pair_distance(const int64_t *left, const int64_t *right, int k,
+                       int metric, int pairwise, int do_balance, int do_scale, int down,
+                       double *out);
+
+/* ---------------------------------------------------- counting: device API
+ * (bench harness, multi-GPU sharding: every pointer is a device pointer)    */
+
+/*
+ * Accumulate the windows of a packed stream into a device table of 4^k
+ * counters (counter_bits = 32 or 64; the caller zeroes the table).
+ * 32-bit counters are exact while n_bases < 2^32.
+ */
+int kpal_dev_count_packed(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_bases,
+                          int k, void *d_table, int counter_bits, void *stream);
+
+/* table (u32/u64) -> int64 counts, optionally fused with balance
+ * (out[i] = t[i] + t[rc(i)], kpal/klib.py:290-298). */
+int kpal_dev_finalize_counts(const void *d_table, int counter_bits, int k, int balance,
+                             int64_t *d_counts, void *stream);
+
+/* out[i] = in[i] + in[rc(i)] on int64 device vectors (in != out). */
+int kpal_dev_balance(const int64_t *d_in, int64_t *d_out, int k, void *stream);
+
+/* rows [first, first+n) of the per-record count matrix, device resident. */
+int kpal_dev_count_by_record(const uint32_t *d_codes, const uint32_t *d_valid,
+                             const uint64_t *d_rec_starts, uint64_t first, uint64_t n,
+                             int k, int balance, int64_t *d_rows, void *stream);
+
+/* --------------------------------------------------- distances: device API */
+
+/* stride (in doubles) of one prepared profile row for a given k */
+uint64_t kpal_prepared_stride(int k);
+
+/*
+ * Per-profile pre-pass (done once per profile instead of once per pair as in
+ * kpal/kdistlib.py:136-157): optional balance, total S (kpal/metrics.py:64-65),
+ * F = x/S (x when do_scale == 0), R = 1/(x+1), non-zero bitmap, sum(F^2).
+ *   d_counts  [n][4^k] int64
+ *   d_F, d_R  [n][stride] float64 (d_R may be NULL unless multiset/prod)
+ *   d_bitmap  [n][stride/32] uint32
+ *   d_totals  [n] float64, d_norm2 [n] float64
+ */
+int kpal_dev_profiles_prepare(const int64_t *d_counts, uint64_t n, int k, int do_balance,
+                              int do_scale, double *d_F, double *d_R, uint32_t *d_bitmap,
+                              double *d_totals, double *d_norm2, void *stream);
+
+/*
+ * Profile order by total for the scaled metrics: ascending (the scaled profile
+ * of a pair is the one with the smaller total, kpal/metrics.py:67-70), or
+ * descending when down != 0 (kpal/metrics.py:84-86: then the larger one is
+ * scaled).  Tiny host-side stable sort of n doubles; synchronises the stream.
+ */
+int kpal_dev_order_by_total(const double *d_totals, uint64_t n, int down, int32_t *d_order,
+                            void *stream);
+
+/* number of tiles of the (sorted) upper triangle the tile kernel walks */
+uint64_t kpal_distance_num_tiles(uint64_t n_profiles);
+
+/*
+ * Distances for tiles [tile_begin, tile_end) (multi-GPU: each rank takes a
+ * slice; tiles are independent).  d_order[n] is the profile order by total
+ * (ascending; descending when down != 0) or NULL for identity (do_scale == 0).
+ * Writes both out[i][j] and out[j][i] (row-major [n][n]) for every pair of
+ * the tiles; other entries are left untouched.
+ */
+int kpal_dev_distance_tiles(const double *d_F, const double *d_R, const uint32_t *d_bitmap,
+                            const double *d_totals, const double *d_norm2,
+                            const int32_t *d_order, uint64_t n, int k,
+                            int metric, int pairwise, int do_scale, int down,
+                            uint64_t tile_begin, uint64_t tile_end,
+                            double *d_out, void *stream);
+
+/* counters for bench.py's "gpu_launches": kernels launched by this library
+ * in the calling process since load / since the last reset. */
+uint64_t kpal_kernel_launches(void);
+void     kpal_reset_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KPAL_B200_H */

@@ -1,0 +1,303 @@
+"""
+ctypes binding of ``libkpal_b200.so`` (C ABI declared in ``include/kpal_b200.h``).
+
+There is deliberately no CPU fallback: if the shared library is missing or no
+CUDA device is visible, every compute call raises.  Argument errors map to
+``ValueError`` (as the reference raises for bad input), CUDA failures to
+``RuntimeError``, allocation failures to ``MemoryError``.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkpal_b200.so")
+
+KPAL_OK, KPAL_EINVAL, KPAL_ECUDA, KPAL_ENOMEM, KPAL_EOVERFLOW = range(5)
+METRICS = {"multiset": 0, "euclidean": 1, "cosine": 2}
+PAIRWISE = {"prod": 0, "sum": 1}
+MAX_K = 15
+
+#: every symbol include/kpal_b200.h declares (checked by tests/test_cabi.py)
+SYMBOLS = (
+    "kpal_abi_version", "kpal_last_error", "kpal_device_count", "kpal_set_device",
+    "kpal_host_alloc", "kpal_host_free", "kpal_dev_alloc", "kpal_dev_free",
+    "kpal_memcpy_h2d", "kpal_memcpy_d2h", "kpal_stream_sync",
+    "kpal_packed_words", "kpal_pack_sequences", "kpal_fasta_scan", "kpal_fasta_pack",
+    "kpal_count_sequences", "kpal_count_fasta", "kpal_count_by_record", "kpal_balance",
+    "kpal_distance_matrix", "kpal_pair_distance",
+    "kpal_dev_count_packed", "kpal_dev_finalize_counts", "kpal_dev_balance",
+    "kpal_dev_count_by_record", "kpal_prepared_stride", "kpal_dev_profiles_prepare",
+    "kpal_dev_order_by_total", "kpal_distance_num_tiles", "kpal_dev_distance_tiles",
+    "kpal_kernel_launches", "kpal_reset_kernel_launches",
+)
+
+_lib = None
+
+
+class KpalB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KpalB200Error(
+            "libkpal_b200.so not found at %s; build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`make -C kpal_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+    c = ctypes
+    L = c.CDLL(LIB_PATH)
+    u64, i32, vp = c.c_uint64, c.c_int, c.c_void_p
+    pu64 = c.POINTER(c.c_uint64)
+
+    def sig(name, restype, *argtypes):
+        fn = getattr(L, name)
+        fn.restype = restype
+        fn.argtypes = list(argtypes)
+
+    sig("kpal_abi_version", i32)
+    sig("kpal_last_error", c.c_char_p)
+    sig("kpal_device_count", i32)
+    sig("kpal_set_device", i32, i32)
+    sig("kpal_host_alloc", vp, c.c_size_t)
+    sig("kpal_host_free", None, vp)
+    sig("kpal_dev_alloc", vp, c.c_size_t)
+    sig("kpal_dev_free", None, vp)
+    sig("kpal_memcpy_h2d", i32, vp, vp, c.c_size_t, vp)
+    sig("kpal_memcpy_d2h", i32, vp, vp, c.c_size_t, vp)
+    sig("kpal_stream_sync", i32, vp)
+    sig("kpal_packed_words", None, u64, pu64, pu64)
+    sig("kpal_pack_sequences", i32, vp, vp, u64, vp, vp, vp, pu64)
+    sig("kpal_fasta_scan", i32, vp, u64, pu64, pu64, pu64)
+    sig("kpal_fasta_pack", i32, vp, u64, vp, vp, vp, vp)
+    sig("kpal_count_sequences", i32, vp, vp, u64, i32, i32, vp)
+    sig("kpal_count_fasta", i32, vp, u64, i32, i32, vp)
+    sig("kpal_count_by_record", i32, vp, vp, u64, vp, u64, u64, i32, i32, vp)
+    sig("kpal_balance", i32, vp, i32)
+    sig("kpal_distance_matrix", i32, vp, u64, i32, i32, i32, i32, i32, i32, vp)
+    sig("kpal_pair_distance", i32, vp, vp, i32, i32, i32, i32, i32, i32, vp)
+    sig("kpal_dev_count_packed", i32, vp, vp, u64, i32, vp, i32, vp)
+    sig("kpal_dev_finalize_counts", i32, vp, i32, i32, i32, vp, vp)
+    sig("kpal_dev_balance", i32, vp, vp, i32, vp)
+    sig("kpal_dev_count_by_record", i32, vp, vp, vp, u64, u64, i32, i32, vp, vp)
+    sig("kpal_prepared_stride", u64, i32)
+    sig("kpal_dev_profiles_prepare", i32, vp, u64, i32, i32, i32, vp, vp, vp, vp, vp, vp)
+    sig("kpal_dev_order_by_total", i32, vp, u64, i32, vp, vp)
+    sig("kpal_distance_num_tiles", u64, u64)
+    sig("kpal_dev_distance_tiles", i32, vp, vp, vp, vp, vp, vp, u64, i32, i32, i32, i32, i32,
+        u64, u64, vp, vp)
+    sig("kpal_kernel_launches", u64)
+    sig("kpal_reset_kernel_launches", None)
+    _lib = L
+    return L
+
+
+def check(code):
+    """Map a C-ABI return code to a Python exception."""
+    if code == KPAL_OK:
+        return
+    msg = (load().kpal_last_error() or b"").decode("utf-8", "replace")
+    if code == KPAL_EINVAL:
+        raise ValueError(msg)
+    if code == KPAL_ENOMEM:
+        raise MemoryError(msg)
+    if code == KPAL_EOVERFLOW:
+        raise OverflowError(msg)
+    raise KpalB200Error(msg)
+
+
+def device_count():
+    return int(load().kpal_device_count())
+
+
+def require_gpu():
+    if device_count() < 1:
+        raise KpalB200Error("no CUDA device visible: kpal_b200 runs its hot path on a "
+                            "B200 GPU only (there is no CPU fallback)")
+
+
+def ptr(a):
+    """Host pointer of a C-contiguous NumPy array (or None)."""
+    if a is None:
+        return None
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class PinnedArray(object):
+    """NumPy view over page-locked host memory owned by the library
+    (fast H2D / D2H).  Keep the object alive while the array is in use."""
+
+    def __init__(self, shape, dtype):
+        L = load()
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(np.atleast_1d(shape).tolist())
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._ptr = L.kpal_host_alloc(max(nbytes, 1))
+        if not self._ptr:
+            raise MemoryError("kpal_host_alloc(%d) failed" % nbytes)
+        buf = (ctypes.c_char * max(nbytes, 1)).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            load().kpal_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------- host API
+
+def _join_sequences(sequences):
+    """bytes blob + uint64 offsets for an iterable of str / bytes."""
+    parts = []
+    offsets = [0]
+    total = 0
+    for s in sequences:
+        if isinstance(s, str):
+            s = s.encode("latin-1", "replace")
+        else:
+            s = bytes(s)
+        parts.append(s)
+        total += len(s)
+        offsets.append(total)
+    return b"".join(parts), np.asarray(offsets, dtype=np.uint64)
+
+
+def count_sequences(sequences, k, balance=False):
+    """int64[4**k] counts of an iterable of sequences (kpal_count_sequences)."""
+    _check_k(k)
+    L = load()
+    require_gpu()
+    blob, offsets = _join_sequences(sequences)
+    out = np.empty(4 ** k, dtype=np.int64)
+    check(L.kpal_count_sequences(ctypes.c_char_p(blob) if blob else None, ptr(offsets),
+                                 len(offsets) - 1, int(k), int(bool(balance)), ptr(out)))
+    return out
+
+
+def count_fasta(text, k, balance=False):
+    """int64[4**k] counts of FASTA text (str or bytes) (kpal_count_fasta)."""
+    _check_k(k)
+    L = load()
+    require_gpu()
+    if isinstance(text, str):
+        text = text.encode("latin-1", "replace")
+    out = np.empty(4 ** k, dtype=np.int64)
+    check(L.kpal_count_fasta(ctypes.c_char_p(text) if text else None, len(text), int(k),
+                             int(bool(balance)), ptr(out)))
+    return out
+
+
+def fasta_pack(text):
+    """Host-side scan + pack of FASTA text.  Returns (codes, valid, rec_starts,
+    names, n_bases).  No GPU needed."""
+    L = load()
+    if isinstance(text, str):
+        text = text.encode("latin-1", "replace")
+    n_rec, n_bases, name_bytes = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+    buf = ctypes.c_char_p(text) if text else None
+    check(L.kpal_fasta_scan(buf, len(text), ctypes.byref(n_rec), ctypes.byref(n_bases),
+                            ctypes.byref(name_bytes)))
+    cw, vw = ctypes.c_uint64(), ctypes.c_uint64()
+    L.kpal_packed_words(n_bases.value, ctypes.byref(cw), ctypes.byref(vw))
+    codes = np.zeros(cw.value, dtype=np.uint32)
+    valid = np.zeros(vw.value, dtype=np.uint32)
+    rec_starts = np.zeros(n_rec.value + 1, dtype=np.uint64)
+    names = ctypes.create_string_buffer(max(1, name_bytes.value))
+    check(L.kpal_fasta_pack(buf, len(text), ptr(codes), ptr(valid), ptr(rec_starts), names))
+    name_list = names.raw[:name_bytes.value].split(b"\0")[:n_rec.value] if n_rec.value else []
+    return codes, valid, rec_starts, [n.decode("latin-1") for n in name_list], n_bases.value
+
+
+def pack_sequences(sequences):
+    """Host-side pack of a sequence list: (codes, valid, rec_starts, n_bases)."""
+    L = load()
+    blob, offsets = _join_sequences(sequences)
+    n_bases = ctypes.c_uint64()
+    n_rec = len(offsets) - 1
+    check(L.kpal_pack_sequences(None, ptr(offsets), n_rec, None, None, None, ctypes.byref(n_bases)))
+    cw, vw = ctypes.c_uint64(), ctypes.c_uint64()
+    L.kpal_packed_words(n_bases.value, ctypes.byref(cw), ctypes.byref(vw))
+    codes = np.zeros(cw.value, dtype=np.uint32)
+    valid = np.zeros(vw.value, dtype=np.uint32)
+    rec_starts = np.zeros(n_rec + 1, dtype=np.uint64)
+    check(L.kpal_pack_sequences(ctypes.c_char_p(blob) if blob else None, ptr(offsets), n_rec,
+                                ptr(codes), ptr(valid), ptr(rec_starts), ctypes.byref(n_bases)))
+    return codes, valid, rec_starts, n_bases.value
+
+
+def count_by_record(codes, valid, n_bases, rec_starts, first, n, k, balance=False):
+    """Dense [n][4**k] int64 rows for records [first, first+n)."""
+    _check_k(k)
+    L = load()
+    require_gpu()
+    out = np.empty((n, 4 ** k), dtype=np.int64)
+    check(L.kpal_count_by_record(ptr(codes), ptr(valid), int(n_bases), ptr(rec_starts), int(first),
+                                 int(n), int(k), int(bool(balance)), ptr(out)))
+    return out
+
+
+def balance(counts):
+    """In-place Profile.balance on a C-contiguous int64 array."""
+    L = load()
+    require_gpu()
+    k = _k_of(counts.size)
+    if counts.dtype != np.int64 or not counts.flags.c_contiguous:
+        raise ValueError("counts must be a C-contiguous int64 array")
+    check(L.kpal_balance(ptr(counts), k))
+    return counts
+
+
+def distance_matrix(profiles, metric="multiset", pairwise="prod", do_balance=False,
+                    do_scale=False, down=False):
+    """Symmetric [n][n] float64 matrix for a C-contiguous [n][4**k] int64 array."""
+    L = load()
+    require_gpu()
+    profiles = np.ascontiguousarray(profiles, dtype=np.int64)
+    n, size = profiles.shape
+    k = _k_of(size)
+    out = np.empty((n, n), dtype=np.float64)
+    check(L.kpal_distance_matrix(ptr(profiles), n, k, METRICS[metric], PAIRWISE[pairwise],
+                                 int(bool(do_balance)), int(bool(do_scale)), int(bool(down)),
+                                 ptr(out)))
+    return out
+
+
+def pair_distance(left, right, metric="multiset", pairwise="prod", do_balance=False,
+                  do_scale=False, down=False):
+    L = load()
+    require_gpu()
+    left = np.ascontiguousarray(left, dtype=np.int64)
+    right = np.ascontiguousarray(right, dtype=np.int64)
+    if left.shape != right.shape or left.ndim != 1:
+        raise ValueError("profiles must be 1-D and of equal length")
+    k = _k_of(left.size)
+    out = ctypes.c_double()
+    check(L.kpal_pair_distance(ptr(left), ptr(right), k, METRICS[metric], PAIRWISE[pairwise],
+                               int(bool(do_balance)), int(bool(do_scale)), int(bool(down)),
+                               ctypes.byref(out)))
+    return out.value
+
+
+def _check_k(k):
+    if not (1 <= int(k) <= MAX_K):
+        raise ValueError("k-mer length %r out of range [1, %d]" % (k, MAX_K))
+
+
+def _k_of(size):
+    k = int(size).bit_length() // 2
+    if size < 4 or 4 ** k != size:
+        raise ValueError("profile length %d is not a power of 4" % size)
+    _check_k(k)
+    return k

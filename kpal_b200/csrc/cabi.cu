@@ -1,0 +1,460 @@
+// extern "C" surface of libkpal_b200.so (see include/kpal_b200.h).
+//
+// The "host" entry points own the H2D / D2H traffic and the scratch memory;
+// the "dev" entry points are thin launch wrappers for callers that already
+// hold device memory (bench harness, multi-GPU driver in kpal_b200/multigpu.py).
+#include "common.cuh"
+
+#include <algorithm>
+#include <mutex>
+#include <numeric>
+#include <string.h>
+#include <vector>
+
+namespace kpal {
+
+// launchers (count.cu / distance.cu)
+int launch_count(const uint32_t *, const uint32_t *, uint64_t, int, void *, int, cudaStream_t);
+int launch_finalize(const void *, int, int, int, int64_t *, cudaStream_t);
+int launch_balance(const int64_t *, int64_t *, int, cudaStream_t);
+int launch_by_record(const uint32_t *, const uint32_t *, const uint64_t *, uint64_t, uint64_t, int,
+                     int, int64_t *, cudaStream_t);
+int launch_prepare(const int64_t *, uint64_t, int, int, int, double *, double *, uint32_t *,
+                   double *, double *, unsigned long long *, cudaStream_t);
+int launch_distance_tiles(const double *, const double *, const uint32_t *, const double *,
+                          const double *, const int32_t *, uint64_t, int, int, int, int, int,
+                          uint64_t, uint64_t, double *, uint32_t *, double *, cudaStream_t);
+uint64_t distance_num_tiles(uint64_t n);
+uint64_t prepared_stride_host(int k);
+
+static thread_local char t_error[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_error, sizeof(t_error), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count()
+{
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
+        cached = prop.multiProcessorCount;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+// RAII device / pinned buffers for the host-level entry points
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes)
+    {
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            cudaGetLastError();
+            return e == cudaErrorMemoryAllocation ? KPAL_ENOMEM : KPAL_ECUDA;
+        }
+        return KPAL_OK;
+    }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+struct PinBuf {
+    void *p = nullptr;
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    int alloc(size_t bytes)
+    {
+        cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMallocHost(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            cudaGetLastError();
+            return e == cudaErrorMemoryAllocation ? KPAL_ENOMEM : KPAL_ECUDA;
+        }
+        return KPAL_OK;
+    }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+static int require_device()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); libkpal_b200 has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return KPAL_ECUDA;
+    }
+    return KPAL_OK;
+}
+
+// Scratch for the dev-level distance entry point (acc / cnt matrices), cached
+// per device and grown on demand.
+struct DistScratch {
+    int device = -1;
+    uint64_t n = 0;
+    double *acc = nullptr;
+    uint32_t *cnt = nullptr;
+};
+static std::mutex g_scratch_mutex;
+static std::vector<DistScratch> g_scratch;
+
+static int get_dist_scratch(uint64_t n, double **acc, uint32_t **cnt)
+{
+    int dev = 0;
+    KPAL_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    DistScratch *s = nullptr;
+    for (auto &x : g_scratch) if (x.device == dev) s = &x;
+    if (!s) { g_scratch.push_back(DistScratch()); s = &g_scratch.back(); s->device = dev; }
+    if (s->n < n) {
+        if (s->acc) cudaFree(s->acc);
+        if (s->cnt) cudaFree(s->cnt);
+        s->acc = nullptr; s->cnt = nullptr; s->n = 0;
+        KPAL_CUDA(cudaMalloc(&s->acc, n * n * sizeof(double)));
+        KPAL_CUDA(cudaMalloc(&s->cnt, n * n * sizeof(uint32_t)));
+        s->n = n;
+    }
+    *acc = s->acc; *cnt = s->cnt;
+    return KPAL_OK;
+}
+
+// order of the profiles by total: ascending (the scaled profile A has the
+// smaller total), descending with `down` (A has the larger total).  Stable, so
+// ties keep input order (either role gives the same value for equal totals).
+static int make_order(const double *d_totals, uint64_t n, int down, int32_t *d_order,
+                      cudaStream_t stream)
+{
+    std::vector<double> tot(n);
+    KPAL_CUDA(cudaMemcpyAsync(tot.data(), d_totals, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    KPAL_CUDA(cudaStreamSynchronize(stream));
+    std::vector<int32_t> ord(n);
+    std::iota(ord.begin(), ord.end(), 0);
+    // NaN-free: totals are finite non-negative
+    if (down) std::stable_sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) { return tot[x] > tot[y]; });
+    else std::stable_sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) { return tot[x] < tot[y]; });
+    KPAL_CUDA(cudaMemcpyAsync(d_order, ord.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    KPAL_CUDA(cudaStreamSynchronize(stream));
+    return KPAL_OK;
+}
+
+}  // namespace kpal
+
+using namespace kpal;
+
+// ------------------------------------------------------------------ misc
+extern "C" int kpal_abi_version(void) { return KPAL_B200_ABI_VERSION; }
+extern "C" const char *kpal_last_error(void) { return t_error; }
+
+extern "C" int kpal_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int kpal_set_device(int device)
+{
+    KPAL_CHECK(require_device());
+    KPAL_CUDA(cudaSetDevice(device));
+    return KPAL_OK;
+}
+
+extern "C" void *kpal_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        set_error("cudaMallocHost(%zu) failed", bytes);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void kpal_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" void *kpal_dev_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void kpal_dev_free(void *p) { if (p) cudaFree(p); }
+
+extern "C" int kpal_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream)
+{
+    KPAL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return KPAL_OK;
+}
+extern "C" int kpal_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream)
+{
+    KPAL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return KPAL_OK;
+}
+extern "C" int kpal_stream_sync(void *stream)
+{
+    KPAL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return KPAL_OK;
+}
+
+extern "C" uint64_t kpal_kernel_launches(void) { return g_launches.load(); }
+extern "C" void kpal_reset_kernel_launches(void) { g_launches.store(0); }
+
+// ---------------------------------------------------- counting: device API
+extern "C" int kpal_dev_count_packed(const uint32_t *d_codes, const uint32_t *d_valid,
+                                     uint64_t n_bases, int k, void *d_table, int counter_bits,
+                                     void *stream)
+{
+    if (!d_table || ((!d_codes || !d_valid) && n_bases)) return bad_arg("null device pointer");
+    return launch_count(d_codes, d_valid, n_bases, k, d_table, counter_bits, (cudaStream_t)stream);
+}
+
+extern "C" int kpal_dev_finalize_counts(const void *d_table, int counter_bits, int k, int balance,
+                                        int64_t *d_counts, void *stream)
+{
+    if (!d_table || !d_counts) return bad_arg("null device pointer");
+    return launch_finalize(d_table, counter_bits, k, balance, d_counts, (cudaStream_t)stream);
+}
+
+extern "C" int kpal_dev_balance(const int64_t *d_in, int64_t *d_out, int k, void *stream)
+{
+    if (!d_in || !d_out) return bad_arg("null device pointer");
+    return launch_balance(d_in, d_out, k, (cudaStream_t)stream);
+}
+
+extern "C" int kpal_dev_count_by_record(const uint32_t *d_codes, const uint32_t *d_valid,
+                                        const uint64_t *d_rec_starts, uint64_t first, uint64_t n,
+                                        int k, int balance, int64_t *d_rows, void *stream)
+{
+    if (n && (!d_codes || !d_valid || !d_rec_starts || !d_rows)) return bad_arg("null device pointer");
+    return launch_by_record(d_codes, d_valid, d_rec_starts, first, n, k, balance, d_rows,
+                            (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------ counting: host API
+static int count_packed_host(const uint32_t *codes, const uint32_t *valid, uint64_t n_bases, int k,
+                             int balance, int64_t *counts_out)
+{
+    if (k < 1 || k > KPAL_MAX_K) { set_error("k-mer length %d out of range [1, %d]", k, KPAL_MAX_K); return KPAL_EINVAL; }
+    KPAL_CHECK(require_device());
+    const uint64_t bins = 1ull << (2 * k);
+    uint64_t cw, vw;
+    kpal_packed_words(n_bases, &cw, &vw);
+    const int bits = (n_bases >= (1ull << 32)) ? 64 : 32;
+    DevBuf d_codes, d_valid, d_table, d_counts;
+    KPAL_CHECK(d_codes.alloc(cw * 4));
+    KPAL_CHECK(d_valid.alloc(vw * 4));
+    KPAL_CHECK(d_table.alloc(bins * (bits / 8)));
+    KPAL_CHECK(d_counts.alloc(bins * 8));
+    cudaStream_t st = 0;
+    KPAL_CUDA(cudaMemcpyAsync(d_codes.p, codes, cw * 4, cudaMemcpyHostToDevice, st));
+    KPAL_CUDA(cudaMemcpyAsync(d_valid.p, valid, vw * 4, cudaMemcpyHostToDevice, st));
+    KPAL_CUDA(cudaMemsetAsync(d_table.p, 0, bins * (bits / 8), st));
+    KPAL_CHECK(launch_count(d_codes.as<uint32_t>(), d_valid.as<uint32_t>(), n_bases, k, d_table.p, bits, st));
+    KPAL_CHECK(launch_finalize(d_table.p, bits, k, balance, d_counts.as<int64_t>(), st));
+    KPAL_CUDA(cudaMemcpyAsync(counts_out, d_counts.p, bins * 8, cudaMemcpyDeviceToHost, st));
+    KPAL_CUDA(cudaStreamSynchronize(st));
+    return KPAL_OK;
+}
+
+extern "C" int kpal_count_sequences(const char *text, const uint64_t *offsets, uint64_t n_records,
+                                    int k, int balance, int64_t *counts_out)
+{
+    if (!counts_out || !offsets) return bad_arg("null pointer");
+    uint64_t n_bases = 0;
+    KPAL_CHECK(kpal_pack_sequences(text, offsets, n_records, nullptr, nullptr, nullptr, &n_bases));
+    uint64_t cw, vw;
+    kpal_packed_words(n_bases, &cw, &vw);
+    KPAL_CHECK(require_device());
+    PinBuf codes, valid;
+    KPAL_CHECK(codes.alloc(cw * 4));
+    KPAL_CHECK(valid.alloc(vw * 4));
+    KPAL_CHECK(kpal_pack_sequences(text, offsets, n_records, codes.as<uint32_t>(), valid.as<uint32_t>(),
+                                   nullptr, &n_bases));
+    return count_packed_host(codes.as<uint32_t>(), valid.as<uint32_t>(), n_bases, k, balance, counts_out);
+}
+
+extern "C" int kpal_count_fasta(const char *fasta, uint64_t n_bytes, int k, int balance,
+                                int64_t *counts_out)
+{
+    if (!counts_out || (!fasta && n_bytes)) return bad_arg("null pointer");
+    uint64_t n_rec = 0, n_bases = 0, name_bytes = 0;
+    KPAL_CHECK(kpal_fasta_scan(fasta, n_bytes, &n_rec, &n_bases, &name_bytes));
+    uint64_t cw, vw;
+    kpal_packed_words(n_bases, &cw, &vw);
+    KPAL_CHECK(require_device());
+    PinBuf codes, valid;
+    KPAL_CHECK(codes.alloc(cw * 4));
+    KPAL_CHECK(valid.alloc(vw * 4));
+    KPAL_CHECK(kpal_fasta_pack(fasta, n_bytes, codes.as<uint32_t>(), valid.as<uint32_t>(), nullptr, nullptr));
+    return count_packed_host(codes.as<uint32_t>(), valid.as<uint32_t>(), n_bases, k, balance, counts_out);
+}
+
+extern "C" int kpal_count_by_record(const uint32_t *codes, const uint32_t *valid, uint64_t n_bases,
+                                    const uint64_t *rec_starts, uint64_t first, uint64_t n, int k,
+                                    int balance, int64_t *rows_out)
+{
+    if (k < 1 || k > KPAL_MAX_K) { set_error("k-mer length %d out of range [1, %d]", k, KPAL_MAX_K); return KPAL_EINVAL; }
+    if (n == 0) return KPAL_OK;
+    if (!codes || !valid || !rec_starts || !rows_out) return bad_arg("null pointer");
+    KPAL_CHECK(require_device());
+    const uint64_t bins = 1ull << (2 * k);
+    // upload only the chunks the requested records touch
+    const uint64_t b0 = rec_starts[first], b1 = rec_starts[first + n];
+    if (b1 > n_bases || b0 > b1) return bad_arg("record starts outside the packed stream");
+    const uint64_t c0 = b0 / 64, c1 = (b1 + 63) / 64 + 1;       // + halo chunk
+    std::vector<uint64_t> rs(n + 1);
+    for (uint64_t r = 0; r <= n; ++r) rs[r] = rec_starts[first + r] - c0 * 64;
+    DevBuf d_codes, d_valid, d_rs, d_rows;
+    KPAL_CHECK(d_codes.alloc((c1 - c0) * 16));
+    KPAL_CHECK(d_valid.alloc((c1 - c0) * 8));
+    KPAL_CHECK(d_rs.alloc((n + 1) * 8));
+    // rows in batches that fit comfortably on the device
+    const uint64_t batch = std::max<uint64_t>(1, std::min<uint64_t>(n, (4ull << 30) / (bins * 8)));
+    KPAL_CHECK(d_rows.alloc(batch * bins * 8));
+    cudaStream_t st = 0;
+    KPAL_CUDA(cudaMemcpyAsync(d_codes.p, codes + c0 * 4, (c1 - c0) * 16, cudaMemcpyHostToDevice, st));
+    KPAL_CUDA(cudaMemcpyAsync(d_valid.p, valid + c0 * 2, (c1 - c0) * 8, cudaMemcpyHostToDevice, st));
+    KPAL_CUDA(cudaMemcpyAsync(d_rs.p, rs.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    for (uint64_t r = 0; r < n; r += batch) {
+        const uint64_t m = std::min(batch, n - r);
+        KPAL_CHECK(launch_by_record(d_codes.as<uint32_t>(), d_valid.as<uint32_t>(), d_rs.as<uint64_t>(),
+                                    r, m, k, balance, d_rows.as<int64_t>(), st));
+        KPAL_CUDA(cudaMemcpyAsync(rows_out + r * bins, d_rows.p, m * bins * 8, cudaMemcpyDeviceToHost, st));
+        KPAL_CUDA(cudaStreamSynchronize(st));
+    }
+    return KPAL_OK;
+}
+
+extern "C" int kpal_balance(int64_t *counts, int k)
+{
+    if (!counts) return bad_arg("null pointer");
+    if (k < 1 || k > KPAL_MAX_K) { set_error("k-mer length %d out of range [1, %d]", k, KPAL_MAX_K); return KPAL_EINVAL; }
+    KPAL_CHECK(require_device());
+    const uint64_t bins = 1ull << (2 * k);
+    DevBuf d_in, d_out;
+    KPAL_CHECK(d_in.alloc(bins * 8));
+    KPAL_CHECK(d_out.alloc(bins * 8));
+    cudaStream_t st = 0;
+    KPAL_CUDA(cudaMemcpyAsync(d_in.p, counts, bins * 8, cudaMemcpyHostToDevice, st));
+    KPAL_CHECK(launch_balance(d_in.as<int64_t>(), d_out.as<int64_t>(), k, st));
+    KPAL_CUDA(cudaMemcpyAsync(counts, d_out.p, bins * 8, cudaMemcpyDeviceToHost, st));
+    KPAL_CUDA(cudaStreamSynchronize(st));
+    return KPAL_OK;
+}
+
+// --------------------------------------------------- distances: device API
+extern "C" uint64_t kpal_prepared_stride(int k) { return prepared_stride_host(k); }
+extern "C" uint64_t kpal_distance_num_tiles(uint64_t n) { return distance_num_tiles(n); }
+
+extern "C" int kpal_dev_profiles_prepare(const int64_t *d_counts, uint64_t n, int k, int do_balance,
+                                         int do_scale, double *d_F, double *d_R, uint32_t *d_bitmap,
+                                         double *d_totals, double *d_norm2, void *stream)
+{
+    if (n && (!d_counts || !d_F || !d_bitmap || !d_totals || !d_norm2)) return bad_arg("null device pointer");
+    DevBuf tot;
+    KPAL_CHECK(tot.alloc(n * 8));
+    int r = launch_prepare(d_counts, n, k, do_balance, do_scale, d_F, d_R, d_bitmap, d_totals, d_norm2,
+                           tot.as<unsigned long long>(), (cudaStream_t)stream);
+    if (r == KPAL_OK) KPAL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));   // tot is freed on return
+    return r;
+}
+
+extern "C" int kpal_dev_order_by_total(const double *d_totals, uint64_t n, int down, int32_t *d_order,
+                                       void *stream)
+{
+    if (!d_totals || !d_order) return bad_arg("null device pointer");
+    return make_order(d_totals, n, down, d_order, (cudaStream_t)stream);
+}
+
+extern "C" int kpal_dev_distance_tiles(const double *d_F, const double *d_R, const uint32_t *d_bitmap,
+                                       const double *d_totals, const double *d_norm2,
+                                       const int32_t *d_order, uint64_t n, int k, int metric,
+                                       int pairwise, int do_scale, int down, uint64_t tile_begin,
+                                       uint64_t tile_end, double *d_out, void *stream)
+{
+    if (!d_F || !d_bitmap || !d_totals || !d_norm2 || !d_out) return bad_arg("null device pointer");
+    double *acc; uint32_t *cnt;
+    KPAL_CHECK(get_dist_scratch(n, &acc, &cnt));
+    return launch_distance_tiles(d_F, d_R, d_bitmap, d_totals, d_norm2, d_order, n, k, metric, pairwise,
+                                 do_scale, down, tile_begin, tile_end, acc, cnt, d_out,
+                                 (cudaStream_t)stream);
+}
+
+// ----------------------------------------------------- distances: host API
+extern "C" int kpal_distance_matrix(const int64_t *profiles, uint64_t n, int k, int metric,
+                                    int pairwise, int do_balance, int do_scale, int down, double *out)
+{
+    if (!profiles || !out) return bad_arg("null pointer");
+    if (n < 1) return bad_arg("need at least one profile");
+    if (k < 1 || k > KPAL_MAX_K) { set_error("k-mer length %d out of range [1, %d]", k, KPAL_MAX_K); return KPAL_EINVAL; }
+    KPAL_CHECK(require_device());
+    const uint64_t d = 1ull << (2 * k), stride = prepared_stride_host(k);
+    const bool need_r = (metric == KPAL_METRIC_MULTISET && pairwise == KPAL_PAIRWISE_PROD);
+    DevBuf F, R, bitmap, totals, norm2, order, tot_i64, slab, d_out;
+    KPAL_CHECK(F.alloc(n * stride * 8));
+    if (need_r) KPAL_CHECK(R.alloc(n * stride * 8));
+    KPAL_CHECK(bitmap.alloc(n * (stride / 32) * 4));
+    KPAL_CHECK(totals.alloc(n * 8));
+    KPAL_CHECK(norm2.alloc(n * 8));
+    KPAL_CHECK(order.alloc(n * 4));
+    KPAL_CHECK(d_out.alloc(n * n * 8));
+    // raw int64 profiles go through a bounded slab (<= 1 GiB) instead of living on the device
+    const uint64_t slab_rows = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(n, 65535), (1ull << 30) / (d * 8)));
+    KPAL_CHECK(slab.alloc(slab_rows * d * 8));
+    KPAL_CHECK(tot_i64.alloc(slab_rows * 8));
+    cudaStream_t st = 0;
+    for (uint64_t r = 0; r < n; r += slab_rows) {
+        const uint64_t m = std::min(slab_rows, n - r);
+        KPAL_CUDA(cudaMemcpyAsync(slab.p, profiles + r * d, m * d * 8, cudaMemcpyHostToDevice, st));
+        KPAL_CHECK(launch_prepare(slab.as<int64_t>(), m, k, do_balance, do_scale,
+                                  F.as<double>() + r * stride,
+                                  need_r ? R.as<double>() + r * stride : nullptr,
+                                  bitmap.as<uint32_t>() + r * (stride / 32), totals.as<double>() + r,
+                                  norm2.as<double>() + r, tot_i64.as<unsigned long long>(), st));
+    }
+    const int32_t *d_order = nullptr;
+    if (do_scale) {
+        KPAL_CHECK(make_order(totals.as<double>(), n, down, order.as<int32_t>(), st));
+        d_order = order.as<int32_t>();
+    }
+    double *acc; uint32_t *cnt;
+    KPAL_CHECK(get_dist_scratch(n, &acc, &cnt));
+    KPAL_CHECK(launch_distance_tiles(F.as<double>(), R.as<double>(), bitmap.as<uint32_t>(),
+                                     totals.as<double>(), norm2.as<double>(), d_order, n, k, metric,
+                                     pairwise, do_scale, down, 0, distance_num_tiles(n), acc, cnt,
+                                     d_out.as<double>(), st));
+    KPAL_CUDA(cudaMemcpyAsync(out, d_out.p, n * n * 8, cudaMemcpyDeviceToHost, st));
+    KPAL_CUDA(cudaStreamSynchronize(st));
+    return KPAL_OK;
+}
+
+extern "C" int kpal_pair_distance(const int64_t *left, const int64_t *right, int k, int metric,
+                                  int pairwise, int do_balance, int do_scale, int down, double *out)
+{
+    if (!left || !right || !out) return bad_arg("null pointer");
+    if (k < 1 || k > KPAL_MAX_K) { set_error("k-mer length %d out of range [1, %d]", k, KPAL_MAX_K); return KPAL_EINVAL; }
+    const uint64_t d = 1ull << (2 * k);
+    std::vector<int64_t> both(2 * d);
+    memcpy(both.data(), left, d * 8);
+    memcpy(both.data() + d, right, d * 8);
+    double m[4];
+    KPAL_CHECK(kpal_distance_matrix(both.data(), 2, k, metric, pairwise, do_balance, do_scale, down, m));
+    *out = m[1];
+    return KPAL_OK;
+}

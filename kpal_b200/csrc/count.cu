@@ -1,0 +1,328 @@
+// k-mer counting kernels for sm_100a.
+//
+// Replaces the per-base Python loop of Profile.from_sequences
+// (reference kpal/klib.py:154-168) and Profile.balance (kpal/klib.py:285-298).
+//
+// Input is the packed stream described in include/kpal_b200.h: 2-bit codes
+// (16 bases / u32, first base in the most significant bits) + 1-bit validity
+// (32 bases / u32).  One thread consumes one 64-base chunk with a single
+// 128-bit code load and a 64-bit validity load; the k-1 look-ahead bases come
+// from the next lane by warp shuffle (lane 31 re-reads one halo word).
+//
+//   count_global_kernel   any k: RED.ADD into a table resident in L2 / HBM
+//   count_smem_kernel     k <= 7: per-CTA privatised shared-memory histogram,
+//                         lane-replicated for tiny k, flushed with RED
+//   finalize_kernel       u32/u64 table -> int64 profile, fused with balance
+//   by_record_kernel      one CTA per record: zero-fill the row, then RED
+#include "common.cuh"
+
+namespace kpal {
+
+// ---------------------------------------------------------------------------
+// Per-chunk front end shared by all count kernels.
+// ---------------------------------------------------------------------------
+struct Chunk {
+    uint32_t w[5];      // 64 bases of codes + 16 look-ahead bases
+    uint64_t starts;    // bit (63 - o) set <=> the window starting at base o is all-valid
+};
+
+__device__ __forceinline__ void shl128(uint64_t hi, uint64_t lo, int s, uint64_t &ohi, uint64_t &olo)
+{
+    // 0 < s < 64
+    ohi = (hi << s) | (lo >> (64 - s));
+    olo = lo << s;
+}
+
+// `active` may differ between lanes, but every lane of the warp must call this
+// (it shuffles).  codes/valid are padded so chunk+1 is always readable.
+__device__ __forceinline__ Chunk load_chunk(const uint4 *__restrict__ codes,
+                                            const uint2 *__restrict__ valid,
+                                            uint64_t chunk, bool active, int k)
+{
+    Chunk c;
+    uint4 cw = make_uint4(0, 0, 0, 0);
+    uint2 vw = make_uint2(0, 0);
+    if (active) {
+        cw = __ldg(codes + chunk);
+        vw = __ldg(valid + chunk);
+    }
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t next_c = __shfl_down_sync(0xffffffffu, cw.x, 1);
+    uint32_t next_v = __shfl_down_sync(0xffffffffu, vw.x, 1);
+    if (lane == 31u && active) {   // halo of the warp's last lane: one extra word each
+        next_c = __ldg(reinterpret_cast<const uint32_t *>(codes + chunk + 1));
+        next_v = __ldg(reinterpret_cast<const uint32_t *>(valid + chunk + 1));
+    }
+    c.w[0] = cw.x; c.w[1] = cw.y; c.w[2] = cw.z; c.w[3] = cw.w; c.w[4] = next_c;
+
+    // run mask: A_L(p) = AND_{t<L} V(p+t), built by the binary method on k.
+    const uint64_t vhi = (uint64_t(vw.x) << 32) | vw.y;
+    const uint64_t vlo = uint64_t(next_v) << 32;
+    uint64_t ahi = vhi, alo = vlo;
+    int len = 1;
+    for (int b = 30 - __clz(k); b >= 0; --b) {       // bits of k below its top bit
+        uint64_t shi, slo;
+        shl128(ahi, alo, len, shi, slo);
+        ahi &= shi; alo &= slo; len <<= 1;
+        if ((k >> b) & 1) {
+            shl128(vhi, vlo, len, shi, slo);
+            ahi &= shi; alo &= slo; len += 1;
+        }
+    }
+    c.starts = ahi;
+    return c;
+}
+
+// k-mer index of the window starting at base o (compile-time) of the chunk.
+template <int O>
+__device__ __forceinline__ uint32_t window_index(const Chunk &c, int shift)
+{
+    constexpr int j = O / 16, r = O % 16;
+    const uint32_t x = (r == 0) ? c.w[j] : __funnelshift_l(c.w[j + 1], c.w[j], 2 * r);
+    return x >> shift;
+}
+
+template <int O, typename F>
+__device__ __forceinline__ void for_each_window_from(const Chunk &c, int shift, F &&f)
+{
+    if constexpr (O < 64) {
+        if ((c.starts >> (63 - O)) & 1ull) f(window_index<O>(c, shift));
+        for_each_window_from<O + 1>(c, shift, f);
+    }
+}
+
+template <typename F>
+__device__ __forceinline__ void for_each_window(const Chunk &c, int shift, F &&f)
+{
+    for_each_window_from<0>(c, shift, f);
+}
+
+// ---------------------------------------------------------------------------
+// Any k: RED.ADD into the global table (L2 resident for k <= 12 with u32).
+// ---------------------------------------------------------------------------
+template <typename CounterT>
+__global__ void __launch_bounds__(256)
+count_global_kernel(const uint4 *__restrict__ codes, const uint2 *__restrict__ valid,
+                    uint64_t n_chunks, int k, CounterT *__restrict__ table)
+{
+    const int shift = 32 - 2 * k;
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    // warp-uniform trip count so the halo shuffle always has 32 participants
+    const uint64_t first = uint64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31u);
+    for (uint64_t base = first; base < n_chunks; base += stride) {
+        const uint64_t chunk = base + (threadIdx.x & 31u);
+        const Chunk c = load_chunk(codes, valid, chunk, chunk < n_chunks, k);
+        for_each_window(c, shift, [&](uint32_t idx) { atomicAdd(table + idx, CounterT(1)); });
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k <= 7: shared-memory privatised histogram.  `rep` lane-indexed copies of the
+// histogram (layout [bin][copy], copy = lane % rep) remove same-address
+// serialisation for tiny k (k=1: 4 bins would otherwise take 8-way conflicts).
+// ---------------------------------------------------------------------------
+template <typename CounterT>
+__global__ void __launch_bounds__(256)
+count_smem_kernel(const uint4 *__restrict__ codes, const uint2 *__restrict__ valid,
+                  uint64_t n_chunks, int k, int rep_log2, CounterT *__restrict__ table)
+{
+    extern __shared__ uint32_t hist[];
+    const uint32_t bins = 1u << (2 * k);
+    const uint32_t words = bins << rep_log2;
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+
+    const int shift = 32 - 2 * k;
+    const uint32_t copy = threadIdx.x & ((1u << rep_log2) - 1u);
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    const uint64_t first = uint64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31u);
+    for (uint64_t base = first; base < n_chunks; base += stride) {
+        const uint64_t chunk = base + (threadIdx.x & 31u);
+        const Chunk c = load_chunk(codes, valid, chunk, chunk < n_chunks, k);
+        for_each_window(c, shift, [&](uint32_t idx) {
+            atomicAdd(&hist[(idx << rep_log2) + copy], 1u);
+        });
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < bins; b += blockDim.x) {
+        uint32_t s = 0;
+        for (uint32_t r = 0; r < (1u << rep_log2); ++r) s += hist[(b << rep_log2) + r];
+        if (s) atomicAdd(table + b, CounterT(s));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// table -> int64 profile, fused with balance: out[i] = t[i] + t[rc(i)]
+// (pairs get the sum, palindromes are doubled: kpal/klib.py:293-298).
+// ---------------------------------------------------------------------------
+template <typename CounterT>
+__global__ void __launch_bounds__(256)
+finalize_kernel(const CounterT *__restrict__ table, int k, int balance, int64_t *__restrict__ out)
+{
+    const uint32_t n = 1u << (2 * k);
+    const int shift = 32 - 2 * k;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int64_t v = int64_t(table[i]);
+        if (balance) v += int64_t(__ldg(table + rc_index(i, shift)));
+        out[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Per-record profiles (Profile.from_fasta_by_record, kpal/klib.py:114-133).
+// One CTA per record: stream zeros over the record's int64 row (the row stays
+// in L2 while the CTA works on it), then RED the record's windows into it.
+// HBM traffic = one write of the dense row: the path is write-bandwidth bound.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+by_record_kernel(const uint4 *__restrict__ codes, const uint2 *__restrict__ valid,
+                 const uint64_t *__restrict__ rec_starts, uint64_t first_rec, uint64_t n_rec,
+                 int k, int balance, int64_t *__restrict__ rows)
+{
+    const uint64_t bins = 1ull << (2 * k);
+    const int shift = 32 - 2 * k;
+    for (uint64_t r = blockIdx.x; r < n_rec; r += gridDim.x) {
+        unsigned long long *row = reinterpret_cast<unsigned long long *>(rows + r * bins);
+        // 1. zero fill (16-byte stores; bins*8 is a multiple of 16 for k >= 1)
+        ulonglong2 *row2 = reinterpret_cast<ulonglong2 *>(row);
+        for (uint64_t i = threadIdx.x; i < bins / 2; i += blockDim.x)
+            row2[i] = make_ulonglong2(0ull, 0ull);
+        __threadfence();
+        __syncthreads();
+        // 2. windows of bases [b0, b1)
+        const uint64_t b0 = rec_starts[first_rec + r], b1 = rec_starts[first_rec + r + 1];
+        const uint64_t c0 = b0 / kChunkBases, c1 = (b1 + kChunkBases - 1) / kChunkBases;
+        for (uint64_t base = c0 + (threadIdx.x & ~31u); base < c1; base += blockDim.x) {
+            const uint64_t chunk = base + (threadIdx.x & 31u);
+            Chunk c = load_chunk(codes, valid, chunk, chunk < c1, k);
+            // keep only windows that start inside this record
+            const uint64_t p0 = chunk * kChunkBases;
+            uint64_t keep = ~0ull;
+            if (p0 < b0) keep &= (b0 - p0 >= 64) ? 0ull : (~0ull >> (b0 - p0));
+            if (p0 + 64 > b1) keep &= (b1 <= p0) ? 0ull : ~(~0ull >> (b1 - p0));
+            c.starts &= keep;
+            for_each_window(c, shift, [&](uint32_t idx) {
+                atomicAdd(row + idx, 1ull);
+                if (balance) atomicAdd(row + rc_index(idx, shift), 1ull);
+            });
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+balance_i64_kernel(const int64_t *__restrict__ in, int k, int64_t *__restrict__ out)
+{
+    const uint32_t n = 1u << (2 * k);
+    const int shift = 32 - 2 * k;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        out[i] = in[i] + __ldg(in + rc_index(i, shift));
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+static int check_k(int k)
+{
+    if (k < 1 || k > KPAL_MAX_K) {
+        set_error("k-mer length %d out of range [1, %d]", k, KPAL_MAX_K);
+        return KPAL_EINVAL;
+    }
+    return KPAL_OK;
+}
+
+int launch_count(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_bases, int k,
+                 void *d_table, int counter_bits, cudaStream_t stream)
+{
+    KPAL_CHECK(check_k(k));
+    if (counter_bits != 32 && counter_bits != 64) return bad_arg("counter_bits must be 32 or 64");
+    if (n_bases == 0) return KPAL_OK;
+    if (counter_bits == 32 && n_bases >= (1ull << 32)) {
+        set_error("%llu bases would overflow 32-bit counters; use counter_bits=64",
+                  (unsigned long long)n_bases);
+        return KPAL_EOVERFLOW;
+    }
+    const uint64_t n_chunks = n_chunks_of(n_bases);
+    const uint4 *codes = reinterpret_cast<const uint4 *>(d_codes);
+    const uint2 *valid = reinterpret_cast<const uint2 *>(d_valid);
+    const int sms = sm_count();
+    if (k <= 7) {
+        // copies: as many as fit in 64 KB, at most one per lane
+        int rep_log2 = 0;
+        while (rep_log2 < 5 && ((4ull << (2 * k)) << (rep_log2 + 1)) <= 65536ull) ++rep_log2;
+        const size_t smem = (size_t(4) << (2 * k)) << rep_log2;
+        uint64_t want = (n_chunks + 255) / 256;
+        const unsigned grid = unsigned(want < uint64_t(sms) * 3 ? want : uint64_t(sms) * 3);
+        if (counter_bits == 32) {
+            KPAL_CUDA(cudaFuncSetAttribute(count_smem_kernel<uint32_t>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+            count_smem_kernel<uint32_t><<<grid, 256, smem, stream>>>(
+                codes, valid, n_chunks, k, rep_log2, static_cast<uint32_t *>(d_table));
+        } else {
+            KPAL_CUDA(cudaFuncSetAttribute(count_smem_kernel<unsigned long long>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+            count_smem_kernel<unsigned long long><<<grid, 256, smem, stream>>>(
+                codes, valid, n_chunks, k, rep_log2, static_cast<unsigned long long *>(d_table));
+        }
+        KPAL_LAUNCH_CHECK("count_smem_kernel");
+    } else {
+        uint64_t want = (n_chunks + 255) / 256;
+        const uint64_t cap = uint64_t(sms) * 8 * 4;      // a few waves of 8 CTAs/SM
+        const unsigned grid = unsigned(want < cap ? want : cap);
+        if (counter_bits == 32)
+            count_global_kernel<uint32_t><<<grid, 256, 0, stream>>>(
+                codes, valid, n_chunks, k, static_cast<uint32_t *>(d_table));
+        else
+            count_global_kernel<unsigned long long><<<grid, 256, 0, stream>>>(
+                codes, valid, n_chunks, k, static_cast<unsigned long long *>(d_table));
+        KPAL_LAUNCH_CHECK("count_global_kernel");
+    }
+    return KPAL_OK;
+}
+
+int launch_finalize(const void *d_table, int counter_bits, int k, int balance, int64_t *d_counts,
+                    cudaStream_t stream)
+{
+    KPAL_CHECK(check_k(k));
+    if (counter_bits != 32 && counter_bits != 64) return bad_arg("counter_bits must be 32 or 64");
+    const uint64_t n = 1ull << (2 * k);
+    uint64_t want = (n + 255) / 256;
+    const uint64_t cap = uint64_t(sm_count()) * 32;
+    const unsigned grid = unsigned(want < cap ? want : cap);
+    if (counter_bits == 32)
+        finalize_kernel<uint32_t><<<grid, 256, 0, stream>>>(
+            static_cast<const uint32_t *>(d_table), k, balance, d_counts);
+    else
+        finalize_kernel<unsigned long long><<<grid, 256, 0, stream>>>(
+            static_cast<const unsigned long long *>(d_table), k, balance, d_counts);
+    KPAL_LAUNCH_CHECK("finalize_kernel");
+    return KPAL_OK;
+}
+
+int launch_balance(const int64_t *d_in, int64_t *d_out, int k, cudaStream_t stream)
+{
+    KPAL_CHECK(check_k(k));
+    if (d_in == d_out) return bad_arg("kpal_dev_balance needs in != out");
+    const uint64_t n = 1ull << (2 * k);
+    uint64_t want = (n + 255) / 256;
+    const uint64_t cap = uint64_t(sm_count()) * 32;
+    balance_i64_kernel<<<unsigned(want < cap ? want : cap), 256, 0, stream>>>(d_in, k, d_out);
+    KPAL_LAUNCH_CHECK("balance_i64_kernel");
+    return KPAL_OK;
+}
+
+int launch_by_record(const uint32_t *d_codes, const uint32_t *d_valid, const uint64_t *d_rec_starts,
+                     uint64_t first, uint64_t n, int k, int balance, int64_t *d_rows,
+                     cudaStream_t stream)
+{
+    KPAL_CHECK(check_k(k));
+    if (n == 0) return KPAL_OK;
+    const uint64_t cap = uint64_t(sm_count()) * 8;
+    by_record_kernel<<<unsigned(n < cap ? n : cap), 256, 0, stream>>>(
+        reinterpret_cast<const uint4 *>(d_codes), reinterpret_cast<const uint2 *>(d_valid),
+        d_rec_starts, first, n, k, balance, d_rows);
+    KPAL_LAUNCH_CHECK("by_record_kernel");
+    return KPAL_OK;
+}
+
+}  // namespace kpal

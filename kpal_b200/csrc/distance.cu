@@ -1,0 +1,601 @@
+// N x N profile distance matrix for sm_100a.
+//
+// Replaces the pair loop of kdistlib.distance_matrix (reference
+// kpal/kdistlib.py:179-184) over ProfileDistance.distance
+// (kpal/kdistlib.py:126-161) and metrics.multiset / euclidean /
+// cosine_similarity with the scale step (kpal/metrics.py:49-86,101-147,159-162).
+//
+// Algebra (DESIGN.md "Distance kernel").  With S the profile totals, the
+// reference scales the profile with the smaller total by s = S_big/S_small
+// (or, with `down`, the larger one by 1/s).  Call A the scaled and B the
+// unscaled profile of a pair, F = x/S the per-profile frequencies, R = 1/(x+1)
+// and t_B = 1/S_B.  Dividing numerator and denominator by S_B:
+//
+//   prod: |sA-b| / ((sA+1)(b+1)) = |F_A - F_B| * R_B / (F_A + t_B)
+//   sum : |sA-b| / (sA+b+1)      = |F_A - F_B| / (F_A + F_B + t_B)
+//   euclidean = S_B * sqrt(sum (F_A - F_B)^2),   cosine = <F_A,F_B>/(|F_A||F_B|)
+//
+// so everything pair-dependent is ONE per-column scalar (t_B), F and R are
+// computed once per profile (the reference redoes copy/balance/scale per
+// pair), and identical profiles give exactly 0.  Unscaled: S := 1 (F = x).
+// Profiles are visited in order of total, so in every tile the row panel is
+// the A side and the column panel the B side.
+//
+// The one fp64 division per element pair is a MUFU.RCP64H seed + one Newton
+// step (relative error <= 2^-39, far inside the 1e-9 parity bound; the exact
+// IEEE path is kept behind KPAL_EXACT_DIV=1 for validation).
+//
+// Tile kernel: CTA = 128 A-rows x 64 B-rows, 8 compute warps (each thread owns
+// an 8 x 4 block of pairs, accumulators in registers) + 1 producer warp that
+// streams 32-element row segments into a 3-stage shared-memory ring with
+// cp.async.bulk (TMA bulk copies) completing on mbarriers.
+#include "common.cuh"
+
+#include <stdlib.h>
+#include <vector>
+#include <algorithm>
+
+namespace kpal {
+
+// ---------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------
+constexpr int TA = 128;                 // A rows (scaled side) per tile
+constexpr int TB = 64;                  // B rows (unscaled side) per tile
+constexpr int DC = 32;                  // profile elements per stage
+constexpr int ROW_BYTES = DC * 8 + 16;  // +16: consecutive rows land in different bank groups
+constexpr int STAGES = 3;
+constexpr int A_BYTES = TA * ROW_BYTES;
+constexpr int B_BYTES = TB * ROW_BYTES;
+constexpr int COMPUTE_WARPS = 8;
+constexpr int TILE_THREADS = (COMPUTE_WARPS + 1) * 32;
+constexpr uint64_t kStrideAlign = 128;  // prepared row stride: multiple of 128 doubles (bitmap rows 16 B aligned)
+constexpr uint64_t kSliceLen = 1u << 16;  // elements of D per work item
+
+__host__ __device__ inline uint64_t prepared_stride(int k)
+{
+    const uint64_t d = 1ull << (2 * k);
+    return (d + kStrideAlign - 1) / kStrideAlign * kStrideAlign;
+}
+
+enum : int { M_PROD = 0, M_SUM = 1, M_EUCLID = 2, M_COSINE = 3 };
+
+// ---------------------------------------------------------------------------
+// per-profile pre-pass
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+profile_totals_kernel(const int64_t *__restrict__ counts, uint64_t d,
+                      unsigned long long *__restrict__ totals)
+{
+    const int64_t *row = counts + uint64_t(blockIdx.y) * d;
+    long long s = 0;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < d;
+         i += uint64_t(gridDim.x) * blockDim.x)
+        s += row[i];
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    __shared__ long long ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int w = 0; w < 8; ++w) t += ws[w];
+        atomicAdd(totals + blockIdx.y, (unsigned long long)t);
+    }
+}
+
+// F = x/S (x if !do_scale), R = 1/(x+1), non-zero bitmap, sum F^2.
+// x = c[i] (+ c[rc(i)] when balancing, kpal/klib.py:290-298).
+__global__ void __launch_bounds__(256)
+profile_convert_kernel(const int64_t *__restrict__ counts, uint64_t d, uint64_t stride, int k,
+                       int do_balance, int do_scale,
+                       const unsigned long long *__restrict__ totals_i64,
+                       double *__restrict__ F, double *__restrict__ R,
+                       uint32_t *__restrict__ bitmap, double *__restrict__ totals,
+                       double *__restrict__ norm2)
+{
+    const uint64_t p = blockIdx.y;
+    const int64_t *row = counts + p * d;
+    long long tot = (long long)totals_i64[p];
+    if (do_balance) tot *= 2;                       // sum(c[i] + c[rc(i)]) = 2 sum(c)
+    const double S = double(tot);
+    if (blockIdx.x == 0 && threadIdx.x == 0) totals[p] = S;
+    const int shift = 32 - 2 * k;
+    double n2 = 0.0;
+    // stride is a multiple of 64, the loop covers whole warps: ballot is safe
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < stride;
+         i += uint64_t(gridDim.x) * blockDim.x) {
+        long long x = 0;
+        if (i < d) {
+            x = row[i];
+            if (do_balance) x += __ldg(row + rc_index(uint32_t(i), shift));
+        }
+        const double xd = double(x);
+        double f = do_scale ? xd / S : xd;
+        if (i >= d) f = 0.0;                        // padding contributes nothing
+        F[p * stride + i] = f;
+        if (R) R[p * stride + i] = 1.0 / (xd + 1.0);
+        n2 += f * f;
+        const uint32_t bits = __ballot_sync(0xffffffffu, x != 0);
+        if ((threadIdx.x & 31) == 0) bitmap[p * (stride / 32) + i / 32] = bits;
+    }
+    for (int o = 16; o; o >>= 1) n2 += __shfl_down_sync(0xffffffffu, n2, o);
+    __shared__ double ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = n2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += ws[w];
+        atomicAdd(norm2 + p, t);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// PTX helpers: mbarrier + bulk async copy (TMA, SASS UBLKCP)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+
+// reciprocal: MUFU.RCP64H seed (>= 20 good bits) + one Newton step, or IEEE
+template <bool EXACT>
+__device__ __forceinline__ double recip(double u)
+{
+    if constexpr (EXACT) {
+        return 1.0 / u;
+    } else {
+        double q;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(u));
+        const double e = fma(-u, q, 1.0);
+        return fma(q, e, q);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// tile enumeration over the (sorted) upper triangle:
+// row blocks I of TA sorted positions, column blocks J of TB; tile (I, J) holds
+// a pair p < q iff J >= 2I (TA == 2 TB).
+// ---------------------------------------------------------------------------
+__host__ __device__ inline uint64_t tiles_in_row(uint64_t I, uint64_t NJ)
+{
+    return NJ > 2 * I ? NJ - 2 * I : 0;
+}
+__host__ __device__ inline uint64_t num_tiles(uint64_t n)
+{
+    const uint64_t NI = (n + TA - 1) / TA, NJ = (n + TB - 1) / TB;
+    uint64_t t = 0;
+    for (uint64_t I = 0; I < NI; ++I) t += tiles_in_row(I, NJ);
+    return t;
+}
+__device__ inline void tile_coords(uint64_t t, uint64_t n, uint32_t &I, uint32_t &J)
+{
+    const uint64_t NJ = (n + TB - 1) / TB;
+    uint64_t i = 0;
+    while (t >= tiles_in_row(i, NJ)) { t -= tiles_in_row(i, NJ); ++i; }
+    I = uint32_t(i);
+    J = uint32_t(2 * i + t);
+}
+
+struct TileArgs {
+    const double *F, *R;
+    const uint32_t *bitmap;
+    const double *totals;
+    const int32_t *order;       // sorted position -> profile index (NULL: identity)
+    uint64_t n, d, stride;
+    uint64_t tile_begin, n_tiles_range;
+    uint64_t slice_len, n_slices;
+    int do_scale;
+    double *acc;                // [n][n] sums, sorted-position space (p < q)
+    uint32_t *cnt;              // [n][n] union counts
+};
+
+template <int METRIC, bool EXACT>
+__global__ void __launch_bounds__(TILE_THREADS, 1)
+distance_tile_kernel(const TileArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bars[2 * STAGES];
+    __shared__ int32_t rowsA[TA], rowsB[TB];
+
+    constexpr bool NEED_R = (METRIC == M_PROD);
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES + (NEED_R ? B_BYTES : 0);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t item = blockIdx.x;
+    const uint64_t slice = item / a.n_tiles_range;
+    const uint64_t tile = a.tile_begin + item % a.n_tiles_range;
+    uint32_t I, J;
+    tile_coords(tile, a.n, I, J);
+    const uint64_t d0 = slice * a.slice_len;
+    const uint64_t d1 = min(d0 + a.slice_len, a.stride);
+    const uint32_t n_iter = uint32_t((d1 - d0) / DC);
+
+    // sorted positions -> profile rows (clamped: out-of-range rows are masked at the end)
+    for (uint32_t r = threadIdx.x; r < TA + TB; r += blockDim.x) {
+        const bool isA = r < TA;
+        uint64_t pos = isA ? uint64_t(I) * TA + r : uint64_t(J) * TB + (r - TA);
+        if (pos >= a.n) pos = a.n - 1;
+        const int32_t prof = a.order ? a.order[pos] : int32_t(pos);
+        if (isA) rowsA[r] = prof; else rowsB[r - TA] = prof;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);                       // full: producer's expect_tx
+            mbar_init(smem_u32(&bars[STAGES + s]), COMPUTE_WARPS);  // empty: one arrive per warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == COMPUTE_WARPS) {
+        // ===== producer warp: stream row segments with bulk async copies =====
+        for (uint32_t it = 0; it < n_iter; ++it) {
+            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(smem_u32(&bars[STAGES + s]), ph ^ 1);
+            const uint32_t full = smem_u32(&bars[s]);
+            if (lane == 0) mbar_arrive_expect_tx(full, (TA + TB + (NEED_R ? TB : 0)) * DC * 8);
+            __syncwarp();
+            const uint32_t base = smem_u32(smem) + s * STAGE_BYTES;
+            const uint64_t col = d0 + uint64_t(it) * DC;
+#pragma unroll
+            for (int r = 0; r < TA / 32; ++r) {
+                const uint32_t row = lane + 32 * r;
+                bulk_g2s(base + row * ROW_BYTES, a.F + uint64_t(rowsA[row]) * a.stride + col, DC * 8, full);
+            }
+#pragma unroll
+            for (int r = 0; r < TB / 32; ++r) {
+                const uint32_t row = lane + 32 * r;
+                const uint64_t off = uint64_t(rowsB[row]) * a.stride + col;
+                bulk_g2s(base + A_BYTES + row * ROW_BYTES, a.F + off, DC * 8, full);
+                if constexpr (NEED_R)
+                    bulk_g2s(base + A_BYTES + B_BYTES + row * ROW_BYTES, a.R + off, DC * 8, full);
+            }
+        }
+        return;
+    }
+
+    // ===== compute warps =====
+    // thread (ti, tj): A rows ti*8 + r (r < 8), B rows tj + 16*c (c < 4).
+    // lane = ti_l*8 + tj_l: a quarter-warp shares its A address (broadcast) and
+    // reads 8 consecutive B rows (conflict free thanks to the row padding).
+    const uint32_t ti = (warp >> 1) * 4 + (lane >> 3);
+    const uint32_t tj = (warp & 1) * 8 + (lane & 7);
+
+    double t[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        t[c] = a.do_scale ? 1.0 / a.totals[rowsB[tj + 16 * c]] : 1.0;
+
+    double acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+
+    for (uint32_t it = 0; it < n_iter; ++it) {
+        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+        mbar_wait(smem_u32(&bars[s]), ph);
+        const unsigned char *sA = smem + s * STAGE_BYTES + ti * 8 * ROW_BYTES;
+        const unsigned char *sB = smem + s * STAGE_BYTES + A_BYTES + tj * ROW_BYTES;
+#pragma unroll 2
+        for (int dd = 0; dd < DC / 2; ++dd) {
+            double2 av[8], bf[4], br[4];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                av[r] = *reinterpret_cast<const double2 *>(sA + r * ROW_BYTES + dd * 16);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                bf[c] = *reinterpret_cast<const double2 *>(sB + c * 16 * ROW_BYTES + dd * 16);
+                if constexpr (NEED_R)
+                    br[c] = *reinterpret_cast<const double2 *>(sB + B_BYTES + c * 16 * ROW_BYTES + dd * 16);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                double gx = 0.0, gy = 0.0;
+                if constexpr (METRIC == M_SUM) { gx = bf[c].x + t[c]; gy = bf[c].y + t[c]; }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    if constexpr (METRIC == M_PROD) {
+                        const double nx = av[r].x - bf[c].x, ny = av[r].y - bf[c].y;
+                        const double qx = recip<EXACT>(av[r].x + t[c]);
+                        const double qy = recip<EXACT>(av[r].y + t[c]);
+                        acc[r][c] = fma(fabs(nx) * qx, br[c].x, acc[r][c]);
+                        acc[r][c] = fma(fabs(ny) * qy, br[c].y, acc[r][c]);
+                    } else if constexpr (METRIC == M_SUM) {
+                        const double nx = av[r].x - bf[c].x, ny = av[r].y - bf[c].y;
+                        const double qx = recip<EXACT>(av[r].x + gx);
+                        const double qy = recip<EXACT>(av[r].y + gy);
+                        acc[r][c] = fma(fabs(nx), qx, acc[r][c]);
+                        acc[r][c] = fma(fabs(ny), qy, acc[r][c]);
+                    } else if constexpr (METRIC == M_EUCLID) {
+                        const double nx = av[r].x - bf[c].x, ny = av[r].y - bf[c].y;
+                        acc[r][c] = fma(nx, nx, acc[r][c]);
+                        acc[r][c] = fma(ny, ny, acc[r][c]);
+                    } else {
+                        acc[r][c] = fma(av[r].x, bf[c].x, acc[r][c]);
+                        acc[r][c] = fma(av[r].y, bf[c].y, acc[r][c]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars[STAGES + s]));
+    }
+
+    // ===== epilogue: partial sums (+ union counts for the multiset metrics) =====
+    constexpr bool NEED_CNT = (METRIC == M_PROD || METRIC == M_SUM);
+    const uint64_t words_per_row = a.stride / 32;
+    const uint64_t w0 = d0 / 32, w1 = d1 / 32;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint64_t q = uint64_t(J) * TB + tj + 16 * c;
+        if (q >= a.n) continue;
+        const uint32_t *zb = a.bitmap + uint64_t(rowsB[tj + 16 * c]) * words_per_row;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const uint64_t p = uint64_t(I) * TA + ti * 8 + r;
+            if (p >= q) continue;
+            atomicAdd(a.acc + p * a.n + q, acc[r][c]);
+            if constexpr (NEED_CNT) {
+                const uint32_t *za = a.bitmap + uint64_t(rowsA[ti * 8 + r]) * words_per_row;
+                uint32_t u = 0;
+                for (uint64_t w = w0; w < w1; w += 4) {      // slices are multiples of 128 elements
+                    const uint4 x = __ldg(reinterpret_cast<const uint4 *>(za + w));
+                    const uint4 y = __ldg(reinterpret_cast<const uint4 *>(zb + w));
+                    u += __popc(x.x | y.x) + __popc(x.y | y.y) + __popc(x.z | y.z) + __popc(x.w | y.w);
+                }
+                atomicAdd(a.cnt + p * a.n + q, u);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Few profiles (ProfileDistance.distance on one pair, small matrices): the
+// 128 x 64 tile would be almost empty, so use one CTA per (pair, slice) with
+// the threads striding over the profile elements instead.  HBM bound.
+// ---------------------------------------------------------------------------
+template <int METRIC, bool EXACT>
+__global__ void __launch_bounds__(256)
+distance_small_kernel(const TileArgs a)
+{
+    // pair index -> sorted positions p < q
+    uint64_t pair = blockIdx.x, q = 1;
+    while (pair >= q) { pair -= q; ++q; }
+    const uint64_t p = pair;
+    const int32_t ia = a.order ? a.order[p] : int32_t(p), ib = a.order ? a.order[q] : int32_t(q);
+    const double *FA = a.F + uint64_t(ia) * a.stride, *FB = a.F + uint64_t(ib) * a.stride;
+    const double *RB = (METRIC == M_PROD) ? a.R + uint64_t(ib) * a.stride : nullptr;
+    const double t = a.do_scale ? 1.0 / a.totals[ib] : 1.0;
+    const uint64_t d0 = uint64_t(blockIdx.y) * a.slice_len;
+    const uint64_t d1 = min(d0 + a.slice_len, a.stride);
+    double s = 0.0;
+    uint32_t u = 0;
+    for (uint64_t i = d0 + threadIdx.x; i < d1; i += blockDim.x) {
+        const double fa = FA[i], fb = FB[i];
+        if constexpr (METRIC == M_PROD) {
+            s = fma(fabs(fa - fb) * recip<EXACT>(fa + t), RB[i], s);
+            u += (fa != 0.0 || fb != 0.0);
+        } else if constexpr (METRIC == M_SUM) {
+            s = fma(fabs(fa - fb), recip<EXACT>(fa + (fb + t)), s);
+            u += (fa != 0.0 || fb != 0.0);
+        } else if constexpr (METRIC == M_EUCLID) {
+            s = fma(fa - fb, fa - fb, s);
+        } else {
+            s = fma(fa, fb, s);
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, o);
+        u += __shfl_down_sync(0xffffffffu, u, o);
+    }
+    __shared__ double ws[8];
+    __shared__ uint32_t wu[8];
+    if ((threadIdx.x & 31) == 0) { ws[threadIdx.x >> 5] = s; wu[threadIdx.x >> 5] = u; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { s += ws[w]; u += wu[w]; }
+        atomicAdd(a.acc + p * a.n + q, s);
+        if (METRIC == M_PROD || METRIC == M_SUM) atomicAdd(a.cnt + p * a.n + q, u);
+    }
+}
+
+// acc/cnt (sorted-position space) -> symmetric output in profile-index space
+__global__ void __launch_bounds__(256)
+distance_finalize_kernel(const double *__restrict__ acc, const uint32_t *__restrict__ cnt,
+                         const double *__restrict__ totals, const double *__restrict__ norm2,
+                         const int32_t *__restrict__ order, uint64_t n, int metric, int do_scale,
+                         uint64_t tile_begin, uint64_t tile_end, double *__restrict__ out)
+{
+    // one CTA per tile of the range, threads over its pairs
+    const uint64_t tile = tile_begin + blockIdx.x;
+    if (tile >= tile_end) return;
+    uint32_t I, J;
+    tile_coords(tile, n, I, J);
+    for (uint32_t e = threadIdx.x; e < TA * TB; e += blockDim.x) {
+        const uint64_t p = uint64_t(I) * TA + e / TB, q = uint64_t(J) * TB + e % TB;
+        if (p >= q || q >= n) continue;
+        const int32_t ip = order ? order[p] : int32_t(p), iq = order ? order[q] : int32_t(q);
+        const double s = acc[p * n + q];
+        double v;
+        if (metric == M_PROD || metric == M_SUM) {
+            v = s / double(cnt[p * n + q] + 1u);                  // kpal/metrics.py:123
+        } else if (metric == M_EUCLID) {
+            v = sqrt(s);                                          // kpal/metrics.py:46,135
+            if (do_scale) v *= totals[iq];                        // S_B (unscaled side)
+        } else {
+            v = s / (sqrt(norm2[ip]) * sqrt(norm2[iq]));          // kpal/metrics.py:147
+        }
+        out[uint64_t(ip) * n + iq] = v;
+        out[uint64_t(iq) * n + ip] = v;
+    }
+}
+
+// d(p, p): 0 for the distances (nan when scaling a zero-total profile, as the
+// reference), cosine similarity 1 (nan for an all-zero profile).
+__global__ void distance_diagonal_kernel(const double *__restrict__ totals,
+                                         const double *__restrict__ norm2, uint64_t n, int metric,
+                                         int do_scale, double *__restrict__ out)
+{
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = 0.0;
+    if (metric == M_COSINE) v = norm2[i] / (sqrt(norm2[i]) * sqrt(norm2[i]));
+    else if (do_scale && !(totals[i] > 0.0)) v = nan("");
+    out[i * n + i] = v;
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+static int metric_id(int metric, int pairwise, int *out)
+{
+    if (metric == KPAL_METRIC_MULTISET && pairwise == KPAL_PAIRWISE_PROD) *out = M_PROD;
+    else if (metric == KPAL_METRIC_MULTISET && pairwise == KPAL_PAIRWISE_SUM) *out = M_SUM;
+    else if (metric == KPAL_METRIC_EUCLIDEAN) *out = M_EUCLID;
+    else if (metric == KPAL_METRIC_COSINE) *out = M_COSINE;
+    else return bad_arg("unknown metric / pairwise selector");
+    return KPAL_OK;
+}
+
+int launch_prepare(const int64_t *d_counts, uint64_t n, int k, int do_balance, int do_scale,
+                   double *d_F, double *d_R, uint32_t *d_bitmap, double *d_totals,
+                   double *d_norm2, unsigned long long *d_totals_i64, cudaStream_t stream)
+{
+    if (k < 1 || k > KPAL_MAX_K) return bad_arg("k out of range");
+    if (n == 0) return KPAL_OK;
+    if (n > 65535) return bad_arg("at most 65535 profiles per prepare call");
+    const uint64_t d = 1ull << (2 * k), stride = prepared_stride(k);
+    KPAL_CUDA(cudaMemsetAsync(d_totals_i64, 0, n * sizeof(unsigned long long), stream));
+    KPAL_CUDA(cudaMemsetAsync(d_norm2, 0, n * sizeof(double), stream));
+    const unsigned bx = unsigned(std::min<uint64_t>((d + 255) / 256, 64));
+    profile_totals_kernel<<<dim3(bx, unsigned(n)), 256, 0, stream>>>(d_counts, d, d_totals_i64);
+    KPAL_LAUNCH_CHECK("profile_totals_kernel");
+    const unsigned cx = unsigned(std::min<uint64_t>((stride + 255) / 256, 64));
+    profile_convert_kernel<<<dim3(cx, unsigned(n)), 256, 0, stream>>>(
+        d_counts, d, stride, k, do_balance, do_scale, d_totals_i64, d_F, d_R, d_bitmap, d_totals,
+        d_norm2);
+    KPAL_LAUNCH_CHECK("profile_convert_kernel");
+    return KPAL_OK;
+}
+
+constexpr uint64_t kSmallN = 12;   // up to 66 pairs go through distance_small_kernel
+
+template <int METRIC>
+static int launch_tiles_metric(const TileArgs &a, bool exact, unsigned grid, cudaStream_t stream)
+{
+    if (a.n <= kSmallN) {
+        // NOTE: in the small path the NaN-counts-as-set corner of np.logical_or
+        // does not matter: the result is NaN anyway.
+        const dim3 g(unsigned(a.n * (a.n - 1) / 2), unsigned(a.n_slices));
+        if (g.x == 0) return KPAL_OK;
+        if (exact) distance_small_kernel<METRIC, true><<<g, 256, 0, stream>>>(a);
+        else distance_small_kernel<METRIC, false><<<g, 256, 0, stream>>>(a);
+        KPAL_LAUNCH_CHECK("distance_small_kernel");
+        return KPAL_OK;
+    }
+    constexpr int stage_bytes = A_BYTES + B_BYTES + (METRIC == M_PROD ? B_BYTES : 0);
+    constexpr int smem = stage_bytes * STAGES;
+    if (exact) {
+        KPAL_CUDA(cudaFuncSetAttribute(distance_tile_kernel<METRIC, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        distance_tile_kernel<METRIC, true><<<grid, TILE_THREADS, smem, stream>>>(a);
+    } else {
+        KPAL_CUDA(cudaFuncSetAttribute(distance_tile_kernel<METRIC, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        distance_tile_kernel<METRIC, false><<<grid, TILE_THREADS, smem, stream>>>(a);
+    }
+    KPAL_LAUNCH_CHECK("distance_tile_kernel");
+    return KPAL_OK;
+}
+
+int launch_distance_tiles(const double *d_F, const double *d_R, const uint32_t *d_bitmap,
+                          const double *d_totals, const double *d_norm2, const int32_t *d_order,
+                          uint64_t n, int k, int metric, int pairwise, int do_scale, int down,
+                          uint64_t tile_begin, uint64_t tile_end, double *d_acc, uint32_t *d_cnt,
+                          double *d_out, cudaStream_t stream)
+{
+    (void)down;   // the order array already encodes ascending / descending totals
+    int m;
+    KPAL_CHECK(metric_id(metric, pairwise, &m));
+    if (k < 1 || k > KPAL_MAX_K) return bad_arg("k out of range");
+    if (n < 1) return bad_arg("no profiles");
+    if (m == M_PROD && !d_R) return bad_arg("multiset/prod needs the R array");
+    const uint64_t total_tiles = num_tiles(n);
+    if (tile_end > total_tiles) tile_end = total_tiles;
+    if (tile_begin >= tile_end) return KPAL_OK;
+
+    TileArgs a;
+    a.F = d_F; a.R = d_R; a.bitmap = d_bitmap; a.totals = d_totals; a.order = d_order;
+    a.n = n; a.d = 1ull << (2 * k); a.stride = prepared_stride(k);
+    a.tile_begin = tile_begin; a.n_tiles_range = tile_end - tile_begin;
+    a.slice_len = std::min<uint64_t>(kSliceLen, a.stride);
+    a.n_slices = (a.stride + a.slice_len - 1) / a.slice_len;
+    a.do_scale = do_scale;
+    a.acc = d_acc; a.cnt = d_cnt;
+
+    KPAL_CUDA(cudaMemsetAsync(d_acc, 0, n * n * sizeof(double), stream));
+    KPAL_CUDA(cudaMemsetAsync(d_cnt, 0, n * n * sizeof(uint32_t), stream));
+    const uint64_t items = a.n_tiles_range * a.n_slices;
+    if (items > 0x7fffffffull) return bad_arg("too many work items");
+    static const bool exact = [] {
+        const char *e = getenv("KPAL_EXACT_DIV");
+        return e && e[0] == '1';
+    }();
+    switch (m) {
+    case M_PROD: KPAL_CHECK(launch_tiles_metric<M_PROD>(a, exact, unsigned(items), stream)); break;
+    case M_SUM: KPAL_CHECK(launch_tiles_metric<M_SUM>(a, exact, unsigned(items), stream)); break;
+    case M_EUCLID: KPAL_CHECK(launch_tiles_metric<M_EUCLID>(a, exact, unsigned(items), stream)); break;
+    default: KPAL_CHECK(launch_tiles_metric<M_COSINE>(a, exact, unsigned(items), stream)); break;
+    }
+    distance_finalize_kernel<<<unsigned(a.n_tiles_range), 256, 0, stream>>>(
+        d_acc, d_cnt, d_totals, d_norm2, d_order, n, m, do_scale, tile_begin, tile_end, d_out);
+    KPAL_LAUNCH_CHECK("distance_finalize_kernel");
+    if (tile_begin == 0) {   // the rank that owns tile 0 also writes the diagonal
+        distance_diagonal_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(
+            d_totals, d_norm2, n, m, do_scale, d_out);
+        KPAL_LAUNCH_CHECK("distance_diagonal_kernel");
+    }
+    return KPAL_OK;
+}
+
+uint64_t distance_num_tiles(uint64_t n) { return num_tiles(n); }
+uint64_t prepared_stride_host(int k) { return prepared_stride(k); }
+
+}  // namespace kpal
