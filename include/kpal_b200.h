@@ -164,6 +164,15 @@ int kpal_pair_distance(const int64_t *left, const int64_t *right, int k,
 int kpal_dev_count_packed(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_bases,
                           int k, void *d_table, int counter_bits, void *stream);
 
+/*
+ * Host FASTA bytes -> windows accumulated into a caller-owned DEVICE table
+ * (Profile.from_fasta, kpal/klib.py:97-112, split for the multi-GPU driver:
+ * every rank counts its shard of records, the tables are then summed with an
+ * NCCL reduce and finalised once).  Synchronises `stream` before returning.
+ */
+int kpal_count_fasta_to_dev(const char *fasta, uint64_t n_bytes, int k, void *d_table,
+                            int counter_bits, void *stream, uint64_t *n_bases_out);
+
 /* table (u32/u64) -> int64 counts, optionally fused with balance
  * (out[i] = t[i] + t[rc(i)], kpal/klib.py:290-298). */
 int kpal_dev_finalize_counts(const void *d_table, int counter_bits, int k, int balance,

@@ -27,7 +27,7 @@ SYMBOLS = (
     "kpal_packed_words", "kpal_pack_sequences", "kpal_fasta_scan", "kpal_fasta_pack",
     "kpal_count_sequences", "kpal_count_fasta", "kpal_count_by_record", "kpal_balance",
     "kpal_distance_matrix", "kpal_pair_distance",
-    "kpal_dev_count_packed", "kpal_dev_finalize_counts", "kpal_dev_balance",
+    "kpal_dev_count_packed", "kpal_count_fasta_to_dev", "kpal_dev_finalize_counts", "kpal_dev_balance",
     "kpal_dev_count_by_record", "kpal_prepared_stride", "kpal_dev_profiles_prepare",
     "kpal_dev_order_by_total", "kpal_distance_num_tiles", "kpal_dev_distance_tiles",
     "kpal_kernel_launches", "kpal_reset_kernel_launches",
@@ -82,6 +82,7 @@ def load():
     sig("kpal_distance_matrix", i32, vp, u64, i32, i32, i32, i32, i32, i32, vp)
     sig("kpal_pair_distance", i32, vp, vp, i32, i32, i32, i32, i32, i32, vp)
     sig("kpal_dev_count_packed", i32, vp, vp, u64, i32, vp, i32, vp)
+    sig("kpal_count_fasta_to_dev", i32, vp, u64, i32, vp, i32, vp, pu64)
     sig("kpal_dev_finalize_counts", i32, vp, i32, i32, i32, vp, vp)
     sig("kpal_dev_balance", i32, vp, vp, i32, vp)
     sig("kpal_dev_count_by_record", i32, vp, vp, vp, u64, u64, i32, i32, vp, vp)

@@ -86,6 +86,63 @@ struct PinBuf {
     template <typename T> T *as() const { return static_cast<T *>(p); }
 };
 
+// Grow-only per-device workspace of the host-level counting entry points, so
+// that repeated calls (kpal count over many files, the bench's end-to-end loop)
+// do not pay cudaMalloc / cudaMallocHost every time.  One call at a time.
+struct GrowDev {
+    void *p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return KPAL_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            p = nullptr; cudaGetLastError();
+            set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            return e == cudaErrorMemoryAllocation ? KPAL_ENOMEM : KPAL_ECUDA;
+        }
+        cap = bytes;
+        return KPAL_OK;
+    }
+};
+struct GrowPin {
+    void *p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return KPAL_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e != cudaSuccess) {
+            p = nullptr; cudaGetLastError();
+            set_error("cudaMallocHost(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            return e == cudaErrorMemoryAllocation ? KPAL_ENOMEM : KPAL_ECUDA;
+        }
+        cap = bytes;
+        return KPAL_OK;
+    }
+};
+struct CountWorkspace {
+    int device = -1;
+    GrowDev codes, valid, table, counts;
+    GrowPin pcodes, pvalid;
+};
+static std::mutex g_count_mutex;                 // held for the whole host-level call
+static std::vector<CountWorkspace *> g_count_ws;
+
+static int get_count_ws(CountWorkspace **out)
+{
+    int dev = 0;
+    KPAL_CUDA(cudaGetDevice(&dev));
+    for (auto *w : g_count_ws) if (w->device == dev) { *out = w; return KPAL_OK; }
+    CountWorkspace *w = new CountWorkspace();
+    w->device = dev;
+    g_count_ws.push_back(w);
+    *out = w;
+    return KPAL_OK;
+}
+
 static int require_device()
 {
     int n = 0;
@@ -247,62 +304,115 @@ extern "C" int kpal_dev_count_by_record(const uint32_t *d_codes, const uint32_t 
 }
 
 // ------------------------------------------------------ counting: host API
-static int count_packed_host(const uint32_t *codes, const uint32_t *valid, uint64_t n_bases, int k,
-                             int balance, int64_t *counts_out)
+// packed host stream (pinned workspace) -> device table (accumulated)
+static int upload_and_count(CountWorkspace *w, uint64_t n_bases, int k, void *d_table, int bits,
+                            cudaStream_t st)
 {
-    if (k < 1 || k > KPAL_MAX_K) { set_error("k-mer length %d out of range [1, %d]", k, KPAL_MAX_K); return KPAL_EINVAL; }
-    KPAL_CHECK(require_device());
-    const uint64_t bins = 1ull << (2 * k);
     uint64_t cw, vw;
     kpal_packed_words(n_bases, &cw, &vw);
+    KPAL_CHECK(w->codes.ensure(cw * 4));
+    KPAL_CHECK(w->valid.ensure(vw * 4));
+    KPAL_CUDA(cudaMemcpyAsync(w->codes.p, w->pcodes.p, cw * 4, cudaMemcpyHostToDevice, st));
+    KPAL_CUDA(cudaMemcpyAsync(w->valid.p, w->pvalid.p, vw * 4, cudaMemcpyHostToDevice, st));
+    return launch_count(static_cast<uint32_t *>(w->codes.p), static_cast<uint32_t *>(w->valid.p),
+                        n_bases, k, d_table, bits, st);
+}
+
+static int count_packed_to_host(CountWorkspace *w, uint64_t n_bases, int k, int balance,
+                                int64_t *counts_out)
+{
+    const uint64_t bins = 1ull << (2 * k);
     const int bits = (n_bases >= (1ull << 32)) ? 64 : 32;
-    DevBuf d_codes, d_valid, d_table, d_counts;
-    KPAL_CHECK(d_codes.alloc(cw * 4));
-    KPAL_CHECK(d_valid.alloc(vw * 4));
-    KPAL_CHECK(d_table.alloc(bins * (bits / 8)));
-    KPAL_CHECK(d_counts.alloc(bins * 8));
+    KPAL_CHECK(w->table.ensure(bins * (bits / 8)));
+    KPAL_CHECK(w->counts.ensure(bins * 8));
     cudaStream_t st = 0;
-    KPAL_CUDA(cudaMemcpyAsync(d_codes.p, codes, cw * 4, cudaMemcpyHostToDevice, st));
-    KPAL_CUDA(cudaMemcpyAsync(d_valid.p, valid, vw * 4, cudaMemcpyHostToDevice, st));
-    KPAL_CUDA(cudaMemsetAsync(d_table.p, 0, bins * (bits / 8), st));
-    KPAL_CHECK(launch_count(d_codes.as<uint32_t>(), d_valid.as<uint32_t>(), n_bases, k, d_table.p, bits, st));
-    KPAL_CHECK(launch_finalize(d_table.p, bits, k, balance, d_counts.as<int64_t>(), st));
-    KPAL_CUDA(cudaMemcpyAsync(counts_out, d_counts.p, bins * 8, cudaMemcpyDeviceToHost, st));
+    KPAL_CUDA(cudaMemsetAsync(w->table.p, 0, bins * (bits / 8), st));
+    KPAL_CHECK(upload_and_count(w, n_bases, k, w->table.p, bits, st));
+    KPAL_CHECK(launch_finalize(w->table.p, bits, k, balance, static_cast<int64_t *>(w->counts.p), st));
+    KPAL_CUDA(cudaMemcpyAsync(counts_out, w->counts.p, bins * 8, cudaMemcpyDeviceToHost, st));
     KPAL_CUDA(cudaStreamSynchronize(st));
     return KPAL_OK;
+}
+
+static int check_k_host(int k)
+{
+    if (k < 1 || k > KPAL_MAX_K) {
+        set_error("k-mer length %d out of range [1, %d]", k, KPAL_MAX_K);
+        return KPAL_EINVAL;
+    }
+    return KPAL_OK;
+}
+
+static int pack_sequences_ws(CountWorkspace *w, const char *text, const uint64_t *offsets,
+                             uint64_t n_records, uint64_t *n_bases)
+{
+    KPAL_CHECK(kpal_pack_sequences(text, offsets, n_records, nullptr, nullptr, nullptr, n_bases));
+    uint64_t cw, vw;
+    kpal_packed_words(*n_bases, &cw, &vw);
+    KPAL_CHECK(w->pcodes.ensure(cw * 4));
+    KPAL_CHECK(w->pvalid.ensure(vw * 4));
+    return kpal_pack_sequences(text, offsets, n_records, static_cast<uint32_t *>(w->pcodes.p),
+                               static_cast<uint32_t *>(w->pvalid.p), nullptr, n_bases);
+}
+
+static int pack_fasta_ws(CountWorkspace *w, const char *fasta, uint64_t n_bytes, uint64_t *n_bases)
+{
+    uint64_t n_rec = 0, name_bytes = 0;
+    KPAL_CHECK(kpal_fasta_scan(fasta, n_bytes, &n_rec, n_bases, &name_bytes));
+    uint64_t cw, vw;
+    kpal_packed_words(*n_bases, &cw, &vw);
+    KPAL_CHECK(w->pcodes.ensure(cw * 4));
+    KPAL_CHECK(w->pvalid.ensure(vw * 4));
+    return kpal_fasta_pack(fasta, n_bytes, static_cast<uint32_t *>(w->pcodes.p),
+                           static_cast<uint32_t *>(w->pvalid.p), nullptr, nullptr);
 }
 
 extern "C" int kpal_count_sequences(const char *text, const uint64_t *offsets, uint64_t n_records,
                                     int k, int balance, int64_t *counts_out)
 {
     if (!counts_out || !offsets) return bad_arg("null pointer");
-    uint64_t n_bases = 0;
-    KPAL_CHECK(kpal_pack_sequences(text, offsets, n_records, nullptr, nullptr, nullptr, &n_bases));
-    uint64_t cw, vw;
-    kpal_packed_words(n_bases, &cw, &vw);
+    KPAL_CHECK(check_k_host(k));
     KPAL_CHECK(require_device());
-    PinBuf codes, valid;
-    KPAL_CHECK(codes.alloc(cw * 4));
-    KPAL_CHECK(valid.alloc(vw * 4));
-    KPAL_CHECK(kpal_pack_sequences(text, offsets, n_records, codes.as<uint32_t>(), valid.as<uint32_t>(),
-                                   nullptr, &n_bases));
-    return count_packed_host(codes.as<uint32_t>(), valid.as<uint32_t>(), n_bases, k, balance, counts_out);
+    std::lock_guard<std::mutex> lock(g_count_mutex);
+    CountWorkspace *w;
+    KPAL_CHECK(get_count_ws(&w));
+    uint64_t n_bases = 0;
+    KPAL_CHECK(pack_sequences_ws(w, text, offsets, n_records, &n_bases));
+    return count_packed_to_host(w, n_bases, k, balance, counts_out);
 }
 
 extern "C" int kpal_count_fasta(const char *fasta, uint64_t n_bytes, int k, int balance,
                                 int64_t *counts_out)
 {
     if (!counts_out || (!fasta && n_bytes)) return bad_arg("null pointer");
-    uint64_t n_rec = 0, n_bases = 0, name_bytes = 0;
-    KPAL_CHECK(kpal_fasta_scan(fasta, n_bytes, &n_rec, &n_bases, &name_bytes));
-    uint64_t cw, vw;
-    kpal_packed_words(n_bases, &cw, &vw);
+    KPAL_CHECK(check_k_host(k));
     KPAL_CHECK(require_device());
-    PinBuf codes, valid;
-    KPAL_CHECK(codes.alloc(cw * 4));
-    KPAL_CHECK(valid.alloc(vw * 4));
-    KPAL_CHECK(kpal_fasta_pack(fasta, n_bytes, codes.as<uint32_t>(), valid.as<uint32_t>(), nullptr, nullptr));
-    return count_packed_host(codes.as<uint32_t>(), valid.as<uint32_t>(), n_bases, k, balance, counts_out);
+    std::lock_guard<std::mutex> lock(g_count_mutex);
+    CountWorkspace *w;
+    KPAL_CHECK(get_count_ws(&w));
+    uint64_t n_bases = 0;
+    KPAL_CHECK(pack_fasta_ws(w, fasta, n_bytes, &n_bases));
+    return count_packed_to_host(w, n_bases, k, balance, counts_out);
+}
+
+// Host FASTA bytes -> accumulate into a caller-owned DEVICE table (multi-GPU
+// driver: every rank counts its shard, then the tables are reduced with NCCL).
+extern "C" int kpal_count_fasta_to_dev(const char *fasta, uint64_t n_bytes, int k, void *d_table,
+                                       int counter_bits, void *stream, uint64_t *n_bases_out)
+{
+    if (!d_table || (!fasta && n_bytes)) return bad_arg("null pointer");
+    KPAL_CHECK(check_k_host(k));
+    KPAL_CHECK(require_device());
+    std::lock_guard<std::mutex> lock(g_count_mutex);
+    CountWorkspace *w;
+    KPAL_CHECK(get_count_ws(&w));
+    uint64_t n_bases = 0;
+    KPAL_CHECK(pack_fasta_ws(w, fasta, n_bytes, &n_bases));
+    if (n_bases_out) *n_bases_out = n_bases;
+    KPAL_CHECK(upload_and_count(w, n_bases, k, d_table, counter_bits, (cudaStream_t)stream));
+    // the pinned staging buffers are reused by the next call: wait for the copies
+    KPAL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return KPAL_OK;
 }
 
 extern "C" int kpal_count_by_record(const uint32_t *codes, const uint32_t *valid, uint64_t n_bases,

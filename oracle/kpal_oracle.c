@@ -79,21 +79,28 @@ void oracle_count_mt(const unsigned char *text, size_t n, int k,
     const size_t number = (size_t)1 << (2 * k);
     const int private_tables = (number * sizeof(int64_t) * (size_t)threads)
                                <= ((size_t)1 << 30);
+    int64_t **mine = (int64_t **)calloc((size_t)threads, sizeof(int64_t *));
     #pragma omp parallel num_threads(threads)
     {
         int t = omp_get_thread_num(), nt = omp_get_num_threads();
         size_t b = n / (size_t)nt * (size_t)t;
         size_t e = (t == nt - 1) ? n : n / (size_t)nt * (size_t)(t + 1);
         if (private_tables) {
-            int64_t *mine = (int64_t *)calloc(number, sizeof(int64_t));
-            count_range(text, n, b, e, k, mine, 0);
-            #pragma omp critical
-            for (size_t i = 0; i < number; ++i) counts[i] += mine[i];
-            free(mine);
+            mine[t] = (int64_t *)calloc(number, sizeof(int64_t));
+            count_range(text, n, b, e, k, mine[t], 0);
+            #pragma omp barrier
+            #pragma omp for schedule(static)
+            for (long i = 0; i < (long)number; ++i) {
+                int64_t s = 0;
+                for (int u = 0; u < nt; ++u) if (mine[u]) s += mine[u][i];
+                counts[i] += s;
+            }
+            free(mine[t]);
         } else {
             count_range(text, n, b, e, k, counts, 1);
         }
     }
+    free(mine);
 #else
     oracle_count(text, n, k, counts);
 #endif

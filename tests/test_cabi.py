@@ -1,0 +1,150 @@
+"""
+CPU tests of the C-ABI boundary: the library loads, exports every symbol the
+header declares, the host packers agree with the oracle's reading of the same
+text, and -- without a GPU -- every compute entry point fails loudly instead
+of falling back to a CPU path.
+"""
+import ctypes
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from kpal_b200 import _cabi
+from oracle import kpal_oracle as ko
+
+
+def header_symbols():
+    with open(os.path.join(ROOT, "include", "kpal_b200.h")) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kpal_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _cabi.load()
+    declared = header_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(L, name), "libkpal_b200.so does not export %s" % name
+    assert sorted(_cabi.SYMBOLS) == declared
+    assert L.kpal_abi_version() == 1
+
+
+def unpack(codes, valid, n_bases):
+    """Packed stream -> list of codes (0-3, or 4 for invalid), test helper."""
+    out = []
+    for p in range(n_bases):
+        c = (int(codes[p // 16]) >> (30 - 2 * (p % 16))) & 3
+        v = (int(valid[p // 32]) >> (31 - (p % 32))) & 1
+        out.append(c if v else 4)
+    return out
+
+
+def expected_stream(seqs):
+    lut = {"A": 0, "C": 1, "G": 2, "T": 3}
+    out = []
+    for s in seqs:
+        out.extend(lut.get(ch.upper(), 4) for ch in s)
+        out.append(4)
+    return out
+
+
+def test_pack_sequences_matches_text():
+    rng = random.Random(5)
+    for _ in range(40):
+        seqs = ["".join(rng.choice("ACGTacgtNn-x") for _ in range(rng.randint(0, 150)))
+                for _ in range(rng.randint(0, 7))]
+        codes, valid, rec_starts, n_bases = _cabi.pack_sequences(seqs)
+        assert n_bases == sum(len(s) + 1 for s in seqs)
+        assert unpack(codes, valid, n_bases) == expected_stream(seqs)
+        starts = np.cumsum([0] + [len(s) + 1 for s in seqs])
+        assert rec_starts.tolist() == starts.tolist()
+        # padding stays zero and one halo chunk is present
+        assert len(codes) == ((n_bases + 63) // 64 + 1) * 4
+        assert not codes[(n_bases + 15) // 16:].any()
+
+
+def test_pack_sequences_large_parallel():
+    # > 1 MiB so that several worker threads cut the output stream
+    rng = np.random.default_rng(1)
+    seqs = []
+    for n in (3_000_001, 0, 17, 2_500_000, 1):
+        seqs.append(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=n).tobytes().decode())
+    codes, valid, rec_starts, n_bases = _cabi.pack_sequences(seqs)
+    flat = np.array(expected_stream(seqs), dtype=np.uint8)
+    pos = np.arange(n_bases)
+    got_v = (valid[pos // 32] >> (31 - pos % 32).astype(np.uint32)) & 1
+    got_c = (codes[pos // 16] >> (30 - 2 * (pos % 16)).astype(np.uint32)) & 3
+    assert np.array_equal(got_v == 1, flat != 4)
+    assert np.array_equal(got_c[flat != 4], flat[flat != 4])
+    assert not got_c[flat == 4].any()
+
+
+def test_fasta_pack_matches_oracle_reader(golden, tutorial_texts):
+    texts = [golden["fasta_text"], tutorial_texts["a_1"], "", "no header at all\nACGT\n",
+             ">only\n", ">a\nAC GT\r\nNN\n\n>\nTT\n>b\tz\n", ">x y z\n\n\nACGT", "\n\n>q\nA\n"]
+    for text in texts:
+        records = ko.parse_fasta(text)
+        codes, valid, rec_starts, names, n_bases = _cabi.fasta_pack(text)
+        assert names == [n for n, _ in records]
+        assert unpack(codes, valid, n_bases) == expected_stream([s for _, s in records])
+        assert rec_starts.tolist() == np.cumsum([0] + [len(s) + 1 for _, s in records]).tolist()
+
+
+def test_fasta_pack_large_parallel():
+    rng = np.random.default_rng(2)
+    recs = []
+    lines = []
+    for i in range(3000):
+        seq = rng.choice(np.frombuffer(b"ACGTacgtN", dtype=np.uint8),
+                         size=int(rng.integers(0, 2500))).tobytes().decode()
+        recs.append(("r%07d" % i, seq))
+        lines.append(">r%07d some text" % i)
+        lines.extend(seq[p:p + 70] for p in range(0, len(seq), 70))
+    text = "\n".join(lines) + "\n"
+    assert len(text) > (3 << 20)
+    codes, valid, rec_starts, names, n_bases = _cabi.fasta_pack(text)
+    assert names == [n for n, _ in recs]
+    assert rec_starts.tolist() == np.cumsum([0] + [len(s) + 1 for _, s in recs]).tolist()
+    flat = np.array(expected_stream([s for _, s in recs]), dtype=np.uint8)
+    pos = np.arange(n_bases)
+    got_v = (valid[pos // 32] >> (31 - pos % 32).astype(np.uint32)) & 1
+    got_c = (codes[pos // 16] >> (30 - 2 * (pos % 16)).astype(np.uint32)) & 3
+    assert np.array_equal(got_v == 1, flat != 4)
+    assert np.array_equal(got_c[flat != 4], flat[flat != 4])
+
+
+def test_argument_errors_map_to_valueerror():
+    with pytest.raises(ValueError):
+        _cabi._check_k(0)
+    with pytest.raises(ValueError):
+        _cabi._check_k(16)
+    with pytest.raises(ValueError):
+        _cabi._k_of(20)
+    L = _cabi.load()
+    assert L.kpal_dev_count_packed(None, None, 10, 3, None, 32, None) == _cabi.KPAL_EINVAL
+    assert b"null" in L.kpal_last_error()
+
+
+@pytest.mark.skipif(_cabi.device_count() > 0, reason="a GPU is present")
+def test_no_cpu_fallback_without_gpu():
+    """On a box without a GPU the product path must refuse, not emulate."""
+    from kpal_b200 import klib, kdistlib
+    with pytest.raises(RuntimeError):
+        klib.Profile.from_sequences(["ACGTACGT"], 2)
+    p = klib.Profile(np.zeros(16, dtype=np.int64))
+    with pytest.raises(RuntimeError):
+        p.balance()
+    with pytest.raises(RuntimeError):
+        kdistlib.ProfileDistance().distance(p, p)
+    L = _cabi.load()
+    out = np.zeros(16, dtype=np.int64)
+    blob = b"ACGT"
+    off = np.array([0, 4], dtype=np.uint64)
+    rc = L.kpal_count_sequences(ctypes.c_char_p(blob), _cabi.ptr(off), 1, 2, 0, _cabi.ptr(out))
+    assert rc == _cabi.KPAL_ECUDA
+    assert b"no CPU fallback" in L.kpal_last_error()

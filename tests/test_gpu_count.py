@@ -1,0 +1,254 @@
+"""
+GPU parity tests for the counting path (run on the B200 box: pytest -m gpu).
+Everything goes through the public API / C ABI of kpal_b200 and is compared
+bit-exactly with the oracle and with the golden vectors of the reference.
+Mirrors reference tests/test_klib.py:32-99,164-180.
+"""
+import ctypes
+import io
+import random
+
+import numpy as np
+import pytest
+
+from conftest import dense
+from kpal_b200 import _cabi, klib
+from oracle import c_oracle, kpal_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+
+def check_profile(profile, want, k, name=None):
+    """Same assertions as reference tests/utils.py:139-148."""
+    assert profile.length == k
+    assert profile.total == want.sum()
+    assert profile.non_zero == np.count_nonzero(want)
+    assert profile.counts.dtype == np.int64
+    assert np.array_equal(profile.counts, want)
+    if name:
+        assert profile.name == name
+
+
+def fasta_of(sequences, names=None):
+    """One line per record, like reference tests/utils.py:184-196."""
+    names = names or ["sequence_%d" % (i + 1) for i in range(len(sequences))]
+    return "\n".join(">" + n + "\n" + s for n, s in zip(names, sequences)) + "\n"
+
+
+def test_from_fasta_reference_fixtures(golden):
+    for case in golden["count_cases"]:
+        k, seqs = case["k"], case["sequences"]
+        profile = klib.Profile.from_fasta(io.StringIO(fasta_of(seqs)), k, name="abc")
+        check_profile(profile, dense(case["counts"]), k, name="abc")
+        profile = klib.Profile.from_sequences(seqs, k)
+        check_profile(profile, dense(case["counts"]), k)
+
+
+def test_from_sequences_odd_characters(golden):
+    for case in golden["odd_cases"]:
+        profile = klib.Profile.from_sequences(iter(case["sequences"]), case["k"])
+        check_profile(profile, dense(case["counts"]), case["k"])
+
+
+def test_from_fasta_by_record(golden):
+    seqs = golden["fixtures"]["LENGTH_60"]
+    names = [str(i) for i in range(len(seqs))]
+    for prefix in (None, "pre"):
+        profiles = list(klib.Profile.from_fasta_by_record(
+            io.StringIO(fasta_of(seqs, names)), 4, prefix=prefix))
+        assert len(profiles) == len(seqs)
+        for name, seq, profile in zip(names, seqs, profiles):
+            check_profile(profile, ko.count_sequences([seq], 4), 4,
+                          name=(prefix + "_" + name) if prefix else name)
+
+
+def test_fasta_text_golden(golden):
+    text = golden["fasta_text"]
+    for case in golden["fasta_cases"]:
+        k = case["k"]
+        check_profile(klib.Profile.from_fasta(io.StringIO(text), k), dense(case["counts"]), k)
+        got = list(klib.Profile.from_fasta_by_record(io.StringIO(text), k, prefix="pre"))
+        assert [p.name for p in got] == [n for n, _ in case["by_record"]]
+        for profile, (_, want) in zip(got, case["by_record"]):
+            check_profile(profile, dense(want), k)
+
+
+def test_balance_golden(golden):
+    for case in golden["balance_cases"]:
+        profile = klib.Profile(dense(case["before"]))
+        profile.balance()
+        check_profile(profile, dense(case["after"]), case["k"])
+
+
+def test_balance_fused_equals_count_then_balance():
+    rng = random.Random(2)
+    seqs = ["".join(rng.choice("ACGTN") for _ in range(500)) for _ in range(20)]
+    for k in (1, 2, 5, 6, 8, 9, 11):
+        plain = _cabi.count_sequences(seqs, k)
+        fused = _cabi.count_sequences(seqs, k, balance=True)
+        assert np.array_equal(fused, ko.balance(plain))
+        assert fused.sum() == 2 * plain.sum()
+        p = klib.Profile(plain.copy())
+        p.balance()
+        assert np.array_equal(p.counts, fused)
+
+
+def test_tutorial_fixture(golden, tutorial_texts):
+    """60-column wrapped FASTA: reference doc/tutorial.rst:44-82."""
+    tut = golden["tutorial"]
+    for name, text in tutorial_texts.items():
+        profile = klib.Profile.from_fasta(io.StringIO(text), tut["k"], name=name)
+        assert int(profile.total) == tut["profiles"][name]["total"]
+        assert int(profile.non_zero) == tut["profiles"][name]["non_zero"]
+        assert np.array_equal(profile.counts, ko.count_fasta(text, tut["k"]))
+
+
+def test_randomised_against_oracle():
+    rng = random.Random(7)
+    alphabet = "ACGT" * 10 + "acgtNnRY-*"
+    for trial in range(60):
+        k = rng.randint(1, 13)
+        n_rec = rng.choice([0, 1, 2, 5, 40])
+        seqs = ["".join(rng.choice(alphabet) for _ in range(rng.choice([0, 1, k - 1, k, k + 1, 63, 64, 65, 200, 3000])))
+                for _ in range(n_rec)]
+        got = _cabi.count_sequences(seqs, k)
+        assert np.array_equal(got, ko.count_sequences(seqs, k)), (k, n_rec)
+
+
+def test_empty_and_short_inputs():
+    for k in (1, 4, 12):
+        for seqs in ([], [""], ["A" * (k - 1)], ["N" * 100]):
+            assert not _cabi.count_sequences(seqs, k).any()
+        assert _cabi.count_sequences(["a" * k], k)[0] == 1
+        assert _cabi.count_sequences(["T" * k], k)[-1] == 1
+    assert not _cabi.count_fasta("", 3).any()
+    assert not _cabi.count_fasta(">x\n", 3).any()
+
+
+def test_k_out_of_range():
+    with pytest.raises(ValueError):
+        klib.Profile.from_sequences(["ACGT"], 0)
+    with pytest.raises(ValueError):
+        klib.Profile.from_sequences(["ACGT"], 16)
+
+
+def random_reads(seed, n_reads, read_len, p_n=0.001, p_lower=0.05):
+    rng = np.random.default_rng(seed)
+    n = n_reads * read_len
+    bases = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)]
+    lower = rng.random(n) < p_lower
+    bases = np.where(lower, bases + 32, bases).astype(np.uint8)
+    bases[rng.random(n) < p_n] = ord("N")
+    return bases.reshape(n_reads, read_len)
+
+
+def reads_to_fasta(reads):
+    n_reads, read_len = reads.shape
+    header = np.frombuffer(b">r0000000\n", dtype=np.uint8)
+    out = np.empty((n_reads, len(header) + read_len + 1), dtype=np.uint8)
+    out[:, :len(header)] = header
+    digits = np.arange(n_reads)
+    for d in range(7):
+        out[:, 8 - d] = ord("0") + (digits // 10 ** d) % 10
+    out[:, len(header):-1] = reads
+    out[:, -1] = ord("\n")
+    return out.tobytes()
+
+
+@pytest.mark.parametrize("k,n_reads,read_len,balance", [
+    (6, 1, 1_000_000, False),         # BASELINE config 1
+    (12, 66_667, 150, True),          # BASELINE config 2 at 1/10 size
+    (13, 4, 2_500_000, True),
+    (9, 20_000, 150, False),
+])
+def test_large_synthetic_fasta(k, n_reads, read_len, balance):
+    reads = random_reads(k * 1000 + n_reads, n_reads, read_len)
+    fasta = reads_to_fasta(reads)
+    got = _cabi.count_fasta(fasta, k, balance=balance)
+    want = c_oracle.count_bytes(np.insert(reads, read_len, ord("\n"), axis=1).tobytes(), k,
+                                threads=c_oracle.max_threads())
+    if balance:
+        want = ko.balance(want)
+    assert np.array_equal(got, want)
+    windows = want.sum() // (2 if balance else 1)
+    assert windows <= n_reads * (read_len - k + 1)
+
+
+def test_by_record_many_records():
+    k = 8
+    reads = random_reads(33, 3000, 1000)
+    fasta = reads_to_fasta(reads)
+    profiles = list(klib.Profile.from_fasta_by_record(io.BytesIO(fasta), k))
+    assert len(profiles) == 3000
+    assert profiles[0].name == "r0000000" and profiles[-1].name == "r0002999"
+    for i in (0, 1, 2, 777, 1500, 2998, 2999):
+        assert np.array_equal(profiles[i].counts,
+                              c_oracle.count_bytes(reads[i].tobytes(), k)), i
+    total = sum(int(p.counts.sum()) for p in profiles)
+    assert total == int(c_oracle.count_bytes(
+        np.insert(reads, 1000, ord("\n"), axis=1).tobytes(), k).sum())
+
+
+def test_by_record_balance_and_long_records():
+    rng = random.Random(9)
+    seqs = ["".join(rng.choice("ACGTN") for _ in range(n)) for n in (0, 5, 64, 65, 100_000, 3, 12_345)]
+    codes, valid, rec_starts, n_bases = _cabi.pack_sequences(seqs)
+    for k in (2, 5, 9):
+        rows = _cabi.count_by_record(codes, valid, n_bases, rec_starts, 0, len(seqs), k, balance=True)
+        for seq, row in zip(seqs, rows):
+            assert np.array_equal(row, ko.balance(ko.count_sequences([seq], k)))
+        part = _cabi.count_by_record(codes, valid, n_bases, rec_starts, 2, 3, k)
+        for seq, row in zip(seqs[2:5], part):
+            assert np.array_equal(row, ko.count_sequences([seq], k))
+
+
+def test_device_api_counter_widths():
+    """kpal_dev_count_packed with 32- and 64-bit counters + finalize."""
+    L = _cabi.load()
+    reads = random_reads(5, 5000, 200)
+    codes, valid, _, n_bases = _cabi.pack_sequences([r.tobytes() for r in reads])
+    k = 10
+    bins = 4 ** k
+    want = ko.count_sequences([r.tobytes().decode() for r in reads], k)
+    d_codes = L.kpal_dev_alloc(codes.nbytes)
+    d_valid = L.kpal_dev_alloc(valid.nbytes)
+    d_counts = L.kpal_dev_alloc(bins * 8)
+    d_bal = L.kpal_dev_alloc(bins * 8)
+    try:
+        _cabi.check(L.kpal_memcpy_h2d(d_codes, _cabi.ptr(codes), codes.nbytes, None))
+        _cabi.check(L.kpal_memcpy_h2d(d_valid, _cabi.ptr(valid), valid.nbytes, None))
+        for bits in (32, 64):
+            d_table = L.kpal_dev_alloc(bins * bits // 8)
+            zero = np.zeros(bins * bits // 8, dtype=np.uint8)
+            _cabi.check(L.kpal_memcpy_h2d(d_table, _cabi.ptr(zero), zero.nbytes, None))
+            _cabi.check(L.kpal_dev_count_packed(d_codes, d_valid, n_bases, k, d_table, bits, None))
+            _cabi.check(L.kpal_dev_finalize_counts(d_table, bits, k, 0, d_counts, None))
+            _cabi.check(L.kpal_dev_balance(d_counts, d_bal, k, None))
+            out = np.empty(bins, dtype=np.int64)
+            bal = np.empty(bins, dtype=np.int64)
+            _cabi.check(L.kpal_memcpy_d2h(_cabi.ptr(out), d_counts, out.nbytes, None))
+            _cabi.check(L.kpal_memcpy_d2h(_cabi.ptr(bal), d_bal, bal.nbytes, None))
+            _cabi.check(L.kpal_stream_sync(None))
+            L.kpal_dev_free(d_table)
+            assert np.array_equal(out, want)
+            assert np.array_equal(bal, ko.balance(want))
+        assert L.kpal_kernel_launches() > 0
+    finally:
+        for p in (d_codes, d_valid, d_counts, d_bal):
+            L.kpal_dev_free(p)
+
+
+def test_full_size_config2_properties():
+    """BASELINE config 2 at full size (100 Mbp of 150-bp reads, k=12, balance):
+    bit-exact against the multi-threaded C oracle, plus size-independent
+    properties (balanced total = 2 x windows, symmetry under rc)."""
+    k = 12
+    reads = random_reads(2, 666_667, 150)
+    fasta = reads_to_fasta(reads)
+    got = _cabi.count_fasta(fasta, k, balance=True)
+    plain = c_oracle.count_bytes(np.insert(reads, 150, ord("\n"), axis=1).tobytes(), k,
+                                 threads=c_oracle.max_threads())
+    assert got.sum() == 2 * plain.sum()
+    rc = ko.reverse_complement_table(k)
+    assert np.array_equal(got, got[rc])
+    assert np.array_equal(got, plain + plain[rc])
