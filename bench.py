@@ -375,9 +375,10 @@ def bench_count(args):
                        "l2": "512 MB memset between steps (untimed); table memset is inside the step",
                        "parallelism": "records sharded per GPU, NCCL reduce of u32 tables" if world > 1 else "1 GPU"},
             "e2e": {"value": total_bases / 1e9 / e2e_s, "unit": "Gbases/s",
-                    "h2d_bytes_per_step": int((codes.nbytes + valid.nbytes) * world),
+                    "h2d_bytes_per_step": int(n_fasta * world),
                     "d2h_bytes_per_step": int(bins * 8), "ms_per_step": e2e_s * 1e3,
-                    "path": "pinned FASTA bytes -> kpal_count_fasta (C++ scan/pack, H2D, kernels, D2H int64)"},
+                    "path": "pinned FASTA bytes -> kpal_count_fasta (H2D of the raw text, GPU scan/pack, "
+                            "count + balance kernels, D2H int64)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "count_global_kernel<u32>", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,

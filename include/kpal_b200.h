@@ -194,14 +194,14 @@ uint64_t kpal_prepared_stride(int k);
 /*
  * Per-profile pre-pass (done once per profile instead of once per pair as in
  * kpal/kdistlib.py:136-157): optional balance, total S (kpal/metrics.py:64-65),
- * F = x/S (x when do_scale == 0), R = 1/(x+1), non-zero bitmap, sum(F^2).
+ * F = x/S (x when do_scale == 0), P = x + 1, non-zero bitmap, sum(F^2).
  *   d_counts  [n][4^k] int64
- *   d_F, d_R  [n][stride] float64 (d_R may be NULL unless multiset/prod)
+ *   d_F, d_P  [n][stride] float64: F = x/S, P = x + 1 (d_P may be NULL unless multiset/prod)
  *   d_bitmap  [n][stride/32] uint32
  *   d_totals  [n] float64, d_norm2 [n] float64
  */
 int kpal_dev_profiles_prepare(const int64_t *d_counts, uint64_t n, int k, int do_balance,
-                              int do_scale, double *d_F, double *d_R, uint32_t *d_bitmap,
+                              int do_scale, double *d_F, double *d_P, uint32_t *d_bitmap,
                               double *d_totals, double *d_norm2, void *stream);
 
 /*
@@ -223,12 +223,34 @@ uint64_t kpal_distance_num_tiles(uint64_t n_profiles);
  * Writes both out[i][j] and out[j][i] (row-major [n][n]) for every pair of
  * the tiles; other entries are left untouched.
  */
-int kpal_dev_distance_tiles(const double *d_F, const double *d_R, const uint32_t *d_bitmap,
+int kpal_dev_distance_tiles(const double *d_F, const double *d_P, const uint32_t *d_bitmap,
                             const double *d_totals, const double *d_norm2,
                             const int32_t *d_order, uint64_t n, int k,
                             int metric, int pairwise, int do_scale, int down,
                             uint64_t tile_begin, uint64_t tile_end,
                             double *d_out, void *stream);
+
+/* ------------------------------------------------ FASTA scan/pack: device API
+ *
+ * GPU version of kpal_fasta_scan + kpal_fasta_pack for whole-file counting
+ * (Bio.SeqIO.parse + str(record.seq), kpal/klib.py:111): raw FASTA bytes in
+ * device memory -> packed stream.  d_text must be readable up to the next
+ * multiple of 16 bytes; d_codes / d_valid must hold kpal_packed_words(n_bytes)
+ * words (one base per input byte is the upper bound) and the count kernel can
+ * be run with n_bases = n_bytes (the tail is invalid padding).  One invalid
+ * base is emitted per header line.  d_scratch (kpal_fasta_scratch_bytes) starts
+ * with { uint64 first_header; uint64 n_bases; uint32 flags; } -- flags bit 0 =
+ * the text has tabs / VT / FF / FS..US on sequence lines, whose rstrip()
+ * semantics need the host packer.
+ */
+uint64_t kpal_fasta_scratch_bytes(uint64_t n_bytes);
+int kpal_dev_fasta_pack(const void *d_text, uint64_t n_bytes, uint32_t *d_codes, uint32_t *d_valid,
+                        void *d_scratch, void *stream);
+
+/* run-time switches: "host_fasta" (1 = kpal_count_fasta uses the C++ packer
+ * instead of the GPU one), "exact_div" (1 = IEEE division in the distance
+ * kernels instead of MUFU.RCP64H + Newton). */
+int kpal_set_option(const char *name, int value);
 
 /* counters for bench.py's "gpu_launches": kernels launched by this library
  * in the calling process since load / since the last reset. */

@@ -9,6 +9,7 @@
 #include <mutex>
 #include <numeric>
 #include <string.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace kpal {
@@ -17,6 +18,7 @@ namespace kpal {
 int launch_count(const uint32_t *, const uint32_t *, uint64_t, int, void *, int, cudaStream_t);
 int launch_finalize(const void *, int, int, int, int64_t *, cudaStream_t);
 int launch_balance(const int64_t *, int64_t *, int, cudaStream_t);
+int launch_accumulate(const void *, void *, int, uint64_t, cudaStream_t);
 int launch_by_record(const uint32_t *, const uint32_t *, const uint64_t *, uint64_t, uint64_t, int,
                      int, int64_t *, cudaStream_t);
 int launch_prepare(const int64_t *, uint64_t, int, int, int, double *, double *, uint32_t *,
@@ -26,9 +28,13 @@ int launch_distance_tiles(const double *, const double *, const uint32_t *, cons
                           uint64_t, uint64_t, double *, uint32_t *, double *, cudaStream_t);
 uint64_t distance_num_tiles(uint64_t n);
 uint64_t prepared_stride_host(int k);
+uint64_t fasta_scratch_bytes(uint64_t n_bytes);
+void set_exact_div(bool on);
+int launch_fasta_pack(const uint8_t *, uint64_t, uint32_t *, uint32_t *, void *, cudaStream_t);
 
 static thread_local char t_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_host_fasta{-1};       // -1: from the environment (KPAL_HOST_FASTA=1)
 
 void set_error(const char *fmt, ...)
 {
@@ -125,8 +131,8 @@ struct GrowPin {
 };
 struct CountWorkspace {
     int device = -1;
-    GrowDev codes, valid, table, counts;
-    GrowPin pcodes, pvalid;
+    GrowDev codes, valid, table, counts, text, fscratch;
+    GrowPin pcodes, pvalid, pstatus;
 };
 static std::mutex g_count_mutex;                 // held for the whole host-level call
 static std::vector<CountWorkspace *> g_count_ws;
@@ -269,6 +275,25 @@ extern "C" int kpal_stream_sync(void *stream)
     return KPAL_OK;
 }
 
+extern "C" int kpal_set_option(const char *name, int value)
+{
+    if (!name) return bad_arg("null option name");
+    if (!strcmp(name, "host_fasta")) { g_host_fasta.store(value ? 1 : 0); return KPAL_OK; }
+    if (!strcmp(name, "exact_div")) { set_exact_div(value != 0); return KPAL_OK; }
+    set_error("unknown option '%s'", name);
+    return KPAL_EINVAL;
+}
+
+extern "C" uint64_t kpal_fasta_scratch_bytes(uint64_t n_bytes) { return fasta_scratch_bytes(n_bytes); }
+
+extern "C" int kpal_dev_fasta_pack(const void *d_text, uint64_t n_bytes, uint32_t *d_codes,
+                                   uint32_t *d_valid, void *d_scratch, void *stream)
+{
+    if ((!d_text && n_bytes) || !d_codes || !d_valid || !d_scratch) return bad_arg("null device pointer");
+    return launch_fasta_pack(static_cast<const uint8_t *>(d_text), n_bytes, d_codes, d_valid, d_scratch,
+                             (cudaStream_t)stream);
+}
+
 extern "C" uint64_t kpal_kernel_launches(void) { return g_launches.load(); }
 extern "C" void kpal_reset_kernel_launches(void) { g_launches.store(0); }
 
@@ -381,6 +406,55 @@ extern "C" int kpal_count_sequences(const char *text, const uint64_t *offsets, u
     return count_packed_to_host(w, n_bases, k, balance, counts_out);
 }
 
+// Device scalars written by the GPU FASTA packer (fasta.cu: FastaScratch).
+struct FastaStatus {
+    unsigned long long first_header, total_bases;
+    unsigned int flags, pad;
+};
+
+// Raw FASTA bytes (host) -> device text -> GPU scan/pack -> windows accumulated
+// into d_table.  *flags gets bit 0 when the text holds bytes the GPU packer
+// does not handle (tabs & co on sequence lines): the caller then redoes the
+// file through the host packer.  Synchronises the stream.
+static int fasta_gpu_count(CountWorkspace *w, const char *fasta, uint64_t n_bytes, int k,
+                           void *d_table, int bits, cudaStream_t st, unsigned *flags,
+                           uint64_t *n_bases)
+{
+    uint64_t cw, vw;
+    kpal_packed_words(n_bytes, &cw, &vw);           // capacity: one base per input byte
+    KPAL_CHECK(w->text.ensure(n_bytes + 32));
+    KPAL_CHECK(w->codes.ensure(cw * 4));
+    KPAL_CHECK(w->valid.ensure(vw * 4));
+    KPAL_CHECK(w->fscratch.ensure(fasta_scratch_bytes(n_bytes)));
+    KPAL_CHECK(w->pstatus.ensure(sizeof(FastaStatus)));
+    KPAL_CUDA(cudaMemcpyAsync(w->text.p, fasta, n_bytes, cudaMemcpyHostToDevice, st));
+    KPAL_CHECK(launch_fasta_pack(static_cast<const uint8_t *>(w->text.p), n_bytes,
+                                 static_cast<uint32_t *>(w->codes.p),
+                                 static_cast<uint32_t *>(w->valid.p), w->fscratch.p, st));
+    // n_bytes is an upper bound of the packed length; the tail is all-invalid padding
+    KPAL_CHECK(launch_count(static_cast<uint32_t *>(w->codes.p), static_cast<uint32_t *>(w->valid.p),
+                            n_bytes, k, d_table, bits, st));
+    KPAL_CUDA(cudaMemcpyAsync(w->pstatus.p, w->fscratch.p, sizeof(FastaStatus),
+                              cudaMemcpyDeviceToHost, st));
+    KPAL_CUDA(cudaStreamSynchronize(st));
+    const FastaStatus *fs = static_cast<const FastaStatus *>(w->pstatus.p);
+    *flags = fs->flags;
+    if (n_bases) *n_bases = fs->total_bases;
+    return KPAL_OK;
+}
+
+
+static bool use_gpu_fasta()
+{
+    int v = g_host_fasta.load();
+    if (v < 0) {
+        const char *e = getenv("KPAL_HOST_FASTA");
+        v = (e && e[0] == '1') ? 1 : 0;
+        g_host_fasta.store(v);
+    }
+    return v == 0;
+}
+
 extern "C" int kpal_count_fasta(const char *fasta, uint64_t n_bytes, int k, int balance,
                                 int64_t *counts_out)
 {
@@ -390,6 +464,23 @@ extern "C" int kpal_count_fasta(const char *fasta, uint64_t n_bytes, int k, int 
     std::lock_guard<std::mutex> lock(g_count_mutex);
     CountWorkspace *w;
     KPAL_CHECK(get_count_ws(&w));
+    if (use_gpu_fasta() && n_bytes > 0) {
+        const uint64_t bins = 1ull << (2 * k);
+        const int bits = (n_bytes >= (1ull << 32)) ? 64 : 32;
+        KPAL_CHECK(w->table.ensure(bins * (bits / 8)));
+        KPAL_CHECK(w->counts.ensure(bins * 8));
+        cudaStream_t st = 0;
+        KPAL_CUDA(cudaMemsetAsync(w->table.p, 0, bins * (bits / 8), st));
+        unsigned flags = 0;
+        KPAL_CHECK(fasta_gpu_count(w, fasta, n_bytes, k, w->table.p, bits, st, &flags, nullptr));
+        if (!flags) {
+            KPAL_CHECK(launch_finalize(w->table.p, bits, k, balance, static_cast<int64_t *>(w->counts.p), st));
+            KPAL_CUDA(cudaMemcpyAsync(counts_out, w->counts.p, bins * 8, cudaMemcpyDeviceToHost, st));
+            KPAL_CUDA(cudaStreamSynchronize(st));
+            return KPAL_OK;
+        }
+        // exotic whitespace: fall through to the host packer (exact rstrip semantics)
+    }
     uint64_t n_bases = 0;
     KPAL_CHECK(pack_fasta_ws(w, fasta, n_bytes, &n_bases));
     return count_packed_to_host(w, n_bases, k, balance, counts_out);
@@ -407,6 +498,22 @@ extern "C" int kpal_count_fasta_to_dev(const char *fasta, uint64_t n_bytes, int 
     CountWorkspace *w;
     KPAL_CHECK(get_count_ws(&w));
     uint64_t n_bases = 0;
+    if (use_gpu_fasta() && n_bytes > 0) {
+        // The GPU packer may turn out to be unusable for this text only after the
+        // windows were accumulated, so count into a scratch table first.
+        const uint64_t bins = 1ull << (2 * k);
+        KPAL_CHECK(w->table.ensure(bins * (counter_bits / 8)));
+        cudaStream_t st = (cudaStream_t)stream;
+        KPAL_CUDA(cudaMemsetAsync(w->table.p, 0, bins * (counter_bits / 8), st));
+        unsigned flags = 0;
+        KPAL_CHECK(fasta_gpu_count(w, fasta, n_bytes, k, w->table.p, counter_bits, st, &flags, &n_bases));
+        if (!flags) {
+            KPAL_CHECK(launch_accumulate(w->table.p, d_table, counter_bits, bins, st));
+            KPAL_CUDA(cudaStreamSynchronize(st));
+            if (n_bases_out) *n_bases_out = n_bases;
+            return KPAL_OK;
+        }
+    }
     KPAL_CHECK(pack_fasta_ws(w, fasta, n_bytes, &n_bases));
     if (n_bases_out) *n_bases_out = n_bases;
     KPAL_CHECK(upload_and_count(w, n_bases, k, d_table, counter_bits, (cudaStream_t)stream));

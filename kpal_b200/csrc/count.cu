@@ -219,9 +219,33 @@ balance_i64_kernel(const int64_t *__restrict__ in, int k, int64_t *__restrict__ 
         out[i] = in[i] + __ldg(in + rc_index(i, shift));
 }
 
+template <typename CounterT>
+__global__ void __launch_bounds__(256)
+accumulate_kernel(const CounterT *__restrict__ src, CounterT *__restrict__ dst, uint64_t n)
+{
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += uint64_t(gridDim.x) * blockDim.x)
+        dst[i] += src[i];
+}
+
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
+int launch_accumulate(const void *d_src, void *d_dst, int counter_bits, uint64_t n, cudaStream_t stream)
+{
+    uint64_t want = (n + 255) / 256;
+    const uint64_t cap = uint64_t(sm_count()) * 32;
+    const unsigned grid = unsigned(want < cap ? want : cap);
+    if (counter_bits == 32)
+        accumulate_kernel<uint32_t><<<grid, 256, 0, stream>>>(static_cast<const uint32_t *>(d_src),
+                                                              static_cast<uint32_t *>(d_dst), n);
+    else
+        accumulate_kernel<unsigned long long><<<grid, 256, 0, stream>>>(
+            static_cast<const unsigned long long *>(d_src), static_cast<unsigned long long *>(d_dst), n);
+    KPAL_LAUNCH_CHECK("accumulate_kernel");
+    return KPAL_OK;
+}
+
 static int check_k(int k)
 {
     if (k < 1 || k > KPAL_MAX_K) {

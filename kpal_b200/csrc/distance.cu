@@ -8,31 +8,35 @@
 // Algebra (DESIGN.md "Distance kernel").  With S the profile totals, the
 // reference scales the profile with the smaller total by s = S_big/S_small
 // (or, with `down`, the larger one by 1/s).  Call A the scaled and B the
-// unscaled profile of a pair, F = x/S the per-profile frequencies, R = 1/(x+1)
-// and t_B = 1/S_B.  Dividing numerator and denominator by S_B:
+// unscaled profile of a pair, x the raw counts, F = x/S the per-profile
+// frequencies, P = x + 1 and t_B = 1/S_B.  Dividing numerator and denominator
+// by S_B:
 //
-//   prod: |sA-b| / ((sA+1)(b+1)) = |F_A - F_B| * R_B / (F_A + t_B)
-//   sum : |sA-b| / (sA+b+1)      = |F_A - F_B| / (F_A + F_B + t_B)
+//   prod: |sA-b| / ((sA+1)(b+1)) = |F_A - F_B| / (F_A * P_B + (F_B + t_B))
+//   sum : |sA-b| / (sA+b+1)      = |F_A - F_B| / (F_A + (F_B + t_B))
 //   euclidean = S_B * sqrt(sum (F_A - F_B)^2),   cosine = <F_A,F_B>/(|F_A||F_B|)
 //
-// so everything pair-dependent is ONE per-column scalar (t_B), F and R are
-// computed once per profile (the reference redoes copy/balance/scale per
-// pair), and identical profiles give exactly 0.  Unscaled: S := 1 (F = x).
+// Everything pair-dependent is gone: F and P are computed once per profile
+// (the reference redoes copy/balance/scale per pair), the numerator is exact
+// (identical profiles give exactly 0), and one element pair costs 5 fp64
+// instructions + 1 MUFU:
+//     n   = F_A - F_B                      DADD
+//     den = fma(F_A, P_B, F_B + t_B)       DFMA   (F_B + t_B: once per B element)
+//     q0  = rcp.approx(den)                MUFU.RCP64H, ~20 good bits
+//     h   = fma(-den, q0, 2)               DFMA   (Newton: 1/den = q0 * h, rel. err <= 2^-39)
+//     acc = fma(|n| * q0, h, acc)          DMUL + DFMA
+// Unscaled: S := 1 (F = x, t = 1).  The exact IEEE division is kept as a
+// run-time option (kpal_set_option("exact_div", 1)) for validation.
 // Profiles are visited in order of total, so in every tile the row panel is
 // the A side and the column panel the B side.
 //
-// The one fp64 division per element pair is a MUFU.RCP64H seed + one Newton
-// step (relative error <= 2^-39, far inside the 1e-9 parity bound; the exact
-// IEEE path is kept behind KPAL_EXACT_DIV=1 for validation).
-//
-// Tile kernel: CTA = 128 A-rows x 64 B-rows, 8 compute warps (each thread owns
-// an 8 x 4 block of pairs, accumulators in registers) + 1 producer warp that
-// streams 32-element row segments into a 3-stage shared-memory ring with
-// cp.async.bulk (TMA bulk copies) completing on mbarriers.
+// Tile kernel: CTA = TA A-rows x TB B-rows, compute warps own 32 x 32 pairs
+// (each thread an 8 x 4 block, accumulators in registers) + 1 producer warp that
+// streams DC-element row segments into a shared-memory ring with cp.async.bulk
+// (TMA bulk copies, SASS UBLKCP) completing on mbarriers.
 #include "common.cuh"
 
 #include <stdlib.h>
-#include <vector>
 #include <algorithm>
 
 namespace kpal {
@@ -40,14 +44,18 @@ namespace kpal {
 // ---------------------------------------------------------------------------
 // geometry
 // ---------------------------------------------------------------------------
-constexpr int TA = 128;                 // A rows (scaled side) per tile
-constexpr int TB = 64;                  // B rows (unscaled side) per tile
+constexpr int WI = 4;                   // compute warps along the A (row) side
+constexpr int WJ = 2;                   // compute warps along the B (column) side
+constexpr int NTI = WI * 4;             // threads along i (a warp is 4 x 8 threads)
+constexpr int NTJ = WJ * 8;             // threads along j
+constexpr int TA = NTI * 8;             // A rows (scaled side) per tile   = 128
+constexpr int TB = NTJ * 4;             // B rows (unscaled side) per tile = 64
 constexpr int DC = 32;                  // profile elements per stage
 constexpr int ROW_BYTES = DC * 8 + 16;  // +16: consecutive rows land in different bank groups
 constexpr int STAGES = 3;
 constexpr int A_BYTES = TA * ROW_BYTES;
 constexpr int B_BYTES = TB * ROW_BYTES;
-constexpr int COMPUTE_WARPS = 8;
+constexpr int COMPUTE_WARPS = WI * WJ;
 constexpr int TILE_THREADS = (COMPUTE_WARPS + 1) * 32;
 constexpr uint64_t kStrideAlign = 128;  // prepared row stride: multiple of 128 doubles (bitmap rows 16 B aligned)
 constexpr uint64_t kSliceLen = 1u << 16;  // elements of D per work item
@@ -59,6 +67,9 @@ __host__ __device__ inline uint64_t prepared_stride(int k)
 }
 
 enum : int { M_PROD = 0, M_SUM = 1, M_EUCLID = 2, M_COSINE = 3 };
+
+static bool g_exact_div = false;
+void set_exact_div(bool on) { g_exact_div = on; }
 
 // ---------------------------------------------------------------------------
 // per-profile pre-pass
@@ -83,13 +94,13 @@ profile_totals_kernel(const int64_t *__restrict__ counts, uint64_t d,
     }
 }
 
-// F = x/S (x if !do_scale), R = 1/(x+1), non-zero bitmap, sum F^2.
+// F = x/S (x if !do_scale), P = x + 1, non-zero bitmap, sum F^2.
 // x = c[i] (+ c[rc(i)] when balancing, kpal/klib.py:290-298).
 __global__ void __launch_bounds__(256)
 profile_convert_kernel(const int64_t *__restrict__ counts, uint64_t d, uint64_t stride, int k,
                        int do_balance, int do_scale,
                        const unsigned long long *__restrict__ totals_i64,
-                       double *__restrict__ F, double *__restrict__ R,
+                       double *__restrict__ F, double *__restrict__ P,
                        uint32_t *__restrict__ bitmap, double *__restrict__ totals,
                        double *__restrict__ norm2)
 {
@@ -101,7 +112,7 @@ profile_convert_kernel(const int64_t *__restrict__ counts, uint64_t d, uint64_t 
     if (blockIdx.x == 0 && threadIdx.x == 0) totals[p] = S;
     const int shift = 32 - 2 * k;
     double n2 = 0.0;
-    // stride is a multiple of 64, the loop covers whole warps: ballot is safe
+    // stride is a multiple of 128, the loop covers whole warps: ballot is safe
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < stride;
          i += uint64_t(gridDim.x) * blockDim.x) {
         long long x = 0;
@@ -113,7 +124,7 @@ profile_convert_kernel(const int64_t *__restrict__ counts, uint64_t d, uint64_t 
         double f = do_scale ? xd / S : xd;
         if (i >= d) f = 0.0;                        // padding contributes nothing
         F[p * stride + i] = f;
-        if (R) R[p * stride + i] = 1.0 / (xd + 1.0);
+        if (P) P[p * stride + i] = xd + 1.0;
         n2 += f * f;
         const uint32_t bits = __ballot_sync(0xffffffffu, x != 0);
         if ((threadIdx.x & 31) == 0) bitmap[p * (stride / 32) + i / 32] = bits;
@@ -172,28 +183,31 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
         : "memory");
 }
 
-// reciprocal: MUFU.RCP64H seed (>= 20 good bits) + one Newton step, or IEEE
+// |n| / den: MUFU.RCP64H seed + one Newton step folded into the accumulate
+// (3 fp64 instructions), or the IEEE division.
 template <bool EXACT>
-__device__ __forceinline__ double recip(double u)
+__device__ __forceinline__ double add_term(double acc, double n, double den)
 {
     if constexpr (EXACT) {
-        return 1.0 / u;
+        return acc + fabs(n) / den;
     } else {
-        double q;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(u));
-        const double e = fma(-u, q, 1.0);
-        return fma(q, e, q);
+        double q0;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q0) : "d"(den));
+        const double h = fma(-den, q0, 2.0);
+        return fma(fabs(n) * q0, h, acc);
     }
 }
 
 // ---------------------------------------------------------------------------
-// tile enumeration over the (sorted) upper triangle:
-// row blocks I of TA sorted positions, column blocks J of TB; tile (I, J) holds
-// a pair p < q iff J >= 2I (TA == 2 TB).
+// tile enumeration over the (sorted) upper triangle: row blocks I of TA sorted
+// positions, column blocks J of TB; tile (I, J) holds a pair p < q iff
+// TA * I < TB * (J + 1), i.e. J >= (TA * I) / TB.
 // ---------------------------------------------------------------------------
+__host__ __device__ inline uint64_t first_col_tile(uint64_t I) { return (uint64_t(TA) * I) / TB; }
 __host__ __device__ inline uint64_t tiles_in_row(uint64_t I, uint64_t NJ)
 {
-    return NJ > 2 * I ? NJ - 2 * I : 0;
+    const uint64_t j0 = first_col_tile(I);
+    return NJ > j0 ? NJ - j0 : 0;
 }
 __host__ __device__ inline uint64_t num_tiles(uint64_t n)
 {
@@ -208,11 +222,11 @@ __device__ inline void tile_coords(uint64_t t, uint64_t n, uint32_t &I, uint32_t
     uint64_t i = 0;
     while (t >= tiles_in_row(i, NJ)) { t -= tiles_in_row(i, NJ); ++i; }
     I = uint32_t(i);
-    J = uint32_t(2 * i + t);
+    J = uint32_t(first_col_tile(i) + t);
 }
 
 struct TileArgs {
-    const double *F, *R;
+    const double *F, *P;
     const uint32_t *bitmap;
     const double *totals;
     const int32_t *order;       // sorted position -> profile index (NULL: identity)
@@ -232,8 +246,8 @@ distance_tile_kernel(const TileArgs a)
     __shared__ __align__(8) uint64_t bars[2 * STAGES];
     __shared__ int32_t rowsA[TA], rowsB[TB];
 
-    constexpr bool NEED_R = (METRIC == M_PROD);
-    constexpr int STAGE_BYTES = A_BYTES + B_BYTES + (NEED_R ? B_BYTES : 0);
+    constexpr bool NEED_P = (METRIC == M_PROD);
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES + (NEED_P ? B_BYTES : 0);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t item = blockIdx.x;
@@ -269,7 +283,7 @@ distance_tile_kernel(const TileArgs a)
             const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(smem_u32(&bars[STAGES + s]), ph ^ 1);
             const uint32_t full = smem_u32(&bars[s]);
-            if (lane == 0) mbar_arrive_expect_tx(full, (TA + TB + (NEED_R ? TB : 0)) * DC * 8);
+            if (lane == 0) mbar_arrive_expect_tx(full, (TA + TB + (NEED_P ? TB : 0)) * DC * 8);
             __syncwarp();
             const uint32_t base = smem_u32(smem) + s * STAGE_BYTES;
             const uint64_t col = d0 + uint64_t(it) * DC;
@@ -283,24 +297,25 @@ distance_tile_kernel(const TileArgs a)
                 const uint32_t row = lane + 32 * r;
                 const uint64_t off = uint64_t(rowsB[row]) * a.stride + col;
                 bulk_g2s(base + A_BYTES + row * ROW_BYTES, a.F + off, DC * 8, full);
-                if constexpr (NEED_R)
-                    bulk_g2s(base + A_BYTES + B_BYTES + row * ROW_BYTES, a.R + off, DC * 8, full);
+                if constexpr (NEED_P)
+                    bulk_g2s(base + A_BYTES + B_BYTES + row * ROW_BYTES, a.P + off, DC * 8, full);
             }
         }
         return;
     }
 
     // ===== compute warps =====
-    // thread (ti, tj): A rows ti*8 + r (r < 8), B rows tj + 16*c (c < 4).
-    // lane = ti_l*8 + tj_l: a quarter-warp shares its A address (broadcast) and
-    // reads 8 consecutive B rows (conflict free thanks to the row padding).
-    const uint32_t ti = (warp >> 1) * 4 + (lane >> 3);
-    const uint32_t tj = (warp & 1) * 8 + (lane & 7);
+    // warp (wi, wj), lane = ti_l * 8 + tj_l.  Thread (ti, tj) owns A rows ti + NTI*r
+    // (r < 8) and B rows tj + NTJ*c (c < 4): the four quarter-warps of an LDS.128
+    // read 4 consecutive A rows (4 bank groups, broadcast inside a quarter) and
+    // 8 consecutive B rows (8 bank groups) -- conflict free with the row padding.
+    const uint32_t ti = (warp / WJ) * 4 + (lane >> 3);
+    const uint32_t tj = (warp % WJ) * 8 + (lane & 7);
 
     double t[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-        t[c] = a.do_scale ? 1.0 / a.totals[rowsB[tj + 16 * c]] : 1.0;
+        t[c] = a.do_scale ? 1.0 / a.totals[rowsB[tj + NTJ * c]] : 1.0;
 
     double acc[8][4];
 #pragma unroll
@@ -311,38 +326,32 @@ distance_tile_kernel(const TileArgs a)
     for (uint32_t it = 0; it < n_iter; ++it) {
         const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait(smem_u32(&bars[s]), ph);
-        const unsigned char *sA = smem + s * STAGE_BYTES + ti * 8 * ROW_BYTES;
+        const unsigned char *sA = smem + s * STAGE_BYTES + ti * ROW_BYTES;
         const unsigned char *sB = smem + s * STAGE_BYTES + A_BYTES + tj * ROW_BYTES;
 #pragma unroll 2
         for (int dd = 0; dd < DC / 2; ++dd) {
-            double2 av[8], bf[4], br[4];
+            double2 av[8], bf[4], bp[4];
 #pragma unroll
             for (int r = 0; r < 8; ++r)
-                av[r] = *reinterpret_cast<const double2 *>(sA + r * ROW_BYTES + dd * 16);
+                av[r] = *reinterpret_cast<const double2 *>(sA + r * NTI * ROW_BYTES + dd * 16);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                bf[c] = *reinterpret_cast<const double2 *>(sB + c * 16 * ROW_BYTES + dd * 16);
-                if constexpr (NEED_R)
-                    br[c] = *reinterpret_cast<const double2 *>(sB + B_BYTES + c * 16 * ROW_BYTES + dd * 16);
+                bf[c] = *reinterpret_cast<const double2 *>(sB + c * NTJ * ROW_BYTES + dd * 16);
+                if constexpr (NEED_P)
+                    bp[c] = *reinterpret_cast<const double2 *>(sB + B_BYTES + c * NTJ * ROW_BYTES + dd * 16);
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 double gx = 0.0, gy = 0.0;
-                if constexpr (METRIC == M_SUM) { gx = bf[c].x + t[c]; gy = bf[c].y + t[c]; }
+                if constexpr (METRIC == M_PROD || METRIC == M_SUM) { gx = bf[c].x + t[c]; gy = bf[c].y + t[c]; }
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     if constexpr (METRIC == M_PROD) {
-                        const double nx = av[r].x - bf[c].x, ny = av[r].y - bf[c].y;
-                        const double qx = recip<EXACT>(av[r].x + t[c]);
-                        const double qy = recip<EXACT>(av[r].y + t[c]);
-                        acc[r][c] = fma(fabs(nx) * qx, br[c].x, acc[r][c]);
-                        acc[r][c] = fma(fabs(ny) * qy, br[c].y, acc[r][c]);
+                        acc[r][c] = add_term<EXACT>(acc[r][c], av[r].x - bf[c].x, fma(av[r].x, bp[c].x, gx));
+                        acc[r][c] = add_term<EXACT>(acc[r][c], av[r].y - bf[c].y, fma(av[r].y, bp[c].y, gy));
                     } else if constexpr (METRIC == M_SUM) {
-                        const double nx = av[r].x - bf[c].x, ny = av[r].y - bf[c].y;
-                        const double qx = recip<EXACT>(av[r].x + gx);
-                        const double qy = recip<EXACT>(av[r].y + gy);
-                        acc[r][c] = fma(fabs(nx), qx, acc[r][c]);
-                        acc[r][c] = fma(fabs(ny), qy, acc[r][c]);
+                        acc[r][c] = add_term<EXACT>(acc[r][c], av[r].x - bf[c].x, av[r].x + gx);
+                        acc[r][c] = add_term<EXACT>(acc[r][c], av[r].y - bf[c].y, av[r].y + gy);
                     } else if constexpr (METRIC == M_EUCLID) {
                         const double nx = av[r].x - bf[c].x, ny = av[r].y - bf[c].y;
                         acc[r][c] = fma(nx, nx, acc[r][c]);
@@ -358,32 +367,54 @@ distance_tile_kernel(const TileArgs a)
         if (lane == 0) mbar_arrive(smem_u32(&bars[STAGES + s]));
     }
 
-    // ===== epilogue: partial sums (+ union counts for the multiset metrics) =====
-    constexpr bool NEED_CNT = (METRIC == M_PROD || METRIC == M_SUM);
-    const uint64_t words_per_row = a.stride / 32;
-    const uint64_t w0 = d0 / 32, w1 = d1 / 32;
+    // ===== epilogue: partial sums, then union counts for the multiset metrics =====
+    bool okA[8], okB[4];
+    uint64_t p[8], q[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const uint64_t q = uint64_t(J) * TB + tj + 16 * c;
-        if (q >= a.n) continue;
-        const uint32_t *zb = a.bitmap + uint64_t(rowsB[tj + 16 * c]) * words_per_row;
+    for (int r = 0; r < 8; ++r) { p[r] = uint64_t(I) * TA + ti + NTI * r; okA[r] = p[r] < a.n; }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const uint64_t p = uint64_t(I) * TA + ti * 8 + r;
-            if (p >= q) continue;
-            atomicAdd(a.acc + p * a.n + q, acc[r][c]);
-            if constexpr (NEED_CNT) {
-                const uint32_t *za = a.bitmap + uint64_t(rowsA[ti * 8 + r]) * words_per_row;
-                uint32_t u = 0;
-                for (uint64_t w = w0; w < w1; w += 4) {      // slices are multiples of 128 elements
-                    const uint4 x = __ldg(reinterpret_cast<const uint4 *>(za + w));
-                    const uint4 y = __ldg(reinterpret_cast<const uint4 *>(zb + w));
-                    u += __popc(x.x | y.x) + __popc(x.y | y.y) + __popc(x.z | y.z) + __popc(x.w | y.w);
-                }
-                atomicAdd(a.cnt + p * a.n + q, u);
-            }
+    for (int c = 0; c < 4; ++c) { q[c] = uint64_t(J) * TB + tj + NTJ * c; okB[c] = q[c] < a.n; }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (okB[c] && p[r] < q[c]) atomicAdd(a.acc + p[r] * a.n + q[c], acc[r][c]);
+
+    if constexpr (METRIC == M_PROD || METRIC == M_SUM) {
+        // |{i : x_A[i] != 0 or x_B[i] != 0}| over this slice from the per-profile bitmaps
+        // (kpal/metrics.py:121-123); 12 x 128-bit loads feed 32 pairs x 128 elements.
+        const uint64_t words_per_row = a.stride / 32;
+        const uint64_t w0 = d0 / 32, w1 = d1 / 32;       // slices are multiples of 128 elements
+        const uint32_t *za[8], *zb[4];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) za[r] = a.bitmap + uint64_t(rowsA[ti + NTI * r]) * words_per_row;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) zb[c] = a.bitmap + uint64_t(rowsB[tj + NTJ * c]) * words_per_row;
+        uint32_t u[8][4];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) u[r][c] = 0;
+        for (uint64_t w = w0; w < w1; w += 4) {
+            uint4 x[8], y[4];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) x[r] = __ldg(reinterpret_cast<const uint4 *>(za[r] + w));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) y[c] = __ldg(reinterpret_cast<const uint4 *>(zb[c] + w));
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    u[r][c] += __popc(x[r].x | y[c].x) + __popc(x[r].y | y[c].y) +
+                               __popc(x[r].z | y[c].z) + __popc(x[r].w | y[c].w);
         }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (okB[c] && p[r] < q[c]) atomicAdd(a.cnt + p[r] * a.n + q[c], u[r][c]);
     }
+    (void)okA;
 }
 
 // ---------------------------------------------------------------------------
@@ -401,7 +432,7 @@ distance_small_kernel(const TileArgs a)
     const uint64_t p = pair;
     const int32_t ia = a.order ? a.order[p] : int32_t(p), ib = a.order ? a.order[q] : int32_t(q);
     const double *FA = a.F + uint64_t(ia) * a.stride, *FB = a.F + uint64_t(ib) * a.stride;
-    const double *RB = (METRIC == M_PROD) ? a.R + uint64_t(ib) * a.stride : nullptr;
+    const double *PB = (METRIC == M_PROD) ? a.P + uint64_t(ib) * a.stride : nullptr;
     const double t = a.do_scale ? 1.0 / a.totals[ib] : 1.0;
     const uint64_t d0 = uint64_t(blockIdx.y) * a.slice_len;
     const uint64_t d1 = min(d0 + a.slice_len, a.stride);
@@ -410,10 +441,10 @@ distance_small_kernel(const TileArgs a)
     for (uint64_t i = d0 + threadIdx.x; i < d1; i += blockDim.x) {
         const double fa = FA[i], fb = FB[i];
         if constexpr (METRIC == M_PROD) {
-            s = fma(fabs(fa - fb) * recip<EXACT>(fa + t), RB[i], s);
+            s = add_term<EXACT>(s, fa - fb, fma(fa, PB[i], fb + t));
             u += (fa != 0.0 || fb != 0.0);
         } else if constexpr (METRIC == M_SUM) {
-            s = fma(fabs(fa - fb), recip<EXACT>(fa + (fb + t)), s);
+            s = add_term<EXACT>(s, fa - fb, fa + (fb + t));
             u += (fa != 0.0 || fb != 0.0);
         } else if constexpr (METRIC == M_EUCLID) {
             s = fma(fa - fb, fa - fb, s);
@@ -495,7 +526,7 @@ static int metric_id(int metric, int pairwise, int *out)
 }
 
 int launch_prepare(const int64_t *d_counts, uint64_t n, int k, int do_balance, int do_scale,
-                   double *d_F, double *d_R, uint32_t *d_bitmap, double *d_totals,
+                   double *d_F, double *d_P, uint32_t *d_bitmap, double *d_totals,
                    double *d_norm2, unsigned long long *d_totals_i64, cudaStream_t stream)
 {
     if (k < 1 || k > KPAL_MAX_K) return bad_arg("k out of range");
@@ -509,7 +540,7 @@ int launch_prepare(const int64_t *d_counts, uint64_t n, int k, int do_balance, i
     KPAL_LAUNCH_CHECK("profile_totals_kernel");
     const unsigned cx = unsigned(std::min<uint64_t>((stride + 255) / 256, 64));
     profile_convert_kernel<<<dim3(cx, unsigned(n)), 256, 0, stream>>>(
-        d_counts, d, stride, k, do_balance, do_scale, d_totals_i64, d_F, d_R, d_bitmap, d_totals,
+        d_counts, d, stride, k, do_balance, do_scale, d_totals_i64, d_F, d_P, d_bitmap, d_totals,
         d_norm2);
     KPAL_LAUNCH_CHECK("profile_convert_kernel");
     return KPAL_OK;
@@ -545,7 +576,7 @@ static int launch_tiles_metric(const TileArgs &a, bool exact, unsigned grid, cud
     return KPAL_OK;
 }
 
-int launch_distance_tiles(const double *d_F, const double *d_R, const uint32_t *d_bitmap,
+int launch_distance_tiles(const double *d_F, const double *d_P, const uint32_t *d_bitmap,
                           const double *d_totals, const double *d_norm2, const int32_t *d_order,
                           uint64_t n, int k, int metric, int pairwise, int do_scale, int down,
                           uint64_t tile_begin, uint64_t tile_end, double *d_acc, uint32_t *d_cnt,
@@ -556,13 +587,13 @@ int launch_distance_tiles(const double *d_F, const double *d_R, const uint32_t *
     KPAL_CHECK(metric_id(metric, pairwise, &m));
     if (k < 1 || k > KPAL_MAX_K) return bad_arg("k out of range");
     if (n < 1) return bad_arg("no profiles");
-    if (m == M_PROD && !d_R) return bad_arg("multiset/prod needs the R array");
+    if (m == M_PROD && !d_P) return bad_arg("multiset/prod needs the P (= x + 1) array");
     const uint64_t total_tiles = num_tiles(n);
     if (tile_end > total_tiles) tile_end = total_tiles;
     if (tile_begin >= tile_end) return KPAL_OK;
 
     TileArgs a;
-    a.F = d_F; a.R = d_R; a.bitmap = d_bitmap; a.totals = d_totals; a.order = d_order;
+    a.F = d_F; a.P = d_P; a.bitmap = d_bitmap; a.totals = d_totals; a.order = d_order;
     a.n = n; a.d = 1ull << (2 * k); a.stride = prepared_stride(k);
     a.tile_begin = tile_begin; a.n_tiles_range = tile_end - tile_begin;
     a.slice_len = std::min<uint64_t>(kSliceLen, a.stride);
@@ -574,10 +605,7 @@ int launch_distance_tiles(const double *d_F, const double *d_R, const uint32_t *
     KPAL_CUDA(cudaMemsetAsync(d_cnt, 0, n * n * sizeof(uint32_t), stream));
     const uint64_t items = a.n_tiles_range * a.n_slices;
     if (items > 0x7fffffffull) return bad_arg("too many work items");
-    static const bool exact = [] {
-        const char *e = getenv("KPAL_EXACT_DIV");
-        return e && e[0] == '1';
-    }();
+    const bool exact = g_exact_div;
     switch (m) {
     case M_PROD: KPAL_CHECK(launch_tiles_metric<M_PROD>(a, exact, unsigned(items), stream)); break;
     case M_SUM: KPAL_CHECK(launch_tiles_metric<M_SUM>(a, exact, unsigned(items), stream)); break;

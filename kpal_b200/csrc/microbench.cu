@@ -45,6 +45,22 @@ __global__ void smem_atomic_kernel(uint32_t *out, int per_thread, uint32_t mask)
     if (threadIdx.x == 0) out[blockIdx.x] = h[0];
 }
 
+// returning shared atomics (what a block-level multisplit needs for ranking)
+__global__ void smem_atomic_ret_kernel(uint32_t *out, int per_thread, uint32_t mask)
+{
+    extern __shared__ uint32_t h[];
+    for (uint32_t i = threadIdx.x; i <= mask; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u, acc = 0;
+#pragma unroll 8
+    for (int i = 0; i < per_thread; ++i) {
+        s = hash32(s + i);
+        acc += atomicAdd(&h[s & mask], 1u);
+    }
+    __syncthreads();
+    if (acc == 0xdeadbeef || threadIdx.x == 0) out[blockIdx.x] = h[0] + acc;
+}
+
 __global__ void dfma_kernel(double *out, int iters)
 {
     double a[8];
@@ -175,6 +191,14 @@ int main()
         CK(cudaFuncSetAttribute(smem_atomic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         float ms = time_ms([&] { smem_atomic_kernel<<<blocks, threads, smem>>>(o32, per_thread, (1u << lg) - 1); });
         printf("{\"bench\": \"smem_atomic\", \"bins\": %d, \"gatomics_per_s\": %.2f}\n", 1 << lg,
+               double(per_thread) * threads * blocks / ms * 1e-6);
+    }
+
+    for (int lg = 9; lg <= 13; lg += 4) {
+        const int per_thread = 256, threads = 256, blocks = sms * 8;
+        const size_t smem = (size_t(4) << lg);
+        float ms = time_ms([&] { smem_atomic_ret_kernel<<<blocks, threads, smem>>>(o32, per_thread, (1u << lg) - 1); });
+        printf("{\"bench\": \"smem_atomic_returning\", \"bins\": %d, \"gatomics_per_s\": %.2f}\n", 1 << lg,
                double(per_thread) * threads * blocks / ms * 1e-6);
     }
 

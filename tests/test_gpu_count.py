@@ -252,3 +252,94 @@ def test_full_size_config2_properties():
     rc = ko.reverse_complement_table(k)
     assert np.array_equal(got, got[rc])
     assert np.array_equal(got, plain + plain[rc])
+
+
+# ------------------------------------------------------------- GPU FASTA packer
+def _set_option(name, value):
+    _cabi.check(_cabi.load().kpal_set_option(name.encode(), int(value)))
+
+
+def _unpack(codes, valid, n_bases):
+    pos = np.arange(n_bases)
+    v = (valid[pos // 32] >> (31 - pos % 32).astype(np.uint32)) & 1
+    c = (codes[pos // 16] >> (30 - 2 * (pos % 16)).astype(np.uint32)) & 3
+    return np.where(v == 1, c, 4).astype(np.uint8)
+
+
+FASTA_EDGE_TEXTS = [
+    "", "\n", ">only\n", "no header at all\nACGT\n", ">a\nAC GT\r\nNN\n\n>\nTT\n>b z\n",
+    ">x y z\n\n\nACGT", "\n\n>q\nA\n", "junk\n>r1\nACGT\nAC>GT\n>r2\n>r3\nGGGG",
+    ">crlf\r\nACGT\r\nTTGA\r\n", "ACGT\n>late\nGGCC\n",
+]
+
+
+def test_dev_fasta_pack_stream_matches_host_packer(golden, tutorial_texts):
+    """kpal_dev_fasta_pack emits the same base stream as the C++ packer (one
+    separator in front of every record instead of behind it)."""
+    L = _cabi.load()
+    reads = random_reads(4, 3000, 150)
+    texts = FASTA_EDGE_TEXTS + [golden["fasta_text"], tutorial_texts["c_2"],
+                                reads_to_fasta(reads).decode()]
+    for text in texts:
+        raw = text.encode("latin-1")
+        h_codes, h_valid, _, names, h_n = _cabi.fasta_pack(raw)
+        host = _unpack(h_codes, h_valid, h_n)
+        n = len(raw)
+        cw, vw = ctypes.c_uint64(), ctypes.c_uint64()
+        L.kpal_packed_words(n, ctypes.byref(cw), ctypes.byref(vw))
+        d_text = L.kpal_dev_alloc(n + 32)
+        d_codes = L.kpal_dev_alloc(cw.value * 4)
+        d_valid = L.kpal_dev_alloc(vw.value * 4)
+        d_scr = L.kpal_dev_alloc(L.kpal_fasta_scratch_bytes(n))
+        try:
+            if n:
+                buf = np.frombuffer(raw, dtype=np.uint8)
+                _cabi.check(L.kpal_memcpy_h2d(d_text, _cabi.ptr(buf), n, None))
+            _cabi.check(L.kpal_dev_fasta_pack(d_text, n, d_codes, d_valid, d_scr, None))
+            codes = np.empty(cw.value, dtype=np.uint32)
+            valid = np.empty(vw.value, dtype=np.uint32)
+            status = np.empty(3, dtype=np.uint64)
+            _cabi.check(L.kpal_memcpy_d2h(_cabi.ptr(codes), d_codes, codes.nbytes, None))
+            _cabi.check(L.kpal_memcpy_d2h(_cabi.ptr(valid), d_valid, valid.nbytes, None))
+            _cabi.check(L.kpal_memcpy_d2h(_cabi.ptr(status), d_scr, 24, None))
+            _cabi.check(L.kpal_stream_sync(None))
+        finally:
+            for p in (d_text, d_codes, d_valid, d_scr):
+                L.kpal_dev_free(p)
+        n_gpu = int(status[1])
+        assert n_gpu == h_n, text[:40]
+        assert int(status[2]) & 0xffffffff == 0
+        gpu = _unpack(codes, valid, n_gpu)
+        if n_gpu:
+            assert gpu[0] == 4
+            assert np.array_equal(np.append(gpu[1:], 4), host), text[:40]
+        # everything past the packed stream stays zero (the count kernel reads it as invalid)
+        assert not codes[(n_gpu + 15) // 16:].any() and not valid[(n_gpu + 31) // 32:].any()
+
+
+def test_count_fasta_gpu_and_host_packers_agree(golden, tutorial_texts):
+    reads = random_reads(8, 20000, 150)
+    texts = FASTA_EDGE_TEXTS + [golden["fasta_text"], tutorial_texts["a_1"],
+                                reads_to_fasta(reads).decode()]
+    try:
+        for text in texts:
+            for k in (1, 5, 9, 12):
+                _set_option("host_fasta", 0)
+                gpu = _cabi.count_fasta(text, k, balance=True)
+                _set_option("host_fasta", 1)
+                host = _cabi.count_fasta(text, k, balance=True)
+                assert np.array_equal(gpu, host), (text[:30], k)
+                if len(text) < 100000:
+                    assert np.array_equal(gpu, ko.balance(ko.count_fasta(text, k)))
+    finally:
+        _set_option("host_fasta", 0)
+
+
+def test_count_fasta_exotic_whitespace_falls_back_to_host_packer():
+    """Tabs on sequence lines need Python's rstrip() semantics: trailing ones are
+    dropped (lines join), inner ones split k-mers.  The GPU packer flags them
+    and the library re-packs on the host; the result stays exact."""
+    text = ">a\nACGT\t\nACGT\n>b\nAC\tGT\nTTTT\x0b\n"
+    assert ko.parse_fasta(text) == [("a", "ACGTACGT"), ("b", "AC\tGTTTTT")]
+    for k in (2, 4, 6):
+        assert np.array_equal(_cabi.count_fasta(text, k), ko.count_fasta(text, k))
