@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkpal_b200.so")
+#: KPAL_B200_LIB selects another build of the same library (kernel tuning variants)
+LIB_PATH = os.environ.get("KPAL_B200_LIB") or os.path.join(_HERE, "libkpal_b200.so")
 
 KPAL_OK, KPAL_EINVAL, KPAL_ECUDA, KPAL_ENOMEM, KPAL_EOVERFLOW = range(5)
 METRICS = {"multiset": 0, "euclidean": 1, "cosine": 2}

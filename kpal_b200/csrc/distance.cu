@@ -44,19 +44,41 @@ namespace kpal {
 // ---------------------------------------------------------------------------
 // geometry
 // ---------------------------------------------------------------------------
-constexpr int WI = 4;                   // compute warps along the A (row) side
-constexpr int WJ = 2;                   // compute warps along the B (column) side
+// (overridable at compile time for tuning experiments: -DKPAL_WI=.. etc.)
+#ifndef KPAL_WI
+#define KPAL_WI 4
+#endif
+#ifndef KPAL_WJ
+#define KPAL_WJ 2
+#endif
+#ifndef KPAL_RI
+#define KPAL_RI 8
+#endif
+#ifndef KPAL_RJ
+#define KPAL_RJ 4
+#endif
+#ifndef KPAL_STAGES
+#define KPAL_STAGES 3
+#endif
+#ifndef KPAL_PRODUCER_WARP
+#define KPAL_PRODUCER_WARP 1            // 1: dedicated TMA producer warp; 0: all warps issue their share
+#endif
+constexpr int WI = KPAL_WI;             // compute warps along the A (row) side
+constexpr int WJ = KPAL_WJ;             // compute warps along the B (column) side
+constexpr int RI = KPAL_RI;             // A rows per thread
+constexpr int RJ = KPAL_RJ;             // B rows per thread
 constexpr int NTI = WI * 4;             // threads along i (a warp is 4 x 8 threads)
 constexpr int NTJ = WJ * 8;             // threads along j
-constexpr int TA = NTI * 8;             // A rows (scaled side) per tile   = 128
-constexpr int TB = NTJ * 4;             // B rows (unscaled side) per tile = 64
+constexpr int TA = NTI * RI;            // A rows (scaled side) per tile   (default 128)
+constexpr int TB = NTJ * RJ;            // B rows (unscaled side) per tile (default 64)
 constexpr int DC = 32;                  // profile elements per stage
 constexpr int ROW_BYTES = DC * 8 + 16;  // +16: consecutive rows land in different bank groups
-constexpr int STAGES = 3;
+constexpr int STAGES = KPAL_STAGES;
 constexpr int A_BYTES = TA * ROW_BYTES;
 constexpr int B_BYTES = TB * ROW_BYTES;
 constexpr int COMPUTE_WARPS = WI * WJ;
-constexpr int TILE_THREADS = (COMPUTE_WARPS + 1) * 32;
+constexpr bool PRODUCER_WARP = KPAL_PRODUCER_WARP != 0;
+constexpr int TILE_THREADS = (COMPUTE_WARPS + (PRODUCER_WARP ? 1 : 0)) * 32;
 constexpr uint64_t kStrideAlign = 128;  // prepared row stride: multiple of 128 doubles (bitmap rows 16 B aligned)
 constexpr uint64_t kSliceLen = 1u << 16;  // elements of D per work item
 
@@ -277,75 +299,92 @@ distance_tile_kernel(const TileArgs a)
     }
     __syncthreads();
 
-    if (warp == COMPUTE_WARPS) {
-        // ===== producer warp: stream row segments with bulk async copies =====
-        for (uint32_t it = 0; it < n_iter; ++it) {
-            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-            mbar_wait(smem_u32(&bars[STAGES + s]), ph ^ 1);
-            const uint32_t full = smem_u32(&bars[s]);
-            if (lane == 0) mbar_arrive_expect_tx(full, (TA + TB + (NEED_P ? TB : 0)) * DC * 8);
-            __syncwarp();
-            const uint32_t base = smem_u32(smem) + s * STAGE_BYTES;
-            const uint64_t col = d0 + uint64_t(it) * DC;
-#pragma unroll
-            for (int r = 0; r < TA / 32; ++r) {
-                const uint32_t row = lane + 32 * r;
-                bulk_g2s(base + row * ROW_BYTES, a.F + uint64_t(rowsA[row]) * a.stride + col, DC * 8, full);
-            }
-#pragma unroll
-            for (int r = 0; r < TB / 32; ++r) {
-                const uint32_t row = lane + 32 * r;
-                const uint64_t off = uint64_t(rowsB[row]) * a.stride + col;
-                bulk_g2s(base + A_BYTES + row * ROW_BYTES, a.F + off, DC * 8, full);
-                if constexpr (NEED_P)
-                    bulk_g2s(base + A_BYTES + B_BYTES + row * ROW_BYTES, a.P + off, DC * 8, full);
-            }
+    // Loads of one stage: one bulk async copy (TMA, UBLKCP) per row segment, issued by
+    // `n_issuers` threads starting at thread `first`.  Measured (profiles/): the TMA
+    // unit accepts a small copy only every ~50 cycles, so the 256 copies of a stage
+    // must not sit on a compute warp's critical path.  Default: a dedicated
+    // producer warp that runs ahead of the compute warps (decoupled by the
+    // full/empty mbarriers).  Alternative (KPAL_PRODUCER_WARP=0, kept for tuning):
+    // every warp issues its share after waiting for the slot to drain, which frees
+    // the producer's register allocation but couples the warps once per stage.
+    constexpr uint32_t N_ROWS = TA + TB + (NEED_P ? TB : 0);
+    auto issue_stage = [&](uint32_t it, uint32_t first, uint32_t n_issuers) {
+        const uint32_t s = it % STAGES;
+        const uint32_t full = smem_u32(&bars[s]);
+        if (threadIdx.x == first) mbar_arrive_expect_tx(full, N_ROWS * DC * 8);
+        if (PRODUCER_WARP) __syncwarp();
+        const uint32_t base = smem_u32(smem) + s * STAGE_BYTES;
+        const uint64_t col = d0 + uint64_t(it) * DC;
+        for (uint32_t row = threadIdx.x - first; row < N_ROWS; row += n_issuers) {
+            const double *src;
+            if (row < TA) src = a.F + uint64_t(rowsA[row]) * a.stride;
+            else if (row < TA + TB) src = a.F + uint64_t(rowsB[row - TA]) * a.stride;
+            else src = a.P + uint64_t(rowsB[row - TA - TB]) * a.stride;
+            bulk_g2s(base + row * ROW_BYTES, src + col, DC * 8, full);
         }
-        return;
+    };
+    if constexpr (PRODUCER_WARP) {
+        if (warp == COMPUTE_WARPS) {
+            for (uint32_t it = 0; it < n_iter; ++it) {
+                mbar_wait(smem_u32(&bars[STAGES + it % STAGES]), ((it / STAGES) & 1) ^ 1);
+                issue_stage(it, COMPUTE_WARPS * 32, 32);
+            }
+            return;
+        }
+    } else {
+        for (uint32_t it = 0; it < STAGES - 1 && it < n_iter; ++it) issue_stage(it, 0, TILE_THREADS);
     }
 
     // ===== compute warps =====
     // warp (wi, wj), lane = ti_l * 8 + tj_l.  Thread (ti, tj) owns A rows ti + NTI*r
-    // (r < 8) and B rows tj + NTJ*c (c < 4): the four quarter-warps of an LDS.128
+    // (r < RI) and B rows tj + NTJ*c (c < RJ): the four quarter-warps of an LDS.128
     // read 4 consecutive A rows (4 bank groups, broadcast inside a quarter) and
     // 8 consecutive B rows (8 bank groups) -- conflict free with the row padding.
     const uint32_t ti = (warp / WJ) * 4 + (lane >> 3);
     const uint32_t tj = (warp % WJ) * 8 + (lane & 7);
 
-    double t[4];
+    double t[RJ];
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < RJ; ++c)
         t[c] = a.do_scale ? 1.0 / a.totals[rowsB[tj + NTJ * c]] : 1.0;
 
-    double acc[8][4];
+    double acc[RI][RJ];
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
+    for (int r = 0; r < RI; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+        for (int c = 0; c < RJ; ++c) acc[r][c] = 0.0;
 
     for (uint32_t it = 0; it < n_iter; ++it) {
         const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+        if constexpr (!PRODUCER_WARP) {
+            // refill the slot everybody finished with at iteration it-1
+            const uint32_t nxt = it + STAGES - 1;
+            if (nxt < n_iter) {
+                if (it > 0) mbar_wait(smem_u32(&bars[STAGES + (it - 1) % STAGES]), ((it - 1) / STAGES) & 1);
+                issue_stage(nxt, 0, TILE_THREADS);
+            }
+        }
         mbar_wait(smem_u32(&bars[s]), ph);
         const unsigned char *sA = smem + s * STAGE_BYTES + ti * ROW_BYTES;
         const unsigned char *sB = smem + s * STAGE_BYTES + A_BYTES + tj * ROW_BYTES;
 #pragma unroll 2
         for (int dd = 0; dd < DC / 2; ++dd) {
-            double2 av[8], bf[4], bp[4];
+            double2 av[RI], bf[RJ], bp[RJ];
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
+            for (int r = 0; r < RI; ++r)
                 av[r] = *reinterpret_cast<const double2 *>(sA + r * NTI * ROW_BYTES + dd * 16);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < RJ; ++c) {
                 bf[c] = *reinterpret_cast<const double2 *>(sB + c * NTJ * ROW_BYTES + dd * 16);
                 if constexpr (NEED_P)
                     bp[c] = *reinterpret_cast<const double2 *>(sB + B_BYTES + c * NTJ * ROW_BYTES + dd * 16);
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < RJ; ++c) {
                 double gx = 0.0, gy = 0.0;
                 if constexpr (METRIC == M_PROD || METRIC == M_SUM) { gx = bf[c].x + t[c]; gy = bf[c].y + t[c]; }
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
+                for (int r = 0; r < RI; ++r) {
                     if constexpr (METRIC == M_PROD) {
                         acc[r][c] = add_term<EXACT>(acc[r][c], av[r].x - bf[c].x, fma(av[r].x, bp[c].x, gx));
                         acc[r][c] = add_term<EXACT>(acc[r][c], av[r].y - bf[c].y, fma(av[r].y, bp[c].y, gy));
@@ -368,16 +407,16 @@ distance_tile_kernel(const TileArgs a)
     }
 
     // ===== epilogue: partial sums, then union counts for the multiset metrics =====
-    bool okA[8], okB[4];
-    uint64_t p[8], q[4];
+    bool okA[RI], okB[RJ];
+    uint64_t p[RI], q[RJ];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) { p[r] = uint64_t(I) * TA + ti + NTI * r; okA[r] = p[r] < a.n; }
+    for (int r = 0; r < RI; ++r) { p[r] = uint64_t(I) * TA + ti + NTI * r; okA[r] = p[r] < a.n; }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { q[c] = uint64_t(J) * TB + tj + NTJ * c; okB[c] = q[c] < a.n; }
+    for (int c = 0; c < RJ; ++c) { q[c] = uint64_t(J) * TB + tj + NTJ * c; okB[c] = q[c] < a.n; }
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < RJ; ++c)
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int r = 0; r < RI; ++r)
             if (okB[c] && p[r] < q[c]) atomicAdd(a.acc + p[r] * a.n + q[c], acc[r][c]);
 
     if constexpr (METRIC == M_PROD || METRIC == M_SUM) {
@@ -385,33 +424,33 @@ distance_tile_kernel(const TileArgs a)
         // (kpal/metrics.py:121-123); 12 x 128-bit loads feed 32 pairs x 128 elements.
         const uint64_t words_per_row = a.stride / 32;
         const uint64_t w0 = d0 / 32, w1 = d1 / 32;       // slices are multiples of 128 elements
-        const uint32_t *za[8], *zb[4];
+        const uint32_t *za[RI], *zb[RJ];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) za[r] = a.bitmap + uint64_t(rowsA[ti + NTI * r]) * words_per_row;
+        for (int r = 0; r < RI; ++r) za[r] = a.bitmap + uint64_t(rowsA[ti + NTI * r]) * words_per_row;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) zb[c] = a.bitmap + uint64_t(rowsB[tj + NTJ * c]) * words_per_row;
-        uint32_t u[8][4];
+        for (int c = 0; c < RJ; ++c) zb[c] = a.bitmap + uint64_t(rowsB[tj + NTJ * c]) * words_per_row;
+        uint32_t u[RI][RJ];
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int r = 0; r < RI; ++r)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) u[r][c] = 0;
+            for (int c = 0; c < RJ; ++c) u[r][c] = 0;
         for (uint64_t w = w0; w < w1; w += 4) {
-            uint4 x[8], y[4];
+            uint4 x[RI], y[RJ];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) x[r] = __ldg(reinterpret_cast<const uint4 *>(za[r] + w));
+            for (int r = 0; r < RI; ++r) x[r] = __ldg(reinterpret_cast<const uint4 *>(za[r] + w));
 #pragma unroll
-            for (int c = 0; c < 4; ++c) y[c] = __ldg(reinterpret_cast<const uint4 *>(zb[c] + w));
+            for (int c = 0; c < RJ; ++c) y[c] = __ldg(reinterpret_cast<const uint4 *>(zb[c] + w));
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
+            for (int r = 0; r < RI; ++r)
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < RJ; ++c)
                     u[r][c] += __popc(x[r].x | y[c].x) + __popc(x[r].y | y[c].y) +
                                __popc(x[r].z | y[c].z) + __popc(x[r].w | y[c].w);
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < RJ; ++c)
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
+            for (int r = 0; r < RI; ++r)
                 if (okB[c] && p[r] < q[c]) atomicAdd(a.cnt + p[r] * a.n + q[c], u[r][c]);
     }
     (void)okA;
