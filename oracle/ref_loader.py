@@ -23,7 +23,11 @@ import os
 import sys
 import types
 
-REFERENCE_ROOTS = ("/root/reference",)
+_HERE = os.path.dirname(os.path.abspath(__file__))
+#: the read-only reference tree of the build container, else the (git-ignored)
+#: offline install `pip install --no-deps --target baseline/_ref /root/reference`
+REFERENCE_ROOTS = ("/root/reference",
+                   os.path.join(os.path.dirname(_HERE), "baseline", "_ref"))
 
 
 def reference_root():

@@ -1,0 +1,152 @@
+"""
+N > 1 path.  CPU part: the sharding helpers and the shard -> reduce -> finalise
+flow of kpal_b200.multigpu with world_size 2 on the gloo backend (the count of
+each shard is injected from the oracle: there is no GPU here, and the product
+code has no CPU path of its own).  GPU part (-m gpu, needs >= 2 devices): the
+same flow with the CUDA kernels and NCCL.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from kpal_b200 import _cabi, multigpu
+from oracle import kpal_oracle as ko
+
+
+def make_fasta(seed, n_records, max_len=400):
+    rng = np.random.default_rng(seed)
+    lines = []
+    for i in range(n_records):
+        n = int(rng.integers(0, max_len))
+        seq = rng.choice(np.frombuffer(b"ACGTacgtN", dtype=np.uint8), size=n).tobytes().decode()
+        lines.append(">rec%05d desc" % i)
+        lines.extend(seq[p:p + 70] for p in range(0, n, 70))
+    return ("\n".join(lines) + "\n").encode()
+
+
+def test_balanced_ranges():
+    sizes = [5, 1, 1, 1, 10, 2, 2, 8]
+    for parts in (1, 2, 3, 8, 11):
+        ranges = multigpu.balanced_ranges(sizes, parts)
+        assert len(ranges) == parts
+        assert ranges[0][0] == 0 and ranges[-1][1] == len(sizes)
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        assert all(b <= e for b, e in ranges)
+    two = multigpu.balanced_ranges([10, 10, 10, 10], 2)
+    assert two == [(0, 2), (2, 4)]
+    assert multigpu.balanced_ranges([], 3) == [(0, 0), (0, 0), (0, 0)]
+
+
+def test_split_fasta_cuts_at_record_boundaries():
+    text = make_fasta(3, 200)
+    for parts in (1, 2, 3, 7, 64):
+        ranges = multigpu.split_fasta(text, parts)
+        assert len(ranges) == parts and ranges[0][0] == 0 and ranges[-1][1] == len(text)
+        total = np.zeros(4 ** 5, dtype=np.int64)
+        for b, e in ranges:
+            shard = text[b:e]
+            assert shard == b"" or shard.startswith(b">")
+            total += ko.count_fasta(shard, 5)
+        assert np.array_equal(total, ko.count_fasta(text, 5))
+    # leading junk stays with the first shard and is skipped there
+    junk = b"junk line\nACGT\n" + text
+    ranges = multigpu.split_fasta(junk, 3)
+    total = sum(ko.count_fasta(junk[b:e], 4) for b, e in ranges)
+    assert np.array_equal(total, ko.count_fasta(junk, 4))
+
+
+def test_tile_range_partitions():
+    for n_tiles in (0, 1, 7, 1056):
+        for world in (1, 2, 3, 8):
+            got = [multigpu.tile_range(n_tiles, r, world) for r in range(world)]
+            assert got[0][0] == 0 and got[-1][1] == n_tiles
+            assert all(a[1] == b[0] for a, b in zip(got, got[1:]))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, text, k, out_path):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        b, e = multigpu.split_fasta(text, world)[rank]
+
+        def count_shard(shard, kk):          # stand-in for the CUDA count kernel (test only)
+            return torch.from_numpy(ko.count_fasta(shard, kk).astype(np.int32))
+
+        def finalize(table, kk, balance):    # stand-in for finalize_kernel (test only)
+            counts = (table.numpy() if hasattr(table, "numpy") else table).astype(np.int64)
+            return ko.balance(counts) if balance else counts
+
+        got = multigpu.count_fasta_distributed(text[b:e], k, balance=True, count_shard=count_shard,
+                                               finalize=finalize)
+        if rank == 0:
+            np.save(out_path, got)
+        else:
+            assert got is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_count_distributed_gloo(tmp_path, world):
+    import torch.multiprocessing as mp
+    text = make_fasta(11, 300)
+    k = 6
+    out = str(tmp_path / "counts.npy")
+    mp.spawn(_gloo_worker, args=(world, _free_port(), text, k, out), nprocs=world, join=True)
+    assert np.array_equal(np.load(out), ko.balance(ko.count_fasta(text, k)))
+
+
+# ---------------------------------------------------------------------- GPU
+def _nccl_worker(rank, world, port, text, k, profiles, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    _cabi.check(_cabi.load().kpal_set_device(rank))
+    dist.init_process_group("nccl", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        b, e = multigpu.split_fasta(text, world)[rank]
+        counts = multigpu.count_fasta_distributed(text[b:e], k, balance=True)
+        matrix = multigpu.distance_matrix_distributed(profiles, do_scale=True)
+        if rank == 0:
+            np.save(os.path.join(out_dir, "counts.npy"), counts)
+            np.save(os.path.join(out_dir, "matrix.npy"), matrix)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_distributed_nccl(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from oracle import c_oracle
+    text = make_fasta(21, 5000, max_len=1500)
+    k = 11
+    rng = np.random.default_rng(3)
+    lam = np.exp(rng.uniform(np.log(0.5), np.log(8.0), 300))
+    profiles = np.stack([rng.poisson(l, 4 ** 6) for l in lam]).astype(np.int64)
+    mp.spawn(_nccl_worker, args=(world, _free_port(), text, k, profiles, str(tmp_path)),
+             nprocs=world, join=True)
+    counts = np.load(str(tmp_path / "counts.npy"))
+    assert np.array_equal(counts, ko.balance(ko.count_fasta(text, k)))
+    matrix = np.load(str(tmp_path / "matrix.npy"))
+    want = c_oracle.distance_matrix(profiles, do_scale=True, threads=c_oracle.max_threads())
+    low = np.tril_indices(len(profiles), -1)
+    np.testing.assert_allclose(matrix[low], want[low], rtol=1e-9, atol=0)
+    assert np.array_equal(matrix, matrix.T)
