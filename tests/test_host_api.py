@@ -24,7 +24,7 @@ class FakeDataset(object):
         self.attrs = {}
 
     def __getitem__(self, item):
-        return self.data[item]
+        return np.array(self.data[item])        # h5py hands out copies, never views
 
 
 class FakeGroup(dict):
