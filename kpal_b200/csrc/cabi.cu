@@ -30,6 +30,9 @@ uint64_t distance_num_tiles(uint64_t n);
 uint64_t prepared_stride_host(int k);
 uint64_t fasta_scratch_bytes(uint64_t n_bytes);
 void set_exact_div(bool on);
+void set_count_path(int v);
+void set_tiled_finalize(int v);
+void set_radix_payload_bits(int bits);
 int launch_fasta_pack(const uint8_t *, uint64_t, uint32_t *, uint32_t *, void *, cudaStream_t);
 
 static thread_local char t_error[512] = "";
@@ -280,6 +283,15 @@ extern "C" int kpal_set_option(const char *name, int value)
     if (!name) return bad_arg("null option name");
     if (!strcmp(name, "host_fasta")) { g_host_fasta.store(value ? 1 : 0); return KPAL_OK; }
     if (!strcmp(name, "exact_div")) { set_exact_div(value != 0); return KPAL_OK; }
+    if (!strcmp(name, "count_path")) {
+        if (value < 0 || value > 2) return bad_arg("count_path must be 0 (auto), 1 (RED) or 2 (radix)");
+        set_count_path(value); return KPAL_OK;
+    }
+    if (!strcmp(name, "tiled_finalize")) { set_tiled_finalize(value != 0); return KPAL_OK; }
+    if (!strcmp(name, "radix_payload_bits")) {
+        if (value < 0 || value > 15) return bad_arg("radix_payload_bits must be 0 (auto) .. 15");
+        set_radix_payload_bits(value); return KPAL_OK;
+    }
     set_error("unknown option '%s'", name);
     return KPAL_EINVAL;
 }

@@ -168,6 +168,40 @@ finalize_kernel(const CounterT *__restrict__ table, int k, int balance, int64_t 
     }
 }
 
+// Balanced finalize without the scattered gather.  Index = [h : 3 bases][m : k-6
+// bases][l : 3 bases]; rc(index) = [rc(l)][rc(m)][rc(h)].  A CTA owns the 64 x 64
+// tile of one m together with the tile of rc(m): both are read once in 256-byte
+// rows, transposed through shared memory and written once as int64 -- table
+// read once, profile written once (the plain kernel reads 4 scattered bytes
+// per 32-byte sector for the partner).
+template <typename CounterT>
+__global__ void __launch_bounds__(256)
+finalize_balance_tiled_kernel(const CounterT *__restrict__ table, int k, int64_t *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char fin_smem[];
+    CounterT *A = reinterpret_cast<CounterT *>(fin_smem);      // [64][65] tile of m
+    CounterT *B = A + 64 * 65;                                  // [64][65] tile of rc(m)
+    const uint32_t m = blockIdx.x;
+    const int mid_bits = 2 * (k - 6);
+    const uint32_t mr = mid_bits ? ((~rev2(m)) >> (32 - mid_bits)) : 0u;
+    if (m > mr) return;                                         // done by the CTA of rc(m)
+    const int hshift = 2 * k - 6;
+    for (uint32_t e = threadIdx.x; e < 4096; e += 256) {
+        const uint32_t h = e >> 6, l = e & 63u;
+        A[h * 65 + l] = table[(uint64_t(h) << hshift) | (uint64_t(m) << 6) | l];
+        if (m != mr) B[h * 65 + l] = table[(uint64_t(h) << hshift) | (uint64_t(mr) << 6) | l];
+    }
+    __syncthreads();
+    const CounterT *partner = (m != mr) ? B : A;
+    for (uint32_t e = threadIdx.x; e < 4096; e += 256) {
+        const uint32_t h = e >> 6, l = e & 63u;
+        const uint32_t t = rc_index(l, 26) * 65 + rc_index(h, 26);
+        out[(uint64_t(h) << hshift) | (uint64_t(m) << 6) | l] = int64_t(A[h * 65 + l]) + int64_t(partner[t]);
+        if (m != mr)
+            out[(uint64_t(h) << hshift) | (uint64_t(mr) << 6) | l] = int64_t(B[h * 65 + l]) + int64_t(A[t]);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Per-record profiles (Profile.from_fasta_by_record, kpal/klib.py:114-133).
 // One CTA per record: stream zeros over the record's int64 row (the row stays
@@ -231,6 +265,29 @@ accumulate_kernel(const CounterT *__restrict__ src, CounterT *__restrict__ dst, 
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
+// count_radix.cu
+bool radix_supported(int k);
+int launch_count_radix(const uint32_t *, const uint32_t *, uint64_t, int, void *, int, cudaStream_t);
+
+// run-time switches (kpal_set_option): "count_path" 0 = automatic, 1 = always the
+// scattered-RED kernel, 2 = the radix-partitioned path wherever it is supported;
+// "tiled_finalize" 0 = plain gather kernel for the balanced finalize.
+static std::atomic<int> g_count_path{0};
+static std::atomic<int> g_tiled_finalize{1};
+void set_count_path(int v) { g_count_path.store(v); }
+void set_tiled_finalize(int v) { g_tiled_finalize.store(v); }
+
+static bool use_radix_path(int k, uint64_t n_bases)
+{
+    const int mode = g_count_path.load();
+    if (mode == 1 || !radix_supported(k)) return false;
+    if (mode == 2) return true;
+    // The two passes cost a fixed ~2 x 4^k x 4 bytes of table traffic; below these
+    // sizes the RED kernel wins.  At k = 13 the table no longer fits in L2 and the
+    // RED rate drops ~7x, so the switch comes earlier.
+    return n_bases >= (k >= 13 ? (4ull << 20) : (16ull << 20));
+}
+
 int launch_accumulate(const void *d_src, void *d_dst, int counter_bits, uint64_t n, cudaStream_t stream)
 {
     uint64_t want = (n + 255) / 256;
@@ -289,6 +346,8 @@ int launch_count(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_ba
                 codes, valid, n_chunks, k, rep_log2, static_cast<unsigned long long *>(d_table));
         }
         KPAL_LAUNCH_CHECK("count_smem_kernel");
+    } else if (use_radix_path(k, n_bases)) {
+        return launch_count_radix(d_codes, d_valid, n_bases, k, d_table, counter_bits, stream);
     } else {
         uint64_t want = (n_chunks + 255) / 256;
         const uint64_t cap = uint64_t(sms) * 8 * 4;      // a few waves of 8 CTAs/SM
@@ -313,6 +372,21 @@ int launch_finalize(const void *d_table, int counter_bits, int k, int balance, i
     uint64_t want = (n + 255) / 256;
     const uint64_t cap = uint64_t(sm_count()) * 32;
     const unsigned grid = unsigned(want < cap ? want : cap);
+    if (balance && k >= 6 && g_tiled_finalize.load()) {
+        const unsigned tiles = 1u << (2 * (k - 6));
+        const size_t smem = size_t(2) * 64 * 65 * (counter_bits / 8);
+        if (counter_bits == 32) {
+            finalize_balance_tiled_kernel<uint32_t><<<tiles, 256, smem, stream>>>(
+                static_cast<const uint32_t *>(d_table), k, d_counts);
+        } else {
+            KPAL_CUDA(cudaFuncSetAttribute(finalize_balance_tiled_kernel<unsigned long long>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            finalize_balance_tiled_kernel<unsigned long long><<<tiles, 256, smem, stream>>>(
+                static_cast<const unsigned long long *>(d_table), k, d_counts);
+        }
+        KPAL_LAUNCH_CHECK("finalize_balance_tiled_kernel");
+        return KPAL_OK;
+    }
     if (counter_bits == 32)
         finalize_kernel<uint32_t><<<grid, 256, 0, stream>>>(
             static_cast<const uint32_t *>(d_table), k, balance, d_counts);

@@ -1,0 +1,403 @@
+// Two-pass radix-partitioned k-mer counting for large tables (9 <= k <= 13).
+//
+// Same contract as count_global_kernel (count.cu): accumulate the windows of a
+// packed stream (kpal/klib.py:154-168) into a table of 4^k counters.  A scattered
+// RED per window tops out at the L2 atomic rate (~0.2 T/s, profiles/r01_microbench)
+// and collapses once the table leaves L2 (k = 13); shared-memory atomics run
+// at ~1.6 T/s.  So the index space is cut into `nb` buckets by the high index
+// bits, the low `P` bits (the payload, a u16) are staged bucket-major in HBM,
+// and every bucket is then histogrammed in shared memory:
+//
+//   pass 1  radix_partition_kernel   one persistent CTA per SM walks its contiguous
+//           share of the stream in tiles of 1024 x 32 windows.  A window takes one
+//           returning shared-memory atomic (its rank in the bucket's slot) and one
+//           16-bit shared store.  After each tile every slot writes its complete
+//           32-byte groups (16 payloads) to the CTA's private region of that bucket;
+//           the remainder (< 16) stays in the slot for the next tile, so every global
+//           store is a full, aligned sector.
+//   pass 2  radix_histogram_kernel   one CTA per bucket: shared-memory histogram of 2^P
+//           bins over the bucket's regions (streamed 16 bytes per lane), then one
+//           coalesced read-modify-write of the bucket's slice of the table.
+//
+// Anything that does not fit -- a slot that overflows inside a tile (skewed or
+// repetitive sequence) or a region that fills up -- is counted with a plain
+// RED on the table instead, so the result is exact for every input; only the
+// speed depends on the distribution.
+//
+// Staging memory: 3 x the mean region size, i.e. ~6 bytes per base, owned by a
+// grow-only per-device workspace (HBM is 180 GB; a 100 Mbp call takes 0.6 GB).
+#include "common.cuh"
+
+#include <mutex>
+#include <vector>
+
+namespace kpal {
+
+constexpr int kRadixThreads = 1024;
+constexpr int kUnitBases = 32;          // bases (= window starts) per thread and tile
+constexpr int kGroup = 16;              // payloads per 32-byte group
+
+// ---------------------------------------------------------------------------
+// pass 1
+// ---------------------------------------------------------------------------
+struct Unit {
+    uint32_t w[3];      // 32 bases of codes + 16 look-ahead bases
+    uint32_t starts;    // bit (31 - o) set <=> the window starting at base o is all-valid
+};
+
+template <int O>
+__device__ __forceinline__ uint32_t unit_window(const Unit &u, int shift)
+{
+    constexpr int j = O / 16, r = O % 16;
+    const uint32_t x = (r == 0) ? u.w[j] : __funnelshift_l(u.w[j + 1], u.w[j], 2 * r);
+    return x >> shift;
+}
+
+struct RadixParams {
+    const uint2 *codes;         // 32 bases per uint2
+    const uint32_t *valid;      // 32 bases per word
+    uint64_t unit_begin, unit_end;   // units [begin, end) of this launch
+    uint64_t n_units;           // units readable in the stream (loads are clamped to this)
+    int k, P, nb, cap;          // payload bits, buckets (power of two), slot capacity
+    uint32_t region_groups;     // capacity of one (CTA, bucket) region in groups
+    uint16_t *staging;          // [grid][nb][region_groups * 16]
+    uint32_t *region_fill;      // [grid][nb] payloads stored per region
+};
+
+template <typename CounterT, int O0>
+__device__ __forceinline__ void bin_four(const Unit &u, int shift, const RadixParams &p,
+                                         uint32_t *cnt, uint16_t *slots, CounterT *table)
+{
+    uint32_t idx[4], rank[4];
+    bool ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        ok[j] = (u.starts >> (31 - (O0 + j))) & 1u;
+        rank[j] = 0;
+    }
+    idx[0] = unit_window<O0 + 0>(u, shift);
+    idx[1] = unit_window<O0 + 1>(u, shift);
+    idx[2] = unit_window<O0 + 2>(u, shift);
+    idx[3] = unit_window<O0 + 3>(u, shift);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (ok[j]) rank[j] = atomicAdd(&cnt[idx[j] >> p.P], 1u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (ok[j]) {
+            if (rank[j] < uint32_t(p.cap))
+                slots[(idx[j] >> p.P) * uint32_t(p.cap) + rank[j]] = uint16_t(idx[j] & ((1u << p.P) - 1u));
+            else
+                atomicAdd(table + idx[j], CounterT(1));        // slot full: count directly
+        }
+    }
+}
+
+template <typename CounterT, int O0>
+__device__ __forceinline__ void bin_from(const Unit &u, int shift, const RadixParams &p,
+                                         uint32_t *cnt, uint16_t *slots, CounterT *table)
+{
+    if constexpr (O0 < kUnitBases) {
+        bin_four<CounterT, O0>(u, shift, p, cnt, slots, table);
+        bin_from<CounterT, O0 + 4>(u, shift, p, cnt, slots, table);
+    }
+}
+
+__device__ __forceinline__ void red_group(const uint4 &a, const uint4 &b, uint32_t hi, int n,
+                                          uint32_t *table32, unsigned long long *table64)
+{
+    const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    for (int j = 0; j < n; ++j) {
+        const uint32_t e = (v[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+        if (table32) atomicAdd(table32 + (hi | e), 1u);
+        else atomicAdd(table64 + (hi | e), 1ull);
+    }
+}
+
+template <typename CounterT>
+__global__ void __launch_bounds__(kRadixThreads, 1)
+radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
+{
+    extern __shared__ __align__(16) unsigned char radix_smem[];
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(radix_smem);           // [nb] payloads in the slot
+    uint32_t *fillg = cnt + p.nb;                                        // [nb] groups already stored
+    uint16_t *slots = reinterpret_cast<uint16_t *>(fillg + p.nb);        // [nb][cap] (+ 16 pad)
+
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31u;
+    for (int b = tid; b < p.nb; b += kRadixThreads) { cnt[b] = 0; fillg[b] = 0; }
+    __syncthreads();
+
+    // contiguous share of the units, a multiple of the tile so warps stay aligned
+    const uint64_t total = p.unit_end - p.unit_begin;
+    uint64_t per = (total + gridDim.x - 1) / gridDim.x;
+    per = (per + kRadixThreads - 1) / kRadixThreads * kRadixThreads;
+    const uint64_t u0 = p.unit_begin + uint64_t(blockIdx.x) * per;
+    const uint64_t u1 = (u0 + per < p.unit_end) ? u0 + per : p.unit_end;
+    const int shift = 32 - 2 * p.k;
+    uint32_t *table32 = sizeof(CounterT) == 4 ? reinterpret_cast<uint32_t *>(table) : nullptr;
+    unsigned long long *table64 = sizeof(CounterT) == 8 ? reinterpret_cast<unsigned long long *>(table) : nullptr;
+
+    uint16_t *my_regions = p.staging + uint64_t(blockIdx.x) * p.nb * p.region_groups * kGroup;
+    // bucket(s) this thread flushes: with nb < 1024 several threads share a bucket
+    const int tpb = p.nb >= kRadixThreads ? 1 : kRadixThreads / p.nb;
+    const int sub = p.nb >= kRadixThreads ? 0 : tid / p.nb;
+    const int b_first = p.nb >= kRadixThreads ? tid : (tid & (p.nb - 1));
+
+    for (uint64_t t0 = u0; t0 < u1; t0 += kRadixThreads) {
+        // ---- A: bin this tile's windows into the bucket slots
+        const uint64_t unit = t0 + tid;
+        uint2 cw = make_uint2(0, 0);
+        uint32_t vw = 0;
+        if (unit < p.n_units) { cw = __ldg(p.codes + unit); vw = __ldg(p.valid + unit); }
+        uint32_t next_c = __shfl_down_sync(0xffffffffu, cw.x, 1);
+        uint32_t next_v = __shfl_down_sync(0xffffffffu, vw, 1);
+        if (lane == 31u && unit < p.n_units) {      // the stream is padded by one 64-base chunk
+            next_c = __ldg(reinterpret_cast<const uint32_t *>(p.codes + unit + 1));
+            next_v = __ldg(p.valid + unit + 1);
+        }
+        Unit u;
+        u.w[0] = cw.x; u.w[1] = cw.y; u.w[2] = next_c;
+        {   // run mask by the binary method on k (as load_chunk in count.cu)
+            const uint64_t v = (uint64_t(vw) << 32) | next_v;
+            uint64_t a = v;
+            int len = 1;
+            for (int bit = 30 - __clz(p.k); bit >= 0; --bit) {
+                a &= a << len; len <<= 1;
+                if ((p.k >> bit) & 1) { a &= v << len; len += 1; }
+            }
+            u.starts = (unit < u1) ? uint32_t(a >> 32) : 0u;
+        }
+        if (u.starts) bin_from<CounterT, 0>(u, shift, p, cnt, slots, table);
+        __syncthreads();
+
+        // ---- B1: store the complete groups of every slot, keep the remainder
+        for (int b = b_first; b < p.nb; b += kRadixThreads) {
+            const uint32_t n = min(cnt[b], uint32_t(p.cap));
+            const uint32_t g = n / kGroup, f = fillg[b];
+            const uint4 *src = reinterpret_cast<const uint4 *>(slots + uint32_t(b) * p.cap);
+            uint4 *dst = reinterpret_cast<uint4 *>(my_regions + uint64_t(b) * p.region_groups * kGroup);
+            for (uint32_t gi = sub; gi < g; gi += tpb) {
+                const uint4 x = src[2 * gi], y = src[2 * gi + 1];
+                if (f + gi < p.region_groups) {
+                    __stcs(dst + 2 * (f + gi), x);
+                    __stcs(dst + 2 * (f + gi) + 1, y);
+                } else {
+                    red_group(x, y, uint32_t(b) << p.P, kGroup, table32, table64);   // region full
+                }
+            }
+            if (sub == 0 && g > 0) {        // this thread read group 0 itself, groups >= 1 are untouched
+                const uint4 x = src[2 * g], y = src[2 * g + 1];
+                uint4 *front = reinterpret_cast<uint4 *>(slots + uint32_t(b) * p.cap);
+                front[0] = x; front[1] = y;
+            }
+        }
+        __syncthreads();
+        // ---- B2: new slot / region fill levels
+        if (sub == 0) {
+            for (int b = b_first; b < p.nb; b += kRadixThreads) {
+                const uint32_t n = min(cnt[b], uint32_t(p.cap));
+                const uint32_t g = n / kGroup;
+                cnt[b] = n - g * kGroup;
+                fillg[b] = min(fillg[b] + g, p.region_groups);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- remainders (< 16 per bucket) and the per-region totals
+    if (sub == 0) {
+        for (int b = b_first; b < p.nb; b += kRadixThreads) {
+            const uint32_t n = cnt[b], f = fillg[b];
+            uint32_t stored = f * kGroup;
+            if (n) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(slots + uint32_t(b) * p.cap);
+                const uint4 x = src[0], y = src[1];
+                if (f < p.region_groups) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(my_regions + uint64_t(b) * p.region_groups * kGroup);
+                    dst[2 * f] = x; dst[2 * f + 1] = y;          // payloads beyond n are never read
+                    stored += n;
+                } else {
+                    red_group(x, y, uint32_t(b) << p.P, int(n), table32, table64);
+                }
+            }
+            p.region_fill[uint64_t(blockIdx.x) * p.nb + b] = stored;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// pass 2
+// ---------------------------------------------------------------------------
+template <typename CounterT>
+__global__ void __launch_bounds__(kRadixThreads)
+radix_histogram_kernel(const uint16_t *__restrict__ staging, const uint32_t *__restrict__ region_fill,
+                       int n_part_ctas, int nb, int P, uint32_t region_groups,
+                       CounterT *__restrict__ table)
+{
+    extern __shared__ __align__(16) uint32_t radix_hist[];
+    const uint32_t bins = 1u << P;
+    const int b = blockIdx.x;
+    for (uint32_t i = threadIdx.x * 4; i < bins; i += blockDim.x * 4)
+        *reinterpret_cast<uint4 *>(radix_hist + i) = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    for (int c = warp; c < n_part_ctas; c += n_warps) {
+        const uint64_t region = uint64_t(c) * nb + b;
+        const uint32_t n = __ldg(region_fill + region);
+        const uint4 *src = reinterpret_cast<const uint4 *>(staging + region * region_groups * kGroup);
+        for (uint32_t i = lane; i * 8 < n; i += 32) {
+            const uint4 v = __ldcs(src + i);
+            const uint32_t rem = n - i * 8;
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (uint32_t(j) < rem) atomicAdd(&radix_hist[(w[j >> 1] >> (16 * (j & 1))) & 0xffffu], 1u);
+        }
+    }
+    __syncthreads();
+
+    CounterT *dst = table + (uint64_t(b) << P);
+    for (uint32_t i = threadIdx.x * 4; i < bins; i += blockDim.x * 4) {
+        const uint4 h = *reinterpret_cast<const uint4 *>(radix_hist + i);
+        if ((h.x | h.y | h.z | h.w) == 0) continue;
+        if constexpr (sizeof(CounterT) == 4) {
+            uint4 t = *reinterpret_cast<uint4 *>(dst + i);
+            t.x += h.x; t.y += h.y; t.z += h.z; t.w += h.w;
+            *reinterpret_cast<uint4 *>(dst + i) = t;
+        } else {
+            ulonglong2 t0 = *reinterpret_cast<ulonglong2 *>(dst + i);
+            ulonglong2 t1 = *reinterpret_cast<ulonglong2 *>(dst + i + 2);
+            t0.x += h.x; t0.y += h.y; t1.x += h.z; t1.y += h.w;
+            *reinterpret_cast<ulonglong2 *>(dst + i) = t0;
+            *reinterpret_cast<ulonglong2 *>(dst + i + 2) = t1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// workspace + launcher
+// ---------------------------------------------------------------------------
+struct RadixWorkspace {
+    int device = -1;
+    void *staging = nullptr; size_t staging_cap = 0;
+    uint32_t *fill = nullptr; size_t fill_cap = 0;
+};
+static std::mutex g_radix_mutex;
+static std::vector<RadixWorkspace *> g_radix_ws;
+static std::atomic<int> g_radix_payload_bits{0};     // 0 = automatic
+
+void set_radix_payload_bits(int bits) { g_radix_payload_bits.store(bits); }
+
+static int grow(void **p, size_t *cap, size_t bytes)
+{
+    if (bytes <= *cap) return KPAL_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        *p = nullptr; cudaGetLastError();
+        set_error("cudaMalloc(%zu bytes) for the radix staging failed: %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? KPAL_ENOMEM : KPAL_ECUDA;
+    }
+    *cap = bytes;
+    return KPAL_OK;
+}
+
+bool radix_supported(int k) { return k >= 9 && k <= 13; }
+
+// Geometry for a given k: payload bits P, buckets nb = 4^k >> P, slot capacity
+// cap (payloads; cap % 16 == 8 keeps the 16-byte slot reads of 8 neighbouring
+// buckets on distinct shared-memory banks).
+static void radix_geometry(int k, int *P, int *nb, int *cap, size_t *smem1)
+{
+    int p = g_radix_payload_bits.load();
+    if (p <= 0) p = (k == 13) ? 15 : 2 * k - 9;         // 512 buckets (2048 at k = 13)
+    if (p > 15) p = 15;
+    if (p < 2 * k - 11) p = 2 * k - 11;                 // at most 2048 buckets
+    int n = 1 << (2 * k - p);
+    // slots share ~200 KB
+    int c = int((200u * 1024u) / (2u * unsigned(n)));
+    c = (c - 8) / 16 * 16 + 8;
+    if (c > 1032) c = 1032;
+    *P = p; *nb = n; *cap = c;
+    *smem1 = size_t(n) * 8 + size_t(n) * c * 2 + 64;
+}
+
+// Accumulate units of the packed stream into `table` through the two passes.
+int launch_count_radix(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_bases, int k,
+                       void *d_table, int counter_bits, cudaStream_t stream)
+{
+    int P, nb, cap;
+    size_t smem1;
+    radix_geometry(k, &P, &nb, &cap, &smem1);
+    const int grid1 = sm_count();
+    const size_t smem2 = size_t(4) << P;
+    const int threads2 = P >= 14 ? 1024 : (P >= 12 ? 512 : 256);
+
+    int dev = 0;
+    KPAL_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_radix_mutex);
+    RadixWorkspace *ws = nullptr;
+    for (auto *w : g_radix_ws) if (w->device == dev) ws = w;
+    if (!ws) { ws = new RadixWorkspace(); ws->device = dev; g_radix_ws.push_back(ws); }
+
+    if (counter_bits == 32) {
+        KPAL_CUDA(cudaFuncSetAttribute(radix_partition_kernel<uint32_t>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
+        KPAL_CUDA(cudaFuncSetAttribute(radix_histogram_kernel<uint32_t>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem2)));
+    } else {
+        KPAL_CUDA(cudaFuncSetAttribute(radix_partition_kernel<unsigned long long>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
+        KPAL_CUDA(cudaFuncSetAttribute(radix_histogram_kernel<unsigned long long>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem2)));
+    }
+
+    // the stream is walked in segments so that the staging stays bounded (<= ~3 GB)
+    const uint64_t n_units = 2 * n_chunks_of(n_bases);
+    const uint64_t seg_units = (512ull << 20) / kUnitBases;
+    for (uint64_t s0 = 0; s0 < n_units; s0 += seg_units) {
+        const uint64_t s1 = (s0 + seg_units < n_units) ? s0 + seg_units : n_units;
+        uint64_t per = (s1 - s0 + grid1 - 1) / grid1;
+        per = (per + kRadixThreads - 1) / kRadixThreads * kRadixThreads;
+        const uint64_t windows_per_cta = per * kUnitBases;
+        // 3 x the mean region plus slack, in groups
+        const uint64_t groups = (3 * windows_per_cta / nb + 4 * kGroup + kGroup - 1) / kGroup;
+        KPAL_CHECK(grow(&ws->staging, &ws->staging_cap, size_t(grid1) * nb * groups * kGroup * 2));
+        {
+            void *f = ws->fill;
+            size_t fc = ws->fill_cap;
+            KPAL_CHECK(grow(&f, &fc, size_t(grid1) * nb * 4));
+            ws->fill = static_cast<uint32_t *>(f); ws->fill_cap = fc;
+        }
+        RadixParams p;
+        p.codes = reinterpret_cast<const uint2 *>(d_codes);
+        p.valid = d_valid;
+        p.unit_begin = s0; p.unit_end = s1; p.n_units = n_units;
+        p.k = k; p.P = P; p.nb = nb; p.cap = cap;
+        p.region_groups = uint32_t(groups);
+        p.staging = static_cast<uint16_t *>(ws->staging);
+        p.region_fill = ws->fill;
+        if (counter_bits == 32) {
+            radix_partition_kernel<uint32_t><<<grid1, kRadixThreads, smem1, stream>>>(
+                p, static_cast<uint32_t *>(d_table));
+            KPAL_LAUNCH_CHECK("radix_partition_kernel");
+            radix_histogram_kernel<uint32_t><<<nb, threads2, smem2, stream>>>(
+                p.staging, p.region_fill, grid1, nb, P, p.region_groups, static_cast<uint32_t *>(d_table));
+            KPAL_LAUNCH_CHECK("radix_histogram_kernel");
+        } else {
+            radix_partition_kernel<unsigned long long><<<grid1, kRadixThreads, smem1, stream>>>(
+                p, static_cast<unsigned long long *>(d_table));
+            KPAL_LAUNCH_CHECK("radix_partition_kernel");
+            radix_histogram_kernel<unsigned long long><<<nb, threads2, smem2, stream>>>(
+                p.staging, p.region_fill, grid1, nb, P, p.region_groups,
+                static_cast<unsigned long long *>(d_table));
+            KPAL_LAUNCH_CHECK("radix_histogram_kernel");
+        }
+    }
+    return KPAL_OK;
+}
+
+}  // namespace kpal

@@ -343,3 +343,110 @@ def test_count_fasta_exotic_whitespace_falls_back_to_host_packer():
     assert ko.parse_fasta(text) == [("a", "ACGTACGT"), ("b", "AC\tGTTTTT")]
     for k in (2, 4, 6):
         assert np.array_equal(_cabi.count_fasta(text, k), ko.count_fasta(text, k))
+
+
+# ------------------------------------------------- radix-partitioned count path
+def _composition_bytes(seed, n, letters, p_n=0.0005):
+    """One long text: `letters` uniformly, with sparse N and a newline every ~100 kb."""
+    rng = np.random.default_rng(seed)
+    lut = np.frombuffer(letters.encode(), dtype=np.uint8)
+    buf = lut[rng.integers(0, len(lut), n)].copy()
+    buf[rng.random(n) < p_n] = ord("N")
+    buf[rng.integers(0, n, max(1, n // 100_000))] = ord("\n")
+    return buf
+
+
+def _dev_count(text_bytes, k, bits, balance):
+    """kpal_dev_count_packed + kpal_dev_finalize_counts on a packed stream."""
+    L = _cabi.load()
+    seqs = bytes(text_bytes).split(b"\n")
+    codes, valid, _, n_bases = _cabi.pack_sequences(seqs)
+    bins = 4 ** k
+    d_codes = L.kpal_dev_alloc(codes.nbytes)
+    d_valid = L.kpal_dev_alloc(valid.nbytes)
+    d_table = L.kpal_dev_alloc(bins * bits // 8)
+    d_counts = L.kpal_dev_alloc(bins * 8)
+    try:
+        zero = np.zeros(bins * bits // 8, dtype=np.uint8)
+        _cabi.check(L.kpal_memcpy_h2d(d_codes, _cabi.ptr(codes), codes.nbytes, None))
+        _cabi.check(L.kpal_memcpy_h2d(d_valid, _cabi.ptr(valid), valid.nbytes, None))
+        _cabi.check(L.kpal_memcpy_h2d(d_table, _cabi.ptr(zero), zero.nbytes, None))
+        _cabi.check(L.kpal_dev_count_packed(d_codes, d_valid, n_bases, k, d_table, bits, None))
+        _cabi.check(L.kpal_dev_finalize_counts(d_table, bits, k, int(balance), d_counts, None))
+        out = np.empty(bins, dtype=np.int64)
+        _cabi.check(L.kpal_memcpy_d2h(_cabi.ptr(out), d_counts, out.nbytes, None))
+        _cabi.check(L.kpal_stream_sync(None))
+        return out
+    finally:
+        for p in (d_codes, d_valid, d_table, d_counts):
+            L.kpal_dev_free(p)
+
+
+@pytest.mark.parametrize("k,n,letters,payload_bits", [
+    (12, 12_000_000, "ACGT", 0),       # several tiles per CTA, default geometry (512 buckets)
+    (12, 3_000_000, "ACGT", 14),       # 1024 buckets
+    (12, 3_000_000, "ACG", 0),         # skew: some slots and regions overflow into the RED path
+    (12, 2_000_000, "AC", 0),          # 32 of 512 buckets used: heavy overflow
+    (12, 1_000_000, "A", 0),           # one bin: everything overflows
+    (13, 6_000_000, "ACGTacgt", 0),    # 2048 buckets
+    (13, 1_000_000, "AT", 0),
+    (11, 2_000_000, "ACGT", 0),
+    (10, 2_000_000, "ACGT", 0),
+    (9, 2_000_000, "ACGT", 0),
+    (9, 500_000, "CG", 15),            # 8 buckets of 2^15 bins
+    (12, 70, "ACGT", 0),               # far less than one tile
+])
+def test_radix_count_path_bit_exact(k, n, letters, payload_bits):
+    """The two-pass radix path (count_radix.cu) forced on: bit-exact against the C oracle
+    for uniform, skewed and degenerate compositions, 32- and 64-bit counters."""
+    text = _composition_bytes(k * 7919 + n, n, letters)
+    want = c_oracle.count_bytes(text, k, threads=c_oracle.max_threads())
+    try:
+        _set_option("count_path", 2)
+        _set_option("radix_payload_bits", payload_bits)
+        got32 = _dev_count(text, k, 32, False)
+        assert np.array_equal(got32, want)
+        got64 = _dev_count(text, k, 64, True)
+        assert np.array_equal(got64, ko.balance(want))
+        _set_option("count_path", 1)
+        assert np.array_equal(_dev_count(text, k, 32, False), want)
+    finally:
+        _set_option("count_path", 0)
+        _set_option("radix_payload_bits", 0)
+
+
+def test_radix_count_path_through_host_api():
+    """count_path=2 under kpal_count_fasta / kpal_count_sequences (records, N, lower case)."""
+    reads = random_reads(77, 30_000, 150)
+    fasta = reads_to_fasta(reads)
+    want = c_oracle.count_bytes(np.insert(reads, 150, ord("\n"), axis=1).tobytes(), 12,
+                                threads=c_oracle.max_threads())
+    try:
+        _set_option("count_path", 2)
+        assert np.array_equal(_cabi.count_fasta(fasta, 12, balance=True), ko.balance(want))
+        seqs = [r.tobytes().decode() for r in reads[:2000]]
+        assert np.array_equal(_cabi.count_sequences(seqs, 10), ko.count_sequences(seqs, 10))
+        assert not _cabi.count_sequences([], 12).any()
+        assert not _cabi.count_sequences(["ACGTN" * 2], 12).any()
+    finally:
+        _set_option("count_path", 0)
+
+
+@pytest.mark.parametrize("k", [6, 7, 8, 9, 12, 13])
+def test_tiled_balance_finalize_matches_plain(k):
+    """finalize_balance_tiled_kernel (shared-memory transposition) against the plain gather
+    kernel and the oracle, on a dense random table incl. palindromic middles."""
+    rng = np.random.default_rng(k)
+    n = min(4 ** k * 3, 40_000_000)
+    text = _composition_bytes(k, n, "ACGT")
+    want = ko.balance(c_oracle.count_bytes(text, k, threads=c_oracle.max_threads()))
+    try:
+        for bits in (32, 64):
+            _set_option("tiled_finalize", 1)
+            tiled = _dev_count(text, k, bits, True)
+            _set_option("tiled_finalize", 0)
+            plain = _dev_count(text, k, bits, True)
+            assert np.array_equal(tiled, want)
+            assert np.array_equal(plain, want)
+    finally:
+        _set_option("tiled_finalize", 1)
