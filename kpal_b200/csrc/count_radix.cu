@@ -64,53 +64,85 @@ struct RadixParams {
     uint32_t *region_fill;      // [grid][nb] payloads stored per region
 };
 
-template <typename CounterT, int O0>
-__device__ __forceinline__ void bin_four(const Unit &u, int shift, const RadixParams &p,
-                                         uint32_t *cnt, uint16_t *slots, CounterT *table)
+// Explicit shared-state-space accesses: through generic pointers the compiler
+// emitted generic ATOM / ST (+ QSPC checks) for the slot bookkeeping.
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
-    uint32_t idx[4], rank[4];
-    bool ok[4];
+    return uint32_t(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v)
+{
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+
+struct BinCtx {
+    uint32_t cnt_s, slots_s;        // shared addresses of cnt[] and slots[]
+    uint32_t dummy_cnt_s;           // per-lane counter that absorbs invalid windows
+    uint32_t dummy_slot_s;          // per-lane halfword that absorbs their stores
+    uint32_t cap;
+    int shift, P;
+};
+
+// Eight windows at a time, branch-free: an invalid window increments a per-lane
+// dummy counter and stores into a per-lane dummy halfword, so the atomics of a
+// batch are all in flight before the first dependent store.  The stored
+// halfword is the low 16 index bits; pass 2 masks it to P bits.
+template <typename CounterT, int O0>
+__device__ __forceinline__ void bin_eight(const Unit &u, const BinCtx &c, CounterT *table)
+{
+    // all selects are bit masks (0 / ~0): with 16 live booleans the compiler ran out of
+    // predicate registers and spent more instructions shuffling them than on the work
+    uint32_t idx[8], rank[8], okm[8];
+    idx[0] = unit_window<O0 + 0>(u, c.shift); idx[1] = unit_window<O0 + 1>(u, c.shift);
+    idx[2] = unit_window<O0 + 2>(u, c.shift); idx[3] = unit_window<O0 + 3>(u, c.shift);
+    idx[4] = unit_window<O0 + 4>(u, c.shift); idx[5] = unit_window<O0 + 5>(u, c.shift);
+    idx[6] = unit_window<O0 + 6>(u, c.shift); idx[7] = unit_window<O0 + 7>(u, c.shift);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        ok[j] = (u.starts >> (31 - (O0 + j))) & 1u;
-        rank[j] = 0;
+    for (int j = 0; j < 8; ++j) {
+        okm[j] = uint32_t(int32_t(u.starts << (O0 + j)) >> 31);
+        const uint32_t real = c.cnt_s + 4u * (idx[j] >> c.P);
+        rank[j] = atoms_add(c.dummy_cnt_s ^ ((c.dummy_cnt_s ^ real) & okm[j]), 1u);
     }
-    idx[0] = unit_window<O0 + 0>(u, shift);
-    idx[1] = unit_window<O0 + 1>(u, shift);
-    idx[2] = unit_window<O0 + 2>(u, shift);
-    idx[3] = unit_window<O0 + 3>(u, shift);
+    uint32_t overflow = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (ok[j]) rank[j] = atomicAdd(&cnt[idx[j] >> p.P], 1u);
+    for (int j = 0; j < 8; ++j) {
+        // rank < cap  <=>  rank - cap is negative (ranks stay far below 2^31)
+        const uint32_t inm = uint32_t(int32_t(rank[j] - c.cap) >> 31) & okm[j];
+        overflow |= okm[j] & ~inm;
+        const uint32_t real = c.slots_s + 2u * ((idx[j] >> c.P) * c.cap + rank[j]);
+        sts_u16(c.dummy_slot_s ^ ((c.dummy_slot_s ^ real) & inm), idx[j]);
+    }
+    if (overflow) {                 // slot full (skewed / repetitive sequence): count directly
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (ok[j]) {
-            if (rank[j] < uint32_t(p.cap))
-                slots[(idx[j] >> p.P) * uint32_t(p.cap) + rank[j]] = uint16_t(idx[j] & ((1u << p.P) - 1u));
-            else
-                atomicAdd(table + idx[j], CounterT(1));        // slot full: count directly
-        }
+        for (int j = 0; j < 8; ++j)
+            if (okm[j] && rank[j] >= c.cap) atomicAdd(table + idx[j], CounterT(1));
     }
 }
 
 template <typename CounterT, int O0>
-__device__ __forceinline__ void bin_from(const Unit &u, int shift, const RadixParams &p,
-                                         uint32_t *cnt, uint16_t *slots, CounterT *table)
+__device__ __forceinline__ void bin_from(const Unit &u, const BinCtx &c, CounterT *table)
 {
     if constexpr (O0 < kUnitBases) {
-        bin_four<CounterT, O0>(u, shift, p, cnt, slots, table);
-        bin_from<CounterT, O0 + 4>(u, shift, p, cnt, slots, table);
+        bin_eight<CounterT, O0>(u, c, table);
+        bin_from<CounterT, O0 + 8>(u, c, table);
     }
 }
 
-__device__ __forceinline__ void red_group(const uint4 &a, const uint4 &b, uint32_t hi, int n,
-                                          uint32_t *table32, unsigned long long *table64)
+// rare path: count the (first n of the 8) payloads of one 16-byte piece directly
+template <typename CounterT>
+__device__ __noinline__ void red_piece(uint4 a, uint32_t hi, uint32_t pmask, int n,
+                                       CounterT *__restrict__ table)
 {
-    const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const uint32_t v[4] = {a.x, a.y, a.z, a.w};
     for (int j = 0; j < n; ++j) {
-        const uint32_t e = (v[j >> 1] >> (16 * (j & 1))) & 0xffffu;
-        if (table32) atomicAdd(table32 + (hi | e), 1u);
-        else atomicAdd(table64 + (hi | e), 1ull);
+        const uint32_t e = (v[j >> 1] >> (16 * (j & 1))) & pmask;
+        atomicAdd(table + (hi | e), CounterT(1));
     }
 }
 
@@ -119,13 +151,14 @@ __global__ void __launch_bounds__(kRadixThreads, 1)
 radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
 {
     extern __shared__ __align__(16) unsigned char radix_smem[];
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(radix_smem);           // [nb] payloads in the slot
-    uint32_t *fillg = cnt + p.nb;                                        // [nb] groups already stored
-    uint16_t *slots = reinterpret_cast<uint16_t *>(fillg + p.nb);        // [nb][cap] (+ 16 pad)
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(radix_smem);           // [nb] payloads in the slot (+32 dummies)
+    uint32_t *fillg = cnt + p.nb + 32;                                   // [nb] groups already stored
+    uint16_t *slots = reinterpret_cast<uint16_t *>(fillg + p.nb);        // [nb][cap] (+ 64 B pad / dummies)
 
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31u;
-    for (int b = tid; b < p.nb; b += kRadixThreads) { cnt[b] = 0; fillg[b] = 0; }
+    for (int b = tid; b < p.nb + 32; b += kRadixThreads) cnt[b] = 0;
+    for (int b = tid; b < p.nb; b += kRadixThreads) fillg[b] = 0;
     __syncthreads();
 
     // contiguous share of the units, a multiple of the tile so warps stay aligned
@@ -134,27 +167,39 @@ radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
     per = (per + kRadixThreads - 1) / kRadixThreads * kRadixThreads;
     const uint64_t u0 = p.unit_begin + uint64_t(blockIdx.x) * per;
     const uint64_t u1 = (u0 + per < p.unit_end) ? u0 + per : p.unit_end;
-    const int shift = 32 - 2 * p.k;
-    uint32_t *table32 = sizeof(CounterT) == 4 ? reinterpret_cast<uint32_t *>(table) : nullptr;
-    unsigned long long *table64 = sizeof(CounterT) == 8 ? reinterpret_cast<unsigned long long *>(table) : nullptr;
+
+    BinCtx ctx;
+    ctx.cnt_s = smem_u32(cnt);
+    ctx.slots_s = smem_u32(slots);
+    ctx.dummy_cnt_s = ctx.cnt_s + 4u * (uint32_t(p.nb) + lane);
+    ctx.dummy_slot_s = ctx.slots_s + 2u * (uint32_t(p.nb) * uint32_t(p.cap) + lane);
+    ctx.cap = uint32_t(p.cap);
+    ctx.shift = 32 - 2 * p.k;
+    ctx.P = p.P;
 
     uint16_t *my_regions = p.staging + uint64_t(blockIdx.x) * p.nb * p.region_groups * kGroup;
-    // bucket(s) this thread flushes: with nb < 1024 several threads share a bucket
-    const int tpb = p.nb >= kRadixThreads ? 1 : kRadixThreads / p.nb;
-    const int sub = p.nb >= kRadixThreads ? 0 : tid / p.nb;
-    const int b_first = p.nb >= kRadixThreads ? tid : (tid & (p.nb - 1));
+    const int team = tid >> 3, tl = tid & 7;      // flush teams of 8 lanes
+
+    // software pipeline: the words of the next tile are in flight during this one
+    uint2 cw_next = make_uint2(0, 0);
+    uint32_t vw_next = 0;
+    if (u0 + tid < p.n_units && u0 < u1) { cw_next = __ldg(p.codes + u0 + tid); vw_next = __ldg(p.valid + u0 + tid); }
 
     for (uint64_t t0 = u0; t0 < u1; t0 += kRadixThreads) {
         // ---- A: bin this tile's windows into the bucket slots
         const uint64_t unit = t0 + tid;
-        uint2 cw = make_uint2(0, 0);
-        uint32_t vw = 0;
-        if (unit < p.n_units) { cw = __ldg(p.codes + unit); vw = __ldg(p.valid + unit); }
+        const uint2 cw = cw_next;
+        const uint32_t vw = vw_next;
         uint32_t next_c = __shfl_down_sync(0xffffffffu, cw.x, 1);
         uint32_t next_v = __shfl_down_sync(0xffffffffu, vw, 1);
         if (lane == 31u && unit < p.n_units) {      // the stream is padded by one 64-base chunk
             next_c = __ldg(reinterpret_cast<const uint32_t *>(p.codes + unit + 1));
             next_v = __ldg(p.valid + unit + 1);
+        }
+        {
+            const uint64_t un = unit + kRadixThreads;
+            cw_next = make_uint2(0, 0); vw_next = 0;
+            if (un < p.n_units && t0 + kRadixThreads < u1) { cw_next = __ldg(p.codes + un); vw_next = __ldg(p.valid + un); }
         }
         Unit u;
         u.w[0] = cw.x; u.w[1] = cw.y; u.w[2] = next_c;
@@ -168,61 +213,57 @@ radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
             }
             u.starts = (unit < u1) ? uint32_t(a >> 32) : 0u;
         }
-        if (u.starts) bin_from<CounterT, 0>(u, shift, p, cnt, slots, table);
+        if (u.starts) bin_from<CounterT, 0>(u, ctx, table);
         __syncthreads();
 
-        // ---- B1: store the complete groups of every slot, keep the remainder
-        for (int b = b_first; b < p.nb; b += kRadixThreads) {
-            const uint32_t n = min(cnt[b], uint32_t(p.cap));
-            const uint32_t g = n / kGroup, f = fillg[b];
-            const uint4 *src = reinterpret_cast<const uint4 *>(slots + uint32_t(b) * p.cap);
-            uint4 *dst = reinterpret_cast<uint4 *>(my_regions + uint64_t(b) * p.region_groups * kGroup);
-            for (uint32_t gi = sub; gi < g; gi += tpb) {
-                const uint4 x = src[2 * gi], y = src[2 * gi + 1];
-                if (f + gi < p.region_groups) {
-                    __stcs(dst + 2 * (f + gi), x);
-                    __stcs(dst + 2 * (f + gi) + 1, y);
-                } else {
-                    red_group(x, y, uint32_t(b) << p.P, kGroup, table32, table64);   // region full
+        // ---- B: every slot stores its complete groups and keeps the remainder.  A bucket
+        // is flushed by a team of 8 consecutive lanes, one 16-byte piece per lane, so a
+        // warp store covers 4 contiguous runs instead of 32 scattered sectors (the L1
+        // takes one cycle per distinct line of a store instruction).  The team is
+        // inside one warp: the slot bookkeeping needs no CTA barrier.
+        for (int b0 = 0; b0 < p.nb; b0 += kRadixThreads / 8) {
+            const int b = b0 + team;
+            const bool have = b < p.nb;
+            uint32_t n = 0, f = 0;
+            if (have) { n = min(cnt[b], uint32_t(p.cap)); f = fillg[b]; }
+            __syncwarp();
+            const uint32_t g = n / kGroup;
+            if (have && g) {
+                uint4 *slot = reinterpret_cast<uint4 *>(slots + uint32_t(b) * p.cap);
+                uint4 *dst = reinterpret_cast<uint4 *>(my_regions + uint64_t(b) * p.region_groups * kGroup);
+                for (uint32_t piece = tl; piece < 2 * g; piece += 8) {
+                    const uint4 x = slot[piece];
+                    if (f + piece / 2 < p.region_groups) __stcs(dst + 2 * f + piece, x);
+                    else red_piece<CounterT>(x, uint32_t(b) << p.P, (1u << p.P) - 1u, 8, table);   // region full
                 }
-            }
-            if (sub == 0 && g > 0) {        // this thread read group 0 itself, groups >= 1 are untouched
-                const uint4 x = src[2 * g], y = src[2 * g + 1];
-                uint4 *front = reinterpret_cast<uint4 *>(slots + uint32_t(b) * p.cap);
-                front[0] = x; front[1] = y;
-            }
-        }
-        __syncthreads();
-        // ---- B2: new slot / region fill levels
-        if (sub == 0) {
-            for (int b = b_first; b < p.nb; b += kRadixThreads) {
-                const uint32_t n = min(cnt[b], uint32_t(p.cap));
-                const uint32_t g = n / kGroup;
-                cnt[b] = n - g * kGroup;
-                fillg[b] = min(fillg[b] + g, p.region_groups);
+                // remainder to the front: lanes 0/1 read pieces 0/1 themselves, nobody else does
+                if (tl < 2) { const uint4 x = slot[2 * g + tl]; slot[tl] = x; }
+                if (tl == 0) { cnt[b] = n - g * kGroup; fillg[b] = min(f + g, p.region_groups); }
+            } else if (have && tl == 0) {
+                cnt[b] = n;                     // clamp after a slot overflow
             }
         }
         __syncthreads();
     }
 
     // ---- remainders (< 16 per bucket) and the per-region totals
-    if (sub == 0) {
-        for (int b = b_first; b < p.nb; b += kRadixThreads) {
-            const uint32_t n = cnt[b], f = fillg[b];
-            uint32_t stored = f * kGroup;
-            if (n) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(slots + uint32_t(b) * p.cap);
-                const uint4 x = src[0], y = src[1];
-                if (f < p.region_groups) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(my_regions + uint64_t(b) * p.region_groups * kGroup);
-                    dst[2 * f] = x; dst[2 * f + 1] = y;          // payloads beyond n are never read
-                    stored += n;
-                } else {
-                    red_group(x, y, uint32_t(b) << p.P, int(n), table32, table64);
-                }
+    for (int b0 = 0; b0 < p.nb; b0 += kRadixThreads / 8) {
+        const int b = b0 + team;
+        if (b >= p.nb || tl >= 2) continue;
+        const uint32_t n = cnt[b], f = fillg[b];
+        uint32_t stored = f * kGroup;
+        if (n) {
+            const uint4 x = reinterpret_cast<const uint4 *>(slots + uint32_t(b) * p.cap)[tl];
+            if (f < p.region_groups) {
+                uint4 *dst = reinterpret_cast<uint4 *>(my_regions + uint64_t(b) * p.region_groups * kGroup);
+                dst[2 * f + tl] = x;                     // payloads beyond n are never read
+                stored += n;
+            } else {
+                const int mine = int(n) - 8 * tl;
+                red_piece<CounterT>(x, uint32_t(b) << p.P, (1u << p.P) - 1u, mine < 8 ? mine : 8, table);
             }
-            p.region_fill[uint64_t(blockIdx.x) * p.nb + b] = stored;
         }
+        if (tl == 0) p.region_fill[uint64_t(blockIdx.x) * p.nb + b] = stored;
     }
 }
 
@@ -243,17 +284,30 @@ radix_histogram_kernel(const uint16_t *__restrict__ staging, const uint32_t *__r
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    const uint32_t pmask = bins - 1u;
+    uint32_t n_next = warp < n_part_ctas ? __ldg(region_fill + uint64_t(warp) * nb + b) : 0u;
     for (int c = warp; c < n_part_ctas; c += n_warps) {
         const uint64_t region = uint64_t(c) * nb + b;
-        const uint32_t n = __ldg(region_fill + region);
+        const uint32_t n = n_next;
+        if (c + n_warps < n_part_ctas) n_next = __ldg(region_fill + uint64_t(c + n_warps) * nb + b);
         const uint4 *src = reinterpret_cast<const uint4 *>(staging + region * region_groups * kGroup);
-        for (uint32_t i = lane; i * 8 < n; i += 32) {
-            const uint4 v = __ldcs(src + i);
-            const uint32_t rem = n - i * 8;
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const uint32_t nv = (n + 7u) / 8u;                 // 16-byte vectors holding payloads
+        for (uint32_t i = lane; i < nv; i += 128) {
+            uint4 v[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (uint32_t(j) < rem) atomicAdd(&radix_hist[(w[j >> 1] >> (16 * (j & 1))) & 0xffffu], 1u);
+            for (int q = 0; q < 4; ++q) {
+                v[q] = make_uint4(0, 0, 0, 0);
+                if (i + 32 * q < nv) v[q] = __ldcs(src + i + 32 * q);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t at = (i + 32 * q) * 8u;
+                const uint32_t rem = at < n ? n - at : 0u;
+                const uint32_t w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (uint32_t(j) < rem) atomicAdd(&radix_hist[(w[j >> 1] >> (16 * (j & 1))) & pmask], 1u);
+            }
         }
     }
     __syncthreads();
@@ -322,7 +376,7 @@ static void radix_geometry(int k, int *P, int *nb, int *cap, size_t *smem1)
     c = (c - 8) / 16 * 16 + 8;
     if (c > 1032) c = 1032;
     *P = p; *nb = n; *cap = c;
-    *smem1 = size_t(n) * 8 + size_t(n) * c * 2 + 64;
+    *smem1 = size_t(n) * 8 + 128 + size_t(n) * c * 2 + 64;
 }
 
 // Accumulate units of the packed stream into `table` through the two passes.
@@ -334,7 +388,7 @@ int launch_count_radix(const uint32_t *d_codes, const uint32_t *d_valid, uint64_
     radix_geometry(k, &P, &nb, &cap, &smem1);
     const int grid1 = sm_count();
     const size_t smem2 = size_t(4) << P;
-    const int threads2 = P >= 14 ? 1024 : (P >= 12 ? 512 : 256);
+    const int threads2 = P >= 15 ? 1024 : 512;
 
     int dev = 0;
     KPAL_CUDA(cudaGetDevice(&dev));
