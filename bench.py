@@ -256,6 +256,7 @@ def bench_count(args):
     _cabi.check(L.kpal_set_device(local))
     _cabi.check(L.kpal_set_option(b"count_path", args.count_path))
     _cabi.check(L.kpal_set_option(b"radix_payload_bits", args.radix_payload_bits))
+    _cabi.check(L.kpal_set_option(b"radix_debug", args.radix_debug))
     k, bins = K_COUNT, 4 ** K_COUNT
     dev = torch.device("cuda", local)
 
@@ -519,6 +520,7 @@ def main():
     ap.add_argument("--count-path", type=int, default=0, choices=[0, 1, 2],
                     help="0 = library default, 1 = scattered-RED kernel, 2 = radix-partitioned path")
     ap.add_argument("--radix-payload-bits", type=int, default=0)
+    ap.add_argument("--radix-debug", type=int, default=0, help="timing experiments (results are wrong)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

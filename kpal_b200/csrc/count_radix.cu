@@ -62,6 +62,7 @@ struct RadixParams {
     uint32_t region_groups;     // capacity of one (CTA, bucket) region in groups
     uint16_t *staging;          // [grid][nb][region_groups * 16]
     uint32_t *region_fill;      // [grid][nb] payloads stored per region
+    int debug;                  // timing experiments only: 1 = no flush, 2 = no slot stores, 4 = no atomics
 };
 
 // Explicit shared-state-space accesses: through generic pointers the compiler
@@ -81,12 +82,35 @@ __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v)
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
 }
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4 &v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 struct BinCtx {
     uint32_t cnt_s, slots_s;        // shared addresses of cnt[] and slots[]
     uint32_t dummy_cnt_s;           // per-lane counter that absorbs invalid windows
     uint32_t dummy_slot_s;          // per-lane halfword that absorbs their stores
     uint32_t cap;
     int shift, P;
+    bool no_store;
 };
 
 // Eight windows at a time, branch-free: an invalid window increments a per-lane
@@ -116,7 +140,7 @@ __device__ __forceinline__ void bin_eight(const Unit &u, const BinCtx &c, Counte
         const uint32_t inm = uint32_t(int32_t(rank[j] - c.cap) >> 31) & okm[j];
         overflow |= okm[j] & ~inm;
         const uint32_t real = c.slots_s + 2u * ((idx[j] >> c.P) * c.cap + rank[j]);
-        sts_u16(c.dummy_slot_s ^ ((c.dummy_slot_s ^ real) & inm), idx[j]);
+        if (!c.no_store) sts_u16(c.dummy_slot_s ^ ((c.dummy_slot_s ^ real) & inm), idx[j]);
     }
     if (overflow) {                 // slot full (skewed / repetitive sequence): count directly
 #pragma unroll
@@ -176,14 +200,33 @@ radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
     ctx.cap = uint32_t(p.cap);
     ctx.shift = 32 - 2 * p.k;
     ctx.P = p.P;
+    ctx.no_store = (p.debug & 2) != 0;
 
     uint16_t *my_regions = p.staging + uint64_t(blockIdx.x) * p.nb * p.region_groups * kGroup;
     const int team = tid >> 3, tl = tid & 7;      // flush teams of 8 lanes
 
-    // software pipeline: the words of the next tile are in flight during this one
+    // software pipeline: the words of the next tile (and lane 31's halo words) are in
+    // flight during this one
     uint2 cw_next = make_uint2(0, 0);
-    uint32_t vw_next = 0;
-    if (u0 + tid < p.n_units && u0 < u1) { cw_next = __ldg(p.codes + u0 + tid); vw_next = __ldg(p.valid + u0 + tid); }
+    uint32_t vw_next = 0, hc_next = 0, hv_next = 0;
+    auto prefetch = [&](uint64_t unit, bool tile_exists) {
+        cw_next = make_uint2(0, 0); vw_next = 0; hc_next = 0; hv_next = 0;
+        if (tile_exists && unit < p.n_units) {
+            cw_next = __ldg(p.codes + unit);
+            vw_next = __ldg(p.valid + unit);
+            if (lane == 31u) {                  // the stream is padded by one 64-base chunk
+                hc_next = __ldg(reinterpret_cast<const uint32_t *>(p.codes + unit + 1));
+                hv_next = __ldg(p.valid + unit + 1);
+            }
+        }
+    };
+    prefetch(u0 + tid, u0 < u1);
+
+    // flush bookkeeping of this thread's team (bucket = team + 128 * iteration)
+    const uint32_t fill_s = smem_u32(fillg);
+    const uint32_t slot_bytes = uint32_t(p.cap) * 2u;
+    uint4 *const my_regions4 = reinterpret_cast<uint4 *>(my_regions);
+    const uint32_t region_v4 = p.region_groups * 2u;            // 16-byte pieces per region
 
     for (uint64_t t0 = u0; t0 < u1; t0 += kRadixThreads) {
         // ---- A: bin this tile's windows into the bucket slots
@@ -192,15 +235,8 @@ radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
         const uint32_t vw = vw_next;
         uint32_t next_c = __shfl_down_sync(0xffffffffu, cw.x, 1);
         uint32_t next_v = __shfl_down_sync(0xffffffffu, vw, 1);
-        if (lane == 31u && unit < p.n_units) {      // the stream is padded by one 64-base chunk
-            next_c = __ldg(reinterpret_cast<const uint32_t *>(p.codes + unit + 1));
-            next_v = __ldg(p.valid + unit + 1);
-        }
-        {
-            const uint64_t un = unit + kRadixThreads;
-            cw_next = make_uint2(0, 0); vw_next = 0;
-            if (un < p.n_units && t0 + kRadixThreads < u1) { cw_next = __ldg(p.codes + un); vw_next = __ldg(p.valid + un); }
-        }
+        if (lane == 31u) { next_c = hc_next; next_v = hv_next; }
+        prefetch(unit + kRadixThreads, t0 + kRadixThreads < u1);
         Unit u;
         u.w[0] = cw.x; u.w[1] = cw.y; u.w[2] = next_c;
         {   // run mask by the binary method on k (as load_chunk in count.cu)
@@ -213,7 +249,7 @@ radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
             }
             u.starts = (unit < u1) ? uint32_t(a >> 32) : 0u;
         }
-        if (u.starts) bin_from<CounterT, 0>(u, ctx, table);
+        if (u.starts && !(p.debug & 4)) bin_from<CounterT, 0>(u, ctx, table);
         __syncthreads();
 
         // ---- B: every slot stores its complete groups and keeps the remainder.  A bucket
@@ -221,26 +257,25 @@ radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
         // warp store covers 4 contiguous runs instead of 32 scattered sectors (the L1
         // takes one cycle per distinct line of a store instruction).  The team is
         // inside one warp: the slot bookkeeping needs no CTA barrier.
-        for (int b0 = 0; b0 < p.nb; b0 += kRadixThreads / 8) {
-            const int b = b0 + team;
+        if (p.debug & 1) { for (int b = tid; b < p.nb; b += kRadixThreads) cnt[b] = 0; }
+        else for (int b = team; b - team < p.nb; b += kRadixThreads / 8) {      // warp-uniform trip count
             const bool have = b < p.nb;
+            const uint32_t cnt_a = ctx.cnt_s + 4u * uint32_t(b), fill_a = fill_s + 4u * uint32_t(b);
             uint32_t n = 0, f = 0;
-            if (have) { n = min(cnt[b], uint32_t(p.cap)); f = fillg[b]; }
+            if (have) { n = min(lds_u32(cnt_a), ctx.cap); f = lds_u32(fill_a); }
             __syncwarp();
             const uint32_t g = n / kGroup;
-            if (have && g) {
-                uint4 *slot = reinterpret_cast<uint4 *>(slots + uint32_t(b) * p.cap);
-                uint4 *dst = reinterpret_cast<uint4 *>(my_regions + uint64_t(b) * p.region_groups * kGroup);
+            if (g) {
+                const uint32_t slot_a = ctx.slots_s + uint32_t(b) * slot_bytes;
+                const uint32_t dst0 = uint32_t(b) * region_v4 + 2u * f;
                 for (uint32_t piece = tl; piece < 2 * g; piece += 8) {
-                    const uint4 x = slot[piece];
-                    if (f + piece / 2 < p.region_groups) __stcs(dst + 2 * f + piece, x);
+                    const uint4 x = lds_v4(slot_a + 16u * piece);
+                    if (f + piece / 2 < p.region_groups) __stcs(my_regions4 + dst0 + piece, x);
                     else red_piece<CounterT>(x, uint32_t(b) << p.P, (1u << p.P) - 1u, 8, table);   // region full
                 }
                 // remainder to the front: lanes 0/1 read pieces 0/1 themselves, nobody else does
-                if (tl < 2) { const uint4 x = slot[2 * g + tl]; slot[tl] = x; }
-                if (tl == 0) { cnt[b] = n - g * kGroup; fillg[b] = min(f + g, p.region_groups); }
-            } else if (have && tl == 0) {
-                cnt[b] = n;                     // clamp after a slot overflow
+                if (tl < 2) { const uint4 x = lds_v4(slot_a + 16u * (2 * g + tl)); sts_v4(slot_a + 16u * tl, x); }
+                if (tl == 0) { sts_u32(cnt_a, n - g * kGroup); sts_u32(fill_a, min(f + g, p.region_groups)); }
             }
         }
         __syncthreads();
@@ -285,47 +320,89 @@ radix_histogram_kernel(const uint16_t *__restrict__ staging, const uint32_t *__r
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
     const uint32_t pmask = bins - 1u;
-    uint32_t n_next = warp < n_part_ctas ? __ldg(region_fill + uint64_t(warp) * nb + b) : 0u;
-    for (int c = warp; c < n_part_ctas; c += n_warps) {
-        const uint64_t region = uint64_t(c) * nb + b;
-        const uint32_t n = n_next;
-        if (c + n_warps < n_part_ctas) n_next = __ldg(region_fill + uint64_t(c + n_warps) * nb + b);
-        const uint4 *src = reinterpret_cast<const uint4 *>(staging + region * region_groups * kGroup);
-        const uint32_t nv = (n + 7u) / 8u;                 // 16-byte vectors holding payloads
-        for (uint32_t i = lane; i < nv; i += 128) {
-            uint4 v[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                v[q] = make_uint4(0, 0, 0, 0);
-                if (i + 32 * q < nv) v[q] = __ldcs(src + i + 32 * q);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t at = (i + 32 * q) * 8u;
-                const uint32_t rem = at < n ? n - at : 0u;
-                const uint32_t w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (uint32_t(j) < rem) atomicAdd(&radix_hist[(w[j >> 1] >> (16 * (j & 1))) & pmask], 1u);
-            }
+
+    // A warp walks its regions (c = warp, warp + n_warps, ...) in chunks of 128 vectors of
+    // 16 bytes; the loads of chunk j+1 are issued before the atomics of chunk j.
+    int c = warp;
+    uint32_t n = c < n_part_ctas ? __ldg(region_fill + uint64_t(c) * nb + b) : 0u;
+    uint32_t n_ahead = c + n_warps < n_part_ctas ? __ldg(region_fill + uint64_t(c + n_warps) * nb + b) : 0u;
+    uint32_t i0 = 0;
+    struct Chunk4 { uint4 v[4]; uint32_t at, n; bool ok; };
+    auto fetch = [&](Chunk4 &k) {
+        while (c < n_part_ctas && i0 * 8u >= n) {           // next non-empty region
+            c += n_warps;
+            n = n_ahead; i0 = 0;
+            n_ahead = c + n_warps < n_part_ctas ? __ldg(region_fill + uint64_t(c + n_warps) * nb + b) : 0u;
         }
+        k.ok = c < n_part_ctas;
+        if (!k.ok) return;
+        const uint4 *src = reinterpret_cast<const uint4 *>(staging + (uint64_t(c) * nb + b) * region_groups * kGroup);
+        const uint32_t nv = (n + 7u) / 8u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t i = i0 + lane + 32 * q;
+            k.v[q] = make_uint4(0, 0, 0, 0);
+            if (i < nv) k.v[q] = __ldcs(src + i);
+        }
+        k.at = (i0 + lane) * 8u; k.n = n;
+        i0 += 128;
+    };
+    Chunk4 cur, nxt;
+    fetch(cur);
+    while (cur.ok) {
+        fetch(nxt);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t at = cur.at + 256u * q;
+            const uint32_t rem = at < cur.n ? cur.n - at : 0u;
+            const uint32_t w[4] = {cur.v[q].x, cur.v[q].y, cur.v[q].z, cur.v[q].w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (uint32_t(j) < rem) atomicAdd(&radix_hist[(w[j >> 1] >> (16 * (j & 1))) & pmask], 1u);
+        }
+        cur = nxt;
     }
     __syncthreads();
 
+    // table slice += histogram, four independent 16-byte read-modify-writes in flight
     CounterT *dst = table + (uint64_t(b) << P);
-    for (uint32_t i = threadIdx.x * 4; i < bins; i += blockDim.x * 4) {
-        const uint4 h = *reinterpret_cast<const uint4 *>(radix_hist + i);
-        if ((h.x | h.y | h.z | h.w) == 0) continue;
+    for (uint32_t i0 = threadIdx.x * 4; i0 < bins; i0 += blockDim.x * 16) {
+        uint4 h[4];
         if constexpr (sizeof(CounterT) == 4) {
-            uint4 t = *reinterpret_cast<uint4 *>(dst + i);
-            t.x += h.x; t.y += h.y; t.z += h.z; t.w += h.w;
-            *reinterpret_cast<uint4 *>(dst + i) = t;
+            uint4 t[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t i = i0 + q * blockDim.x * 4;
+                if (i < bins) { h[q] = *reinterpret_cast<const uint4 *>(radix_hist + i); t[q] = *reinterpret_cast<const uint4 *>(dst + i); }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t i = i0 + q * blockDim.x * 4;
+                if (i < bins && (h[q].x | h[q].y | h[q].z | h[q].w)) {
+                    t[q].x += h[q].x; t[q].y += h[q].y; t[q].z += h[q].z; t[q].w += h[q].w;
+                    *reinterpret_cast<uint4 *>(dst + i) = t[q];
+                }
+            }
         } else {
-            ulonglong2 t0 = *reinterpret_cast<ulonglong2 *>(dst + i);
-            ulonglong2 t1 = *reinterpret_cast<ulonglong2 *>(dst + i + 2);
-            t0.x += h.x; t0.y += h.y; t1.x += h.z; t1.y += h.w;
-            *reinterpret_cast<ulonglong2 *>(dst + i) = t0;
-            *reinterpret_cast<ulonglong2 *>(dst + i + 2) = t1;
+            ulonglong2 t0[4], t1[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t i = i0 + q * blockDim.x * 4;
+                if (i < bins) {
+                    h[q] = *reinterpret_cast<const uint4 *>(radix_hist + i);
+                    t0[q] = *reinterpret_cast<const ulonglong2 *>(dst + i);
+                    t1[q] = *reinterpret_cast<const ulonglong2 *>(dst + i + 2);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t i = i0 + q * blockDim.x * 4;
+                if (i < bins && (h[q].x | h[q].y | h[q].z | h[q].w)) {
+                    t0[q].x += h[q].x; t0[q].y += h[q].y; t1[q].x += h[q].z; t1[q].y += h[q].w;
+                    *reinterpret_cast<ulonglong2 *>(dst + i) = t0[q];
+                    *reinterpret_cast<ulonglong2 *>(dst + i + 2) = t1[q];
+                }
+            }
         }
     }
 }
@@ -341,6 +418,8 @@ struct RadixWorkspace {
 static std::mutex g_radix_mutex;
 static std::vector<RadixWorkspace *> g_radix_ws;
 static std::atomic<int> g_radix_payload_bits{0};     // 0 = automatic
+static std::atomic<int> g_radix_debug{0};
+void set_radix_debug(int v) { g_radix_debug.store(v); }
 
 void set_radix_payload_bits(int bits) { g_radix_payload_bits.store(bits); }
 
@@ -434,6 +513,7 @@ int launch_count_radix(const uint32_t *d_codes, const uint32_t *d_valid, uint64_
         p.region_groups = uint32_t(groups);
         p.staging = static_cast<uint16_t *>(ws->staging);
         p.region_fill = ws->fill;
+        p.debug = g_radix_debug.load();
         if (counter_bits == 32) {
             radix_partition_kernel<uint32_t><<<grid1, kRadixThreads, smem1, stream>>>(
                 p, static_cast<uint32_t *>(d_table));
