@@ -257,6 +257,7 @@ def bench_count(args):
     _cabi.check(L.kpal_set_option(b"count_path", args.count_path))
     _cabi.check(L.kpal_set_option(b"radix_payload_bits", args.radix_payload_bits))
     _cabi.check(L.kpal_set_option(b"radix_debug", args.radix_debug))
+    _cabi.check(L.kpal_set_option(b"radix_shape", args.radix_shape))
     k, bins = K_COUNT, 4 ** K_COUNT
     dev = torch.device("cuda", local)
 
@@ -521,6 +522,7 @@ def main():
                     help="0 = library default, 1 = scattered-RED kernel, 2 = radix-partitioned path")
     ap.add_argument("--radix-payload-bits", type=int, default=0)
     ap.add_argument("--radix-debug", type=int, default=0, help="timing experiments (results are wrong)")
+    ap.add_argument("--radix-shape", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -34,6 +34,7 @@ void set_count_path(int v);
 void set_tiled_finalize(int v);
 void set_radix_payload_bits(int bits);
 void set_radix_debug(int v);
+void set_radix_shape(int v);
 int launch_fasta_pack(const uint8_t *, uint64_t, uint32_t *, uint32_t *, void *, cudaStream_t);
 
 static thread_local char t_error[512] = "";
@@ -289,6 +290,10 @@ extern "C" int kpal_set_option(const char *name, int value)
         set_count_path(value); return KPAL_OK;
     }
     if (!strcmp(name, "tiled_finalize")) { set_tiled_finalize(value != 0); return KPAL_OK; }
+    if (!strcmp(name, "radix_shape")) {
+        if (value < 0 || value > 2) return bad_arg("radix_shape must be 0 (auto), 1 (1024 x 1 CTA/SM) or 2 (512 x 2)");
+        set_radix_shape(value); return KPAL_OK;
+    }
     if (!strcmp(name, "radix_debug")) { set_radix_debug(value); return KPAL_OK; }   // timing experiments
     if (!strcmp(name, "radix_payload_bits")) {
         if (value < 0 || value > 15) return bad_arg("radix_payload_bits must be 0 (auto) .. 15");

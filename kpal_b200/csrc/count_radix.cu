@@ -33,7 +33,7 @@
 
 namespace kpal {
 
-constexpr int kRadixThreads = 1024;
+constexpr int kHistThreadsMax = 1024;
 constexpr int kUnitBases = 32;          // bases (= window starts) per thread and tile
 constexpr int kGroup = 16;              // payloads per 32-byte group
 
@@ -170,10 +170,15 @@ __device__ __noinline__ void red_piece(uint4 a, uint32_t hi, uint32_t pmask, int
     }
 }
 
-template <typename CounterT>
-__global__ void __launch_bounds__(kRadixThreads, 1)
+// THREADS x TEAM: 1024 x 8 = one CTA per SM with ~200 KB of slots; 512 x 4 = two CTAs per
+// SM with ~105 KB each, so that the store-bound flush of one CTA overlaps the
+// shared-memory-bound binning of the other (the flush moves 64 KB per tile through the
+// SM's store path and costs as much as a third of the binning when it runs alone).
+template <typename CounterT, int THREADS, int TEAM>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
 {
+    constexpr int kRadixThreads = THREADS;
     extern __shared__ __align__(16) unsigned char radix_smem[];
     uint32_t *cnt = reinterpret_cast<uint32_t *>(radix_smem);           // [nb] payloads in the slot (+32 dummies)
     uint32_t *fillg = cnt + p.nb + 32;                                   // [nb] groups already stored
@@ -203,7 +208,7 @@ radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
     ctx.no_store = (p.debug & 2) != 0;
 
     uint16_t *my_regions = p.staging + uint64_t(blockIdx.x) * p.nb * p.region_groups * kGroup;
-    const int team = tid >> 3, tl = tid & 7;      // flush teams of 8 lanes
+    const int team = tid / TEAM, tl = tid % TEAM;      // flush teams of TEAM consecutive lanes
 
     // software pipeline: the words of the next tile (and lane 31's halo words) are in
     // flight during this one
@@ -253,12 +258,12 @@ radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
         __syncthreads();
 
         // ---- B: every slot stores its complete groups and keeps the remainder.  A bucket
-        // is flushed by a team of 8 consecutive lanes, one 16-byte piece per lane, so a
-        // warp store covers 4 contiguous runs instead of 32 scattered sectors (the L1
+        // is flushed by a team of TEAM consecutive lanes, one 16-byte piece per lane, so a
+        // warp store covers a few contiguous runs instead of 32 scattered sectors (the L1
         // takes one cycle per distinct line of a store instruction).  The team is
         // inside one warp: the slot bookkeeping needs no CTA barrier.
         if (p.debug & 1) { for (int b = tid; b < p.nb; b += kRadixThreads) cnt[b] = 0; }
-        else for (int b = team; b - team < p.nb; b += kRadixThreads / 8) {      // warp-uniform trip count
+        else for (int b = team; b - team < p.nb; b += kRadixThreads / TEAM) {   // warp-uniform trip count
             const bool have = b < p.nb;
             const uint32_t cnt_a = ctx.cnt_s + 4u * uint32_t(b), fill_a = fill_s + 4u * uint32_t(b);
             uint32_t n = 0, f = 0;
@@ -268,7 +273,7 @@ radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
             if (g) {
                 const uint32_t slot_a = ctx.slots_s + uint32_t(b) * slot_bytes;
                 const uint32_t dst0 = uint32_t(b) * region_v4 + 2u * f;
-                for (uint32_t piece = tl; piece < 2 * g; piece += 8) {
+                for (uint32_t piece = tl; piece < 2 * g; piece += TEAM) {
                     const uint4 x = lds_v4(slot_a + 16u * piece);
                     if (f + piece / 2 < p.region_groups) __stcs(my_regions4 + dst0 + piece, x);
                     else red_piece<CounterT>(x, uint32_t(b) << p.P, (1u << p.P) - 1u, 8, table);   // region full
@@ -282,7 +287,7 @@ radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
     }
 
     // ---- remainders (< 16 per bucket) and the per-region totals
-    for (int b0 = 0; b0 < p.nb; b0 += kRadixThreads / 8) {
+    for (int b0 = 0; b0 < p.nb; b0 += kRadixThreads / TEAM) {
         const int b = b0 + team;
         if (b >= p.nb || tl >= 2) continue;
         const uint32_t n = cnt[b], f = fillg[b];
@@ -306,7 +311,7 @@ radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
 // pass 2
 // ---------------------------------------------------------------------------
 template <typename CounterT>
-__global__ void __launch_bounds__(kRadixThreads)
+__global__ void __launch_bounds__(kHistThreadsMax)
 radix_histogram_kernel(const uint16_t *__restrict__ staging, const uint32_t *__restrict__ region_fill,
                        int n_part_ctas, int nb, int P, uint32_t region_groups,
                        CounterT *__restrict__ table)
@@ -418,6 +423,8 @@ struct RadixWorkspace {
 static std::mutex g_radix_mutex;
 static std::vector<RadixWorkspace *> g_radix_ws;
 static std::atomic<int> g_radix_payload_bits{0};     // 0 = automatic
+static std::atomic<int> g_radix_shape{0};            // 0 = automatic
+void set_radix_shape(int v) { g_radix_shape.store(v); }
 static std::atomic<int> g_radix_debug{0};
 void set_radix_debug(int v) { g_radix_debug.store(v); }
 
@@ -440,32 +447,69 @@ static int grow(void **p, size_t *cap, size_t bytes)
 
 bool radix_supported(int k) { return k >= 9 && k <= 13; }
 
-// Geometry for a given k: payload bits P, buckets nb = 4^k >> P, slot capacity
-// cap (payloads; cap % 16 == 8 keeps the 16-byte slot reads of 8 neighbouring
+// Geometry for a given k: payload bits P, buckets nb = 4^k >> P, CTA shape and slot
+// capacity cap (payloads; cap % 16 == 8 keeps the 16-byte slot reads of neighbouring
 // buckets on distinct shared-memory banks).
-static void radix_geometry(int k, int *P, int *nb, int *cap, size_t *smem1)
+struct RadixGeometry {
+    int P, nb, cap, threads, team;
+    size_t smem1;
+};
+static RadixGeometry radix_geometry(int k)
 {
+    RadixGeometry g;
     int p = g_radix_payload_bits.load();
     if (p <= 0) p = (k == 13) ? 15 : 2 * k - 9;         // 512 buckets (2048 at k = 13)
     if (p > 15) p = 15;
     if (p < 2 * k - 11) p = 2 * k - 11;                 // at most 2048 buckets
-    int n = 1 << (2 * k - p);
-    // slots share ~200 KB
-    int c = int((200u * 1024u) / (2u * unsigned(n)));
+    g.P = p;
+    g.nb = 1 << (2 * k - p);
+    int shape = g_radix_shape.load();                   // 1 = 1024 threads x 1 CTA/SM, 2 = 512 x 2
+    if (shape == 0) shape = 1;      // measured: two half-size CTAs per SM do not beat one (147 vs 154 us)
+    g.threads = shape == 2 ? 512 : 1024;
+    // shared memory per SM: 233472 B, minus 1 KB per resident CTA
+    const size_t budget = (shape == 2 ? (233472 / 2 - 1024) : (233472 - 1024 - 4096)) - (size_t(g.nb) * 8 + 192);
+    int c = int(budget / (2u * unsigned(g.nb)));
     c = (c - 8) / 16 * 16 + 8;
     if (c > 1032) c = 1032;
-    *P = p; *nb = n; *cap = c;
-    *smem1 = size_t(n) * 8 + 128 + size_t(n) * c * 2 + 64;
+    g.cap = c;
+    // lanes per flush team ~ 16-byte pieces a slot gains per tile (2 per 16 payloads)
+    const int mean_pieces = g.threads * kUnitBases / g.nb / 8;
+    g.team = mean_pieces >= 8 ? 8 : 4;
+    g.smem1 = size_t(g.nb) * 8 + 128 + size_t(g.nb) * c * 2 + 64;
+    return g;
+}
+
+template <typename CounterT>
+static int launch_radix_passes(const RadixGeometry &g, RadixParams &p, int grid1, size_t smem2, int threads2,
+                               CounterT *table, cudaStream_t stream)
+{
+#define KPAL_RADIX_LAUNCH(THREADS, TEAM)                                                              \
+    do {                                                                                              \
+        KPAL_CUDA(cudaFuncSetAttribute(radix_partition_kernel<CounterT, THREADS, TEAM>,               \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(g.smem1)));   \
+        radix_partition_kernel<CounterT, THREADS, TEAM><<<grid1, THREADS, g.smem1, stream>>>(p, table); \
+    } while (0)
+    if (g.threads == 512 && g.team == 4) KPAL_RADIX_LAUNCH(512, 4);
+    else if (g.threads == 512) KPAL_RADIX_LAUNCH(512, 8);
+    else if (g.team == 4) KPAL_RADIX_LAUNCH(1024, 4);
+    else KPAL_RADIX_LAUNCH(1024, 8);
+#undef KPAL_RADIX_LAUNCH
+    KPAL_LAUNCH_CHECK("radix_partition_kernel");
+    KPAL_CUDA(cudaFuncSetAttribute(radix_histogram_kernel<CounterT>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem2)));
+    radix_histogram_kernel<CounterT><<<g.nb, threads2, smem2, stream>>>(
+        p.staging, p.region_fill, grid1, g.nb, g.P, p.region_groups, table);
+    KPAL_LAUNCH_CHECK("radix_histogram_kernel");
+    return KPAL_OK;
 }
 
 // Accumulate units of the packed stream into `table` through the two passes.
 int launch_count_radix(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_bases, int k,
                        void *d_table, int counter_bits, cudaStream_t stream)
 {
-    int P, nb, cap;
-    size_t smem1;
-    radix_geometry(k, &P, &nb, &cap, &smem1);
-    const int grid1 = sm_count();
+    const RadixGeometry g = radix_geometry(k);
+    const int P = g.P, nb = g.nb;
+    const int grid1 = sm_count() * (1024 / g.threads);
     const size_t smem2 = size_t(4) << P;
     const int threads2 = P >= 15 ? 1024 : 512;
 
@@ -476,25 +520,13 @@ int launch_count_radix(const uint32_t *d_codes, const uint32_t *d_valid, uint64_
     for (auto *w : g_radix_ws) if (w->device == dev) ws = w;
     if (!ws) { ws = new RadixWorkspace(); ws->device = dev; g_radix_ws.push_back(ws); }
 
-    if (counter_bits == 32) {
-        KPAL_CUDA(cudaFuncSetAttribute(radix_partition_kernel<uint32_t>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
-        KPAL_CUDA(cudaFuncSetAttribute(radix_histogram_kernel<uint32_t>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem2)));
-    } else {
-        KPAL_CUDA(cudaFuncSetAttribute(radix_partition_kernel<unsigned long long>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
-        KPAL_CUDA(cudaFuncSetAttribute(radix_histogram_kernel<unsigned long long>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem2)));
-    }
-
     // the stream is walked in segments so that the staging stays bounded (<= ~3 GB)
     const uint64_t n_units = 2 * n_chunks_of(n_bases);
     const uint64_t seg_units = (512ull << 20) / kUnitBases;
     for (uint64_t s0 = 0; s0 < n_units; s0 += seg_units) {
         const uint64_t s1 = (s0 + seg_units < n_units) ? s0 + seg_units : n_units;
         uint64_t per = (s1 - s0 + grid1 - 1) / grid1;
-        per = (per + kRadixThreads - 1) / kRadixThreads * kRadixThreads;
+        per = (per + g.threads - 1) / g.threads * g.threads;
         const uint64_t windows_per_cta = per * kUnitBases;
         // 3 x the mean region plus slack, in groups
         const uint64_t groups = (3 * windows_per_cta / nb + 4 * kGroup + kGroup - 1) / kGroup;
@@ -509,27 +541,17 @@ int launch_count_radix(const uint32_t *d_codes, const uint32_t *d_valid, uint64_
         p.codes = reinterpret_cast<const uint2 *>(d_codes);
         p.valid = d_valid;
         p.unit_begin = s0; p.unit_end = s1; p.n_units = n_units;
-        p.k = k; p.P = P; p.nb = nb; p.cap = cap;
+        p.k = k; p.P = P; p.nb = nb; p.cap = g.cap;
         p.region_groups = uint32_t(groups);
         p.staging = static_cast<uint16_t *>(ws->staging);
         p.region_fill = ws->fill;
         p.debug = g_radix_debug.load();
-        if (counter_bits == 32) {
-            radix_partition_kernel<uint32_t><<<grid1, kRadixThreads, smem1, stream>>>(
-                p, static_cast<uint32_t *>(d_table));
-            KPAL_LAUNCH_CHECK("radix_partition_kernel");
-            radix_histogram_kernel<uint32_t><<<nb, threads2, smem2, stream>>>(
-                p.staging, p.region_fill, grid1, nb, P, p.region_groups, static_cast<uint32_t *>(d_table));
-            KPAL_LAUNCH_CHECK("radix_histogram_kernel");
-        } else {
-            radix_partition_kernel<unsigned long long><<<grid1, kRadixThreads, smem1, stream>>>(
-                p, static_cast<unsigned long long *>(d_table));
-            KPAL_LAUNCH_CHECK("radix_partition_kernel");
-            radix_histogram_kernel<unsigned long long><<<nb, threads2, smem2, stream>>>(
-                p.staging, p.region_fill, grid1, nb, P, p.region_groups,
-                static_cast<unsigned long long *>(d_table));
-            KPAL_LAUNCH_CHECK("radix_histogram_kernel");
-        }
+        if (counter_bits == 32)
+            KPAL_CHECK(launch_radix_passes<uint32_t>(g, p, grid1, smem2, threads2,
+                                                     static_cast<uint32_t *>(d_table), stream));
+        else
+            KPAL_CHECK(launch_radix_passes<unsigned long long>(g, p, grid1, smem2, threads2,
+                                                               static_cast<unsigned long long *>(d_table), stream));
     }
     return KPAL_OK;
 }

@@ -404,15 +404,18 @@ def test_radix_count_path_bit_exact(k, n, letters, payload_bits):
     try:
         _set_option("count_path", 2)
         _set_option("radix_payload_bits", payload_bits)
-        got32 = _dev_count(text, k, 32, False)
-        assert np.array_equal(got32, want)
-        got64 = _dev_count(text, k, 64, True)
-        assert np.array_equal(got64, ko.balance(want))
+        for shape in (1, 2):           # one 1024-thread CTA per SM / two 512-thread CTAs per SM
+            _set_option("radix_shape", shape)
+            got32 = _dev_count(text, k, 32, False)
+            assert np.array_equal(got32, want), shape
+            got64 = _dev_count(text, k, 64, True)
+            assert np.array_equal(got64, ko.balance(want)), shape
         _set_option("count_path", 1)
         assert np.array_equal(_dev_count(text, k, 32, False), want)
     finally:
         _set_option("count_path", 0)
         _set_option("radix_payload_bits", 0)
+        _set_option("radix_shape", 0)
 
 
 def test_radix_count_path_through_host_api():
