@@ -78,7 +78,15 @@ constexpr int A_BYTES = TA * ROW_BYTES;
 constexpr int B_BYTES = TB * ROW_BYTES;
 constexpr int COMPUTE_WARPS = WI * WJ;
 constexpr bool PRODUCER_WARP = KPAL_PRODUCER_WARP != 0;
-constexpr int TILE_THREADS = (COMPUTE_WARPS + (PRODUCER_WARP ? 1 : 0)) * 32;
+// KPAL_SETMAXNREG: the producer sits in a warpgroup of its own (3 of its 4 warps retire at
+// once) and hands its registers to the compute warpgroups with setmaxnreg, so the compute
+// code is no longer held to the 168 registers a 9-warp CTA allows (3 warps on one scheduler).
+#ifndef KPAL_SETMAXNREG
+#define KPAL_SETMAXNREG 0
+#endif
+constexpr bool SETMAXNREG = (KPAL_SETMAXNREG != 0) && PRODUCER_WARP;
+constexpr int PRODUCER_WARPS = PRODUCER_WARP ? (SETMAXNREG ? 4 : 1) : 0;
+constexpr int TILE_THREADS = (COMPUTE_WARPS + PRODUCER_WARPS) * 32;
 constexpr uint64_t kStrideAlign = 128;  // prepared row stride: multiple of 128 doubles (bitmap rows 16 B aligned)
 constexpr uint64_t kSliceLen = 1u << 16;  // elements of D per work item
 
@@ -324,13 +332,19 @@ distance_tile_kernel(const TileArgs a)
         }
     };
     if constexpr (PRODUCER_WARP) {
-        if (warp == COMPUTE_WARPS) {
-            for (uint32_t it = 0; it < n_iter; ++it) {
-                mbar_wait(smem_u32(&bars[STAGES + it % STAGES]), ((it / STAGES) & 1) ^ 1);
-                issue_stage(it, COMPUTE_WARPS * 32, 32);
+        if (warp >= COMPUTE_WARPS) {
+            // everything the producer warpgroup ever runs is inside this branch, so that
+            // the register budget after setmaxnreg.dec cannot leak into the compute code
+            if constexpr (SETMAXNREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+            if (warp == COMPUTE_WARPS) {
+                for (uint32_t it = 0; it < n_iter; ++it) {
+                    mbar_wait(smem_u32(&bars[STAGES + it % STAGES]), ((it / STAGES) & 1) ^ 1);
+                    issue_stage(it, COMPUTE_WARPS * 32, 32);
+                }
             }
             return;
         }
+        if constexpr (SETMAXNREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(KPAL_SETMAXNREG));
     } else {
         for (uint32_t it = 0; it < STAGES - 1 && it < n_iter; ++it) issue_stage(it, 0, TILE_THREADS);
     }
