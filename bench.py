@@ -84,6 +84,43 @@ def reads_to_fasta(reads, wrap=70):
     return out.reshape(-1)
 
 
+def synthetic_chromosomes(seed, n_records, record_len):
+    """SURVEY.md section 8d, cfg 5: long records with 2-6 blocks of N (10 k - 1 M bases) and
+    ~40 % soft-masked (lower case) stretches.  Returns a list of uint8 arrays."""
+    rng = np.random.default_rng(seed)
+    records = []
+    for _ in range(n_records):
+        seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, record_len, dtype=np.uint8)]
+        # soft-masked stretches: alternate segments of ~2-40 kb, 40 % of them lower case
+        n_seg = max(2, record_len // 20_000)
+        cuts = np.sort(rng.integers(0, record_len, n_seg - 1))
+        masked = rng.random(n_seg) < 0.4
+        lower = np.repeat(masked, np.diff(np.concatenate(([0], cuts, [record_len]))))
+        seq = np.where(lower, seq + 32, seq).astype(np.uint8)
+        for _ in range(int(rng.integers(2, 7))):
+            size = int(min(rng.integers(10_000, 1_000_001), max(1, record_len // 8)))
+            at = int(rng.integers(0, max(1, record_len - size)))
+            seq[at:at + size] = ord("N")
+        records.append(seq)
+    return records
+
+
+def records_to_fasta(records, wrap=70, first=0):
+    """Vectorised 70-column FASTA of a few long records ('>chrNN' headers)."""
+    parts = []
+    for i, seq in enumerate(records):
+        parts.append(np.frombuffer((">chr%02d\n" % (first + i)).encode(), dtype=np.uint8))
+        full = len(seq) // wrap
+        body = np.empty((full, wrap + 1), dtype=np.uint8)
+        body[:, :wrap] = seq[:full * wrap].reshape(full, wrap)
+        body[:, wrap] = ord("\n")
+        parts.append(body.reshape(-1))
+        if len(seq) > full * wrap:
+            parts.append(seq[full * wrap:])
+            parts.append(np.frombuffer(b"\n", dtype=np.uint8))
+    return np.concatenate(parts)
+
+
 # -------------------------------------------------------------------- clocks
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons during the timed region
@@ -258,18 +295,39 @@ def bench_count(args):
     _cabi.check(L.kpal_set_option(b"radix_payload_bits", args.radix_payload_bits))
     _cabi.check(L.kpal_set_option(b"radix_debug", args.radix_debug))
     _cabi.check(L.kpal_set_option(b"radix_shape", args.radix_shape))
-    k, bins = K_COUNT, 4 ** K_COUNT
     dev = torch.device("cuda", local)
 
     # ---- this rank's shard of records (same size on every rank: weak scaling)
-    reads = synthetic_reads(1000 + rank)
-    fasta_np = reads_to_fasta(reads)
+    if args.config == 5:
+        # BASELINE configs[4]: k = 13, human-genome-sized FASTA sharded over the GPUs
+        # (3 x 125 Mbp records per GPU at the full 8-GPU size)
+        k = args.k or 13
+        rec_len = int(args.mbp_per_gpu * 1e6) // 3
+        records = synthetic_chromosomes(5000 + rank, 3, rec_len)
+        fasta_np = records_to_fasta(records, first=3 * rank)
+        oracle_text = np.concatenate([np.append(r, np.uint8(10)) for r in records])
+        seq_bases_total = sum(len(r) for r in records)
+        n_windows = None
+        workload = ("kpal count k=%d, %d x %.1f Mbp records per GPU with N blocks and soft-masking, balance; "
+                    "BASELINE configs[4]" % (k, 3, rec_len / 1e6))
+        del records
+    else:
+        k = args.k or K_COUNT
+        reads = synthetic_reads(1000 + rank)
+        fasta_np = reads_to_fasta(reads)
+        oracle_text = np.insert(reads, READ_LEN, ord("\n"), axis=1).reshape(-1)
+        seq_bases_total = reads.size
+        n_windows = reads.size - N_READS * (k - 1)
+        workload = ("kpal count k=%d, 100 Mbp of 150-bp reads (666667 records/GPU), balance; "
+                    "BASELINE configs[1]" % k)
+        del reads
+    bins = 4 ** k
     n_fasta = fasta_np.size
     pinned_fasta = _cabi.PinnedArray(n_fasta, np.uint8)
     pinned_fasta.array[:] = fasta_np
     pinned_out = _cabi.PinnedArray(bins, np.int64)
     codes, valid, _, _, n_bases = _cabi.fasta_pack(fasta_np.tobytes())
-    seq_bases = reads.size
+    seq_bases = seq_bases_total
     d_codes = torch.from_numpy(codes.view(np.int32)).to(dev)
     d_valid = torch.from_numpy(valid.view(np.int32)).to(dev)
     d_table = torch.zeros(bins, dtype=torch.int32, device=dev)
@@ -351,11 +409,12 @@ def bench_count(args):
     result_ok = None
     if rank == 0 and world == 1:
         from oracle import c_oracle, kpal_oracle as ko
-        text = np.insert(reads, READ_LEN, ord("\n"), axis=1).reshape(-1)
         t0 = time.perf_counter()
-        want = c_oracle.count_bytes(text, k, threads=c_oracle.max_threads())
-        want = want + want[ko.reverse_complement_table(k)]
+        want = c_oracle.count_bytes(oracle_text, k, threads=c_oracle.max_threads())
+        want = c_oracle.balance(want)                 # literal klib.py:285-298 loop in C
         cpu_s = time.perf_counter() - t0
+        if n_windows is None:
+            n_windows = int(want.sum()) // 2
         result_ok = bool(np.array_equal(d_counts.cpu().numpy(), want)
                          and np.array_equal(pinned_out.array, want))
         cpu = {"value": seq_bases / 1e9 / cpu_s, "unit": "Gbases/s", "cores": c_oracle.max_threads(),
@@ -370,17 +429,18 @@ def bench_count(args):
         total_bases = seq_bases * world
         peak, peak_src = measured_peak("hbm_gbs", 6650.0)
         alg_bytes = 0.375 * n_bases + 4 * bins      # packed stream read once + u32 table written once
-        radix = args.count_path == 2 or (args.count_path == 0 and n_bases >= (16 << 20))
+        radix = args.count_path == 2 or (args.count_path == 0 and n_bases >= ((16 << 20) if k <= 12 else (4 << 20)))
+        if n_windows is None:
+            n_windows = seq_bases
         count_kernel_name = ("radix_partition_kernel<u32> + radix_histogram_kernel<u32>" if radix
                              else "count_global_kernel<u32>")
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
         out = {
-            "metric": "gbases_per_sec_counted_k12", "value": total_bases / 1e9 / (step_ms * 1e-3),
+            "metric": "gbases_per_sec_counted_k%d" % k, "value": total_bases / 1e9 / (step_ms * 1e-3),
             "unit": "Gbases/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 counters -> int64", "data": "synthetic",
-            "config": {"workload": "kpal count k=12, 100 Mbp of 150-bp reads (666667 records/GPU), "
-                                   "balance; BASELINE configs[1]",
+            "config": {"workload": workload,
                        "k": k, "bases_per_gpu": int(seq_bases), "packed_bases_per_gpu": int(n_bases),
                        "l2": "512 MB memset between steps (untimed); table memset is inside the step",
                        "parallelism": "records sharded per GPU, NCCL reduce of u32 tables" if world > 1 else "1 GPU"},
@@ -394,7 +454,7 @@ def bench_count(args):
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(count_kernel_name.split("<")[0].split(" ")[0]),
                          "algorithmic_bytes": alg_bytes, "kernel_ms": kern_ms, "peak_source": peak_src,
-                         "atomics_per_s": (seq_bases - N_READS * (k - 1)) / (kern_ms * 1e-3)},
+                         "windows_per_s": n_windows / (kern_ms * 1e-3)},
             "cpu_baseline": cpu, "clocks": clocks, "parity_ok": result_ok,
             "wall_s_timed_region": wall,
         }
@@ -518,6 +578,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="count", choices=["count", "matrix"])
     ap.add_argument("--profiles", type=int, default=N_PROFILES)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 5],
+                    help="count workload: 2 = BASELINE configs[1] (default), 5 = configs[4] (k=13 genome shards)")
+    ap.add_argument("--k", type=int, default=0, help="override the k-mer length of the count workload")
+    ap.add_argument("--mbp-per-gpu", type=float, default=375.0, help="config 5: Mbp per GPU")
     ap.add_argument("--count-path", type=int, default=0, choices=[0, 1, 2],
                     help="0 = library default, 1 = scattered-RED kernel, 2 = radix-partitioned path")
     ap.add_argument("--radix-payload-bits", type=int, default=0)

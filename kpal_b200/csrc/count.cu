@@ -282,10 +282,11 @@ static bool use_radix_path(int k, uint64_t n_bases)
     const int mode = g_count_path.load();
     if (mode == 1 || !radix_supported(k)) return false;
     if (mode == 2) return true;
-    // The two passes cost a fixed ~2 x 4^k x 4 bytes of table traffic; below these
-    // sizes the RED kernel wins.  At k = 13 the table no longer fits in L2 and the
-    // RED rate drops ~7x, so the switch comes earlier.
-    return n_bases >= (k >= 13 ? (4ull << 20) : (16ull << 20));
+    // The two passes cost a fixed ~2 x 4^k x 4 bytes of table traffic; below these sizes
+    // the RED kernel wins.  From k = 13 on the table no longer fits in L2 and the RED
+    // rate drops ~7x, so the switch comes earlier relative to the table size.
+    const uint64_t threshold = k <= 12 ? (16ull << 20) : (4ull << 20) << (2 * (k - 13));
+    return n_bases >= threshold;
 }
 
 int launch_accumulate(const void *d_src, void *d_dst, int counter_bits, uint64_t n, cudaStream_t stream)

@@ -59,6 +59,7 @@ struct RadixParams {
     uint64_t unit_begin, unit_end;   // units [begin, end) of this launch
     uint64_t n_units;           // units readable in the stream (loads are clamped to this)
     int k, P, nb, cap;          // payload bits, buckets (power of two), slot capacity
+    int bucket_lo, nb_active;   // this launch bins buckets [bucket_lo, bucket_lo + nb_active) only
     uint32_t region_groups;     // capacity of one (CTA, bucket) region in groups
     uint16_t *staging;          // [grid][nb][region_groups * 16]
     uint32_t *region_fill;      // [grid][nb] payloads stored per region
@@ -109,6 +110,7 @@ struct BinCtx {
     uint32_t dummy_cnt_s;           // per-lane counter that absorbs invalid windows
     uint32_t dummy_slot_s;          // per-lane halfword that absorbs their stores
     uint32_t cap;
+    uint32_t bucket_lo, nb_active;
     int shift, P;
     bool no_store;
 };
@@ -117,7 +119,7 @@ struct BinCtx {
 // dummy counter and stores into a per-lane dummy halfword, so the atomics of a
 // batch are all in flight before the first dependent store.  The stored
 // halfword is the low 16 index bits; pass 2 masks it to P bits.
-template <typename CounterT, int O0>
+template <typename CounterT, bool SWEEP, int O0>
 __device__ __forceinline__ void bin_eight(const Unit &u, const BinCtx &c, CounterT *table)
 {
     // all selects are bit masks (0 / ~0): with 16 live booleans the compiler ran out of
@@ -130,7 +132,12 @@ __device__ __forceinline__ void bin_eight(const Unit &u, const BinCtx &c, Counte
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         okm[j] = uint32_t(int32_t(u.starts << (O0 + j)) >> 31);
-        const uint32_t real = c.cnt_s + 4u * (idx[j] >> c.P);
+        uint32_t bl = idx[j] >> c.P;
+        if constexpr (SWEEP) {          // several launches share the buckets: keep ours only
+            bl -= c.bucket_lo;
+            okm[j] &= bl < c.nb_active ? ~0u : 0u;
+        }
+        const uint32_t real = c.cnt_s + 4u * bl;
         rank[j] = atoms_add(c.dummy_cnt_s ^ ((c.dummy_cnt_s ^ real) & okm[j]), 1u);
     }
     uint32_t overflow = 0;
@@ -139,7 +146,8 @@ __device__ __forceinline__ void bin_eight(const Unit &u, const BinCtx &c, Counte
         // rank < cap  <=>  rank - cap is negative (ranks stay far below 2^31)
         const uint32_t inm = uint32_t(int32_t(rank[j] - c.cap) >> 31) & okm[j];
         overflow |= okm[j] & ~inm;
-        const uint32_t real = c.slots_s + 2u * ((idx[j] >> c.P) * c.cap + rank[j]);
+        const uint32_t bl = SWEEP ? (idx[j] >> c.P) - c.bucket_lo : (idx[j] >> c.P);
+        const uint32_t real = c.slots_s + 2u * (bl * c.cap + rank[j]);
         if (!c.no_store) sts_u16(c.dummy_slot_s ^ ((c.dummy_slot_s ^ real) & inm), idx[j]);
     }
     if (overflow) {                 // slot full (skewed / repetitive sequence): count directly
@@ -149,12 +157,12 @@ __device__ __forceinline__ void bin_eight(const Unit &u, const BinCtx &c, Counte
     }
 }
 
-template <typename CounterT, int O0>
+template <typename CounterT, bool SWEEP, int O0>
 __device__ __forceinline__ void bin_from(const Unit &u, const BinCtx &c, CounterT *table)
 {
     if constexpr (O0 < kUnitBases) {
-        bin_eight<CounterT, O0>(u, c, table);
-        bin_from<CounterT, O0 + 8>(u, c, table);
+        bin_eight<CounterT, SWEEP, O0>(u, c, table);
+        bin_from<CounterT, SWEEP, O0 + 8>(u, c, table);
     }
 }
 
@@ -174,20 +182,21 @@ __device__ __noinline__ void red_piece(uint4 a, uint32_t hi, uint32_t pmask, int
 // SM with ~105 KB each, so that the store-bound flush of one CTA overlaps the
 // shared-memory-bound binning of the other (the flush moves 64 KB per tile through the
 // SM's store path and costs as much as a third of the binning when it runs alone).
-template <typename CounterT, int THREADS, int TEAM>
+template <typename CounterT, int THREADS, int TEAM, bool SWEEP>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
 {
     constexpr int kRadixThreads = THREADS;
     extern __shared__ __align__(16) unsigned char radix_smem[];
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(radix_smem);           // [nb] payloads in the slot (+32 dummies)
-    uint32_t *fillg = cnt + p.nb + 32;                                   // [nb] groups already stored
-    uint16_t *slots = reinterpret_cast<uint16_t *>(fillg + p.nb);        // [nb][cap] (+ 64 B pad / dummies)
+    const int na = p.nb_active;                                          // buckets binned by this launch
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(radix_smem);           // [na] payloads in the slot (+32 dummies)
+    uint32_t *fillg = cnt + na + 32;                                     // [na] groups already stored
+    uint16_t *slots = reinterpret_cast<uint16_t *>(fillg + na);          // [na][cap] (+ 64 B pad / dummies)
 
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31u;
-    for (int b = tid; b < p.nb + 32; b += kRadixThreads) cnt[b] = 0;
-    for (int b = tid; b < p.nb; b += kRadixThreads) fillg[b] = 0;
+    for (int b = tid; b < na + 32; b += kRadixThreads) cnt[b] = 0;
+    for (int b = tid; b < na; b += kRadixThreads) fillg[b] = 0;
     __syncthreads();
 
     // contiguous share of the units, a multiple of the tile so warps stay aligned
@@ -200,11 +209,13 @@ radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
     BinCtx ctx;
     ctx.cnt_s = smem_u32(cnt);
     ctx.slots_s = smem_u32(slots);
-    ctx.dummy_cnt_s = ctx.cnt_s + 4u * (uint32_t(p.nb) + lane);
-    ctx.dummy_slot_s = ctx.slots_s + 2u * (uint32_t(p.nb) * uint32_t(p.cap) + lane);
+    ctx.dummy_cnt_s = ctx.cnt_s + 4u * (uint32_t(na) + lane);
+    ctx.dummy_slot_s = ctx.slots_s + 2u * (uint32_t(na) * uint32_t(p.cap) + lane);
     ctx.cap = uint32_t(p.cap);
     ctx.shift = 32 - 2 * p.k;
     ctx.P = p.P;
+    ctx.bucket_lo = uint32_t(p.bucket_lo);
+    ctx.nb_active = uint32_t(p.nb_active);
     ctx.no_store = (p.debug & 2) != 0;
 
     uint16_t *my_regions = p.staging + uint64_t(blockIdx.x) * p.nb * p.region_groups * kGroup;
@@ -254,7 +265,7 @@ radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
             }
             u.starts = (unit < u1) ? uint32_t(a >> 32) : 0u;
         }
-        if (u.starts && !(p.debug & 4)) bin_from<CounterT, 0>(u, ctx, table);
+        if (u.starts && !(p.debug & 4)) bin_from<CounterT, SWEEP, 0>(u, ctx, table);
         __syncthreads();
 
         // ---- B: every slot stores its complete groups and keeps the remainder.  A bucket
@@ -262,9 +273,10 @@ radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
         // warp store covers a few contiguous runs instead of 32 scattered sectors (the L1
         // takes one cycle per distinct line of a store instruction).  The team is
         // inside one warp: the slot bookkeeping needs no CTA barrier.
-        if (p.debug & 1) { for (int b = tid; b < p.nb; b += kRadixThreads) cnt[b] = 0; }
-        else for (int b = team; b - team < p.nb; b += kRadixThreads / TEAM) {   // warp-uniform trip count
-            const bool have = b < p.nb;
+        if (p.debug & 1) { for (int b = tid; b < na; b += kRadixThreads) cnt[b] = 0; }
+        else for (int b = team; b - team < na; b += kRadixThreads / TEAM) {     // warp-uniform trip count
+            const bool have = b < na;
+            const uint32_t bg = uint32_t(b + p.bucket_lo);                      // bucket id in the table
             const uint32_t cnt_a = ctx.cnt_s + 4u * uint32_t(b), fill_a = fill_s + 4u * uint32_t(b);
             uint32_t n = 0, f = 0;
             if (have) { n = min(lds_u32(cnt_a), ctx.cap); f = lds_u32(fill_a); }
@@ -272,11 +284,11 @@ radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
             const uint32_t g = n / kGroup;
             if (g) {
                 const uint32_t slot_a = ctx.slots_s + uint32_t(b) * slot_bytes;
-                const uint32_t dst0 = uint32_t(b) * region_v4 + 2u * f;
+                const uint32_t dst0 = bg * region_v4 + 2u * f;
                 for (uint32_t piece = tl; piece < 2 * g; piece += TEAM) {
                     const uint4 x = lds_v4(slot_a + 16u * piece);
                     if (f + piece / 2 < p.region_groups) __stcs(my_regions4 + dst0 + piece, x);
-                    else red_piece<CounterT>(x, uint32_t(b) << p.P, (1u << p.P) - 1u, 8, table);   // region full
+                    else red_piece<CounterT>(x, bg << p.P, (1u << p.P) - 1u, 8, table);   // region full
                 }
                 // remainder to the front: lanes 0/1 read pieces 0/1 themselves, nobody else does
                 if (tl < 2) { const uint4 x = lds_v4(slot_a + 16u * (2 * g + tl)); sts_v4(slot_a + 16u * tl, x); }
@@ -287,23 +299,24 @@ radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
     }
 
     // ---- remainders (< 16 per bucket) and the per-region totals
-    for (int b0 = 0; b0 < p.nb; b0 += kRadixThreads / TEAM) {
+    for (int b0 = 0; b0 < na; b0 += kRadixThreads / TEAM) {
         const int b = b0 + team;
-        if (b >= p.nb || tl >= 2) continue;
+        if (b >= na || tl >= 2) continue;
+        const uint32_t bg = uint32_t(b + p.bucket_lo);
         const uint32_t n = cnt[b], f = fillg[b];
         uint32_t stored = f * kGroup;
         if (n) {
             const uint4 x = reinterpret_cast<const uint4 *>(slots + uint32_t(b) * p.cap)[tl];
             if (f < p.region_groups) {
-                uint4 *dst = reinterpret_cast<uint4 *>(my_regions + uint64_t(b) * p.region_groups * kGroup);
+                uint4 *dst = reinterpret_cast<uint4 *>(my_regions + uint64_t(bg) * p.region_groups * kGroup);
                 dst[2 * f + tl] = x;                     // payloads beyond n are never read
                 stored += n;
             } else {
                 const int mine = int(n) - 8 * tl;
-                red_piece<CounterT>(x, uint32_t(b) << p.P, (1u << p.P) - 1u, mine < 8 ? mine : 8, table);
+                red_piece<CounterT>(x, bg << p.P, (1u << p.P) - 1u, mine < 8 ? mine : 8, table);
             }
         }
-        if (tl == 0) p.region_fill[uint64_t(blockIdx.x) * p.nb + b] = stored;
+        if (tl == 0) p.region_fill[uint64_t(blockIdx.x) * p.nb + bg] = stored;
     }
 }
 
@@ -445,37 +458,42 @@ static int grow(void **p, size_t *cap, size_t bytes)
     return KPAL_OK;
 }
 
-bool radix_supported(int k) { return k >= 9 && k <= 13; }
+bool radix_supported(int k) { return k >= 9 && k <= KPAL_MAX_K; }
 
 // Geometry for a given k: payload bits P, buckets nb = 4^k >> P, CTA shape and slot
 // capacity cap (payloads; cap % 16 == 8 keeps the 16-byte slot reads of neighbouring
 // buckets on distinct shared-memory banks).
 struct RadixGeometry {
-    int P, nb, cap, threads, team;
+    int P, nb, na, cap, threads, team;      // na: buckets binned per pass-1 launch (nb / na sweeps)
     size_t smem1;
 };
 static RadixGeometry radix_geometry(int k)
 {
     RadixGeometry g;
     int p = g_radix_payload_bits.load();
-    if (p <= 0) p = (k == 13) ? 15 : 2 * k - 9;         // 512 buckets (2048 at k = 13)
+    if (p <= 0) p = (k >= 13) ? 15 : 2 * k - 9;         // 512 buckets up to k = 12, 2^(2k-15) beyond
     if (p > 15) p = 15;
-    if (p < 2 * k - 11) p = 2 * k - 11;                 // at most 2048 buckets
+    if (p < 2 * k - 15) p = 2 * k - 15;                 // at most 32768 buckets
     g.P = p;
     g.nb = 1 << (2 * k - p);
+    // More than 1024 buckets do not fit the slots with a useful capacity: pass 1 then runs
+    // nb / 1024 times over the stream, each launch binning its own 1024 buckets (the stream
+    // is 0.375 B/base; re-reading it is cheap next to 5 B/base of RED traffic out of L2).
+    g.na = g.nb > 1024 ? 1024 : g.nb;
     int shape = g_radix_shape.load();                   // 1 = 1024 threads x 1 CTA/SM, 2 = 512 x 2
     if (shape == 0) shape = 1;      // measured: two half-size CTAs per SM do not beat one (147 vs 154 us)
+    if (g.na > 512) shape = 1;
     g.threads = shape == 2 ? 512 : 1024;
     // shared memory per SM: 233472 B, minus 1 KB per resident CTA
-    const size_t budget = (shape == 2 ? (233472 / 2 - 1024) : (233472 - 1024 - 4096)) - (size_t(g.nb) * 8 + 192);
-    int c = int(budget / (2u * unsigned(g.nb)));
+    const size_t budget = (shape == 2 ? (233472 / 2 - 1024) : (233472 - 1024 - 4096)) - (size_t(g.na) * 8 + 192);
+    int c = int(budget / (2u * unsigned(g.na)));
     c = (c - 8) / 16 * 16 + 8;
     if (c > 1032) c = 1032;
     g.cap = c;
     // lanes per flush team ~ 16-byte pieces a slot gains per tile (2 per 16 payloads)
     const int mean_pieces = g.threads * kUnitBases / g.nb / 8;
     g.team = mean_pieces >= 8 ? 8 : 4;
-    g.smem1 = size_t(g.nb) * 8 + 128 + size_t(g.nb) * c * 2 + 64;
+    g.smem1 = size_t(g.na) * 8 + 128 + size_t(g.na) * c * 2 + 64;
     return g;
 }
 
@@ -483,18 +501,22 @@ template <typename CounterT>
 static int launch_radix_passes(const RadixGeometry &g, RadixParams &p, int grid1, size_t smem2, int threads2,
                                CounterT *table, cudaStream_t stream)
 {
-#define KPAL_RADIX_LAUNCH(THREADS, TEAM)                                                              \
+#define KPAL_RADIX_LAUNCH(THREADS, TEAM, SWEEP)                                                       \
     do {                                                                                              \
-        KPAL_CUDA(cudaFuncSetAttribute(radix_partition_kernel<CounterT, THREADS, TEAM>,               \
+        KPAL_CUDA(cudaFuncSetAttribute(radix_partition_kernel<CounterT, THREADS, TEAM, SWEEP>,        \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, int(g.smem1)));   \
-        radix_partition_kernel<CounterT, THREADS, TEAM><<<grid1, THREADS, g.smem1, stream>>>(p, table); \
+        radix_partition_kernel<CounterT, THREADS, TEAM, SWEEP><<<grid1, THREADS, g.smem1, stream>>>(p, table); \
     } while (0)
-    if (g.threads == 512 && g.team == 4) KPAL_RADIX_LAUNCH(512, 4);
-    else if (g.threads == 512) KPAL_RADIX_LAUNCH(512, 8);
-    else if (g.team == 4) KPAL_RADIX_LAUNCH(1024, 4);
-    else KPAL_RADIX_LAUNCH(1024, 8);
+    for (int lo = 0; lo < g.nb; lo += g.na) {
+        p.bucket_lo = lo; p.nb_active = g.na;
+        if (g.na < g.nb) KPAL_RADIX_LAUNCH(1024, 4, true);
+        else if (g.threads == 512 && g.team == 4) KPAL_RADIX_LAUNCH(512, 4, false);
+        else if (g.threads == 512) KPAL_RADIX_LAUNCH(512, 8, false);
+        else if (g.team == 4) KPAL_RADIX_LAUNCH(1024, 4, false);
+        else KPAL_RADIX_LAUNCH(1024, 8, false);
+        KPAL_LAUNCH_CHECK("radix_partition_kernel");
+    }
 #undef KPAL_RADIX_LAUNCH
-    KPAL_LAUNCH_CHECK("radix_partition_kernel");
     KPAL_CUDA(cudaFuncSetAttribute(radix_histogram_kernel<CounterT>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem2)));
     radix_histogram_kernel<CounterT><<<g.nb, threads2, smem2, stream>>>(

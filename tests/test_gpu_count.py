@@ -388,8 +388,10 @@ def _dev_count(text_bytes, k, bits, balance):
     (12, 3_000_000, "ACG", 0),         # skew: some slots and regions overflow into the RED path
     (12, 2_000_000, "AC", 0),          # 32 of 512 buckets used: heavy overflow
     (12, 1_000_000, "A", 0),           # one bin: everything overflows
-    (13, 6_000_000, "ACGTacgt", 0),    # 2048 buckets
+    (13, 6_000_000, "ACGTacgt", 0),    # 2048 buckets: pass 1 runs twice, 1024 buckets each
     (13, 1_000_000, "AT", 0),
+    (14, 3_000_000, "ACGT", 0),        # 8192 buckets, 8 sweeps
+    (12, 2_000_000, "ACGT", 13),       # forced 2048 buckets at k = 12
     (11, 2_000_000, "ACGT", 0),
     (10, 2_000_000, "ACGT", 0),
     (9, 2_000_000, "ACGT", 0),
@@ -453,3 +455,17 @@ def test_tiled_balance_finalize_matches_plain(k):
             assert np.array_equal(plain, want)
     finally:
         _set_option("tiled_finalize", 1)
+
+
+def test_radix_count_path_k15():
+    """Largest supported k: 32768 buckets, 32 pass-1 sweeps (32-bit counters only: the
+    int64 result alone is 8 GiB)."""
+    k = 15
+    text = _composition_bytes(15, 1_500_000, "ACGT")
+    want = c_oracle.count_bytes(text, k, threads=c_oracle.max_threads())
+    try:
+        _set_option("count_path", 2)
+        got = _dev_count(text, k, 32, False)
+    finally:
+        _set_option("count_path", 0)
+    assert np.array_equal(got, want)
