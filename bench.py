@@ -295,6 +295,7 @@ def bench_count(args):
     _cabi.check(L.kpal_set_option(b"radix_payload_bits", args.radix_payload_bits))
     _cabi.check(L.kpal_set_option(b"radix_debug", args.radix_debug))
     _cabi.check(L.kpal_set_option(b"radix_shape", args.radix_shape))
+    _cabi.check(L.kpal_set_option(b"fasta_chunks", args.fasta_chunks))
     dev = torch.device("cuda", local)
 
     # ---- this rank's shard of records (same size on every rank: weak scaling)
@@ -587,6 +588,7 @@ def main():
     ap.add_argument("--radix-payload-bits", type=int, default=0)
     ap.add_argument("--radix-debug", type=int, default=0, help="timing experiments (results are wrong)")
     ap.add_argument("--radix-shape", type=int, default=0)
+    ap.add_argument("--fasta-chunks", type=int, default=0, help="chunks of the pipelined FASTA upload (0 = auto)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

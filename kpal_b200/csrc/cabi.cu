@@ -36,10 +36,15 @@ void set_radix_payload_bits(int bits);
 void set_radix_debug(int v);
 void set_radix_shape(int v);
 int launch_fasta_pack(const uint8_t *, uint64_t, uint32_t *, uint32_t *, void *, cudaStream_t);
+int launch_fasta_pack_begin(uint64_t, uint32_t *, uint32_t *, void *, cudaStream_t);
+int launch_fasta_pack_tiles(const uint8_t *, uint64_t, uint64_t, uint64_t, uint32_t *, uint32_t *, void *,
+                            cudaStream_t);
+uint64_t fasta_tile_bytes();
 
 static thread_local char t_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_host_fasta{-1};       // -1: from the environment (KPAL_HOST_FASTA=1)
+static std::atomic<int> g_fasta_chunks{0};      // 0 = automatic (one chunk per ~6 MB, at most 16)
 
 void set_error(const char *fmt, ...)
 {
@@ -102,6 +107,7 @@ struct PinBuf {
 // do not pay cudaMalloc / cudaMallocHost every time.  One call at a time.
 struct GrowDev {
     void *p = nullptr; size_t cap = 0;
+    unsigned char *as_bytes() const { return static_cast<unsigned char *>(p); }
     int ensure(size_t bytes)
     {
         if (bytes <= cap) return KPAL_OK;
@@ -138,6 +144,8 @@ struct CountWorkspace {
     int device = -1;
     GrowDev codes, valid, table, counts, text, fscratch;
     GrowPin pcodes, pvalid, pstatus;
+    cudaStream_t copy_stream = nullptr;          // H2D of the FASTA text, chunk by chunk
+    cudaEvent_t chunk_done[16] = {};
 };
 static std::mutex g_count_mutex;                 // held for the whole host-level call
 static std::vector<CountWorkspace *> g_count_ws;
@@ -284,6 +292,10 @@ extern "C" int kpal_set_option(const char *name, int value)
 {
     if (!name) return bad_arg("null option name");
     if (!strcmp(name, "host_fasta")) { g_host_fasta.store(value ? 1 : 0); return KPAL_OK; }
+    if (!strcmp(name, "fasta_chunks")) {
+        if (value < 0 || value > 16) return bad_arg("fasta_chunks must be 0 (auto) .. 16");
+        g_fasta_chunks.store(value); return KPAL_OK;
+    }
     if (!strcmp(name, "exact_div")) { set_exact_div(value != 0); return KPAL_OK; }
     if (!strcmp(name, "count_path")) {
         if (value < 0 || value > 2) return bad_arg("count_path must be 0 (auto), 1 (RED) or 2 (radix)");
@@ -446,10 +458,32 @@ static int fasta_gpu_count(CountWorkspace *w, const char *fasta, uint64_t n_byte
     KPAL_CHECK(w->valid.ensure(vw * 4));
     KPAL_CHECK(w->fscratch.ensure(fasta_scratch_bytes(n_bytes)));
     KPAL_CHECK(w->pstatus.ensure(sizeof(FastaStatus)));
-    KPAL_CUDA(cudaMemcpyAsync(w->text.p, fasta, n_bytes, cudaMemcpyHostToDevice, st));
-    KPAL_CHECK(launch_fasta_pack(static_cast<const uint8_t *>(w->text.p), n_bytes,
-                                 static_cast<uint32_t *>(w->codes.p),
-                                 static_cast<uint32_t *>(w->valid.p), w->fscratch.p, st));
+    // The text goes up in up to 16 chunks on a copy stream; the packer runs on the tiles of
+    // a chunk as soon as it has landed, so scan/pack hides behind the PCIe transfer.
+    uint32_t *d_codes = static_cast<uint32_t *>(w->codes.p), *d_valid = static_cast<uint32_t *>(w->valid.p);
+    const uint8_t *d_text = static_cast<const uint8_t *>(w->text.p);
+    KPAL_CHECK(launch_fasta_pack_begin(n_bytes, d_codes, d_valid, w->fscratch.p, st));
+    const uint64_t tile = fasta_tile_bytes();
+    uint64_t n_chunks = n_bytes / (6ull << 20);
+    n_chunks = std::min<uint64_t>(std::max<uint64_t>(n_chunks, 1), 16);
+    if (g_fasta_chunks.load() > 0) n_chunks = std::min<uint64_t>(uint64_t(g_fasta_chunks.load()), 16);
+    if (n_chunks > 1 && !w->copy_stream) {
+        KPAL_CUDA(cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
+        for (auto &e : w->chunk_done) KPAL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const uint64_t chunk = ((n_bytes + n_chunks - 1) / n_chunks + tile - 1) / tile * tile;
+    for (uint64_t c = 0, off = 0; off < n_bytes; ++c, off += chunk) {
+        const uint64_t len = std::min(chunk, n_bytes - off);
+        if (n_chunks > 1) {
+            KPAL_CUDA(cudaMemcpyAsync(w->text.as_bytes() + off, fasta + off, len, cudaMemcpyHostToDevice, w->copy_stream));
+            KPAL_CUDA(cudaEventRecord(w->chunk_done[c], w->copy_stream));
+            KPAL_CUDA(cudaStreamWaitEvent(st, w->chunk_done[c], 0));
+        } else {
+            KPAL_CUDA(cudaMemcpyAsync(w->text.as_bytes() + off, fasta + off, len, cudaMemcpyHostToDevice, st));
+        }
+        KPAL_CHECK(launch_fasta_pack_tiles(d_text, n_bytes, off / tile, (off + len + tile - 1) / tile, d_codes,
+                                           d_valid, w->fscratch.p, st));
+    }
     // n_bytes is an upper bound of the packed length; the tail is all-invalid padding
     KPAL_CHECK(launch_count(static_cast<uint32_t *>(w->codes.p), static_cast<uint32_t *>(w->valid.p),
                             n_bytes, k, d_table, bits, st));

@@ -39,6 +39,7 @@ struct FastaScratch {            // device scalars
     unsigned long long total_bases;
     unsigned int flags;                // bit 0: exotic whitespace seen on a sequence line
     unsigned int pad;
+    long long carry_last_nl;           // last newline before the next tile range (chunked packing)
 };
 
 __device__ __forceinline__ int64_t block_reduce_max(int64_t v, int64_t *smem)
@@ -67,11 +68,12 @@ __device__ __forceinline__ void load16(const uint8_t *text, uint64_t n, uint64_t
 
 // pass 1
 __global__ void __launch_bounds__(kTileThreads)
-fasta_newlines_kernel(const uint8_t *__restrict__ text, uint64_t n, int64_t *__restrict__ tile_last_nl,
-                      FastaScratch *__restrict__ sc)
+fasta_newlines_kernel(const uint8_t *__restrict__ text, uint64_t n, uint64_t tile0,
+                      int64_t *__restrict__ tile_last_nl, FastaScratch *__restrict__ sc)
 {
     __shared__ int64_t red[kTileThreads / 32];
-    const uint64_t pos = uint64_t(blockIdx.x) * kTileBytes + threadIdx.x * kBytesPerThread;
+    const uint64_t tile = tile0 + blockIdx.x;
+    const uint64_t pos = tile * kTileBytes + threadIdx.x * kBytesPerThread;
     uint8_t b[16];
     load16(text, n, pos, b);
     int64_t last = -1;
@@ -85,20 +87,27 @@ fasta_newlines_kernel(const uint8_t *__restrict__ text, uint64_t n, int64_t *__r
         }
         prev = b[i];
     }
-    if (first_hdr != ~0ull) atomicMin(&sc->first_header, first_hdr);
+    // first header of the file: one guarded atomic per tile (a read FASTA has a header every
+    // few lines; one atomicMin per header on a single address serialised the whole pass)
+    const int64_t fh = -block_reduce_max(first_hdr == ~0ull ? INT64_MIN + 1 : -int64_t(first_hdr), red);
     const int64_t m = block_reduce_max(last, red);
-    if (threadIdx.x == 0) tile_last_nl[blockIdx.x] = m;
+    if (threadIdx.x == 0) {
+        tile_last_nl[tile] = m;
+        if (fh != INT64_MAX && (unsigned long long)fh < *(volatile unsigned long long *)&sc->first_header)
+            atomicMin(&sc->first_header, (unsigned long long)fh);
+    }
 }
 
 // exclusive running max over the tiles (single CTA)
 __global__ void __launch_bounds__(1024)
-scan_max_kernel(const int64_t *__restrict__ in, int64_t *__restrict__ out, uint64_t n_tiles)
+scan_max_kernel(const int64_t *__restrict__ in, int64_t *__restrict__ out, uint64_t tile0,
+                uint64_t n_tiles, FastaScratch *__restrict__ sc)
 {
     __shared__ int64_t warp_max[32];
     __shared__ int64_t carry_s;
-    if (threadIdx.x == 0) carry_s = -1;
+    if (threadIdx.x == 0) carry_s = tile0 ? sc->carry_last_nl : -1;
     __syncthreads();
-    for (uint64_t base = 0; base < n_tiles; base += blockDim.x) {
+    for (uint64_t base = tile0; base < n_tiles; base += blockDim.x) {
         const uint64_t i = base + threadIdx.x;
         const int64_t v = i < n_tiles ? in[i] : -1;
         int64_t inc = v;                                   // inclusive scan in the warp
@@ -117,18 +126,19 @@ scan_max_kernel(const int64_t *__restrict__ in, int64_t *__restrict__ out, uint6
         if (threadIdx.x == blockDim.x - 1) carry_s = max(before, inc);
         __syncthreads();
     }
+    if (threadIdx.x == 0) sc->carry_last_nl = carry_s;
 }
 
 // exclusive running sum over the tiles (single CTA); also stores the total
 __global__ void __launch_bounds__(1024)
-scan_sum_kernel(const uint32_t *__restrict__ in, unsigned long long *__restrict__ out,
+scan_sum_kernel(const uint32_t *__restrict__ in, unsigned long long *__restrict__ out, uint64_t tile0,
                 uint64_t n_tiles, FastaScratch *__restrict__ sc)
 {
     __shared__ unsigned long long warp_sum[32];
     __shared__ unsigned long long carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
+    if (threadIdx.x == 0) carry_s = tile0 ? sc->total_bases : 0;
     __syncthreads();
-    for (uint64_t base = 0; base < n_tiles; base += blockDim.x) {
+    for (uint64_t base = tile0; base < n_tiles; base += blockDim.x) {
         const uint64_t i = base + threadIdx.x;
         const unsigned long long v = i < n_tiles ? in[i] : 0ull;
         unsigned long long inc = v;
@@ -227,13 +237,15 @@ __device__ __forceinline__ int64_t thread_prev_nl(const uint8_t *__restrict__ te
 
 // pass 2
 __global__ void __launch_bounds__(kTileThreads)
-fasta_count_kernel(const uint8_t *__restrict__ text, uint64_t n, const int64_t *__restrict__ tile_prev_nl,
-                   uint32_t *__restrict__ tile_count, FastaScratch *__restrict__ sc)
+fasta_count_kernel(const uint8_t *__restrict__ text, uint64_t n, uint64_t tile0,
+                   const int64_t *__restrict__ tile_prev_nl, uint32_t *__restrict__ tile_count,
+                   FastaScratch *__restrict__ sc)
 {
     __shared__ int64_t red[kTileThreads / 32];
     __shared__ uint32_t sums[kTileThreads / 32];
-    const uint64_t pos = uint64_t(blockIdx.x) * kTileBytes + threadIdx.x * kBytesPerThread;
-    const int64_t prev = thread_prev_nl(text, n, pos, tile_prev_nl[blockIdx.x], red);
+    const uint64_t tile = tile0 + blockIdx.x;
+    const uint64_t pos = tile * kTileBytes + threadIdx.x * kBytesPerThread;
+    const int64_t prev = thread_prev_nl(text, n, pos, tile_prev_nl[tile], red);
     uint32_t codes, valid;
     bool exotic = false;
     const uint32_t mask = classify16(text, n, pos, prev, sc->first_header, codes, valid, exotic);
@@ -245,20 +257,22 @@ fasta_count_kernel(const uint8_t *__restrict__ text, uint64_t n, const int64_t *
     if (threadIdx.x == 0) {
         uint32_t t = 0;
         for (int w = 0; w < kTileThreads / 32; ++w) t += sums[w];
-        tile_count[blockIdx.x] = t;
+        tile_count[tile] = t;
     }
 }
 
 // pass 3
 __global__ void __launch_bounds__(kTileThreads)
-fasta_write_kernel(const uint8_t *__restrict__ text, uint64_t n, const int64_t *__restrict__ tile_prev_nl,
+fasta_write_kernel(const uint8_t *__restrict__ text, uint64_t n, uint64_t tile0,
+                   const int64_t *__restrict__ tile_prev_nl,
                    const unsigned long long *__restrict__ tile_base, const FastaScratch *__restrict__ sc,
                    uint32_t *__restrict__ out_codes, uint32_t *__restrict__ out_valid)
 {
     __shared__ int64_t red[kTileThreads / 32];
     __shared__ uint32_t sums[kTileThreads / 32];
-    const uint64_t pos = uint64_t(blockIdx.x) * kTileBytes + threadIdx.x * kBytesPerThread;
-    const int64_t prev = thread_prev_nl(text, n, pos, tile_prev_nl[blockIdx.x], red);
+    const uint64_t tile = tile0 + blockIdx.x;
+    const uint64_t pos = tile * kTileBytes + threadIdx.x * kBytesPerThread;
+    const int64_t prev = thread_prev_nl(text, n, pos, tile_prev_nl[tile], red);
     uint32_t codes, valid;
     bool exotic = false;
     const uint32_t mask = classify16(text, n, pos, prev, sc->first_header, codes, valid, exotic);
@@ -273,7 +287,7 @@ fasta_write_kernel(const uint8_t *__restrict__ text, uint64_t n, const int64_t *
     uint32_t before = 0;
     for (unsigned w = 0; w < (threadIdx.x >> 5); ++w) before += sums[w];
     if (cnt == 0) return;
-    const uint64_t o = tile_base[blockIdx.x] + before + (inc - cnt);    // first output base of this thread
+    const uint64_t o = tile_base[tile] + before + (inc - cnt);    // first output base of this thread
     // codes: 32 bits (16 bases) left aligned, placed at base offset o
     {
         const uint64_t w = o / 16;
@@ -300,8 +314,9 @@ uint64_t fasta_scratch_bytes(uint64_t n_bytes)
     return 64 + tiles * (8 + 8 + 8 + 8);
 }
 
-int launch_fasta_pack(const uint8_t *d_text, uint64_t n_bytes, uint32_t *d_codes, uint32_t *d_valid,
-                      void *d_scratch, cudaStream_t stream)
+// Zero the outputs and the scalars: once per text, before the first tile range.
+int launch_fasta_pack_begin(uint64_t n_bytes, uint32_t *d_codes, uint32_t *d_valid, void *d_scratch,
+                            cudaStream_t stream)
 {
     // output capacity: one base per input byte (kpal_packed_words(n_bytes))
     uint64_t cw, vw;
@@ -311,27 +326,49 @@ int launch_fasta_pack(const uint8_t *d_text, uint64_t n_bytes, uint32_t *d_codes
     FastaScratch *sc = static_cast<FastaScratch *>(d_scratch);
     KPAL_CUDA(cudaMemsetAsync(sc, 0, sizeof(FastaScratch), stream));
     KPAL_CUDA(cudaMemsetAsync(sc, 0xff, sizeof(unsigned long long), stream));    // first_header = ~0
-    if (n_bytes == 0) return KPAL_OK;
+    return KPAL_OK;
+}
+
+uint64_t fasta_tile_bytes() { return kTileBytes; }
+
+// Pack the bytes of tiles [tile0, tile1) (tile = 4096 bytes).  Ranges must be submitted in
+// order on one stream; only bytes below tile1 * 4096 are read, so a range can run as soon
+// as its part of the text has arrived (the host-level entry points overlap the H2D copy of
+// chunk c+1 with the packing of chunk c this way).
+int launch_fasta_pack_tiles(const uint8_t *d_text, uint64_t n_bytes, uint64_t tile0, uint64_t tile1,
+                            uint32_t *d_codes, uint32_t *d_valid, void *d_scratch, cudaStream_t stream)
+{
     const uint64_t tiles = (n_bytes + kTileBytes - 1) / kTileBytes;
+    if (tile1 > tiles) tile1 = tiles;
+    if (tile0 >= tile1) return KPAL_OK;
     if (tiles > 0x7fffffffull) return bad_arg("FASTA text too large for one launch");
+    FastaScratch *sc = static_cast<FastaScratch *>(d_scratch);
     unsigned char *base = static_cast<unsigned char *>(d_scratch) + 64;
     int64_t *tile_last = reinterpret_cast<int64_t *>(base);
     int64_t *tile_prev = tile_last + tiles + 1;
     unsigned long long *tile_base = reinterpret_cast<unsigned long long *>(tile_prev + tiles + 1);
     uint32_t *tile_count = reinterpret_cast<uint32_t *>(tile_base + tiles + 1);
+    const unsigned grid = unsigned(tile1 - tile0);
 
-    fasta_newlines_kernel<<<unsigned(tiles), kTileThreads, 0, stream>>>(d_text, n_bytes, tile_last, sc);
+    fasta_newlines_kernel<<<grid, kTileThreads, 0, stream>>>(d_text, n_bytes, tile0, tile_last, sc);
     KPAL_LAUNCH_CHECK("fasta_newlines_kernel");
-    scan_max_kernel<<<1, 1024, 0, stream>>>(tile_last, tile_prev, tiles);
+    scan_max_kernel<<<1, 1024, 0, stream>>>(tile_last, tile_prev, tile0, tile1, sc);
     KPAL_LAUNCH_CHECK("scan_max_kernel");
-    fasta_count_kernel<<<unsigned(tiles), kTileThreads, 0, stream>>>(d_text, n_bytes, tile_prev, tile_count, sc);
+    fasta_count_kernel<<<grid, kTileThreads, 0, stream>>>(d_text, n_bytes, tile0, tile_prev, tile_count, sc);
     KPAL_LAUNCH_CHECK("fasta_count_kernel");
-    scan_sum_kernel<<<1, 1024, 0, stream>>>(tile_count, tile_base, tiles, sc);
+    scan_sum_kernel<<<1, 1024, 0, stream>>>(tile_count, tile_base, tile0, tile1, sc);
     KPAL_LAUNCH_CHECK("scan_sum_kernel");
-    fasta_write_kernel<<<unsigned(tiles), kTileThreads, 0, stream>>>(d_text, n_bytes, tile_prev, tile_base,
-                                                                    sc, d_codes, d_valid);
+    fasta_write_kernel<<<grid, kTileThreads, 0, stream>>>(d_text, n_bytes, tile0, tile_prev, tile_base,
+                                                          sc, d_codes, d_valid);
     KPAL_LAUNCH_CHECK("fasta_write_kernel");
     return KPAL_OK;
+}
+
+int launch_fasta_pack(const uint8_t *d_text, uint64_t n_bytes, uint32_t *d_codes, uint32_t *d_valid,
+                      void *d_scratch, cudaStream_t stream)
+{
+    KPAL_CHECK(launch_fasta_pack_begin(n_bytes, d_codes, d_valid, d_scratch, stream));
+    return launch_fasta_pack_tiles(d_text, n_bytes, 0, ~0ull, d_codes, d_valid, d_scratch, stream);
 }
 
 }  // namespace kpal

@@ -469,3 +469,22 @@ def test_radix_count_path_k15():
     finally:
         _set_option("count_path", 0)
     assert np.array_equal(got, want)
+
+
+def test_count_fasta_chunked_upload_pipeline(tutorial_texts):
+    """kpal_count_fasta uploads the text in chunks and packs every chunk as it lands; the
+    scans carry their state from chunk to chunk.  Any chunk count must give the same bits
+    (chunk boundaries fall inside headers, lines and records)."""
+    reads = random_reads(21, 4000, 150)
+    texts = [reads_to_fasta(reads).decode(), tutorial_texts["b_1"],
+             "leading junk\n" * 400 + ">late header\n" + "ACGTNacgt" * 3000 + "\n>x\n" + "G" * 9000,
+             ">only one long line\n" + "ACGGT" * 20000]
+    try:
+        for text in texts:
+            want = {k: ko.balance(ko.count_fasta(text, k)) for k in (3, 9)}
+            for chunks in (1, 2, 7, 16):
+                _set_option("fasta_chunks", chunks)
+                for k in (3, 9):
+                    assert np.array_equal(_cabi.count_fasta(text, k, balance=True), want[k]), (chunks, k)
+    finally:
+        _set_option("fasta_chunks", 0)
