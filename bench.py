@@ -187,6 +187,32 @@ def measured_peak(key, fallback):
         return fallback, "fallback (B200_PROFILING.md)"
 
 
+def measured_fp64_peak():
+    """FP64 FMA peak in TFLOP/s: MEASURED_PEAKS.json has no fp64 entry, so the denominator is
+    this repo's own DFMA microbenchmark on a B200 of this pool (kpal_b200/csrc/microbench.cu,
+    result committed in profiles/r01_microbench.jsonl), else the nominal figure."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_microbench.jsonl")) as f:
+            for line in f:
+                rec = json.loads(line)
+                if rec.get("bench") == "dfma":
+                    return float(rec["tflops"]), "measured DFMA microbenchmark (profiles/r01_microbench.jsonl)"
+    except Exception:
+        pass
+    return 2 * 64 * 148 * 1.965e9 / 1e12, "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz"
+
+
+def host_mem_available():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    return None
+
+
 def recorded_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu capture."""
     try:
@@ -493,12 +519,25 @@ def bench_matrix(args):
     out = torch.zeros((n, n), dtype=torch.float64, device=dev)
     slab = 256
     first_rows = None
+    # end-to-end leg: the same profile set as int64 rows in pinned host memory (the array
+    # kmer.distance_matrix hands to kpal_distance_matrix); bounded by the host's free RAM
+    n_e2e = n if (world == 1 and not args.no_e2e) else 0
+    if n_e2e:
+        avail = host_mem_available()
+        while n_e2e > 64 and avail is not None and n_e2e * d * 8 * 2.5 > avail:
+            n_e2e //= 2
+        host_profiles = _cabi.PinnedArray((n_e2e, d), np.int64)
+        host_out = _cabi.PinnedArray((n_e2e, n_e2e), np.float64)
+        h_t = torch.from_numpy(host_profiles.array)
     for r0 in range(0, n, slab):
         m = min(slab, n - r0)
         rates = lam[r0:r0 + m, None].expand(m, d).to(torch.float32)
         counts = torch.poisson(rates, generator=gen).to(torch.int64)
         if r0 == 0:
             first_rows = counts[:64].cpu().numpy()
+        if r0 < n_e2e:
+            mm = min(m, n_e2e - r0)
+            h_t[r0:r0 + mm].copy_(counts[:mm])
         _cabi.check(L.kpal_dev_profiles_prepare(
             counts.data_ptr(), m, k, 0, 1, F[r0].data_ptr(), R[r0].data_ptr(),
             bitmap[r0].data_ptr(), totals[r0:].data_ptr(), norm2[r0:].data_ptr(), sp))
@@ -536,10 +575,38 @@ def bench_matrix(args):
     step_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs) / args.steps, world)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- end to end through the host-buffer C ABI (every rank on its own replica of the
+    # call at N>1 would only repeat rank 0: measured on rank 0 at N=1)
+    e2e = None
+    got = out[:64, :64].cpu().numpy() if rank == 0 else None
+    if world == 1 and n_e2e:
+        check_block = out[:64, :64].clone()
+        del F, R, bitmap, out
+        torch.cuda.empty_cache()
+
+        def e2e_step():
+            _cabi.check(L.kpal_distance_matrix(host_profiles._ptr, n_e2e, k, 0, 0, 0, 1, 0, host_out._ptr))
+        e2e_step()
+        e2e_steps = max(1, min(args.steps, 2))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        e2e_pairs = n_e2e * (n_e2e - 1) // 2
+        e2e_ok = None
+        if n_e2e == n:
+            a, b = host_out.array[:64, :64], check_block.cpu().numpy()
+            e2e_ok = bool(np.allclose(a, b, rtol=1e-12, atol=0))
+        e2e = {"value": e2e_pairs / e2e_s, "unit": "profile-pairs/s",
+               "h2d_bytes_per_step": int(n_e2e * d * 8), "d2h_bytes_per_step": int(n_e2e * n_e2e * 8),
+               "ms_per_step": e2e_s * 1e3, "profiles": n_e2e, "steps": e2e_steps,
+               "matches_device_result": e2e_ok,
+               "path": "pinned int64 profiles -> kpal_distance_matrix (H2D in 1 GiB slabs, prepare, order, "
+                       "tile kernel, D2H of the N x N float64 matrix)"}
+
     if rank == 0:
         pairs = n * (n - 1) // 2
         from oracle import c_oracle
-        got = out[:64, :64].cpu().numpy()
         t0 = time.perf_counter()
         want = c_oracle.distance_matrix(first_rows[:24], do_scale=True, threads=c_oracle.max_threads())
         cpu_s = time.perf_counter() - t0
@@ -547,7 +614,7 @@ def bench_matrix(args):
         rel = float(np.max(np.abs(got[:24, :24][low] - want[low]) / np.abs(want[low])))
         # per-GPU roofline: rank 0's share of the tiles (the tile kernel is >99 % of the step)
         flops = 8.0 * d * pairs * (t_end - t_begin) / max(tiles, 1)
-        peak_tf = 2 * 64 * 148 * 1.965e9 / 1e12          # nominal DFMA peak (no measured fp64 figure)
+        peak_tf, peak_src = measured_fp64_peak()
         achieved_tf = flops / (step_ms * 1e-3) / 1e12
         print(json.dumps({
             "metric": "profile_pairs_per_sec_k10_multiset", "value": pairs / (step_ms * 1e-3),
@@ -561,7 +628,8 @@ def bench_matrix(args):
             "roofline": {"bound": "fp64", "kernel": "distance_tile_kernel<prod>",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf, "traffic": recorded_traffic("distance_tile_kernel"),
-                         "flops_per_element_pair": 8, "peak_source": "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz"},
+                         "flops_per_element_pair": 8, "peak_source": peak_src},
+            "e2e": e2e,
             "cpu_baseline": {"value": 276 / cpu_s, "unit": "profile-pairs/s",
                              "cores": c_oracle.max_threads(), "kind": "port",
                              "sample": "leading 24 profiles (276 pairs), C port, OpenMP"},
@@ -588,6 +656,7 @@ def main():
     ap.add_argument("--radix-payload-bits", type=int, default=0)
     ap.add_argument("--radix-debug", type=int, default=0, help="timing experiments (results are wrong)")
     ap.add_argument("--radix-shape", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true", help="matrix workload: skip the host-buffer end-to-end leg")
     ap.add_argument("--fasta-chunks", type=int, default=0, help="chunks of the pipelined FASTA upload (0 = auto)")
     args = ap.parse_args()
     if args.impl == "reference":
