@@ -148,10 +148,67 @@ int kpal_distance_matrix(const int64_t *profiles, uint64_t n_profiles, int k,
                          int metric, int pairwise, int do_balance, int do_scale, int down,
                          double *out);
 
+/*
+ * The same matrix with the profile set handed over in slabs, replacing the
+ * load-everything loop of kpal/kmer.py:694-698 (a list of N Profile objects,
+ * 34 GB at N = 4096, k = 10): open a session for n_profiles, push the profiles
+ * in order in any number of calls (rows is row-major [m][4^k] int64, ideally
+ * in kpal_host_alloc memory; it may be reused as soon as push returns -- the
+ * upload of one slab overlaps the preparation of the previous one), then
+ * finish, which runs the distance kernels and fills out[n][n] as above.
+ * A session belongs to the device current at open and to one thread at a time.
+ */
+int  kpal_matrix_open(uint64_t n_profiles, int k, int metric, int pairwise, int do_balance,
+                      int do_scale, int down, void **session);
+int  kpal_matrix_push(void *session, const int64_t *rows, uint64_t m);
+int  kpal_matrix_finish(void *session, double *out);
+void kpal_matrix_close(void *session);
+
+/*
+ * Replaces the text loop of kdistlib.distance_matrix (kpal/kdistlib.py:179-186):
+ * rows i = 1 .. n-1 of the lower triangle of values (row-major, leading
+ * dimension ld >= n), every value as Python's '{0:.{precision}f}', separated
+ * by one space, one '\n' per row.  Host only (multi-threaded C++), no GPU.
+ * *length receives the text length; when it exceeds capacity (or text is NULL)
+ * nothing is written and KPAL_EOVERFLOW is returned, so a caller can size the
+ * buffer with a first call.
+ */
+int kpal_format_matrix(const double *values, uint64_t n, uint64_t ld, int precision,
+                       char *text, uint64_t capacity, uint64_t *length);
+
 /* ProfileDistance.distance for one pair (kpal/kdistlib.py:126-161). */
 int kpal_pair_distance(const int64_t *left, const int64_t *right, int k,
                        int metric, int pairwise, int do_balance, int do_scale, int down,
                        double *out);
+
+/*
+ * ProfileDistance.distance with do_positive (kpal/kdistlib.py:139-157): after the
+ * optional balance, both profiles keep only the positions that are non-zero
+ * in both (metrics.positive, kpal/metrics.py:89-98); the scale factors then
+ * come from the MASKED totals, which makes them pair-dependent -- hence a pair
+ * entry point and no matrix form.
+ */
+int kpal_pair_distance_positive(const int64_t *left, const int64_t *right, int k,
+                                int metric, int pairwise, int do_balance, int do_scale, int down,
+                                double *out);
+
+/* ------------------------------------- split / showbalance: host API
+ *
+ * Replaces Profile.split (kpal/klib.py:300-327): forward / reverse receive
+ * kpal_split_length(k) = (4^k + #palindromes) / 2 entries each -- for every
+ * index i <= rc(i), in index order, (2 c[i], 2 c[rc(i)]), or (c[i], c[i]) when
+ * i is its own reverse complement.
+ */
+uint64_t kpal_split_length(int k);
+int kpal_split(const int64_t *counts, int k, int64_t *forward, int64_t *reverse);
+
+/*
+ * The figure kmer.get_balance prints (kpal/kmer.py:240-245):
+ * metrics.multiset(forward, reverse, pairwise['prod']) of the two split lists,
+ * computed in one pass without materialising them, in the reference's
+ * arithmetic (int64 numerator / denominator, one IEEE division per term).
+ */
+int kpal_show_balance(const int64_t *counts, int k, double *out);
 
 /* ---------------------------------------------------- counting: device API
  * (bench harness, multi-GPU sharding: every pointer is a device pointer)    */

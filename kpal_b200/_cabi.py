@@ -28,6 +28,9 @@ SYMBOLS = (
     "kpal_packed_words", "kpal_pack_sequences", "kpal_fasta_scan", "kpal_fasta_pack",
     "kpal_count_sequences", "kpal_count_fasta", "kpal_count_by_record", "kpal_balance",
     "kpal_distance_matrix", "kpal_pair_distance",
+    "kpal_matrix_open", "kpal_matrix_push", "kpal_matrix_finish", "kpal_matrix_close",
+    "kpal_format_matrix", "kpal_pair_distance_positive",
+    "kpal_split_length", "kpal_split", "kpal_show_balance",
     "kpal_dev_count_packed", "kpal_count_fasta_to_dev", "kpal_dev_finalize_counts", "kpal_dev_balance",
     "kpal_dev_count_by_record", "kpal_prepared_stride", "kpal_dev_profiles_prepare",
     "kpal_dev_order_by_total", "kpal_distance_num_tiles", "kpal_dev_distance_tiles",
@@ -83,6 +86,15 @@ def load():
     sig("kpal_balance", i32, vp, i32)
     sig("kpal_distance_matrix", i32, vp, u64, i32, i32, i32, i32, i32, i32, vp)
     sig("kpal_pair_distance", i32, vp, vp, i32, i32, i32, i32, i32, i32, vp)
+    sig("kpal_matrix_open", i32, u64, i32, i32, i32, i32, i32, i32, c.POINTER(vp))
+    sig("kpal_matrix_push", i32, vp, vp, u64)
+    sig("kpal_matrix_finish", i32, vp, vp)
+    sig("kpal_matrix_close", None, vp)
+    sig("kpal_format_matrix", i32, vp, u64, u64, i32, vp, u64, pu64)
+    sig("kpal_pair_distance_positive", i32, vp, vp, i32, i32, i32, i32, i32, i32, vp)
+    sig("kpal_split_length", u64, i32)
+    sig("kpal_split", i32, vp, i32, vp, vp)
+    sig("kpal_show_balance", i32, vp, i32, vp)
     sig("kpal_dev_count_packed", i32, vp, vp, u64, i32, vp, i32, vp)
     sig("kpal_count_fasta_to_dev", i32, vp, u64, i32, vp, i32, vp, pu64)
     sig("kpal_dev_finalize_counts", i32, vp, i32, i32, i32, vp, vp)
@@ -280,8 +292,115 @@ def distance_matrix(profiles, metric="multiset", pairwise="prod", do_balance=Fal
     return out
 
 
+class MatrixSession(object):
+    """Distance matrix over profiles handed over in slabs (kpal_matrix_open /
+    push / finish): the caller never holds the whole ``[n][4**k]`` set.
+
+    ``slab`` is a pinned ``[rows][4**k]`` int64 staging array owned by the
+    session: fill ``slab[:m]`` (for instance ``dataset.read_direct(slab[i])``)
+    and call ``push(m)``; or ``push_rows(array)`` for rows held elsewhere."""
+
+    def __init__(self, n, k, metric="multiset", pairwise="prod", do_balance=False,
+                 do_scale=False, down=False, slab_bytes=256 << 20):
+        L = load()
+        require_gpu()
+        _check_k(k)
+        self.n, self.k = int(n), int(k)
+        self._handle = ctypes.c_void_p()
+        check(L.kpal_matrix_open(self.n, self.k, METRICS[metric], PAIRWISE[pairwise],
+                                 int(bool(do_balance)), int(bool(do_scale)), int(bool(down)),
+                                 ctypes.byref(self._handle)))
+        rows = max(1, min(self.n, slab_bytes // (8 * 4 ** self.k)))
+        self._pinned = PinnedArray((rows, 4 ** self.k), np.int64)
+        self.slab = self._pinned.array
+
+    def push(self, m):
+        """Upload the first `m` rows of ``self.slab``."""
+        check(load().kpal_matrix_push(self._handle, self._pinned._ptr, int(m)))
+
+    def push_rows(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        if rows.ndim != 2 or rows.shape[1] != 4 ** self.k:
+            raise ValueError("rows must be [m][4**k]")
+        check(load().kpal_matrix_push(self._handle, ptr(rows), rows.shape[0]))
+
+    def finish(self):
+        """Run the distance kernels; symmetric ``[n][n]`` float64 result."""
+        out = np.empty((self.n, self.n), dtype=np.float64)
+        check(load().kpal_matrix_finish(self._handle, ptr(out)))
+        return out
+
+    def close(self):
+        if self._handle:
+            load().kpal_matrix_close(self._handle)
+            self._handle = ctypes.c_void_p()
+        if self._pinned is not None:
+            self.slab = None
+            self._pinned.free()
+            self._pinned = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def format_matrix(values, precision):
+    """Lower triangle of a square float64 matrix as the text rows of
+    kdistlib.distance_matrix (kpal_format_matrix; host C++, no GPU needed)."""
+    L = load()
+    values = np.asarray(values, dtype=np.float64)
+    if values.ndim != 2 or values.shape[0] != values.shape[1]:
+        raise ValueError("values must be a square matrix")
+    if values.strides[1] != 8 or values.strides[0] % 8 or values.strides[0] < 8 * values.shape[1]:
+        values = np.ascontiguousarray(values)
+    n, ld = values.shape[0], values.strides[0] // 8 if values.shape[0] > 1 else values.shape[1]
+    cells = n * (n - 1) // 2
+    capacity = cells * (int(precision) + 12) + n + 16
+    length = ctypes.c_uint64()
+    for _ in range(2):
+        buf = ctypes.create_string_buffer(capacity)
+        code = L.kpal_format_matrix(ptr(values), n, ld, int(precision), buf, capacity,
+                                    ctypes.byref(length))
+        if code != KPAL_EOVERFLOW:
+            break
+        capacity = length.value + 1
+    check(code)
+    return buf.raw[:length.value].decode("ascii")
+
+
+def split(counts):
+    """Profile.split on the device: (forward, reverse) int64 arrays."""
+    L = load()
+    require_gpu()
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    k = _k_of(counts.size)
+    half = int(L.kpal_split_length(k))
+    forward = np.empty(half, dtype=np.int64)
+    reverse = np.empty(half, dtype=np.int64)
+    check(L.kpal_split(ptr(counts), k, ptr(forward), ptr(reverse)))
+    return forward, reverse
+
+
+def show_balance(counts):
+    """multiset/prod distance between the two halves of Profile.split."""
+    L = load()
+    require_gpu()
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    out = ctypes.c_double()
+    check(L.kpal_show_balance(ptr(counts), _k_of(counts.size), ctypes.byref(out)))
+    return out.value
+
+
 def pair_distance(left, right, metric="multiset", pairwise="prod", do_balance=False,
-                  do_scale=False, down=False):
+                  do_scale=False, down=False, do_positive=False):
     L = load()
     require_gpu()
     left = np.ascontiguousarray(left, dtype=np.int64)
@@ -290,9 +409,9 @@ def pair_distance(left, right, metric="multiset", pairwise="prod", do_balance=Fa
         raise ValueError("profiles must be 1-D and of equal length")
     k = _k_of(left.size)
     out = ctypes.c_double()
-    check(L.kpal_pair_distance(ptr(left), ptr(right), k, METRICS[metric], PAIRWISE[pairwise],
-                               int(bool(do_balance)), int(bool(do_scale)), int(bool(down)),
-                               ctypes.byref(out)))
+    entry = L.kpal_pair_distance_positive if do_positive else L.kpal_pair_distance
+    check(entry(ptr(left), ptr(right), k, METRICS[metric], PAIRWISE[pairwise],
+                int(bool(do_balance)), int(bool(do_scale)), int(bool(down)), ctypes.byref(out)))
     return out.value
 
 

@@ -40,6 +40,11 @@ int launch_fasta_pack_begin(uint64_t, uint32_t *, uint32_t *, void *, cudaStream
 int launch_fasta_pack_tiles(const uint8_t *, uint64_t, uint64_t, uint64_t, uint32_t *, uint32_t *, void *,
                             cudaStream_t);
 uint64_t fasta_tile_bytes();
+uint64_t split_length(int k);
+uint64_t split_scratch_bytes(int k);
+int launch_split(const int64_t *, int, int64_t *, int64_t *, void *, cudaStream_t);
+int launch_show_balance(const int64_t *, int, double *, unsigned long long *, cudaStream_t);
+int launch_positive_pair(int64_t *, int64_t *, int, cudaStream_t);
 
 static thread_local char t_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
@@ -667,51 +672,154 @@ extern "C" int kpal_dev_distance_tiles(const double *d_F, const double *d_R, con
 }
 
 // ----------------------------------------------------- distances: host API
+// A matrix session takes the profile set in slabs (kpal_matrix_push) so the caller never
+// has to hold all N x 4^k int64 counts in host memory the way kpal/kmer.py:694-698 does:
+// every pushed slab is uploaded into one of two device slabs on a copy stream and turned
+// into the prepared fp64 arrays on the compute stream while the next slab uploads.
+namespace kpal {
+struct MatrixSession {
+    int device = 0;
+    uint64_t n = 0, d = 0, stride = 0, slab_rows = 0, pushed = 0;
+    int k = 0, metric = 0, pairwise = 0, do_balance = 0, do_scale = 0, down = 0;
+    bool need_r = false;
+    int cur = 0;
+    DevBuf F, R, bitmap, totals, norm2, order, tot_i64, slab[2], d_out;
+    cudaStream_t copy = nullptr, compute = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, prepared[2] = {nullptr, nullptr};
+    ~MatrixSession()
+    {
+        for (int i = 0; i < 2; ++i) {
+            if (copied[i]) cudaEventDestroy(copied[i]);
+            if (prepared[i]) cudaEventDestroy(prepared[i]);
+        }
+        if (copy) cudaStreamDestroy(copy);
+        if (compute) cudaStreamDestroy(compute);
+    }
+};
+}  // namespace kpal
+
+static int matrix_open(MatrixSession *s)
+{
+    KPAL_CUDA(cudaGetDevice(&s->device));
+    s->d = 1ull << (2 * s->k);
+    s->stride = prepared_stride_host(s->k);
+    s->need_r = (s->metric == KPAL_METRIC_MULTISET && s->pairwise == KPAL_PAIRWISE_PROD);
+    const uint64_t n = s->n;
+    KPAL_CHECK(s->F.alloc(n * s->stride * 8));
+    if (s->need_r) KPAL_CHECK(s->R.alloc(n * s->stride * 8));
+    KPAL_CHECK(s->bitmap.alloc(n * (s->stride / 32) * 4));
+    KPAL_CHECK(s->totals.alloc(n * 8));
+    KPAL_CHECK(s->norm2.alloc(n * 8));
+    KPAL_CHECK(s->order.alloc(n * 4));
+    KPAL_CHECK(s->d_out.alloc(n * n * 8));
+    // raw int64 profiles pass through two bounded slabs (<= 512 MiB each)
+    s->slab_rows = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(n, 65535), (512ull << 20) / (s->d * 8)));
+    for (int i = 0; i < 2; ++i) KPAL_CHECK(s->slab[i].alloc(s->slab_rows * s->d * 8));
+    KPAL_CHECK(s->tot_i64.alloc(s->slab_rows * 8));
+    KPAL_CUDA(cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking));
+    KPAL_CUDA(cudaStreamCreateWithFlags(&s->compute, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        KPAL_CUDA(cudaEventCreateWithFlags(&s->copied[i], cudaEventDisableTiming));
+        KPAL_CUDA(cudaEventCreateWithFlags(&s->prepared[i], cudaEventDisableTiming));
+        KPAL_CUDA(cudaEventRecord(s->prepared[i], s->compute));
+    }
+    return KPAL_OK;
+}
+
+static int matrix_push(MatrixSession *s, const int64_t *rows, uint64_t m)
+{
+    if (s->pushed + m > s->n) return bad_arg("more profiles pushed than the session was opened for");
+    for (uint64_t r = 0; r < m; r += s->slab_rows) {
+        const uint64_t c = std::min(s->slab_rows, m - r), at = s->pushed;
+        const int b = s->cur;
+        KPAL_CUDA(cudaStreamWaitEvent(s->copy, s->prepared[b], 0));       // slab b is free again
+        KPAL_CUDA(cudaMemcpyAsync(s->slab[b].p, rows + r * s->d, c * s->d * 8, cudaMemcpyHostToDevice, s->copy));
+        KPAL_CUDA(cudaEventRecord(s->copied[b], s->copy));
+        KPAL_CUDA(cudaStreamWaitEvent(s->compute, s->copied[b], 0));
+        KPAL_CHECK(launch_prepare(s->slab[b].as<int64_t>(), c, s->k, s->do_balance, s->do_scale,
+                                  s->F.as<double>() + at * s->stride,
+                                  s->need_r ? s->R.as<double>() + at * s->stride : nullptr,
+                                  s->bitmap.as<uint32_t>() + at * (s->stride / 32),
+                                  s->totals.as<double>() + at, s->norm2.as<double>() + at,
+                                  s->tot_i64.as<unsigned long long>(), s->compute));
+        KPAL_CUDA(cudaEventRecord(s->prepared[b], s->compute));
+        s->pushed += c;
+        s->cur ^= 1;
+    }
+    // the caller may reuse `rows` as soon as this returns
+    KPAL_CUDA(cudaStreamSynchronize(s->copy));
+    return KPAL_OK;
+}
+
+static int matrix_finish(MatrixSession *s, double *out)
+{
+    if (s->pushed != s->n) return bad_arg("fewer profiles pushed than the session was opened for");
+    const uint64_t n = s->n;
+    cudaStream_t st = s->compute;
+    const int32_t *d_order = nullptr;
+    if (s->do_scale) {
+        KPAL_CHECK(make_order(s->totals.as<double>(), n, s->down, s->order.as<int32_t>(), st));
+        d_order = s->order.as<int32_t>();
+    }
+    double *acc; uint32_t *cnt;
+    KPAL_CHECK(get_dist_scratch(n, &acc, &cnt));
+    KPAL_CHECK(launch_distance_tiles(s->F.as<double>(), s->R.as<double>(), s->bitmap.as<uint32_t>(),
+                                     s->totals.as<double>(), s->norm2.as<double>(), d_order, n, s->k,
+                                     s->metric, s->pairwise, s->do_scale, s->down, 0,
+                                     distance_num_tiles(n), acc, cnt, s->d_out.as<double>(), st));
+    KPAL_CUDA(cudaMemcpyAsync(out, s->d_out.p, n * n * 8, cudaMemcpyDeviceToHost, st));
+    KPAL_CUDA(cudaStreamSynchronize(st));
+    return KPAL_OK;
+}
+
+extern "C" int kpal_matrix_open(uint64_t n, int k, int metric, int pairwise, int do_balance,
+                                int do_scale, int down, void **session)
+{
+    if (!session) return bad_arg("null pointer");
+    *session = nullptr;
+    if (n < 1) return bad_arg("need at least one profile");
+    if (k < 1 || k > KPAL_MAX_K) { set_error("k-mer length %d out of range [1, %d]", k, KPAL_MAX_K); return KPAL_EINVAL; }
+    if (metric < 0 || metric > KPAL_METRIC_COSINE || pairwise < 0 || pairwise > KPAL_PAIRWISE_SUM)
+        return bad_arg("unknown metric / pairwise selector");
+    KPAL_CHECK(require_device());
+    MatrixSession *s = new MatrixSession();
+    s->n = n; s->k = k; s->metric = metric; s->pairwise = pairwise;
+    s->do_balance = do_balance; s->do_scale = do_scale; s->down = down;
+    const int r = matrix_open(s);
+    if (r != KPAL_OK) { delete s; return r; }
+    *session = s;
+    return KPAL_OK;
+}
+
+extern "C" int kpal_matrix_push(void *session, const int64_t *rows, uint64_t m)
+{
+    if (!session) return bad_arg("null session");
+    if (m == 0) return KPAL_OK;
+    if (!rows) return bad_arg("null pointer");
+    return matrix_push(static_cast<MatrixSession *>(session), rows, m);
+}
+
+extern "C" int kpal_matrix_finish(void *session, double *out)
+{
+    if (!session || !out) return bad_arg("null pointer");
+    return matrix_finish(static_cast<MatrixSession *>(session), out);
+}
+
+extern "C" void kpal_matrix_close(void *session)
+{
+    delete static_cast<MatrixSession *>(session);
+}
+
 extern "C" int kpal_distance_matrix(const int64_t *profiles, uint64_t n, int k, int metric,
                                     int pairwise, int do_balance, int do_scale, int down, double *out)
 {
     if (!profiles || !out) return bad_arg("null pointer");
-    if (n < 1) return bad_arg("need at least one profile");
-    if (k < 1 || k > KPAL_MAX_K) { set_error("k-mer length %d out of range [1, %d]", k, KPAL_MAX_K); return KPAL_EINVAL; }
-    KPAL_CHECK(require_device());
-    const uint64_t d = 1ull << (2 * k), stride = prepared_stride_host(k);
-    const bool need_r = (metric == KPAL_METRIC_MULTISET && pairwise == KPAL_PAIRWISE_PROD);
-    DevBuf F, R, bitmap, totals, norm2, order, tot_i64, slab, d_out;
-    KPAL_CHECK(F.alloc(n * stride * 8));
-    if (need_r) KPAL_CHECK(R.alloc(n * stride * 8));
-    KPAL_CHECK(bitmap.alloc(n * (stride / 32) * 4));
-    KPAL_CHECK(totals.alloc(n * 8));
-    KPAL_CHECK(norm2.alloc(n * 8));
-    KPAL_CHECK(order.alloc(n * 4));
-    KPAL_CHECK(d_out.alloc(n * n * 8));
-    // raw int64 profiles go through a bounded slab (<= 1 GiB) instead of living on the device
-    const uint64_t slab_rows = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(n, 65535), (1ull << 30) / (d * 8)));
-    KPAL_CHECK(slab.alloc(slab_rows * d * 8));
-    KPAL_CHECK(tot_i64.alloc(slab_rows * 8));
-    cudaStream_t st = 0;
-    for (uint64_t r = 0; r < n; r += slab_rows) {
-        const uint64_t m = std::min(slab_rows, n - r);
-        KPAL_CUDA(cudaMemcpyAsync(slab.p, profiles + r * d, m * d * 8, cudaMemcpyHostToDevice, st));
-        KPAL_CHECK(launch_prepare(slab.as<int64_t>(), m, k, do_balance, do_scale,
-                                  F.as<double>() + r * stride,
-                                  need_r ? R.as<double>() + r * stride : nullptr,
-                                  bitmap.as<uint32_t>() + r * (stride / 32), totals.as<double>() + r,
-                                  norm2.as<double>() + r, tot_i64.as<unsigned long long>(), st));
-    }
-    const int32_t *d_order = nullptr;
-    if (do_scale) {
-        KPAL_CHECK(make_order(totals.as<double>(), n, down, order.as<int32_t>(), st));
-        d_order = order.as<int32_t>();
-    }
-    double *acc; uint32_t *cnt;
-    KPAL_CHECK(get_dist_scratch(n, &acc, &cnt));
-    KPAL_CHECK(launch_distance_tiles(F.as<double>(), R.as<double>(), bitmap.as<uint32_t>(),
-                                     totals.as<double>(), norm2.as<double>(), d_order, n, k, metric,
-                                     pairwise, do_scale, down, 0, distance_num_tiles(n), acc, cnt,
-                                     d_out.as<double>(), st));
-    KPAL_CUDA(cudaMemcpyAsync(out, d_out.p, n * n * 8, cudaMemcpyDeviceToHost, st));
-    KPAL_CUDA(cudaStreamSynchronize(st));
-    return KPAL_OK;
+    void *session = nullptr;
+    KPAL_CHECK(kpal_matrix_open(n, k, metric, pairwise, do_balance, do_scale, down, &session));
+    int r = kpal_matrix_push(session, profiles, n);
+    if (r == KPAL_OK) r = kpal_matrix_finish(session, out);
+    kpal_matrix_close(session);
+    return r;
 }
 
 extern "C" int kpal_pair_distance(const int64_t *left, const int64_t *right, int k, int metric,
@@ -720,11 +828,115 @@ extern "C" int kpal_pair_distance(const int64_t *left, const int64_t *right, int
     if (!left || !right || !out) return bad_arg("null pointer");
     if (k < 1 || k > KPAL_MAX_K) { set_error("k-mer length %d out of range [1, %d]", k, KPAL_MAX_K); return KPAL_EINVAL; }
     const uint64_t d = 1ull << (2 * k);
-    std::vector<int64_t> both(2 * d);
-    memcpy(both.data(), left, d * 8);
-    memcpy(both.data() + d, right, d * 8);
+    void *session = nullptr;
+    KPAL_CHECK(kpal_matrix_open(2, k, metric, pairwise, do_balance, do_scale, down, &session));
     double m[4];
-    KPAL_CHECK(kpal_distance_matrix(both.data(), 2, k, metric, pairwise, do_balance, do_scale, down, m));
+    int r = kpal_matrix_push(session, left, 1);
+    if (r == KPAL_OK) r = kpal_matrix_push(session, right, 1);
+    if (r == KPAL_OK) r = kpal_matrix_finish(session, m);
+    kpal_matrix_close(session);
+    (void)d;
+    if (r == KPAL_OK) *out = m[1];
+    return r;
+}
+
+// ProfileDistance.distance with do_positive (kpal/kdistlib.py:139-157): balance, then the
+// pair-dependent mask, then scale factors from the MASKED totals, then the metric.
+extern "C" int kpal_pair_distance_positive(const int64_t *left, const int64_t *right, int k,
+                                           int metric, int pairwise, int do_balance, int do_scale,
+                                           int down, double *out)
+{
+    if (!left || !right || !out) return bad_arg("null pointer");
+    if (k < 1 || k > KPAL_MAX_K) { set_error("k-mer length %d out of range [1, %d]", k, KPAL_MAX_K); return KPAL_EINVAL; }
+    if (metric < 0 || metric > KPAL_METRIC_COSINE || pairwise < 0 || pairwise > KPAL_PAIRWISE_SUM)
+        return bad_arg("unknown metric / pairwise selector");
+    KPAL_CHECK(require_device());
+    const uint64_t d = 1ull << (2 * k), stride = prepared_stride_host(k);
+    const bool need_r = (metric == KPAL_METRIC_MULTISET && pairwise == KPAL_PAIRWISE_PROD);
+    DevBuf raw, work, F, R, bitmap, totals, norm2, order, tot_i64, d_out;
+    KPAL_CHECK(raw.alloc(2 * d * 8));
+    KPAL_CHECK(work.alloc(2 * d * 8));
+    KPAL_CHECK(F.alloc(2 * stride * 8));
+    if (need_r) KPAL_CHECK(R.alloc(2 * stride * 8));
+    KPAL_CHECK(bitmap.alloc(2 * (stride / 32) * 4));
+    KPAL_CHECK(totals.alloc(16));
+    KPAL_CHECK(norm2.alloc(16));
+    KPAL_CHECK(order.alloc(8));
+    KPAL_CHECK(tot_i64.alloc(16));
+    KPAL_CHECK(d_out.alloc(4 * 8));
+    cudaStream_t st = 0;
+    KPAL_CUDA(cudaMemcpyAsync(raw.p, left, d * 8, cudaMemcpyHostToDevice, st));
+    KPAL_CUDA(cudaMemcpyAsync(raw.as<int64_t>() + d, right, d * 8, cudaMemcpyHostToDevice, st));
+    int64_t *pair = raw.as<int64_t>();
+    if (do_balance) {
+        KPAL_CHECK(launch_balance(raw.as<int64_t>(), work.as<int64_t>(), k, st));
+        KPAL_CHECK(launch_balance(raw.as<int64_t>() + d, work.as<int64_t>() + d, k, st));
+        pair = work.as<int64_t>();
+    }
+    KPAL_CHECK(launch_positive_pair(pair, pair + d, k, st));
+    KPAL_CHECK(launch_prepare(pair, 2, k, 0, do_scale, F.as<double>(), need_r ? R.as<double>() : nullptr,
+                              bitmap.as<uint32_t>(), totals.as<double>(), norm2.as<double>(),
+                              tot_i64.as<unsigned long long>(), st));
+    const int32_t *d_order = nullptr;
+    if (do_scale) {
+        KPAL_CHECK(make_order(totals.as<double>(), 2, down, order.as<int32_t>(), st));
+        d_order = order.as<int32_t>();
+    }
+    double *acc; uint32_t *cnt;
+    KPAL_CHECK(get_dist_scratch(2, &acc, &cnt));
+    KPAL_CHECK(launch_distance_tiles(F.as<double>(), R.as<double>(), bitmap.as<uint32_t>(),
+                                     totals.as<double>(), norm2.as<double>(), d_order, 2, k, metric,
+                                     pairwise, do_scale, down, 0, distance_num_tiles(2), acc, cnt,
+                                     d_out.as<double>(), st));
+    double m[4];
+    KPAL_CUDA(cudaMemcpyAsync(m, d_out.p, 32, cudaMemcpyDeviceToHost, st));
+    KPAL_CUDA(cudaStreamSynchronize(st));
     *out = m[1];
+    return KPAL_OK;
+}
+
+// ------------------------------------------------ split / showbalance: host API
+extern "C" uint64_t kpal_split_length(int k)
+{
+    return (k < 1 || k > KPAL_MAX_K) ? 0 : split_length(k);
+}
+
+extern "C" int kpal_split(const int64_t *counts, int k, int64_t *forward, int64_t *reverse)
+{
+    if (!counts || !forward || !reverse) return bad_arg("null pointer");
+    if (k < 1 || k > KPAL_MAX_K) { set_error("k-mer length %d out of range [1, %d]", k, KPAL_MAX_K); return KPAL_EINVAL; }
+    KPAL_CHECK(require_device());
+    const uint64_t bins = 1ull << (2 * k), half = split_length(k);
+    DevBuf d_in, d_f, d_r, scratch;
+    KPAL_CHECK(d_in.alloc(bins * 8));
+    KPAL_CHECK(d_f.alloc(half * 8));
+    KPAL_CHECK(d_r.alloc(half * 8));
+    KPAL_CHECK(scratch.alloc(split_scratch_bytes(k)));
+    cudaStream_t st = 0;
+    KPAL_CUDA(cudaMemcpyAsync(d_in.p, counts, bins * 8, cudaMemcpyHostToDevice, st));
+    KPAL_CHECK(launch_split(d_in.as<int64_t>(), k, d_f.as<int64_t>(), d_r.as<int64_t>(), scratch.p, st));
+    KPAL_CUDA(cudaMemcpyAsync(forward, d_f.p, half * 8, cudaMemcpyDeviceToHost, st));
+    KPAL_CUDA(cudaMemcpyAsync(reverse, d_r.p, half * 8, cudaMemcpyDeviceToHost, st));
+    KPAL_CUDA(cudaStreamSynchronize(st));
+    return KPAL_OK;
+}
+
+extern "C" int kpal_show_balance(const int64_t *counts, int k, double *out)
+{
+    if (!counts || !out) return bad_arg("null pointer");
+    if (k < 1 || k > KPAL_MAX_K) { set_error("k-mer length %d out of range [1, %d]", k, KPAL_MAX_K); return KPAL_EINVAL; }
+    KPAL_CHECK(require_device());
+    const uint64_t bins = 1ull << (2 * k);
+    DevBuf d_in, res;
+    KPAL_CHECK(d_in.alloc(bins * 8));
+    KPAL_CHECK(res.alloc(16));
+    cudaStream_t st = 0;
+    KPAL_CUDA(cudaMemcpyAsync(d_in.p, counts, bins * 8, cudaMemcpyHostToDevice, st));
+    KPAL_CHECK(launch_show_balance(d_in.as<int64_t>(), k, res.as<double>(),
+                                   res.as<unsigned long long>() + 1, st));
+    struct { double sum; unsigned long long nz; } h;
+    KPAL_CUDA(cudaMemcpyAsync(&h, res.p, 16, cudaMemcpyDeviceToHost, st));
+    KPAL_CUDA(cudaStreamSynchronize(st));
+    *out = h.sum / double(h.nz + 1);                       // kpal/metrics.py:123
     return KPAL_OK;
 }

@@ -6,16 +6,19 @@ kpal/kdistlib.py:21-186).
 GPU fast path (``kpal_distance_matrix`` / ``kpal_pair_distance``): every
 combination of ``do_balance``, ``do_scale``, ``down`` with the multiset
 distance (built-in ``prod`` / ``sum`` pairwise) or the euclidean / cosine
-vector functions.  For those options nothing is computed on the host, and a
-missing library or GPU raises.
+vector functions.  ``do_positive`` (pair-dependent mask and totals) runs on
+the device pair by pair (``kpal_pair_distance_positive``).  For those options
+nothing is computed on the host, and a missing library or GPU raises.
 
 Host path (unchanged NumPy pipeline, as the north star prescribes):
-``do_positive``, ``do_smooth`` (pair-dependent masking / recursive collapse)
-and user-supplied ``pairwise`` / ``distance_function`` callables.
+``do_smooth`` (recursive collapse with data-dependent control flow) and
+user-supplied ``pairwise`` / ``distance_function`` / ``summary`` callables.
 """
 import numpy as np
 
 from . import _cabi, metrics
+
+LENGTH_ERROR = 'k-mer lengths of the files differ'
 
 
 class ProfileDistance(object):
@@ -50,7 +53,7 @@ class ProfileDistance(object):
     def _gpu_options(self):
         """Keyword arguments for the C ABI when this object's options are in
         the device fast path, else ``None``."""
-        if self._do_positive or self._do_smooth:
+        if self._do_smooth:
             return None
         if self._distance_function is None:
             for key in ('prod', 'sum'):
@@ -65,9 +68,13 @@ class ProfileDistance(object):
             metric, pairwise = 'cosine', 'prod'
         else:
             return None
-        return dict(metric=metric, pairwise=pairwise,
-                    do_balance=bool(self._do_balance),
-                    do_scale=bool(self._do_scale), down=bool(self._down))
+        options = dict(metric=metric, pairwise=pairwise,
+                       do_balance=bool(self._do_balance),
+                       do_scale=bool(self._do_scale), down=bool(self._down))
+        if self._do_positive:
+            # pair-dependent mask and totals: device path per pair only (no matrix form)
+            options['do_positive'] = True
+        return options
 
     # -------------------------------------------------------------- host path
     def _collapse(self, vector, start, length):
@@ -136,7 +143,7 @@ def distance_matrix_values(profiles, dist):
     GPU call when the options are in the fast path."""
     n = len(profiles)
     options = dist._gpu_options()
-    if options is not None and n > 0:
+    if options is not None and n > 0 and not options.get('do_positive'):
         stacked = np.empty((n, profiles[0].number), dtype=np.int64)
         for i, profile in enumerate(profiles):
             if profile.number != stacked.shape[1]:
@@ -158,10 +165,59 @@ def distance_matrix(profiles, output, precision, dist):
     """
     n = len(profiles)
     values = distance_matrix_values(profiles, dist) if n > 1 else None
-    lines = [str(n)]
-    lines.extend(str(profile.name) for profile in profiles)
-    template = '{{0:.{0}f}}'.format(precision)
-    for i in range(1, n):
-        row = values[i]
-        lines.append(' '.join(template.format(row[j]) for j in range(i)))
-    output.write('\n'.join(lines) + '\n')
+    write_matrix([profile.name for profile in profiles], values, output, precision)
+
+
+def write_matrix(names, values, output, precision):
+    """The text of kpal/kdistlib.py:176-186 for a computed ``[n][n]`` matrix:
+    ``n``, the names, then the lower triangle (``kpal_format_matrix`` writes
+    the digits exactly as ``'{0:.{precision}f}'.format`` does)."""
+    n = len(names)
+    header = '\n'.join([str(n)] + [str(name) for name in names]) + '\n'
+    output.write(header)
+    if n > 1:
+        output.write(_cabi.format_matrix(values, precision))
+
+
+def distance_matrix_from_file(input_handle, names, output, precision, dist):
+    """
+    ``kpal matrix`` without the list of N in-memory profiles of
+    kpal/kmer.py:694-698: datasets are read straight into a pinned slab and
+    uploaded slab by slab (``kpal_matrix_push``).  Returns ``False`` when
+    `dist` needs the host pipeline (the caller then takes the reference route).
+    """
+    options = dist._gpu_options()
+    if options is None or options.get('do_positive'):
+        return False
+    group = input_handle['profiles']
+    first = group[names[0]]
+    number = int(first.shape[0])
+    length = _length_of(number)
+    with _cabi.MatrixSession(len(names), length, **options) as session:
+        filled = 0
+        for name in names:
+            dataset = group[name]
+            if int(dataset.shape[0]) != number:
+                raise ValueError(LENGTH_ERROR)
+            row = session.slab[filled]
+            if hasattr(dataset, 'read_direct'):
+                dataset.read_direct(row)
+            else:
+                row[...] = dataset[...]
+            filled += 1
+            if filled == session.slab.shape[0]:
+                session.push(filled)
+                filled = 0
+        if filled:
+            session.push(filled)
+        values = session.finish()
+    write_matrix(names, values, output, precision)
+    return True
+
+
+def _length_of(number):
+    """*k* of a count vector of `number` entries (kpal/klib.py:58-61)."""
+    length = int(number).bit_length() // 2
+    if number < 4 or 4 ** length != number:
+        raise ValueError('profile length %d is not a power of 4' % number)
+    return length

@@ -215,14 +215,9 @@ class Profile(object):
         Forward / reverse-complement halves of the profile, every position of
         the first array facing its reverse complement in the second; counts
         are doubled except for palindromes, which appear once in both
-        (kpal/klib.py:300-327).  Host path.
+        (kpal/klib.py:300-327).  On the GPU (``kpal_split``).
         """
-        index = np.arange(self.number, dtype=np.int64)
-        partner = self._rc_table()
-        counts = np.asarray(self.counts)
-        keep = index <= partner
-        factor = np.where(index[keep] < partner[keep], 2, 1)
-        return counts[index[keep]] * factor, counts[partner[keep]] * factor
+        return _cabi.split(self.counts)
 
     def shrink(self, factor=1):
         """Reduce *k* by `factor`, summing groups of ``4**factor`` neighbours

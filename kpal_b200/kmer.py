@@ -154,6 +154,22 @@ def balance(input_handle, output_handle, names=None):
         profile.save(output_handle)
 
 
+def get_balance(input_handle, output_handle, precision=10, names=None):
+    """
+    Show the balance of k-mer profiles.
+
+    One ``<name> <figure>`` line per profile: the multiset/prod distance
+    between the forward and reverse-complement halves of the profile
+    (reference kpal/kmer.py:222-247); one pass on the GPU
+    (``kpal_show_balance``).
+    """
+    from . import _cabi
+    template = '{{0:.{0}f}}'.format(precision)
+    for name in names or sorted(input_handle['profiles']):
+        profile = klib.Profile.from_file(input_handle, name=name)
+        print(name, template.format(_cabi.show_balance(profile.counts)), file=output_handle)
+
+
 def distance(input_handle_left, input_handle_right, output_handle,
              names_left=None, names_right=None, distance_function='default',
              pairwise='prod', custom_pairwise=None, do_smooth=False,
@@ -199,6 +215,9 @@ def distance_matrix(input_handle, output_handle, names=None,
         raise ValueError('you must give at least two k-mer profiles')
     dist = _make_dist(distance_function, pairwise, custom_pairwise, do_smooth, summary,
                       custom_summary, threshold, do_scale, down, do_positive, do_balance)
+    # device fast path: datasets stream through a pinned slab straight to the GPU
+    if kdistlib.distance_matrix_from_file(input_handle, names, output_handle, precision, dist):
+        return
     profiles = []
     for name in names:
         profiles.append(klib.Profile.from_file(input_handle, name=name))
@@ -284,6 +303,12 @@ def main(args=None):
     p = subparsers.add_parser('balance', parents=[profile_in, profile_out],
                               description=_first_paragraph(balance))
     p.set_defaults(func=balance)
+
+    p = subparsers.add_parser('showbalance', parents=[profile_in],
+                              description=_first_paragraph(get_balance))
+    p.add_argument('-n', metavar='INT', dest='precision', type=int, default=10,
+                   help='precision in number of decimals (default: %(default)s)')
+    p.set_defaults(func=get_balance, output_handle=sys.stdout)
 
     p = subparsers.add_parser('distance', parents=[dist_options],
                               description=_first_paragraph(distance))

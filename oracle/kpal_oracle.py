@@ -212,6 +212,49 @@ def balance_python(counts):
     return counts
 
 
+def split(counts):
+    """
+    ``Profile.split`` (kpal/klib.py:300-327): forward / reverse lists over the
+    indices i <= rc(i) in index order; counts doubled for i < rc(i), taken once
+    for palindromes.
+    """
+    counts = np.asarray(counts)
+    k = int(round(math.log(counts.size, 4)))
+    index = np.arange(counts.size, dtype=np.int64)
+    partner = reverse_complement_table(k)
+    keep = index <= partner
+    factor = np.where(index[keep] < partner[keep], 2, 1)
+    return counts[index[keep]] * factor, counts[partner[keep]] * factor
+
+
+def split_python(counts):
+    """Literal loop form of kpal/klib.py:314-327 (small k only)."""
+    counts = np.asarray(counts)
+    k = int(round(math.log(counts.size, 4)))
+    forward, reverse = [], []
+    for i in range(counts.size):
+        i_rc = reverse_complement(i, k)
+        if i < i_rc:
+            forward.append(counts[i] * 2)
+            reverse.append(counts[i_rc] * 2)
+        elif i == i_rc:
+            forward.append(counts[i])
+            reverse.append(counts[i])
+    return np.array(forward), np.array(reverse)
+
+
+def show_balance(counts):
+    """The figure ``kpal showbalance`` prints (kmer.get_balance,
+    kpal/kmer.py:240-245): multiset/prod distance of the two split lists."""
+    forward, reverse = split(counts)
+    return multiset(forward, reverse, pairwise_prod)
+
+
+def positive(vector, mask):
+    """``metrics.positive`` (kpal/metrics.py:89-98)."""
+    return np.multiply(vector, np.asanyarray(mask, dtype=bool))
+
+
 # --------------------------------------------------------------------------
 # metrics + distance
 # --------------------------------------------------------------------------
@@ -273,17 +316,19 @@ def cosine_similarity(left, right):
 
 
 def distance(left, right, do_balance=False, do_scale=False, down=False,
-             metric="multiset", pairwise="prod"):
+             metric="multiset", pairwise="prod", do_positive=False):
     """
-    ``ProfileDistance.distance`` (kpal/kdistlib.py:126-161) for the options
-    of the GPU fast path (no positive / smoothing): copy -> balance ->
-    scale -> metric.  ``metric`` in {'multiset','euclidean','cosine'}.
+    ``ProfileDistance.distance`` (kpal/kdistlib.py:126-161) without smoothing:
+    copy -> balance -> positive -> scale -> metric.  ``metric`` in
+    {'multiset','euclidean','cosine'}.
     """
     left = np.array(left, dtype=np.int64)
     right = np.array(right, dtype=np.int64)
     if do_balance:
         left = balance(left)
         right = balance(right)
+    if do_positive:                                   # kpal/kdistlib.py:143-145
+        left, right = positive(left, right), positive(right, left)
     if do_scale:
         ls, rs = get_scale(left, right)
         if down:

@@ -130,6 +130,36 @@ def test_argument_errors_map_to_valueerror():
     assert b"null" in L.kpal_last_error()
 
 
+def test_format_matrix_equals_python_format():
+    """kpal_format_matrix writes the lower triangle exactly as the reference's
+    '{0:.{precision}f}'.format loop (kpal/kdistlib.py:179-186), including nan,
+    inf, negative zero, exact ties and huge values."""
+    rng = np.random.default_rng(11)
+    for n, precision in ((1, 3), (2, 10), (3, 2), (9, 0), (40, 10), (130, 3), (25, 17)):
+        v = rng.random((n, n)) * rng.choice([1e-12, 1.0, 1e6, 1e15], (n, n))
+        if n > 1:
+            v[1, 0] = float('nan')
+        if n > 2:
+            v[2, 0], v[2, 1] = float('inf'), -0.0
+        if n > 5:
+            v[5, :5] = [-np.nan, -np.inf, 0.5, 2.5, 1e22]
+            v[4, :4] = [0.125, 0.375, 1e-320, 123456789.987654321]
+        template = '{{0:.{0}f}}'.format(precision)
+        want = ''.join(' '.join(template.format(v[i, j]) for j in range(i)) + '\n'
+                       for i in range(1, n))
+        assert _cabi.format_matrix(v, precision) == want
+        # a view with a larger leading dimension (sub-block of a bigger matrix)
+        big = np.zeros((n + 3, n + 5))
+        big[:n, :n] = v
+        assert _cabi.format_matrix(big[:n, :n], precision) == want
+    L = _cabi.load()
+    length = ctypes.c_uint64()
+    v = np.ones((3, 3))
+    assert L.kpal_format_matrix(_cabi.ptr(v), 3, 3, 2, None, 0, ctypes.byref(length)) == _cabi.KPAL_EOVERFLOW
+    assert length.value == len('1.00\n1.00 1.00\n')
+    assert L.kpal_format_matrix(_cabi.ptr(v), 3, 2, 2, None, 0, ctypes.byref(length)) == _cabi.KPAL_EINVAL
+
+
 @pytest.mark.skipif(_cabi.device_count() > 0, reason="a GPU is present")
 def test_no_cpu_fallback_without_gpu():
     """On a box without a GPU the product path must refuse, not emulate."""

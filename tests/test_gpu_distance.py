@@ -208,3 +208,63 @@ def test_host_path_options_still_work(golden):
     assert d == pytest.approx(ko.multiset(left.counts * mask, right.counts * mask))
     custom = kdistlib.ProfileDistance(pairwise=lambda x, y: abs(x - y) / (x + y + 1))
     assert custom.distance(left, right) == pytest.approx(ko.distance(left.counts, right.counts, pairwise="sum"))
+
+
+def test_matrix_session_equals_one_shot_call():
+    """kpal_matrix_open/push/finish (profiles handed over in slabs of any size,
+    the staging buffer reused between pushes) gives the matrix of the one-shot
+    kpal_distance_matrix, for every fast-path option family."""
+    rng = np.random.default_rng(77)
+    n, k = 45, 6
+    lam = np.exp(rng.uniform(np.log(0.3), np.log(6.0), n))
+    profiles = np.stack([rng.poisson(l, 4 ** k) for l in lam]).astype(np.int64)
+    for opts in (dict(do_scale=True), dict(do_balance=True, do_scale=True, down=True),
+                 dict(metric="euclidean", do_scale=True), dict(metric="cosine"),
+                 dict(pairwise="sum", do_balance=True)):
+        want = _cabi.distance_matrix(profiles, **opts)
+        with _cabi.MatrixSession(n, k, slab_bytes=7 * 8 * 4 ** k, **opts) as session:
+            assert session.slab.shape == (7, 4 ** k)
+            at = 0
+            for m in (7, 1, 5, 7, 7, 3, 7, 7, 1):           # ragged pushes through the pinned slab
+                session.slab[:m] = profiles[at:at + m]
+                session.push(m)
+                session.slab[:] = -1                         # the slab is free again after push
+                at += m
+            assert at == n
+            got = session.finish()
+        assert np.array_equal(got, want, equal_nan=True), opts
+        with _cabi.MatrixSession(n, k, **opts) as session:   # rows from ordinary memory, one call
+            session.push_rows(profiles)
+            assert np.array_equal(session.finish(), want, equal_nan=True)
+    with _cabi.MatrixSession(3, 2) as session:
+        session.push_rows(np.ones((2, 16), dtype=np.int64))
+        with pytest.raises(ValueError):
+            session.finish()                                  # one profile missing
+        with pytest.raises(ValueError):
+            session.push_rows(np.ones((2, 16), dtype=np.int64))   # one too many
+
+
+def test_matrix_command_streams_datasets(golden):
+    """kmer.distance_matrix on the fast path reads the datasets slab by slab
+    (kdistlib.distance_matrix_from_file) and writes the reference's text."""
+    from kpal_b200 import kmer
+    from test_host_api import FakeH5
+    rng = np.random.default_rng(5)
+    store = FakeH5()
+    names = ['s%02d' % i for i in range(14)]
+    rows = {}
+    for name in names:
+        rows[name] = rng.poisson(rng.uniform(0.5, 5.0), 4 ** 5).astype(np.int64)
+        klib.Profile(rows[name], name).save(store)
+    out = io.StringIO()
+    kmer.distance_matrix(store, out, do_scale=True, precision=8)
+    lines = out.getvalue().split('\n')
+    assert lines[0] == '14' and lines[1:15] == names and lines[-1] == ''
+    for i in (1, 6, 13):
+        got = [float(x) for x in lines[14 + i].split(' ')]
+        want = [ko.distance(rows[names[i]], rows[names[j]], do_scale=True) for j in range(i)]
+        assert len(got) == i
+        np.testing.assert_allclose(got, want, rtol=0, atol=0.6e-8)
+    klib.Profile(np.ones(4 ** 4, dtype=np.int64), 'short').save(store)
+    with pytest.raises(ValueError):
+        kmer.distance_matrix(store, io.StringIO())           # kmer.py:697-698: lengths differ

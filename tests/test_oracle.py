@@ -177,3 +177,37 @@ def test_reference_fasta_through_reader():
     text = ">x\nACGTACGTTTGA\nACGNNACGTA\n>y\nacgtacgtaa\n"
     prof = klib.Profile.from_fasta(io.StringIO(text), 4)
     assert np.array_equal(prof.counts, ko.count_fasta(text, 4))
+
+
+def test_split_showbalance_positive_golden():
+    """oracle.split / show_balance / distance(do_positive) against vectors made
+    by the unmodified reference (tests/golden/make_golden_split.py), including
+    the upstream golden '1 0.669' (reference tests/test_kmer.py:195-202)."""
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    with open(os.path.join(GOLDEN_DIR, "golden_split.json")) as f:
+        g = json.load(f)
+    for case in g["split_cases"]:
+        counts = dense(case["counts"])
+        for fn in (ko.split, ko.split_python):
+            forward, reverse = fn(counts)
+            assert forward.tolist() == case["forward"] and reverse.tolist() == case["reverse"]
+        assert ko.show_balance(counts) == case["showbalance"]
+    for case in g["positive_cases"]:
+        left, right = dense(case["left"]), dense(case["right"])
+        for key, want in case["values"].items():
+            got = ko.distance(left, right, do_positive=True, **parse_key(key))
+            assert got == want or (np.isnan(got) and np.isnan(want)), key
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+def test_split_showbalance_against_reference_source(golden):
+    rklib, _, rmetrics = ref_loader.load()
+    counts = ko.count_sequences(golden["fixtures"]["LENGTH_60"], 8)
+    forward, reverse = rklib.Profile(counts.copy()).split()
+    a, b = ko.split(counts)
+    assert np.array_equal(a, forward) and np.array_equal(b, reverse)
+    value = ko.show_balance(counts)
+    assert value == rmetrics.multiset(forward, reverse, rmetrics.pairwise['prod'])
+    assert '{0:.3f}'.format(value) == '0.669'
