@@ -363,19 +363,39 @@ def bench_count(args):
     stream = torch.cuda.current_stream()
     sp = ctypes.c_void_p(stream.cuda_stream)
 
+    reducer = None
+    if world > 1 and args.reduce in ("peer", "fused"):
+        from kpal_b200 import multigpu
+        reducer = multigpu.PeerReducer(k, 32)
+
+    def reduce_and_finalize():
+        """Sum of the per-rank u32 tables onto rank 0 + widen/balance there."""
+        summed = d_table.data_ptr()
+        if reducer is not None:
+            summed = reducer.reduce(d_table.data_ptr(), sp)       # peer-memory all-to-all + collect
+        elif world > 1:
+            dist.reduce(d_table, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            _cabi.check(L.kpal_dev_finalize_counts(summed, 32, k, 1, d_counts.data_ptr(), sp))
+
     def device_step(ev=None):
         d_table.zero_()
         if ev:
             ev[0].record(stream)
+        if reducer is not None and args.reduce == "fused":
+            # count + all-to-all in one call: pass 2 of the radix count stores into the inboxes
+            summed = reducer.count_and_reduce(d_codes.data_ptr(), d_valid.data_ptr(), n_bases,
+                                              d_table.data_ptr(), sp)
+            if ev:
+                ev[1].record(stream)
+            if rank == 0:
+                _cabi.check(L.kpal_dev_finalize_counts(summed, 32, k, 1, d_counts.data_ptr(), sp))
+            return
         _cabi.check(L.kpal_dev_count_packed(d_codes.data_ptr(), d_valid.data_ptr(), n_bases, k,
                                             d_table.data_ptr(), 32, sp))
         if ev:
             ev[1].record(stream)
-        if world > 1:
-            dist.reduce(d_table, dst=0, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            _cabi.check(L.kpal_dev_finalize_counts(d_table.data_ptr(), 32, k, 1,
-                                                   d_counts.data_ptr(), sp))
+        reduce_and_finalize()
 
     def e2e_step():
         if world == 1:
@@ -385,10 +405,8 @@ def bench_count(args):
             nb = ctypes.c_uint64()
             _cabi.check(L.kpal_count_fasta_to_dev(pinned_fasta._ptr, n_fasta, k, d_table.data_ptr(),
                                                   32, sp, ctypes.byref(nb)))
-            dist.reduce(d_table, dst=0, op=dist.ReduceOp.SUM)
+            reduce_and_finalize()
             if rank == 0:
-                _cabi.check(L.kpal_dev_finalize_counts(d_table.data_ptr(), 32, k, 1,
-                                                       d_counts.data_ptr(), sp))
                 _cabi.check(L.kpal_memcpy_d2h(pinned_out._ptr, d_counts.data_ptr(), bins * 8, sp))
         torch.cuda.synchronize()
 
@@ -451,6 +469,24 @@ def bench_count(args):
                          "(BASELINE.md)"}
     else:
         cpu = None
+    if world > 1:
+        # N > 1: the job's result (rank 0) must equal, bit for bit, the sum of the per-rank
+        # tables taken with a plain NCCL reduce and finalised the same way; the host-buffer
+        # result of the e2e leg must equal it too.  (Each rank's own table is the N = 1 path,
+        # whose oracle parity is the N = 1 run's check.)
+        device_step()
+        check = d_table.clone()
+        d_table.zero_()
+        _cabi.check(L.kpal_dev_count_packed(d_codes.data_ptr(), d_valid.data_ptr(), n_bases, k,
+                                            d_table.data_ptr(), 32, sp))
+        check.copy_(d_table)
+        dist.reduce(check, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            want_dev = torch.empty_like(d_counts)
+            _cabi.check(L.kpal_dev_finalize_counts(check.data_ptr(), 32, k, 1, want_dev.data_ptr(), sp))
+            torch.cuda.synchronize()
+            result_ok = bool(torch.equal(want_dev, d_counts)
+                             and np.array_equal(pinned_out.array, want_dev.cpu().numpy()))
 
     if rank == 0:
         total_bases = seq_bases * world
@@ -470,7 +506,12 @@ def bench_count(args):
             "config": {"workload": workload,
                        "k": k, "bases_per_gpu": int(seq_bases), "packed_bases_per_gpu": int(n_bases),
                        "l2": "512 MB memset between steps (untimed); table memset is inside the step",
-                       "parallelism": "records sharded per GPU, NCCL reduce of u32 tables" if world > 1 else "1 GPU"},
+                       "parallelism": ("records sharded per GPU, u32 tables summed onto rank 0 " +
+                                       ("over NVLink peer memory (all-to-all fused into the count's histogram pass + collect kernel)"
+                                        if (reducer is not None and args.reduce == "fused") else
+                                        "over NVLink peer memory (all-to-all push + collect kernels)"
+                                        if reducer is not None else "with an NCCL reduce"))
+                       if world > 1 else "1 GPU"},
             "e2e": {"value": total_bases / 1e9 / e2e_s, "unit": "Gbases/s",
                     "h2d_bytes_per_step": int(n_fasta * world),
                     "d2h_bytes_per_step": int(bins * 8), "ms_per_step": e2e_s * 1e3,
@@ -486,6 +527,8 @@ def bench_count(args):
             "wall_s_timed_region": wall,
         }
         print(json.dumps(out))
+    if reducer is not None:
+        reducer.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -656,6 +699,9 @@ def main():
     ap.add_argument("--radix-payload-bits", type=int, default=0)
     ap.add_argument("--radix-debug", type=int, default=0, help="timing experiments (results are wrong)")
     ap.add_argument("--radix-shape", type=int, default=0)
+    ap.add_argument("--reduce", default="fused", choices=["fused", "peer", "nccl"],
+                    help="count workload at N > 1: table sum over NVLink peer memory fused into the count "
+                         "(default), as separate push/collect kernels, or with dist.reduce")
     ap.add_argument("--no-e2e", action="store_true", help="matrix workload: skip the host-buffer end-to-end leg")
     ap.add_argument("--fasta-chunks", type=int, default=0, help="chunks of the pipelined FASTA upload (0 = auto)")
     args = ap.parse_args()

@@ -243,6 +243,45 @@ int kpal_dev_count_by_record(const uint32_t *d_codes, const uint32_t *d_valid,
                              const uint64_t *d_rec_starts, uint64_t first, uint64_t n,
                              int k, int balance, int64_t *d_rows, void *stream);
 
+/* ------------------------------- multi-GPU: peer-memory reduce of count tables
+ *
+ * One process per GPU.  The per-rank tables of a record-sharded count
+ * (the reference's only parallel workflow is one process per
+ * file, kpal/Makefile:3) are summed over NVLink peer memory instead of a
+ * library reduce:
+ *   1. every rank allocates an inbox of kpal_peer_inbox_bytes() with
+ *      kpal_dev_alloc, exports it (kpal_ipc_export -> 64 opaque bytes, exchanged
+ *      by the host, e.g. torch.distributed.all_gather_object) and opens its
+ *      peers' (kpal_ipc_open); the root does the same for its result table;
+ *   2. kpal_dev_reduce_push: slice o of the local table -> slot `rank` of rank
+ *      o's inbox (an all-to-all of 16-byte peer stores);
+ *   3. a cross-GPU barrier on the same stream (caller's: 1-element all-reduce);
+ *   4. kpal_dev_reduce_collect: sum of the `world` slots of the local inbox ->
+ *      the root's table (peer store);  5. barrier;  6. the root finalizes.
+ * inbox_ptrs is a HOST array of `world` device pointers (entry `rank` = the
+ * local inbox).  counter_bits as in kpal_dev_count_packed.
+ */
+int      kpal_ipc_export(const void *d_ptr, void *handle64);
+int      kpal_ipc_open(const void *handle64, void **d_peer_ptr);
+int      kpal_ipc_close(void *d_peer_ptr);
+uint64_t kpal_peer_inbox_bytes(int k, int counter_bits, int world);
+int      kpal_dev_reduce_push(const void *d_table, int counter_bits, int k, int rank, int world,
+                              void *const *inbox_ptrs, void *stream);
+int      kpal_dev_reduce_collect(const void *d_inbox, int counter_bits, int k, int rank, int world,
+                                 void *d_root_table, void *stream);
+/*
+ * kpal_dev_count_packed + kpal_dev_reduce_push in one call: on the radix path
+ * (large inputs, k >= 9, world dividing the bucket count) the second pass of
+ * the count stores every bucket's slice (table + histogram) directly into its
+ * owner's inbox, so the all-to-all overlaps the histogram work and no separate
+ * push kernel runs (*fused_out = 1); otherwise it counts, then pushes (0).
+ * d_table is scratch the caller zeroes first, as for kpal_dev_count_packed.
+ */
+int      kpal_dev_count_packed_push(const uint32_t *d_codes, const uint32_t *d_valid,
+                                    uint64_t n_bases, int k, void *d_table, int counter_bits,
+                                    int rank, int world, void *const *inbox_ptrs, void *stream,
+                                    int *fused_out);
+
 /* --------------------------------------------------- distances: device API */
 
 /* stride (in doubles) of one prepared profile row for a given k */

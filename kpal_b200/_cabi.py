@@ -31,6 +31,8 @@ SYMBOLS = (
     "kpal_matrix_open", "kpal_matrix_push", "kpal_matrix_finish", "kpal_matrix_close",
     "kpal_format_matrix", "kpal_pair_distance_positive",
     "kpal_split_length", "kpal_split", "kpal_show_balance",
+    "kpal_ipc_export", "kpal_ipc_open", "kpal_ipc_close", "kpal_peer_inbox_bytes",
+    "kpal_dev_reduce_push", "kpal_dev_reduce_collect", "kpal_dev_count_packed_push",
     "kpal_dev_count_packed", "kpal_count_fasta_to_dev", "kpal_dev_finalize_counts", "kpal_dev_balance",
     "kpal_dev_count_by_record", "kpal_prepared_stride", "kpal_dev_profiles_prepare",
     "kpal_dev_order_by_total", "kpal_distance_num_tiles", "kpal_dev_distance_tiles",
@@ -95,6 +97,14 @@ def load():
     sig("kpal_split_length", u64, i32)
     sig("kpal_split", i32, vp, i32, vp, vp)
     sig("kpal_show_balance", i32, vp, i32, vp)
+    sig("kpal_ipc_export", i32, vp, vp)
+    sig("kpal_ipc_open", i32, vp, c.POINTER(vp))
+    sig("kpal_ipc_close", i32, vp)
+    sig("kpal_peer_inbox_bytes", u64, i32, i32, i32)
+    sig("kpal_dev_reduce_push", i32, vp, i32, i32, i32, i32, c.POINTER(vp), vp)
+    sig("kpal_dev_reduce_collect", i32, vp, i32, i32, i32, i32, vp, vp)
+    sig("kpal_dev_count_packed_push", i32, vp, vp, u64, i32, vp, i32, i32, i32, c.POINTER(vp), vp,
+        c.POINTER(i32))
     sig("kpal_dev_count_packed", i32, vp, vp, u64, i32, vp, i32, vp)
     sig("kpal_count_fasta_to_dev", i32, vp, u64, i32, vp, i32, vp, pu64)
     sig("kpal_dev_finalize_counts", i32, vp, i32, i32, i32, vp, vp)

@@ -45,6 +45,11 @@ uint64_t split_scratch_bytes(int k);
 int launch_split(const int64_t *, int, int64_t *, int64_t *, void *, cudaStream_t);
 int launch_show_balance(const int64_t *, int, double *, unsigned long long *, cudaStream_t);
 int launch_positive_pair(int64_t *, int64_t *, int, cudaStream_t);
+uint64_t peer_inbox_bytes(int k, int counter_bits, int world);
+int launch_reduce_push(const void *, int, int, int, int, void *const *, cudaStream_t);
+int launch_reduce_collect(const void *, int, int, int, int, void *, cudaStream_t);
+int launch_count_push(const uint32_t *, const uint32_t *, uint64_t, int, void *, int, int, int,
+                      void *const *, cudaStream_t, int *);
 
 static thread_local char t_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
@@ -939,4 +944,60 @@ extern "C" int kpal_show_balance(const int64_t *counts, int k, double *out)
     KPAL_CUDA(cudaStreamSynchronize(st));
     *out = h.sum / double(h.nz + 1);                       // kpal/metrics.py:123
     return KPAL_OK;
+}
+
+// ------------------------------------------- multi-GPU: peer-memory table reduce
+extern "C" int kpal_ipc_export(const void *d_ptr, void *handle64)
+{
+    if (!d_ptr || !handle64) return bad_arg("null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    KPAL_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
+    memcpy(handle64, &h, 64);
+    return KPAL_OK;
+}
+
+extern "C" int kpal_ipc_open(const void *handle64, void **d_peer_ptr)
+{
+    if (!handle64 || !d_peer_ptr) return bad_arg("null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    *d_peer_ptr = nullptr;
+    KPAL_CUDA(cudaIpcOpenMemHandle(d_peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return KPAL_OK;
+}
+
+extern "C" int kpal_ipc_close(void *d_peer_ptr)
+{
+    if (!d_peer_ptr) return KPAL_OK;
+    KPAL_CUDA(cudaIpcCloseMemHandle(d_peer_ptr));
+    return KPAL_OK;
+}
+
+extern "C" uint64_t kpal_peer_inbox_bytes(int k, int counter_bits, int world)
+{
+    if (k < 1 || k > KPAL_MAX_K || world < 1 || (counter_bits != 32 && counter_bits != 64)) return 0;
+    return peer_inbox_bytes(k, counter_bits, world);
+}
+
+extern "C" int kpal_dev_reduce_push(const void *d_table, int counter_bits, int k, int rank, int world,
+                                    void *const *inbox_ptrs, void *stream)
+{
+    return launch_reduce_push(d_table, counter_bits, k, rank, world, inbox_ptrs, (cudaStream_t)stream);
+}
+
+extern "C" int kpal_dev_reduce_collect(const void *d_inbox, int counter_bits, int k, int rank, int world,
+                                       void *d_root_table, void *stream)
+{
+    return launch_reduce_collect(d_inbox, counter_bits, k, rank, world, d_root_table, (cudaStream_t)stream);
+}
+
+extern "C" int kpal_dev_count_packed_push(const uint32_t *d_codes, const uint32_t *d_valid,
+                                          uint64_t n_bases, int k, void *d_table, int counter_bits,
+                                          int rank, int world, void *const *inbox_ptrs, void *stream,
+                                          int *fused_out)
+{
+    if (!d_table || (n_bases && (!d_codes || !d_valid))) return bad_arg("null device pointer");
+    return launch_count_push(d_codes, d_valid, n_bases, k, d_table, counter_bits, rank, world,
+                             inbox_ptrs, (cudaStream_t)stream, fused_out);
 }

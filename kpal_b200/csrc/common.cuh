@@ -71,4 +71,24 @@ __device__ __forceinline__ uint32_t rc_index(uint32_t idx, int shift /* 32 - 2k 
     return (~rev2(idx)) >> shift;
 }
 
+// ---- multi-GPU: peer-memory reduce of counter tables (peer_reduce.cu) --------
+// Rank o owns the table slice [slice_begin(o), slice_begin(o+1)); every rank has an
+// inbox of `world` slots of slot_elems() counters, slot s filled by rank s.
+constexpr int kMaxPeers = 16;
+struct PeerOut {
+    void *inbox[kMaxPeers];     // device pointers valid on THIS device (IPC-mapped peers)
+    int rank, world;
+};
+// first table index of rank o's slice: multiples of 4 elements so that every
+// slice moves as whole 16-byte vectors
+__host__ __device__ inline uint64_t slice_begin(uint64_t bins, int o, int world)
+{
+    if (o >= world) return bins;
+    return (bins * uint64_t(o) / uint64_t(world)) & ~uint64_t(3);
+}
+__host__ __device__ inline uint64_t slot_elems(uint64_t bins, int world)
+{
+    return ((bins + world - 1) / world + 7) & ~uint64_t(3);        // >= the longest slice
+}
+
 }  // namespace kpal

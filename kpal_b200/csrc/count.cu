@@ -267,7 +267,12 @@ accumulate_kernel(const CounterT *__restrict__ src, CounterT *__restrict__ dst, 
 // ---------------------------------------------------------------------------
 // count_radix.cu
 bool radix_supported(int k);
-int launch_count_radix(const uint32_t *, const uint32_t *, uint64_t, int, void *, int, cudaStream_t);
+int launch_count_radix(const uint32_t *, const uint32_t *, uint64_t, int, void *, int, cudaStream_t,
+                       const PeerOut *peer = nullptr);
+bool radix_peer_supported(int k, int world);
+// peer_reduce.cu
+int launch_reduce_push(const void *, int, int, int, int, void *const *, cudaStream_t);
+int peer_check_args(int k, int counter_bits, int rank, int world);
 
 // run-time switches (kpal_set_option): "count_path" 0 = automatic, 1 = always the
 // scattered-RED kernel, 2 = the radix-partitioned path wherever it is supported;
@@ -422,6 +427,38 @@ int launch_by_record(const uint32_t *d_codes, const uint32_t *d_valid, const uin
         d_rec_starts, first, n, k, balance, d_rows);
     KPAL_LAUNCH_CHECK("by_record_kernel");
     return KPAL_OK;
+}
+
+}  // namespace kpal
+
+namespace kpal {
+
+// Multi-GPU: count this rank's stream and deliver every slice of the resulting table
+// (d_table must be zeroed by the caller, as for launch_count) to the inbox of its owner.
+// On the radix path the all-to-all is fused into pass 2 (the histogram kernel stores
+// into the inboxes); otherwise the table is counted locally and pushed by a copy kernel.
+int launch_count_push(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_bases, int k,
+                      void *d_table, int counter_bits, int rank, int world,
+                      void *const *inbox_ptrs, cudaStream_t stream, int *fused_out)
+{
+    KPAL_CHECK(check_k(k));
+    KPAL_CHECK(peer_check_args(k, counter_bits, rank, world));
+    if (!inbox_ptrs) return bad_arg("null pointer");
+    if (counter_bits == 32 && n_bases >= (1ull << 32)) {
+        set_error("%llu bases would overflow 32-bit counters; use counter_bits=64", (unsigned long long)n_bases);
+        return KPAL_EOVERFLOW;
+    }
+    const bool fused = n_bases > 0 && k > 7 && use_radix_path(k, n_bases) && radix_peer_supported(k, world);
+    if (fused_out) *fused_out = fused ? 1 : 0;
+    if (fused) {
+        PeerOut peer;
+        peer.rank = rank; peer.world = world;
+        for (int i = 0; i < kMaxPeers; ++i) peer.inbox[i] = i < world ? inbox_ptrs[i] : nullptr;
+        for (int i = 0; i < world; ++i) if (!peer.inbox[i]) return bad_arg("null inbox pointer");
+        return launch_count_radix(d_codes, d_valid, n_bases, k, d_table, counter_bits, stream, &peer);
+    }
+    KPAL_CHECK(launch_count(d_codes, d_valid, n_bases, k, d_table, counter_bits, stream));
+    return launch_reduce_push(d_table, counter_bits, k, rank, world, inbox_ptrs, stream);
 }
 
 }  // namespace kpal

@@ -323,11 +323,15 @@ radix_partition_kernel(const RadixParams p, CounterT *__restrict__ table)
 // ---------------------------------------------------------------------------
 // pass 2
 // ---------------------------------------------------------------------------
-template <typename CounterT>
+// PEER: multi-GPU mode -- instead of updating the local table, the bucket's slice
+// (local table + histogram) is stored straight into the inbox slot of the rank that
+// owns it (16-byte peer stores over NVLink, see peer_reduce.cu), so the all-to-all of
+// the table reduce rides on this kernel instead of following it.
+template <typename CounterT, bool PEER>
 __global__ void __launch_bounds__(kHistThreadsMax)
 radix_histogram_kernel(const uint16_t *__restrict__ staging, const uint32_t *__restrict__ region_fill,
                        int n_part_ctas, int nb, int P, uint32_t region_groups,
-                       CounterT *__restrict__ table)
+                       CounterT *__restrict__ table, const PeerOut peer)
 {
     extern __shared__ __align__(16) uint32_t radix_hist[];
     const uint32_t bins = 1u << P;
@@ -383,7 +387,15 @@ radix_histogram_kernel(const uint16_t *__restrict__ staging, const uint32_t *__r
     __syncthreads();
 
     // table slice += histogram, four independent 16-byte read-modify-writes in flight
+    const CounterT *src = table + (uint64_t(b) << P);
     CounterT *dst = table + (uint64_t(b) << P);
+    if constexpr (PEER) {
+        // nb is a multiple of the world size: bucket b lies inside the slice of its owner
+        const uint64_t total_bins = uint64_t(nb) << P;
+        const int owner = int(uint64_t(b) * uint64_t(peer.world) / uint64_t(nb));
+        dst = static_cast<CounterT *>(peer.inbox[owner]) + uint64_t(peer.rank) * slot_elems(total_bins, peer.world)
+              + ((uint64_t(b) << P) - slice_begin(total_bins, owner, peer.world));
+    }
     for (uint32_t i0 = threadIdx.x * 4; i0 < bins; i0 += blockDim.x * 16) {
         uint4 h[4];
         if constexpr (sizeof(CounterT) == 4) {
@@ -391,12 +403,12 @@ radix_histogram_kernel(const uint16_t *__restrict__ staging, const uint32_t *__r
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const uint32_t i = i0 + q * blockDim.x * 4;
-                if (i < bins) { h[q] = *reinterpret_cast<const uint4 *>(radix_hist + i); t[q] = *reinterpret_cast<const uint4 *>(dst + i); }
+                if (i < bins) { h[q] = *reinterpret_cast<const uint4 *>(radix_hist + i); t[q] = *reinterpret_cast<const uint4 *>(src + i); }
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const uint32_t i = i0 + q * blockDim.x * 4;
-                if (i < bins && (h[q].x | h[q].y | h[q].z | h[q].w)) {
+                if (i < bins && (PEER || (h[q].x | h[q].y | h[q].z | h[q].w))) {
                     t[q].x += h[q].x; t[q].y += h[q].y; t[q].z += h[q].z; t[q].w += h[q].w;
                     *reinterpret_cast<uint4 *>(dst + i) = t[q];
                 }
@@ -408,14 +420,14 @@ radix_histogram_kernel(const uint16_t *__restrict__ staging, const uint32_t *__r
                 const uint32_t i = i0 + q * blockDim.x * 4;
                 if (i < bins) {
                     h[q] = *reinterpret_cast<const uint4 *>(radix_hist + i);
-                    t0[q] = *reinterpret_cast<const ulonglong2 *>(dst + i);
-                    t1[q] = *reinterpret_cast<const ulonglong2 *>(dst + i + 2);
+                    t0[q] = *reinterpret_cast<const ulonglong2 *>(src + i);
+                    t1[q] = *reinterpret_cast<const ulonglong2 *>(src + i + 2);
                 }
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const uint32_t i = i0 + q * blockDim.x * 4;
-                if (i < bins && (h[q].x | h[q].y | h[q].z | h[q].w)) {
+                if (i < bins && (PEER || (h[q].x | h[q].y | h[q].z | h[q].w))) {
                     t0[q].x += h[q].x; t0[q].y += h[q].y; t1[q].x += h[q].z; t1[q].y += h[q].w;
                     *reinterpret_cast<ulonglong2 *>(dst + i) = t0[q];
                     *reinterpret_cast<ulonglong2 *>(dst + i + 2) = t1[q];
@@ -499,7 +511,7 @@ static RadixGeometry radix_geometry(int k)
 
 template <typename CounterT>
 static int launch_radix_passes(const RadixGeometry &g, RadixParams &p, int grid1, size_t smem2, int threads2,
-                               CounterT *table, cudaStream_t stream)
+                               CounterT *table, const PeerOut *peer, cudaStream_t stream)
 {
 #define KPAL_RADIX_LAUNCH(THREADS, TEAM, SWEEP)                                                       \
     do {                                                                                              \
@@ -517,17 +529,35 @@ static int launch_radix_passes(const RadixGeometry &g, RadixParams &p, int grid1
         KPAL_LAUNCH_CHECK("radix_partition_kernel");
     }
 #undef KPAL_RADIX_LAUNCH
-    KPAL_CUDA(cudaFuncSetAttribute(radix_histogram_kernel<CounterT>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem2)));
-    radix_histogram_kernel<CounterT><<<g.nb, threads2, smem2, stream>>>(
-        p.staging, p.region_fill, grid1, g.nb, g.P, p.region_groups, table);
+    if (peer) {
+        KPAL_CUDA(cudaFuncSetAttribute(radix_histogram_kernel<CounterT, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem2)));
+        radix_histogram_kernel<CounterT, true><<<g.nb, threads2, smem2, stream>>>(
+            p.staging, p.region_fill, grid1, g.nb, g.P, p.region_groups, table, *peer);
+    } else {
+        KPAL_CUDA(cudaFuncSetAttribute(radix_histogram_kernel<CounterT, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem2)));
+        radix_histogram_kernel<CounterT, false><<<g.nb, threads2, smem2, stream>>>(
+            p.staging, p.region_fill, grid1, g.nb, g.P, p.region_groups, table, PeerOut());
+    }
     KPAL_LAUNCH_CHECK("radix_histogram_kernel");
     return KPAL_OK;
 }
 
-// Accumulate units of the packed stream into `table` through the two passes.
+// Can pass 2 write into the peers' inboxes?  Only when every bucket lies inside one
+// owner's slice: the bucket count must be a multiple of the world size.
+bool radix_peer_supported(int k, int world)
+{
+    if (!radix_supported(k) || world < 1 || world > kMaxPeers) return false;
+    const RadixGeometry g = radix_geometry(k);
+    return g.nb % world == 0 && ((uint64_t(1) << g.P) % 4) == 0;
+}
+
+// Accumulate units of the packed stream into `table` through the two passes.  With
+// `peer` (multi-GPU), the last segment's pass 2 stores table + histogram into the
+// owners' inboxes instead of the table.
 int launch_count_radix(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_bases, int k,
-                       void *d_table, int counter_bits, cudaStream_t stream)
+                       void *d_table, int counter_bits, cudaStream_t stream, const PeerOut *peer)
 {
     const RadixGeometry g = radix_geometry(k);
     const int P = g.P, nb = g.nb;
@@ -568,12 +598,13 @@ int launch_count_radix(const uint32_t *d_codes, const uint32_t *d_valid, uint64_
         p.staging = static_cast<uint16_t *>(ws->staging);
         p.region_fill = ws->fill;
         p.debug = g_radix_debug.load();
+        const PeerOut *seg_peer = (s1 == n_units) ? peer : nullptr;      // last segment only
         if (counter_bits == 32)
             KPAL_CHECK(launch_radix_passes<uint32_t>(g, p, grid1, smem2, threads2,
-                                                     static_cast<uint32_t *>(d_table), stream));
+                                                     static_cast<uint32_t *>(d_table), seg_peer, stream));
         else
             KPAL_CHECK(launch_radix_passes<unsigned long long>(g, p, grid1, smem2, threads2,
-                                                               static_cast<unsigned long long *>(d_table), stream));
+                                                               static_cast<unsigned long long *>(d_table), seg_peer, stream));
     }
     return KPAL_OK;
 }

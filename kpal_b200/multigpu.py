@@ -92,15 +92,18 @@ def _gpu_finalize(table, k, balance):
 
 
 def count_fasta_distributed(fasta_shard, k, balance=False, group=None, device=None,
-                            count_shard=None, finalize=None):
+                            count_shard=None, finalize=None, reduce='peer'):
     """
     ``Profile.from_fasta`` (+ ``balance``) over FASTA text that is sharded
     across the ranks of `group`: every rank passes ITS shard (cut at record
     boundaries, see :func:`split_fasta`); rank 0 gets the ``int64[4**k]``
     profile, the other ranks ``None``.
 
-    `count_shard` / `finalize` are injection points for the CPU (gloo) tests
-    of the sharding + reduce logic; by default both run on the GPU.
+    `reduce` = ``'peer'`` sums the tables over NVLink peer memory
+    (:class:`PeerReducer`; GPU ranks, u32 counters), ``'nccl'`` with
+    ``dist.reduce``.  `count_shard` / `finalize` are injection points for the
+    CPU (gloo) tests of the sharding + reduce logic; by default both run on
+    the GPU.
     """
     import torch
     import torch.distributed as dist
@@ -121,6 +124,20 @@ def count_fasta_distributed(fasta_shard, k, balance=False, group=None, device=No
         dist.all_reduce(total, group=group)
         if int(total.item()) >= 2 ** 32:
             table = table.to(torch.int64) & 0xffffffff
+        if reduce == 'peer' and table.is_cuda and table.dtype == torch.int32:
+            reducer = PeerReducer(k, 32, group=group)
+            try:
+                stream = ctypes.c_void_p(torch.cuda.current_stream(table.device).cuda_stream)
+                summed = reducer.reduce(table.data_ptr(), stream)
+                if summed is None:
+                    return None
+                L = _cabi.load()
+                out = torch.empty(4 ** k, dtype=torch.int64, device=table.device)
+                _cabi.check(L.kpal_dev_finalize_counts(summed, 32, int(k), int(bool(balance)),
+                                                       out.data_ptr(), stream))
+                return out.cpu().numpy()
+            finally:
+                reducer.close()
         dist.reduce(table, dst=0, group=group)
         if dist.get_rank(group) != 0:
             return None
@@ -131,6 +148,107 @@ def count_fasta_distributed(fasta_shard, k, balance=False, group=None, device=No
             counts = _cabi.balance(work) if finalize is None else finalize(work, k, True)
         return counts
     return (finalize or _gpu_finalize)(table, k, balance)
+
+
+class PeerReducer(object):
+    """
+    Sum of the per-rank counter tables onto rank `root` over NVLink peer memory
+    (``csrc/peer_reduce.cu``): an all-to-all of table slices into per-rank
+    inboxes, a local sum of every inbox, and a peer store of the summed slice
+    into the root's table -- two kernels around two stream-ordered barriers
+    (1-element all-reduces) instead of ``dist.reduce``.
+
+    One process per GPU; inboxes and the root table are ``cudaMalloc`` buffers
+    shared through CUDA IPC handles (exchanged with ``all_gather_object``).
+    ``reduce(table_ptr)`` returns the device pointer of the summed table on the
+    root (valid until the next call) and ``None`` elsewhere.
+    """
+
+    def __init__(self, k, counter_bits=32, group=None, root=0):
+        import torch
+        import torch.distributed as dist
+        self._L = L = _cabi.load()
+        self.k, self.bits, self.group, self.root = int(k), int(counter_bits), group, int(root)
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        self._opened = []
+        inbox_bytes = int(L.kpal_peer_inbox_bytes(self.k, self.bits, self.world))
+        if inbox_bytes == 0:
+            raise ValueError('bad k / counter_bits / world for the peer reduce')
+        self._inbox = L.kpal_dev_alloc(inbox_bytes)
+        self._root_table = L.kpal_dev_alloc(4 ** self.k * self.bits // 8) if self.rank == self.root else None
+        if not self._inbox or (self.rank == self.root and not self._root_table):
+            raise MemoryError('kpal_dev_alloc failed for the peer-reduce buffers')
+        mine = {'inbox': self._export(self._inbox),
+                'table': self._export(self._root_table) if self._root_table else None}
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine, group=group)
+        self._inboxes = (ctypes.c_void_p * self.world)()
+        for r in range(self.world):
+            self._inboxes[r] = self._inbox if r == self.rank else self._open(handles[r]['inbox'])
+        self.root_table = (self._root_table if self.rank == self.root
+                           else self._open(handles[self.root]['table']))
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        dist.all_reduce(self._flag, group=group)           # everyone has mapped everyone
+        torch.cuda.synchronize()
+
+    def _export(self, dev_ptr):
+        handle = ctypes.create_string_buffer(64)
+        _cabi.check(self._L.kpal_ipc_export(dev_ptr, handle))
+        return handle.raw
+
+    def _open(self, handle):
+        out = ctypes.c_void_p()
+        _cabi.check(self._L.kpal_ipc_open(handle, ctypes.byref(out)))
+        self._opened.append(out.value)
+        return out.value
+
+    def barrier(self):
+        """Stream-ordered cross-GPU barrier: nobody's stream passes it before
+        every rank's stream has reached it."""
+        import torch.distributed as dist
+        dist.all_reduce(self._flag, group=self.group)
+
+    def reduce(self, table_ptr, stream):
+        L = self._L
+        _cabi.check(L.kpal_dev_reduce_push(table_ptr, self.bits, self.k, self.rank, self.world,
+                                           self._inboxes, stream))
+        self.barrier()
+        _cabi.check(L.kpal_dev_reduce_collect(self._inbox, self.bits, self.k, self.rank, self.world,
+                                              self.root_table, stream))
+        self.barrier()
+        return self._root_table if self.rank == self.root else None
+
+    def count_and_reduce(self, codes_ptr, valid_ptr, n_bases, table_ptr, stream):
+        """Count this rank's packed stream and sum all ranks' tables onto the
+        root in one go (``kpal_dev_count_packed_push``): on the radix path the
+        all-to-all is fused into the count's second pass.  `table_ptr` is a
+        zeroed scratch table.  Returns like :meth:`reduce`."""
+        L = self._L
+        fused = ctypes.c_int()
+        _cabi.check(L.kpal_dev_count_packed_push(codes_ptr, valid_ptr, int(n_bases), self.k, table_ptr,
+                                                 self.bits, self.rank, self.world, self._inboxes,
+                                                 stream, ctypes.byref(fused)))
+        self.fused = bool(fused.value)
+        self.barrier()
+        _cabi.check(L.kpal_dev_reduce_collect(self._inbox, self.bits, self.k, self.rank, self.world,
+                                              self.root_table, stream))
+        self.barrier()
+        return self._root_table if self.rank == self.root else None
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize()
+        for p in self._opened:
+            self._L.kpal_ipc_close(p)
+        self._opened = []
+        if self._inbox:
+            self._L.kpal_dev_free(self._inbox)
+            self._inbox = None
+        if self._root_table:
+            self._L.kpal_dev_free(self._root_table)
+            self._root_table = None
 
 
 # ------------------------------------------------------------------ distances

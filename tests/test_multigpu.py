@@ -119,9 +119,11 @@ def _nccl_worker(rank, world, port, text, k, profiles, out_dir):
                             device_id=torch.device("cuda", rank))
     try:
         b, e = multigpu.split_fasta(text, world)[rank]
-        counts = multigpu.count_fasta_distributed(text[b:e], k, balance=True)
+        counts = multigpu.count_fasta_distributed(text[b:e], k, balance=True)        # peer-memory reduce
+        counts_nccl = multigpu.count_fasta_distributed(text[b:e], k, balance=True, reduce='nccl')
         matrix = multigpu.distance_matrix_distributed(profiles, do_scale=True)
         if rank == 0:
+            assert np.array_equal(counts, counts_nccl)
             np.save(os.path.join(out_dir, "counts.npy"), counts)
             np.save(os.path.join(out_dir, "matrix.npy"), matrix)
     finally:
@@ -150,3 +152,90 @@ def test_distributed_nccl(tmp_path):
     low = np.tril_indices(len(profiles), -1)
     np.testing.assert_allclose(matrix[low], want[low], rtol=1e-9, atol=0)
     assert np.array_equal(matrix, matrix.T)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits", [32, 64])
+def test_peer_reduce_kernels_virtual_world(bits):
+    """push / collect kernels of csrc/peer_reduce.cu with every "rank" on ONE device
+    (plain pointers instead of IPC mappings): the root table is the exact sum of
+    the per-rank tables for any world size, also when 4^k is not divisible by it."""
+    import ctypes
+    import torch
+    L = _cabi.load()
+    dev = torch.device("cuda", 0)
+    dtype = torch.int32 if bits == 32 else torch.int64
+    sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(9)
+    for k, world in ((2, 1), (2, 3), (3, 5), (6, 2), (6, 7), (9, 8), (10, 16), (11, 3)):
+        bins = 4 ** k
+        tables = [torch.randint(0, 2 ** 31 - 1, (bins,), dtype=dtype, device=dev, generator=gen)
+                  for _ in range(world)]
+        if bits == 64:
+            tables = [t << 20 for t in tables]
+        slot_bytes = int(L.kpal_peer_inbox_bytes(k, bits, world))
+        assert slot_bytes >= bins * bits // 8
+        inboxes = [torch.full((slot_bytes,), 0xAB, dtype=torch.uint8, device=dev) for _ in range(world)]
+        ptrs = (ctypes.c_void_p * world)(*[b.data_ptr() for b in inboxes])
+        root = torch.full((bins,), -1, dtype=dtype, device=dev)
+        for r in range(world):
+            _cabi.check(L.kpal_dev_reduce_push(tables[r].data_ptr(), bits, k, r, world, ptrs, sp))
+        for r in range(world):
+            _cabi.check(L.kpal_dev_reduce_collect(inboxes[r].data_ptr(), bits, k, r, world,
+                                                  root.data_ptr(), sp))
+        want = torch.stack(tables).sum(dim=0, dtype=dtype)          # wraps like the counters do
+        assert torch.equal(root, want), (k, world)
+    ptrs = (ctypes.c_void_p * 5)()
+    assert L.kpal_dev_reduce_push(root.data_ptr(), bits, 2, 0, 5, ptrs, sp) == _cabi.KPAL_EINVAL
+    assert L.kpal_dev_reduce_push(root.data_ptr(), 16, 6, 0, 2, ptrs, sp) == _cabi.KPAL_EINVAL
+    assert L.kpal_dev_reduce_collect(root.data_ptr(), bits, 6, 2, 2, root.data_ptr(), sp) == _cabi.KPAL_EINVAL
+
+
+@pytest.mark.gpu
+def test_count_push_fused_virtual_world():
+    """kpal_dev_count_packed_push with every "rank" on one device: the radix count's
+    second pass stores its histograms straight into the owners' inboxes (fused = 1
+    when the world divides the bucket count), otherwise count + push kernel; either
+    way collect() yields the exact sum of the per-rank counts."""
+    import ctypes
+    import torch
+    from oracle import c_oracle
+    L = _cabi.load()
+    dev = torch.device("cuda", 0)
+    sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rng = np.random.default_rng(17)
+    letters = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)
+    try:
+        for k, world, path, want_fused in ((9, 2, 2, 1), (10, 8, 2, 1), (11, 4, 2, 1), (10, 3, 2, 0),
+                                           (9, 4, 1, 0), (6, 2, 0, 0), (12, 16, 2, 1)):
+            _cabi.check(L.kpal_set_option(b"count_path", path))
+            bins = 4 ** k
+            slot_bytes = int(L.kpal_peer_inbox_bytes(k, 32, world))
+            inboxes = [torch.full((slot_bytes,), 0xCD, dtype=torch.uint8, device=dev) for _ in range(world)]
+            ptrs = (ctypes.c_void_p * world)(*[b.data_ptr() for b in inboxes])
+            want = np.zeros(bins, dtype=np.int64)
+            keep = []
+            for r in range(world):
+                n = int(rng.integers(150_000, 400_000))
+                seq = letters[rng.choice(9, n, p=[.24, .24, .24, .24, .01, .01, .005, .005, .01])]
+                seq[rng.integers(0, n, 40)] = 10                       # record breaks
+                records = bytes(seq).split(b"\n")
+                want += c_oracle.count_sequences([x.decode() for x in records], k)
+                codes, valid, _, n_bases = _cabi.pack_sequences(records)
+                d_codes = torch.from_numpy(codes.view(np.int32)).to(dev)
+                d_valid = torch.from_numpy(valid.view(np.int32)).to(dev)
+                table = torch.zeros(bins, dtype=torch.int32, device=dev)
+                fused = ctypes.c_int(-1)
+                _cabi.check(L.kpal_dev_count_packed_push(d_codes.data_ptr(), d_valid.data_ptr(), n_bases, k,
+                                                         table.data_ptr(), 32, r, world, ptrs, sp,
+                                                         ctypes.byref(fused)))
+                assert fused.value == want_fused, (k, world, path)
+                keep.append((d_codes, d_valid, table))
+            root = torch.full((bins,), -1, dtype=torch.int32, device=dev)
+            for r in range(world):
+                _cabi.check(L.kpal_dev_reduce_collect(inboxes[r].data_ptr(), 32, k, r, world,
+                                                      root.data_ptr(), sp))
+            assert np.array_equal(root.cpu().numpy().astype(np.int64), want), (k, world, path)
+    finally:
+        _cabi.check(L.kpal_set_option(b"count_path", 0))
