@@ -322,6 +322,7 @@ def bench_count(args):
     _cabi.check(L.kpal_set_option(b"radix_debug", args.radix_debug))
     _cabi.check(L.kpal_set_option(b"radix_shape", args.radix_shape))
     _cabi.check(L.kpal_set_option(b"fasta_chunks", args.fasta_chunks))
+    _cabi.check(L.kpal_set_option(b"narrow_d2h", args.narrow_d2h))
     dev = torch.device("cuda", local)
 
     # ---- this rank's shard of records (same size on every rank: weak scaling)
@@ -364,9 +365,31 @@ def bench_count(args):
     sp = ctypes.c_void_p(stream.cuda_stream)
 
     reducer = None
+    reduce_note = None
     if world > 1 and args.reduce in ("peer", "fused"):
         from kpal_b200 import multigpu
-        reducer = multigpu.PeerReducer(k, 32)
+        # CUDA IPC between the ranks can be refused by the box (container without a shared
+        # PID/IPC namespace, GPUs without peer access): every rank then takes the NCCL reduce,
+        # and the JSON line says so.  The decision is collective so no rank is left waiting.
+        peer_ok = torch.ones(1, dtype=torch.int32, device=dev)
+        for a in range(world):
+            if a != local and not torch.cuda.can_device_access_peer(local, a):
+                peer_ok.zero_()
+        dist.all_reduce(peer_ok, op=dist.ReduceOp.MIN)
+        if int(peer_ok.item()):
+            try:
+                reducer = multigpu.PeerReducer(k, 32)
+            except Exception as exc:        # ranks fail together (IPC open) or not at all
+                reducer = None
+                reduce_note = "peer-memory reduce unavailable (%s): NCCL reduce used" % (exc,)
+        else:
+            reduce_note = "no peer access between all GPU pairs: NCCL reduce used"
+        ok = torch.tensor([1 if reducer is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not int(ok.item()) and reducer is not None:
+            reducer.close()
+            reducer = None
+            reduce_note = "peer-memory reduce unavailable on another rank: NCCL reduce used"
 
     def reduce_and_finalize():
         """Sum of the per-rank u32 tables onto rank 0 + widen/balance there."""
@@ -495,6 +518,7 @@ def bench_count(args):
         radix = args.count_path == 2 or (args.count_path == 0 and n_bases >= ((16 << 20) if k <= 12 else (4 << 20)))
         if n_windows is None:
             n_windows = seq_bases
+        narrow = bool(args.narrow_d2h and world == 1 and bins >= (1 << 20))
         count_kernel_name = ("radix_partition_kernel<u32> + radix_histogram_kernel<u32>" if radix
                              else "count_global_kernel<u32>")
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
@@ -511,12 +535,16 @@ def bench_count(args):
                                         if (reducer is not None and args.reduce == "fused") else
                                         "over NVLink peer memory (all-to-all push + collect kernels)"
                                         if reducer is not None else "with an NCCL reduce"))
-                       if world > 1 else "1 GPU"},
+                       if world > 1 else "1 GPU",
+                       **({"reduce_note": reduce_note} if reduce_note else {})},
             "e2e": {"value": total_bases / 1e9 / e2e_s, "unit": "Gbases/s",
                     "h2d_bytes_per_step": int(n_fasta * world),
-                    "d2h_bytes_per_step": int(bins * 8), "ms_per_step": e2e_s * 1e3,
-                    "path": "pinned FASTA bytes -> kpal_count_fasta (H2D of the raw text, GPU scan/pack, "
-                            "count + balance kernels, D2H int64)"},
+                    "d2h_bytes_per_step": int(bins * 2 + 4) if narrow else int(bins * 8),
+                    "ms_per_step": e2e_s * 1e3,
+                    "path": "pinned FASTA bytes -> kpal_count_fasta (H2D of the raw text in chunks, GPU scan/pack, "
+                            "count + balance kernels, " +
+                            ("D2H as uint16 in chunks, widened to the int64 profile by host threads)"
+                             if narrow else "D2H int64)")},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": count_kernel_name, "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -704,6 +732,9 @@ def main():
                          "(default), as separate push/collect kernels, or with dist.reduce")
     ap.add_argument("--no-e2e", action="store_true", help="matrix workload: skip the host-buffer end-to-end leg")
     ap.add_argument("--fasta-chunks", type=int, default=0, help="chunks of the pipelined FASTA upload (0 = auto)")
+    ap.add_argument("--narrow-d2h", type=int, default=1, choices=[0, 1],
+                    help="e2e leg: 1 = the profile leaves the device as uint16 and host threads widen it "
+                         "(library default), 0 = plain int64 copy")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

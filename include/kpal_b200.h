@@ -176,6 +176,18 @@ void kpal_matrix_close(void *session);
 int kpal_format_matrix(const double *values, uint64_t n, uint64_t ld, int precision,
                        char *text, uint64_t capacity, uint64_t *length);
 
+/*
+ * Host stage of the profile's device->host copy.  Profile.counts is int64[4^k]
+ * (kpal/klib.py:170); from k = 10 on, kpal_count_fasta / kpal_count_sequences move
+ * the counts over PCIe as uint16 (exact: a count above 65535 sends the call down
+ * the int64 copy instead) and a pool of host threads widens chunk c into the
+ * caller's array while chunk c+1 is in flight.  This entry point is that widening
+ * stage alone (host only, no GPU): narrow[0..n) -> counts_out[0..n), consumed in
+ * chunks of `chunk` elements (0 = one chunk).  kpal_set_option("narrow_d2h", 0)
+ * turns the narrow copy off.
+ */
+int kpal_widen_u16(const uint16_t *narrow, uint64_t n, uint64_t chunk, int64_t *counts_out);
+
 /* ProfileDistance.distance for one pair (kpal/kdistlib.py:126-161). */
 int kpal_pair_distance(const int64_t *left, const int64_t *right, int k,
                        int metric, int pairwise, int do_balance, int do_scale, int down,

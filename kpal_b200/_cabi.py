@@ -29,7 +29,7 @@ SYMBOLS = (
     "kpal_count_sequences", "kpal_count_fasta", "kpal_count_by_record", "kpal_balance",
     "kpal_distance_matrix", "kpal_pair_distance",
     "kpal_matrix_open", "kpal_matrix_push", "kpal_matrix_finish", "kpal_matrix_close",
-    "kpal_format_matrix", "kpal_pair_distance_positive",
+    "kpal_format_matrix", "kpal_widen_u16", "kpal_pair_distance_positive",
     "kpal_split_length", "kpal_split", "kpal_show_balance",
     "kpal_ipc_export", "kpal_ipc_open", "kpal_ipc_close", "kpal_peer_inbox_bytes",
     "kpal_dev_reduce_push", "kpal_dev_reduce_collect", "kpal_dev_count_packed_push",
@@ -93,6 +93,7 @@ def load():
     sig("kpal_matrix_finish", i32, vp, vp)
     sig("kpal_matrix_close", None, vp)
     sig("kpal_format_matrix", i32, vp, u64, u64, i32, vp, u64, pu64)
+    sig("kpal_widen_u16", i32, vp, u64, u64, vp)
     sig("kpal_pair_distance_positive", i32, vp, vp, i32, i32, i32, i32, i32, i32, vp)
     sig("kpal_split_length", u64, i32)
     sig("kpal_split", i32, vp, i32, vp, vp)

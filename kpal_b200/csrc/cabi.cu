@@ -17,6 +17,12 @@ namespace kpal {
 // launchers (count.cu / distance.cu)
 int launch_count(const uint32_t *, const uint32_t *, uint64_t, int, void *, int, cudaStream_t);
 int launch_finalize(const void *, int, int, int, int64_t *, cudaStream_t);
+int launch_finalize_u16(const void *, int, int, int, uint16_t *, unsigned int *, cudaStream_t);
+// widen.cpp: host workers that widen the uint16 form of a profile to int64
+struct WidenHandle;
+WidenHandle *widen_begin(const uint16_t *src, int64_t *dst, uint64_t n, uint64_t chunk);
+void widen_publish(WidenHandle *h, uint64_t elements);
+void widen_end(WidenHandle *h, int abort);
 int launch_balance(const int64_t *, int64_t *, int, cudaStream_t);
 int launch_accumulate(const void *, void *, int, uint64_t, cudaStream_t);
 int launch_by_record(const uint32_t *, const uint32_t *, const uint64_t *, uint64_t, uint64_t, int,
@@ -55,6 +61,7 @@ static thread_local char t_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_host_fasta{-1};       // -1: from the environment (KPAL_HOST_FASTA=1)
 static std::atomic<int> g_fasta_chunks{0};      // 0 = automatic (one chunk per ~6 MB, at most 16)
+static std::atomic<int> g_narrow_d2h{1};        // 1: large profiles leave the device as uint16 (see finalize_to_host)
 
 void set_error(const char *fmt, ...)
 {
@@ -152,10 +159,11 @@ struct GrowPin {
 };
 struct CountWorkspace {
     int device = -1;
-    GrowDev codes, valid, table, counts, text, fscratch;
-    GrowPin pcodes, pvalid, pstatus;
+    GrowDev codes, valid, table, counts, text, fscratch, counts16, overflow;
+    GrowPin pcodes, pvalid, pstatus, pnarrow, pflag;
     cudaStream_t copy_stream = nullptr;          // H2D of the FASTA text, chunk by chunk
     cudaEvent_t chunk_done[16] = {};
+    cudaEvent_t d2h_done[16] = {};               // chunks of the narrow D2H of the profile
 };
 static std::mutex g_count_mutex;                 // held for the whole host-level call
 static std::vector<CountWorkspace *> g_count_ws;
@@ -307,6 +315,7 @@ extern "C" int kpal_set_option(const char *name, int value)
         g_fasta_chunks.store(value); return KPAL_OK;
     }
     if (!strcmp(name, "exact_div")) { set_exact_div(value != 0); return KPAL_OK; }
+    if (!strcmp(name, "narrow_d2h")) { g_narrow_d2h.store(value ? 1 : 0); return KPAL_OK; }
     if (!strcmp(name, "count_path")) {
         if (value < 0 || value > 2) return bad_arg("count_path must be 0 (auto), 1 (RED) or 2 (radix)");
         set_count_path(value); return KPAL_OK;
@@ -384,20 +393,76 @@ static int upload_and_count(CountWorkspace *w, uint64_t n_bases, int k, void *d_
                         n_bases, k, d_table, bits, st);
 }
 
+// Counter table on the device -> the caller's int64 profile on the host
+// (widen + optional balance, then D2H).
+//
+// From 4^10 bins on, the profile leaves the device as uint16: a quarter of the PCIe
+// bytes of the int64 array (the longest single piece of the host-level call: 134 MB at
+// k = 12).  The copy runs in up to 16 chunks into pinned staging; host workers
+// (widen.cpp) widen chunk c into `counts_out` while chunk c+1 is in flight, so the
+// caller's array -- pageable or pinned -- is written exactly once, by the CPU.  A
+// count above 65535 (small tables are excluded up front; a large table needs a very
+// repetitive input) raises a device flag that travels ahead of the first chunk: the
+// finalize is then redone in int64 and copied as before.  Exact either way.
+static int finalize_to_host(CountWorkspace *w, int bits, int k, int balance, int64_t *counts_out,
+                            cudaStream_t st)
+{
+    const uint64_t bins = 1ull << (2 * k);
+    if (g_narrow_d2h.load() && bins >= (1ull << 20)) {
+        KPAL_CHECK(w->counts16.ensure(bins * 2));
+        KPAL_CHECK(w->overflow.ensure(16));
+        KPAL_CHECK(w->pnarrow.ensure(bins * 2));
+        KPAL_CHECK(w->pflag.ensure(16));
+        if (!w->d2h_done[0])
+            for (auto &e : w->d2h_done) KPAL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        KPAL_CUDA(cudaMemsetAsync(w->overflow.p, 0, 4, st));
+        KPAL_CHECK(launch_finalize_u16(w->table.p, bits, k, balance, static_cast<uint16_t *>(w->counts16.p),
+                                       static_cast<unsigned int *>(w->overflow.p), st));
+        KPAL_CUDA(cudaMemcpyAsync(w->pflag.p, w->overflow.p, 4, cudaMemcpyDeviceToHost, st));
+        uint64_t n_chunks = std::min<uint64_t>(16, std::max<uint64_t>(1, bins * 2 / (4ull << 20)));
+        const uint64_t chunk = bins / n_chunks;                 // power of two >= 2^16 elements
+        for (uint64_t c = 0; c < n_chunks; ++c) {
+            KPAL_CUDA(cudaMemcpyAsync(static_cast<uint16_t *>(w->pnarrow.p) + c * chunk,
+                                      static_cast<const uint16_t *>(w->counts16.p) + c * chunk, chunk * 2,
+                                      cudaMemcpyDeviceToHost, st));
+            KPAL_CUDA(cudaEventRecord(w->d2h_done[c], st));
+        }
+        // from here on the workers are awake: every exit goes through widen_end
+        WidenHandle *h = widen_begin(static_cast<const uint16_t *>(w->pnarrow.p), counts_out, bins, chunk);
+        cudaError_t err = cudaSuccess;
+        bool overflow = false;
+        for (uint64_t c = 0; c < n_chunks; ++c) {
+            err = cudaEventSynchronize(w->d2h_done[c]);
+            if (err != cudaSuccess) break;
+            if (c == 0 && *static_cast<const volatile unsigned int *>(w->pflag.p)) { overflow = true; break; }
+            widen_publish(h, (c + 1) * chunk);
+        }
+        widen_end(h, (err != cudaSuccess || overflow) ? 1 : 0);
+        if (err != cudaSuccess) {
+            set_error("narrow D2H of the profile failed: %s", cudaGetErrorString(err));
+            cudaGetLastError();
+            return KPAL_ECUDA;
+        }
+        if (!overflow) return KPAL_OK;
+        KPAL_CUDA(cudaStreamSynchronize(st));                   // drain the abandoned chunks
+    }
+    KPAL_CHECK(w->counts.ensure(bins * 8));
+    KPAL_CHECK(launch_finalize(w->table.p, bits, k, balance, static_cast<int64_t *>(w->counts.p), st));
+    KPAL_CUDA(cudaMemcpyAsync(counts_out, w->counts.p, bins * 8, cudaMemcpyDeviceToHost, st));
+    KPAL_CUDA(cudaStreamSynchronize(st));
+    return KPAL_OK;
+}
+
 static int count_packed_to_host(CountWorkspace *w, uint64_t n_bases, int k, int balance,
                                 int64_t *counts_out)
 {
     const uint64_t bins = 1ull << (2 * k);
     const int bits = (n_bases >= (1ull << 32)) ? 64 : 32;
     KPAL_CHECK(w->table.ensure(bins * (bits / 8)));
-    KPAL_CHECK(w->counts.ensure(bins * 8));
     cudaStream_t st = 0;
     KPAL_CUDA(cudaMemsetAsync(w->table.p, 0, bins * (bits / 8), st));
     KPAL_CHECK(upload_and_count(w, n_bases, k, w->table.p, bits, st));
-    KPAL_CHECK(launch_finalize(w->table.p, bits, k, balance, static_cast<int64_t *>(w->counts.p), st));
-    KPAL_CUDA(cudaMemcpyAsync(counts_out, w->counts.p, bins * 8, cudaMemcpyDeviceToHost, st));
-    KPAL_CUDA(cudaStreamSynchronize(st));
-    return KPAL_OK;
+    return finalize_to_host(w, bits, k, balance, counts_out, st);
 }
 
 static int check_k_host(int k)
@@ -531,17 +596,11 @@ extern "C" int kpal_count_fasta(const char *fasta, uint64_t n_bytes, int k, int 
         const uint64_t bins = 1ull << (2 * k);
         const int bits = (n_bytes >= (1ull << 32)) ? 64 : 32;
         KPAL_CHECK(w->table.ensure(bins * (bits / 8)));
-        KPAL_CHECK(w->counts.ensure(bins * 8));
         cudaStream_t st = 0;
         KPAL_CUDA(cudaMemsetAsync(w->table.p, 0, bins * (bits / 8), st));
         unsigned flags = 0;
         KPAL_CHECK(fasta_gpu_count(w, fasta, n_bytes, k, w->table.p, bits, st, &flags, nullptr));
-        if (!flags) {
-            KPAL_CHECK(launch_finalize(w->table.p, bits, k, balance, static_cast<int64_t *>(w->counts.p), st));
-            KPAL_CUDA(cudaMemcpyAsync(counts_out, w->counts.p, bins * 8, cudaMemcpyDeviceToHost, st));
-            KPAL_CUDA(cudaStreamSynchronize(st));
-            return KPAL_OK;
-        }
+        if (!flags) return finalize_to_host(w, bits, k, balance, counts_out, st);
         // exotic whitespace: fall through to the host packer (exact rstrip semantics)
     }
     uint64_t n_bases = 0;

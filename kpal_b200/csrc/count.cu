@@ -155,16 +155,33 @@ count_smem_kernel(const uint4 *__restrict__ codes, const uint2 *__restrict__ val
 // table -> int64 profile, fused with balance: out[i] = t[i] + t[rc(i)]
 // (pairs get the sum, palindromes are doubled: kpal/klib.py:293-298).
 // ---------------------------------------------------------------------------
-template <typename CounterT>
+// OutT = int64_t: the API's profile.  OutT = uint16_t: the narrow form the host entry
+// points move over PCIe (a quarter of the bytes; widened to int64 by host threads while
+// the copy is still running) -- a count that does not fit raises *overflow and the caller
+// redoes the finalize in int64.
+template <typename OutT>
+__device__ __forceinline__ void put_count(OutT *__restrict__ out, uint64_t i, unsigned long long v,
+                                          unsigned int *__restrict__ overflow)
+{
+    if constexpr (sizeof(OutT) == 8) {
+        out[i] = OutT(v);
+    } else {
+        if (v > 0xffffull) *overflow = 1u;      // same value from every writer: a plain store is enough
+        out[i] = OutT(v);
+    }
+}
+
+template <typename CounterT, typename OutT>
 __global__ void __launch_bounds__(256)
-finalize_kernel(const CounterT *__restrict__ table, int k, int balance, int64_t *__restrict__ out)
+finalize_kernel(const CounterT *__restrict__ table, int k, int balance, OutT *__restrict__ out,
+                unsigned int *__restrict__ overflow)
 {
     const uint32_t n = 1u << (2 * k);
     const int shift = 32 - 2 * k;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int64_t v = int64_t(table[i]);
-        if (balance) v += int64_t(__ldg(table + rc_index(i, shift)));
-        out[i] = v;
+        unsigned long long v = table[i];
+        if (balance) v += __ldg(table + rc_index(i, shift));
+        put_count(out, i, v, overflow);
     }
 }
 
@@ -174,9 +191,10 @@ finalize_kernel(const CounterT *__restrict__ table, int k, int balance, int64_t 
 // rows, transposed through shared memory and written once as int64 -- table
 // read once, profile written once (the plain kernel reads 4 scattered bytes
 // per 32-byte sector for the partner).
-template <typename CounterT>
+template <typename CounterT, typename OutT>
 __global__ void __launch_bounds__(256)
-finalize_balance_tiled_kernel(const CounterT *__restrict__ table, int k, int64_t *__restrict__ out)
+finalize_balance_tiled_kernel(const CounterT *__restrict__ table, int k, OutT *__restrict__ out,
+                              unsigned int *__restrict__ overflow)
 {
     extern __shared__ __align__(16) unsigned char fin_smem[];
     CounterT *A = reinterpret_cast<CounterT *>(fin_smem);      // [64][65] tile of m
@@ -196,9 +214,11 @@ finalize_balance_tiled_kernel(const CounterT *__restrict__ table, int k, int64_t
     for (uint32_t e = threadIdx.x; e < 4096; e += 256) {
         const uint32_t h = e >> 6, l = e & 63u;
         const uint32_t t = rc_index(l, 26) * 65 + rc_index(h, 26);
-        out[(uint64_t(h) << hshift) | (uint64_t(m) << 6) | l] = int64_t(A[h * 65 + l]) + int64_t(partner[t]);
+        put_count(out, (uint64_t(h) << hshift) | (uint64_t(m) << 6) | l,
+                  (unsigned long long)(A[h * 65 + l]) + (unsigned long long)(partner[t]), overflow);
         if (m != mr)
-            out[(uint64_t(h) << hshift) | (uint64_t(mr) << 6) | l] = int64_t(B[h * 65 + l]) + int64_t(A[t]);
+            put_count(out, (uint64_t(h) << hshift) | (uint64_t(mr) << 6) | l,
+                      (unsigned long long)(B[h * 65 + l]) + (unsigned long long)(A[t]), overflow);
     }
 }
 
@@ -369,8 +389,9 @@ int launch_count(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_ba
     return KPAL_OK;
 }
 
-int launch_finalize(const void *d_table, int counter_bits, int k, int balance, int64_t *d_counts,
-                    cudaStream_t stream)
+template <typename OutT>
+static int launch_finalize_as(const void *d_table, int counter_bits, int k, int balance, OutT *d_out,
+                              unsigned int *d_overflow, cudaStream_t stream)
 {
     KPAL_CHECK(check_k(k));
     if (counter_bits != 32 && counter_bits != 64) return bad_arg("counter_bits must be 32 or 64");
@@ -382,25 +403,40 @@ int launch_finalize(const void *d_table, int counter_bits, int k, int balance, i
         const unsigned tiles = 1u << (2 * (k - 6));
         const size_t smem = size_t(2) * 64 * 65 * (counter_bits / 8);
         if (counter_bits == 32) {
-            finalize_balance_tiled_kernel<uint32_t><<<tiles, 256, smem, stream>>>(
-                static_cast<const uint32_t *>(d_table), k, d_counts);
+            finalize_balance_tiled_kernel<uint32_t, OutT><<<tiles, 256, smem, stream>>>(
+                static_cast<const uint32_t *>(d_table), k, d_out, d_overflow);
         } else {
-            KPAL_CUDA(cudaFuncSetAttribute(finalize_balance_tiled_kernel<unsigned long long>,
+            KPAL_CUDA(cudaFuncSetAttribute(finalize_balance_tiled_kernel<unsigned long long, OutT>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            finalize_balance_tiled_kernel<unsigned long long><<<tiles, 256, smem, stream>>>(
-                static_cast<const unsigned long long *>(d_table), k, d_counts);
+            finalize_balance_tiled_kernel<unsigned long long, OutT><<<tiles, 256, smem, stream>>>(
+                static_cast<const unsigned long long *>(d_table), k, d_out, d_overflow);
         }
         KPAL_LAUNCH_CHECK("finalize_balance_tiled_kernel");
         return KPAL_OK;
     }
     if (counter_bits == 32)
-        finalize_kernel<uint32_t><<<grid, 256, 0, stream>>>(
-            static_cast<const uint32_t *>(d_table), k, balance, d_counts);
+        finalize_kernel<uint32_t, OutT><<<grid, 256, 0, stream>>>(
+            static_cast<const uint32_t *>(d_table), k, balance, d_out, d_overflow);
     else
-        finalize_kernel<unsigned long long><<<grid, 256, 0, stream>>>(
-            static_cast<const unsigned long long *>(d_table), k, balance, d_counts);
+        finalize_kernel<unsigned long long, OutT><<<grid, 256, 0, stream>>>(
+            static_cast<const unsigned long long *>(d_table), k, balance, d_out, d_overflow);
     KPAL_LAUNCH_CHECK("finalize_kernel");
     return KPAL_OK;
+}
+
+int launch_finalize(const void *d_table, int counter_bits, int k, int balance, int64_t *d_counts,
+                    cudaStream_t stream)
+{
+    return launch_finalize_as<int64_t>(d_table, counter_bits, k, balance, d_counts, nullptr, stream);
+}
+
+// Narrow form for the host entry points: uint16 counts + *d_overflow (a device word the
+// caller zeroed) set when a count exceeds 65535.
+int launch_finalize_u16(const void *d_table, int counter_bits, int k, int balance, uint16_t *d_counts16,
+                        unsigned int *d_overflow, cudaStream_t stream)
+{
+    if (!d_overflow) return bad_arg("null overflow flag");
+    return launch_finalize_as<uint16_t>(d_table, counter_bits, k, balance, d_counts16, d_overflow, stream);
 }
 
 int launch_balance(const int64_t *d_in, int64_t *d_out, int k, cudaStream_t stream)

@@ -185,13 +185,25 @@ class PeerReducer(object):
         handles = [None] * self.world
         dist.all_gather_object(handles, mine, group=group)
         self._inboxes = (ctypes.c_void_p * self.world)()
-        for r in range(self.world):
-            self._inboxes[r] = self._inbox if r == self.rank else self._open(handles[r]['inbox'])
-        self.root_table = (self._root_table if self.rank == self.root
-                           else self._open(handles[self.root]['table']))
-        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
-        dist.all_reduce(self._flag, group=group)           # everyone has mapped everyone
+        error = None
+        try:
+            for r in range(self.world):
+                self._inboxes[r] = self._inbox if r == self.rank else self._open(handles[r]['inbox'])
+            self.root_table = (self._root_table if self.rank == self.root
+                               else self._open(handles[self.root]['table']))
+        except (RuntimeError, ValueError, MemoryError) as exc:        # cudaIpcOpenMemHandle refused (no peer access / IPC namespace)
+            error = exc
+        # everyone has mapped everyone -- or everyone learns that somebody could not, so that
+        # all ranks leave the constructor the same way (no rank is left in a collective)
+        self._flag = torch.tensor([0 if error is None else 1], dtype=torch.int32, device=self.device)
+        dist.all_reduce(self._flag, group=group)
+        failed = int(self._flag.item())
+        self._flag.zero_()
         torch.cuda.synchronize()
+        if failed:
+            self.close()
+            raise RuntimeError('peer-memory reduce unavailable: %d rank(s) could not map the peers (%s)'
+                               % (failed, error if error is not None else 'failure on another rank'))
 
     def _export(self, dev_ptr):
         handle = ctypes.create_string_buffer(64)

@@ -161,6 +161,46 @@ def test_format_matrix_equals_python_format():
 
 
 @pytest.mark.skipif(_cabi.device_count() > 0, reason="a GPU is present")
+def test_widen_u16_stage_is_exact():
+    """The host stage of the narrow profile copy (kpal_widen_u16): uint16 -> the
+    int64 counts of Profile.counts (klib.py:170), chunked, any alignment / length."""
+    L = _cabi.load()
+    rng = np.random.default_rng(11)
+    for n, chunk, offset in ((1, 0, 0), (7, 3, 1), (1000, 0, 0), (2500, 1000, 1), (1 << 20, 1 << 17, 0),
+                             ((1 << 22) + 5, 1 << 18, 1), (1 << 16, 1 << 20, 0)):
+        narrow = rng.integers(0, 65536, n, dtype=np.uint16)
+        narrow[:3] = (65535, 0, 1)[:min(3, n)]
+        backing = np.full(n + 2, -1, dtype=np.int64)
+        out = backing[offset:offset + n]            # offset 1: only 8-byte aligned
+        for _ in range(3):                          # the pool is reused from call to call
+            out[:] = -1
+            assert L.kpal_widen_u16(_cabi.ptr(narrow), n, chunk, out.ctypes.data) == _cabi.KPAL_OK
+            assert np.array_equal(out, narrow.astype(np.int64))
+        assert backing[offset + n] == -1 and (offset == 0 or backing[0] == -1)
+    assert L.kpal_widen_u16(None, 0, 0, None) == _cabi.KPAL_OK
+    assert L.kpal_widen_u16(None, 4, 0, None) == _cabi.KPAL_EINVAL
+
+
+def test_widen_u16_from_many_threads():
+    """Concurrent callers share one worker pool; every call must still be exact."""
+    import threading
+    L = _cabi.load()
+    rng = np.random.default_rng(12)
+    srcs = [rng.integers(0, 65536, (1 << 18) + i, dtype=np.uint16) for i in range(6)]
+    outs = [np.empty(s.size, dtype=np.int64) for s in srcs]
+
+    def run(i):
+        for _ in range(5):
+            assert L.kpal_widen_u16(_cabi.ptr(srcs[i]), srcs[i].size, 1 << 15, outs[i].ctypes.data) == 0
+    threads = [threading.Thread(target=run, args=(i,)) for i in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for s, o in zip(srcs, outs):
+        assert np.array_equal(o, s.astype(np.int64))
+
+
 def test_no_cpu_fallback_without_gpu():
     """On a box without a GPU the product path must refuse, not emulate."""
     from kpal_b200 import klib, kdistlib

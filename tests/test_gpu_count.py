@@ -488,3 +488,34 @@ def test_count_fasta_chunked_upload_pipeline(tutorial_texts):
                     assert np.array_equal(_cabi.count_fasta(text, k, balance=True), want[k]), (chunks, k)
     finally:
         _set_option("fasta_chunks", 0)
+
+
+def test_narrow_profile_copy_and_its_overflow_path():
+    """From k = 10 on the host entry points move the profile over PCIe as uint16 and widen
+    it on the host (cabi.cu finalize_to_host).  Same bits as the plain int64 copy, for
+    counts that fit -- and for counts that do not (a repetitive input pushes one bin past
+    65535: the device flag sends the call down the int64 copy)."""
+    reads = random_reads(5, 20_000, 150)
+    fasta = reads_to_fasta(reads)
+    seqs = [r.tobytes().decode() for r in reads]
+    repetitive = ">poly\n" + "A" * 70_000 + "\n>mix\n" + "ACGTTGCA" * 30_000 + "\n" + fasta.decode()
+    try:
+        for k in (10, 11, 12):
+            want = ko.count_sequences(seqs, k)
+            want_rep = ko.count_fasta(repetitive, k)
+            assert want_rep.max() > 65535 and ko.balance(want_rep).max() > 65535
+            for narrow in (1, 0):
+                _set_option("narrow_d2h", narrow)
+                for balance in (False, True):
+                    w = ko.balance(want) if balance else want
+                    assert np.array_equal(_cabi.count_fasta(fasta, k, balance=balance), w), (k, narrow, balance)
+                    assert np.array_equal(_cabi.count_sequences(seqs, k, balance=balance), w), (k, narrow, balance)
+                    wr = ko.balance(want_rep) if balance else want_rep
+                    assert np.array_equal(_cabi.count_fasta(repetitive, k, balance=balance), wr), (k, narrow, balance)
+            # exactly 65535 fits, 65536 does not: both sides of the threshold
+            for n_a in (65535 + k - 1, 65536 + k - 1):
+                _set_option("narrow_d2h", 1)
+                got = _cabi.count_sequences(["A" * n_a, "ACGT" * 50], k)
+                assert got[0] == n_a - k + 1 and np.array_equal(got, ko.count_sequences(["A" * n_a, "ACGT" * 50], k))
+    finally:
+        _set_option("narrow_d2h", 1)
