@@ -391,13 +391,18 @@ def bench_count(args):
             reducer = None
             reduce_note = "peer-memory reduce unavailable on another rank: NCCL reduce used"
 
-    def reduce_and_finalize():
-        """Sum of the per-rank u32 tables onto rank 0 + widen/balance there."""
+    def reduce_tables():
+        """Sum of the per-rank u32 tables onto rank 0; returns its device pointer there."""
         summed = d_table.data_ptr()
         if reducer is not None:
             summed = reducer.reduce(d_table.data_ptr(), sp)       # peer-memory all-to-all + collect
         elif world > 1:
             dist.reduce(d_table, dst=0, op=dist.ReduceOp.SUM)
+        return summed
+
+    def reduce_and_finalize():
+        """... + widen/balance there."""
+        summed = reduce_tables()
         if rank == 0:
             _cabi.check(L.kpal_dev_finalize_counts(summed, 32, k, 1, d_counts.data_ptr(), sp))
 
@@ -428,9 +433,9 @@ def bench_count(args):
             nb = ctypes.c_uint64()
             _cabi.check(L.kpal_count_fasta_to_dev(pinned_fasta._ptr, n_fasta, k, d_table.data_ptr(),
                                                   32, sp, ctypes.byref(nb)))
-            reduce_and_finalize()
-            if rank == 0:
-                _cabi.check(L.kpal_memcpy_d2h(pinned_out._ptr, d_counts.data_ptr(), bins * 8, sp))
+            summed = reduce_tables()
+            if rank == 0:       # widen + balance + narrow D2H into the host profile
+                _cabi.check(L.kpal_dev_table_to_host(summed, 32, k, 1, pinned_out._ptr, sp))
         torch.cuda.synchronize()
 
     # ---- warm-up (>= 3)
@@ -518,7 +523,7 @@ def bench_count(args):
         radix = args.count_path == 2 or (args.count_path == 0 and n_bases >= ((16 << 20) if k <= 12 else (4 << 20)))
         if n_windows is None:
             n_windows = seq_bases
-        narrow = bool(args.narrow_d2h and world == 1 and bins >= (1 << 20))
+        narrow = bool(args.narrow_d2h and bins >= (1 << 20))
         count_kernel_name = ("radix_partition_kernel<u32> + radix_histogram_kernel<u32>" if radix
                              else "count_global_kernel<u32>")
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
@@ -541,8 +546,10 @@ def bench_count(args):
                     "h2d_bytes_per_step": int(n_fasta * world),
                     "d2h_bytes_per_step": int(bins * 2 + 4) if narrow else int(bins * 8),
                     "ms_per_step": e2e_s * 1e3,
-                    "path": "pinned FASTA bytes -> kpal_count_fasta (H2D of the raw text in chunks, GPU scan/pack, "
-                            "count + balance kernels, " +
+                    "path": ("pinned FASTA bytes -> kpal_count_fasta (H2D of the raw text in chunks, GPU scan/pack, "
+                             "count + balance kernels, " if world == 1 else
+                             "per rank: pinned FASTA bytes -> kpal_count_fasta_to_dev (H2D in chunks, GPU scan/pack, "
+                             "count); table sum onto rank 0; there kpal_dev_table_to_host (widen + balance, ") +
                             ("D2H as uint16 in chunks, widened to the int64 profile by host threads)"
                              if narrow else "D2H int64)")},
             "gpu_launches": launches,

@@ -248,6 +248,17 @@ int kpal_dev_finalize_counts(const void *d_table, int counter_bits, int k, int b
                              int64_t *d_counts, void *stream);
 
 /* out[i] = in[i] + in[rc(i)] on int64 device vectors (in != out). */
+/*
+ * Device counter table -> int64 profile in HOST memory: kpal_dev_finalize_counts
+ * followed by the device->host copy, in the narrow form described at
+ * kpal_widen_u16 (uint16 over PCIe from k = 10 on, widened by host threads while
+ * the copy runs; int64 copy when a count exceeds 65535).  The table is this
+ * GPU's or, on the root of a multi-GPU count, the sum of all ranks' tables.
+ * Synchronises `stream`.
+ */
+int kpal_dev_table_to_host(const void *d_table, int counter_bits, int k, int balance,
+                           int64_t *counts_out, void *stream);
+
 int kpal_dev_balance(const int64_t *d_in, int64_t *d_out, int k, void *stream);
 
 /* rows [first, first+n) of the per-record count matrix, device resident. */

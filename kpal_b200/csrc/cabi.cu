@@ -404,8 +404,8 @@ static int upload_and_count(CountWorkspace *w, uint64_t n_bases, int k, void *d_
 // count above 65535 (small tables are excluded up front; a large table needs a very
 // repetitive input) raises a device flag that travels ahead of the first chunk: the
 // finalize is then redone in int64 and copied as before.  Exact either way.
-static int finalize_to_host(CountWorkspace *w, int bits, int k, int balance, int64_t *counts_out,
-                            cudaStream_t st)
+static int finalize_to_host(CountWorkspace *w, const void *d_table, int bits, int k, int balance,
+                            int64_t *counts_out, cudaStream_t st)
 {
     const uint64_t bins = 1ull << (2 * k);
     if (g_narrow_d2h.load() && bins >= (1ull << 20)) {
@@ -416,7 +416,7 @@ static int finalize_to_host(CountWorkspace *w, int bits, int k, int balance, int
         if (!w->d2h_done[0])
             for (auto &e : w->d2h_done) KPAL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         KPAL_CUDA(cudaMemsetAsync(w->overflow.p, 0, 4, st));
-        KPAL_CHECK(launch_finalize_u16(w->table.p, bits, k, balance, static_cast<uint16_t *>(w->counts16.p),
+        KPAL_CHECK(launch_finalize_u16(d_table, bits, k, balance, static_cast<uint16_t *>(w->counts16.p),
                                        static_cast<unsigned int *>(w->overflow.p), st));
         KPAL_CUDA(cudaMemcpyAsync(w->pflag.p, w->overflow.p, 4, cudaMemcpyDeviceToHost, st));
         uint64_t n_chunks = std::min<uint64_t>(16, std::max<uint64_t>(1, bins * 2 / (4ull << 20)));
@@ -447,7 +447,7 @@ static int finalize_to_host(CountWorkspace *w, int bits, int k, int balance, int
         KPAL_CUDA(cudaStreamSynchronize(st));                   // drain the abandoned chunks
     }
     KPAL_CHECK(w->counts.ensure(bins * 8));
-    KPAL_CHECK(launch_finalize(w->table.p, bits, k, balance, static_cast<int64_t *>(w->counts.p), st));
+    KPAL_CHECK(launch_finalize(d_table, bits, k, balance, static_cast<int64_t *>(w->counts.p), st));
     KPAL_CUDA(cudaMemcpyAsync(counts_out, w->counts.p, bins * 8, cudaMemcpyDeviceToHost, st));
     KPAL_CUDA(cudaStreamSynchronize(st));
     return KPAL_OK;
@@ -462,7 +462,7 @@ static int count_packed_to_host(CountWorkspace *w, uint64_t n_bases, int k, int 
     cudaStream_t st = 0;
     KPAL_CUDA(cudaMemsetAsync(w->table.p, 0, bins * (bits / 8), st));
     KPAL_CHECK(upload_and_count(w, n_bases, k, w->table.p, bits, st));
-    return finalize_to_host(w, bits, k, balance, counts_out, st);
+    return finalize_to_host(w, w->table.p, bits, k, balance, counts_out, st);
 }
 
 static int check_k_host(int k)
@@ -600,7 +600,7 @@ extern "C" int kpal_count_fasta(const char *fasta, uint64_t n_bytes, int k, int 
         KPAL_CUDA(cudaMemsetAsync(w->table.p, 0, bins * (bits / 8), st));
         unsigned flags = 0;
         KPAL_CHECK(fasta_gpu_count(w, fasta, n_bytes, k, w->table.p, bits, st, &flags, nullptr));
-        if (!flags) return finalize_to_host(w, bits, k, balance, counts_out, st);
+        if (!flags) return finalize_to_host(w, w->table.p, bits, k, balance, counts_out, st);
         // exotic whitespace: fall through to the host packer (exact rstrip semantics)
     }
     uint64_t n_bases = 0;
@@ -642,6 +642,22 @@ extern "C" int kpal_count_fasta_to_dev(const char *fasta, uint64_t n_bytes, int 
     // the pinned staging buffers are reused by the next call: wait for the copies
     KPAL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return KPAL_OK;
+}
+
+// A device counter table (this GPU's, or the sum of all ranks' tables after the
+// multi-GPU reduce) -> the caller's int64 profile on the host: widen + optional
+// balance + the narrow D2H of finalize_to_host.  Synchronises the stream.
+extern "C" int kpal_dev_table_to_host(const void *d_table, int counter_bits, int k, int balance,
+                                      int64_t *counts_out, void *stream)
+{
+    if (!d_table || !counts_out) return bad_arg("null pointer");
+    if (counter_bits != 32 && counter_bits != 64) return bad_arg("counter_bits must be 32 or 64");
+    KPAL_CHECK(check_k_host(k));
+    KPAL_CHECK(require_device());
+    std::lock_guard<std::mutex> lock(g_count_mutex);
+    CountWorkspace *w;
+    KPAL_CHECK(get_count_ws(&w));
+    return finalize_to_host(w, d_table, counter_bits, k, balance, counts_out, (cudaStream_t)stream);
 }
 
 extern "C" int kpal_count_by_record(const uint32_t *codes, const uint32_t *valid, uint64_t n_bases,

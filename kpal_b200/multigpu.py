@@ -81,14 +81,19 @@ def _gpu_count_shard(fasta_bytes, k, device):
     return table
 
 
-def _gpu_finalize(table, k, balance):
+def _table_to_host(table_ptr, k, balance, device):
+    """Device u32 table -> the int64 profile as a NumPy array (widen + balance + the
+    narrow device->host copy of ``kpal_dev_table_to_host``)."""
     import torch
     L = _cabi.load()
-    out = torch.empty(4 ** k, dtype=torch.int64, device=table.device)
-    stream = ctypes.c_void_p(torch.cuda.current_stream(table.device).cuda_stream)
-    _cabi.check(L.kpal_dev_finalize_counts(table.data_ptr(), 32, int(k), int(bool(balance)),
-                                           out.data_ptr(), stream))
-    return out.cpu().numpy()
+    out = np.empty(4 ** k, dtype=np.int64)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    _cabi.check(L.kpal_dev_table_to_host(table_ptr, 32, int(k), int(bool(balance)), _cabi.ptr(out), stream))
+    return out
+
+
+def _gpu_finalize(table, k, balance):
+    return _table_to_host(table.data_ptr(), k, balance, table.device)
 
 
 def count_fasta_distributed(fasta_shard, k, balance=False, group=None, device=None,
@@ -131,11 +136,7 @@ def count_fasta_distributed(fasta_shard, k, balance=False, group=None, device=No
                 summed = reducer.reduce(table.data_ptr(), stream)
                 if summed is None:
                     return None
-                L = _cabi.load()
-                out = torch.empty(4 ** k, dtype=torch.int64, device=table.device)
-                _cabi.check(L.kpal_dev_finalize_counts(summed, 32, int(k), int(bool(balance)),
-                                                       out.data_ptr(), stream))
-                return out.cpu().numpy()
+                return _table_to_host(summed, k, balance, table.device)
             finally:
                 reducer.close()
         dist.reduce(table, dst=0, group=group)

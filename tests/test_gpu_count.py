@@ -376,6 +376,10 @@ def _dev_count(text_bytes, k, bits, balance):
         out = np.empty(bins, dtype=np.int64)
         _cabi.check(L.kpal_memcpy_d2h(_cabi.ptr(out), d_counts, out.nbytes, None))
         _cabi.check(L.kpal_stream_sync(None))
+        # the same table through the device-table -> host-profile entry point (narrow copy)
+        direct = np.full(bins, -1, dtype=np.int64)
+        _cabi.check(L.kpal_dev_table_to_host(d_table, bits, k, int(balance), _cabi.ptr(direct), None))
+        assert np.array_equal(direct, out), "kpal_dev_table_to_host differs from finalize + copy"
         return out
     finally:
         for p in (d_codes, d_valid, d_table, d_counts):
