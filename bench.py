@@ -323,6 +323,7 @@ def bench_count(args):
     _cabi.check(L.kpal_set_option(b"radix_shape", args.radix_shape))
     _cabi.check(L.kpal_set_option(b"fasta_chunks", args.fasta_chunks))
     _cabi.check(L.kpal_set_option(b"narrow_d2h", args.narrow_d2h))
+    _cabi.check(L.kpal_set_option(b"dma_share", args.dma_share))
     dev = torch.device("cuda", local)
 
     # ---- this rank's shard of records (same size on every rank: weak scaling)
@@ -524,6 +525,14 @@ def bench_count(args):
         if n_windows is None:
             n_windows = seq_bases
         narrow = bool(args.narrow_d2h and bins >= (1 << 20))
+        # bytes of the narrow copy: uint8 when every count of the result fits, else uint16
+        # (what finalize_to_host decides from the device's flag words), + the 8 flag bytes
+        # -- for the bins below the split; the last dma_share/16 of the (pinned) profile is
+        # copied as int64 by the DMA engine
+        split = bins // 16 * (16 - args.dma_share)
+        top = int(pinned_out.array[:split].max())
+        narrow_width = 8 if (not narrow or top > 65535) else (1 if (args.narrow_d2h == 1 and top <= 255) else 2)
+        d2h_bytes = bins * 8 if narrow_width == 8 else split * narrow_width + (bins - split) * 8 + 8
         count_kernel_name = ("radix_partition_kernel<u32> + radix_histogram_kernel<u32>" if radix
                              else "count_global_kernel<u32>")
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
@@ -544,14 +553,15 @@ def bench_count(args):
                        **({"reduce_note": reduce_note} if reduce_note else {})},
             "e2e": {"value": total_bases / 1e9 / e2e_s, "unit": "Gbases/s",
                     "h2d_bytes_per_step": int(n_fasta * world),
-                    "d2h_bytes_per_step": int(bins * 2 + 4) if narrow else int(bins * 8),
+                    "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": e2e_s * 1e3,
                     "path": ("pinned FASTA bytes -> kpal_count_fasta (H2D of the raw text in chunks, GPU scan/pack, "
                              "count + balance kernels, " if world == 1 else
                              "per rank: pinned FASTA bytes -> kpal_count_fasta_to_dev (H2D in chunks, GPU scan/pack, "
                              "count); table sum onto rank 0; there kpal_dev_table_to_host (widen + balance, ") +
-                            ("D2H as uint16 in chunks, widened to the int64 profile by host threads)"
-                             if narrow else "D2H int64)")},
+                            ("D2H of the first %d/16 of the profile as uint%d in chunks, widened to int64 by host "
+                             "threads, the rest as int64 by the copy engine meanwhile)" % (16 - args.dma_share, 8 * narrow_width)
+                             if narrow and narrow_width < 8 else "D2H int64)")},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": count_kernel_name, "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -739,9 +749,13 @@ def main():
                          "(default), as separate push/collect kernels, or with dist.reduce")
     ap.add_argument("--no-e2e", action="store_true", help="matrix workload: skip the host-buffer end-to-end leg")
     ap.add_argument("--fasta-chunks", type=int, default=0, help="chunks of the pipelined FASTA upload (0 = auto)")
-    ap.add_argument("--narrow-d2h", type=int, default=1, choices=[0, 1],
-                    help="e2e leg: 1 = the profile leaves the device as uint16 and host threads widen it "
-                         "(library default), 0 = plain int64 copy")
+    ap.add_argument("--narrow-d2h", type=int, default=1, choices=[0, 1, 2],
+                    help="e2e leg: 1 = the profile leaves the device as uint8 / uint16 (the narrowest that "
+                         "holds every count) and host threads widen it (library default), 2 = uint16 only, "
+                         "0 = plain int64 copy")
+    ap.add_argument("--dma-share", type=int, default=3,
+                    help="e2e leg: sixteenths of the narrow-copied profile that the copy engine moves as int64 "
+                         "straight into the pinned result while the host threads widen the rest (library default 3)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -179,14 +179,16 @@ int kpal_format_matrix(const double *values, uint64_t n, uint64_t ld, int precis
 /*
  * Host stage of the profile's device->host copy.  Profile.counts is int64[4^k]
  * (kpal/klib.py:170); from k = 10 on, kpal_count_fasta / kpal_count_sequences move
- * the counts over PCIe as uint16 (exact: a count above 65535 sends the call down
- * the int64 copy instead) and a pool of host threads widens chunk c into the
- * caller's array while chunk c+1 is in flight.  This entry point is that widening
- * stage alone (host only, no GPU): narrow[0..n) -> counts_out[0..n), consumed in
- * chunks of `chunk` elements (0 = one chunk).  kpal_set_option("narrow_d2h", 0)
- * turns the narrow copy off.
+ * the counts over PCIe in the narrowest of uint8 / uint16 that holds every count
+ * (exact: the device reports the widths that fit; a count above 65535 sends the
+ * call down the int64 copy instead) and a pool of host threads widens chunk c into
+ * the caller's array while chunk c+1 is in flight.  These entry points are that
+ * widening stage alone (host only, no GPU): narrow[0..n) -> counts_out[0..n),
+ * consumed in chunks of `chunk` elements (0 = one chunk).
+ * kpal_set_option("narrow_d2h", 0) turns the narrow copy off, 2 limits it to uint16.
  */
 int kpal_widen_u16(const uint16_t *narrow, uint64_t n, uint64_t chunk, int64_t *counts_out);
+int kpal_widen_u8(const uint8_t *narrow, uint64_t n, uint64_t chunk, int64_t *counts_out);
 
 /* ProfileDistance.distance for one pair (kpal/kdistlib.py:126-161). */
 int kpal_pair_distance(const int64_t *left, const int64_t *right, int k,
@@ -251,8 +253,8 @@ int kpal_dev_finalize_counts(const void *d_table, int counter_bits, int k, int b
 /*
  * Device counter table -> int64 profile in HOST memory: kpal_dev_finalize_counts
  * followed by the device->host copy, in the narrow form described at
- * kpal_widen_u16 (uint16 over PCIe from k = 10 on, widened by host threads while
- * the copy runs; int64 copy when a count exceeds 65535).  The table is this
+ * kpal_widen_u16 (uint8 or uint16 over PCIe from k = 10 on, widened by host threads
+ * while the copy runs; int64 copy when a count exceeds 65535).  The table is this
  * GPU's or, on the root of a multi-GPU count, the sum of all ranks' tables.
  * Synchronises `stream`.
  */

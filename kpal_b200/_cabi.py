@@ -29,7 +29,7 @@ SYMBOLS = (
     "kpal_count_sequences", "kpal_count_fasta", "kpal_count_by_record", "kpal_balance",
     "kpal_distance_matrix", "kpal_pair_distance",
     "kpal_matrix_open", "kpal_matrix_push", "kpal_matrix_finish", "kpal_matrix_close",
-    "kpal_format_matrix", "kpal_widen_u16", "kpal_pair_distance_positive",
+    "kpal_format_matrix", "kpal_widen_u16", "kpal_widen_u8", "kpal_pair_distance_positive",
     "kpal_split_length", "kpal_split", "kpal_show_balance",
     "kpal_ipc_export", "kpal_ipc_open", "kpal_ipc_close", "kpal_peer_inbox_bytes",
     "kpal_dev_reduce_push", "kpal_dev_reduce_collect", "kpal_dev_count_packed_push",
@@ -94,6 +94,7 @@ def load():
     sig("kpal_matrix_close", None, vp)
     sig("kpal_format_matrix", i32, vp, u64, u64, i32, vp, u64, pu64)
     sig("kpal_widen_u16", i32, vp, u64, u64, vp)
+    sig("kpal_widen_u8", i32, vp, u64, u64, vp)
     sig("kpal_pair_distance_positive", i32, vp, vp, i32, i32, i32, i32, i32, i32, vp)
     sig("kpal_split_length", u64, i32)
     sig("kpal_split", i32, vp, i32, vp, vp)
@@ -216,14 +217,18 @@ def count_sequences(sequences, k, balance=False):
     return out
 
 
-def count_fasta(text, k, balance=False):
-    """int64[4**k] counts of FASTA text (str or bytes) (kpal_count_fasta)."""
+def count_fasta(text, k, balance=False, out=None):
+    """int64[4**k] counts of FASTA text (str or bytes) (kpal_count_fasta).  `out`:
+    optional C-contiguous int64[4**k] destination (e.g. a PinnedArray's array)."""
     _check_k(k)
     L = load()
     require_gpu()
     if isinstance(text, str):
         text = text.encode("latin-1", "replace")
-    out = np.empty(4 ** k, dtype=np.int64)
+    if out is None:
+        out = np.empty(4 ** k, dtype=np.int64)
+    elif out.dtype != np.int64 or out.shape != (4 ** k,) or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous int64 array of length 4**k")
     check(L.kpal_count_fasta(ctypes.c_char_p(text) if text else None, len(text), int(k),
                              int(bool(balance)), ptr(out)))
     return out

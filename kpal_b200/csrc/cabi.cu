@@ -6,6 +6,8 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <stdio.h>
 #include <mutex>
 #include <numeric>
 #include <string.h>
@@ -17,10 +19,11 @@ namespace kpal {
 // launchers (count.cu / distance.cu)
 int launch_count(const uint32_t *, const uint32_t *, uint64_t, int, void *, int, cudaStream_t);
 int launch_finalize(const void *, int, int, int, int64_t *, cudaStream_t);
-int launch_finalize_u16(const void *, int, int, int, uint16_t *, unsigned int *, cudaStream_t);
+int launch_finalize_narrow(const void *, int, int, int, uint16_t *, uint8_t *, int64_t *, uint64_t, unsigned int *,
+                           cudaStream_t);
 // widen.cpp: host workers that widen the uint16 form of a profile to int64
 struct WidenHandle;
-WidenHandle *widen_begin(const uint16_t *src, int64_t *dst, uint64_t n, uint64_t chunk);
+WidenHandle *widen_begin(const void *src, int width, int64_t *dst, uint64_t n, uint64_t chunk);
 void widen_publish(WidenHandle *h, uint64_t elements);
 void widen_end(WidenHandle *h, int abort);
 int launch_balance(const int64_t *, int64_t *, int, cudaStream_t);
@@ -61,7 +64,8 @@ static thread_local char t_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_host_fasta{-1};       // -1: from the environment (KPAL_HOST_FASTA=1)
 static std::atomic<int> g_fasta_chunks{0};      // 0 = automatic (one chunk per ~6 MB, at most 16)
-static std::atomic<int> g_narrow_d2h{1};        // 1: large profiles leave the device as uint16 (see finalize_to_host)
+static std::atomic<int> g_dma_share{3};         // sixteenths of a narrow-copied profile the DMA engine moves as int64 (pinned destinations)
+static std::atomic<int> g_narrow_d2h{1};        // 1: large profiles leave the device as uint8 / uint16, 2: uint16 only (see finalize_to_host)
 
 void set_error(const char *fmt, ...)
 {
@@ -159,11 +163,12 @@ struct GrowPin {
 };
 struct CountWorkspace {
     int device = -1;
-    GrowDev codes, valid, table, counts, text, fscratch, counts16, overflow;
+    GrowDev codes, valid, table, counts, text, fscratch, counts16, counts8, overflow;
     GrowPin pcodes, pvalid, pstatus, pnarrow, pflag;
     cudaStream_t copy_stream = nullptr;          // H2D of the FASTA text, chunk by chunk
     cudaEvent_t chunk_done[16] = {};
     cudaEvent_t d2h_done[16] = {};               // chunks of the narrow D2H of the profile
+    cudaEvent_t flag_done = nullptr;             // ... and the flag words ahead of them
 };
 static std::mutex g_count_mutex;                 // held for the whole host-level call
 static std::vector<CountWorkspace *> g_count_ws;
@@ -315,7 +320,14 @@ extern "C" int kpal_set_option(const char *name, int value)
         g_fasta_chunks.store(value); return KPAL_OK;
     }
     if (!strcmp(name, "exact_div")) { set_exact_div(value != 0); return KPAL_OK; }
-    if (!strcmp(name, "narrow_d2h")) { g_narrow_d2h.store(value ? 1 : 0); return KPAL_OK; }
+    if (!strcmp(name, "narrow_d2h")) {
+        if (value < 0 || value > 2) return bad_arg("narrow_d2h must be 0 (int64), 1 (uint8 / uint16) or 2 (uint16)");
+        g_narrow_d2h.store(value); return KPAL_OK;
+    }
+    if (!strcmp(name, "dma_share")) {
+        if (value < 0 || value > 8) return bad_arg("dma_share must be 0 .. 8 (sixteenths of the profile)");
+        g_dma_share.store(value); return KPAL_OK;
+    }
     if (!strcmp(name, "count_path")) {
         if (value < 0 || value > 2) return bad_arg("count_path must be 0 (auto), 1 (RED) or 2 (radix)");
         set_count_path(value); return KPAL_OK;
@@ -393,63 +405,152 @@ static int upload_and_count(CountWorkspace *w, uint64_t n_bases, int k, void *d_
                         n_bases, k, d_table, bits, st);
 }
 
+// Device scalars written by the GPU FASTA packer (fasta.cu: FastaScratch).
+struct FastaStatus {
+    unsigned long long first_header, total_bases;
+    unsigned int flags, pad;
+};
+
+// KPAL_TRACE=1: host timestamps (us since the call began) of the phases of the host-level
+// count, printed to stderr at the end of the call.  A measuring aid, off by default.
+struct CallTrace {
+    bool on = false;
+    std::chrono::steady_clock::time_point t0;
+    char line[512]; size_t at = 0;
+    void begin()
+    {
+        static const bool enabled = [] { const char *e = getenv("KPAL_TRACE"); return e && e[0] == '1'; }();
+        on = enabled; at = 0;
+        if (on) t0 = std::chrono::steady_clock::now();
+    }
+    void mark(const char *what)
+    {
+        if (!on || at + 48 > sizeof line) return;
+        const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        at += size_t(snprintf(line + at, sizeof line - at, " %s=%.0f", what, us));
+    }
+    void end() { if (on) fprintf(stderr, "[kpal trace us]%s\n", line); }
+};
+static CallTrace g_trace;       // used under g_count_mutex
+
 // Counter table on the device -> the caller's int64 profile on the host
 // (widen + optional balance, then D2H).
 //
-// From 4^10 bins on, the profile leaves the device as uint16: a quarter of the PCIe
-// bytes of the int64 array (the longest single piece of the host-level call: 134 MB at
-// k = 12).  The copy runs in up to 16 chunks into pinned staging; host workers
-// (widen.cpp) widen chunk c into `counts_out` while chunk c+1 is in flight, so the
-// caller's array -- pageable or pinned -- is written exactly once, by the CPU.  A
-// count above 65535 (small tables are excluded up front; a large table needs a very
-// repetitive input) raises a device flag that travels ahead of the first chunk: the
-// finalize is then redone in int64 and copied as before.  Exact either way.
+// From 4^10 bins on, the profile leaves the device narrow: as uint8 when every count fits
+// (an eighth of the PCIe bytes of the int64 array, the longest single piece of the
+// host-level call: 134 MB at k = 12), else as uint16.  The finalize kernel writes both
+// forms and two flag words saying which of them hold every count; the flags travel ahead
+// of the data and the first uint8 chunk is copied speculatively behind them, so the
+// decision costs no bubble on the copy engine.  The copy runs in up to 16 chunks into
+// pinned staging; host workers (widen.cpp) widen chunk c into `counts_out` while chunk c+1
+// is in flight, so the caller's array -- pageable or pinned -- is written exactly once, by
+// the CPU.  A count above 65535 (a large table needs a very repetitive input for that)
+// sends the call down the int64 finalize + copy instead.  Exact either way.
+//
+// `pending` (optional): status words of the GPU FASTA packer whose D2H copy is already
+// queued on `st`.  They are looked at together with the flags; if the packer turned the
+// text down (*text_flags != 0 on return) nothing is written and the caller redoes the
+// file through the host packer.
 static int finalize_to_host(CountWorkspace *w, const void *d_table, int bits, int k, int balance,
-                            int64_t *counts_out, cudaStream_t st)
+                            int64_t *counts_out, cudaStream_t st, const FastaStatus *pending = nullptr,
+                            unsigned *text_flags = nullptr)
 {
     const uint64_t bins = 1ull << (2 * k);
-    if (g_narrow_d2h.load() && bins >= (1ull << 20)) {
-        KPAL_CHECK(w->counts16.ensure(bins * 2));
-        KPAL_CHECK(w->overflow.ensure(16));
-        KPAL_CHECK(w->pnarrow.ensure(bins * 2));
-        KPAL_CHECK(w->pflag.ensure(16));
-        if (!w->d2h_done[0])
-            for (auto &e : w->d2h_done) KPAL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        KPAL_CUDA(cudaMemsetAsync(w->overflow.p, 0, 4, st));
-        KPAL_CHECK(launch_finalize_u16(d_table, bits, k, balance, static_cast<uint16_t *>(w->counts16.p),
-                                       static_cast<unsigned int *>(w->overflow.p), st));
-        KPAL_CUDA(cudaMemcpyAsync(w->pflag.p, w->overflow.p, 4, cudaMemcpyDeviceToHost, st));
-        uint64_t n_chunks = std::min<uint64_t>(16, std::max<uint64_t>(1, bins * 2 / (4ull << 20)));
-        const uint64_t chunk = bins / n_chunks;                 // power of two >= 2^16 elements
-        for (uint64_t c = 0; c < n_chunks; ++c) {
-            KPAL_CUDA(cudaMemcpyAsync(static_cast<uint16_t *>(w->pnarrow.p) + c * chunk,
-                                      static_cast<const uint16_t *>(w->counts16.p) + c * chunk, chunk * 2,
-                                      cudaMemcpyDeviceToHost, st));
-            KPAL_CUDA(cudaEventRecord(w->d2h_done[c], st));
-        }
-        // from here on the workers are awake: every exit goes through widen_end
-        WidenHandle *h = widen_begin(static_cast<const uint16_t *>(w->pnarrow.p), counts_out, bins, chunk);
-        cudaError_t err = cudaSuccess;
-        bool overflow = false;
-        for (uint64_t c = 0; c < n_chunks; ++c) {
-            err = cudaEventSynchronize(w->d2h_done[c]);
-            if (err != cudaSuccess) break;
-            if (c == 0 && *static_cast<const volatile unsigned int *>(w->pflag.p)) { overflow = true; break; }
-            widen_publish(h, (c + 1) * chunk);
-        }
-        widen_end(h, (err != cudaSuccess || overflow) ? 1 : 0);
-        if (err != cudaSuccess) {
-            set_error("narrow D2H of the profile failed: %s", cudaGetErrorString(err));
+    const int narrow = g_narrow_d2h.load();
+    if (text_flags) *text_flags = 0;
+    if (narrow && bins >= (1ull << 20)) {
+        const bool try8 = narrow == 1;
+        // The host threads' store bandwidth, not PCIe, bounds the narrow copy (8 bytes written
+        // per 1 or 2 received).  When the caller's array is pinned, the DMA engine therefore
+        // takes the last `share`/16 of the profile as plain int64, written straight into the
+        // array behind the narrow chunks while the host threads are still widening.
+        uint64_t share = uint64_t(g_dma_share.load());
+        if (share) {
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, counts_out) != cudaSuccess || attr.type != cudaMemoryTypeHost) share = 0;
             cudaGetLastError();
-            return KPAL_ECUDA;
         }
-        if (!overflow) return KPAL_OK;
-        KPAL_CUDA(cudaStreamSynchronize(st));                   // drain the abandoned chunks
+        const uint64_t piece = bins / 16;                           // >= 65536 elements
+        const uint64_t split = piece * (16 - share), tail = bins - split;
+        KPAL_CHECK(w->counts16.ensure(split * 2));
+        if (try8) KPAL_CHECK(w->counts8.ensure(split));
+        if (tail) KPAL_CHECK(w->counts.ensure(tail * 8));
+        KPAL_CHECK(w->overflow.ensure(16));
+        KPAL_CHECK(w->pnarrow.ensure(split * 2));
+        KPAL_CHECK(w->pflag.ensure(16));
+        if (!w->d2h_done[0]) {
+            for (auto &e : w->d2h_done) KPAL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            KPAL_CUDA(cudaEventCreateWithFlags(&w->flag_done, cudaEventDisableTiming));
+        }
+        KPAL_CUDA(cudaMemsetAsync(w->overflow.p, 0, 8, st));
+        KPAL_CHECK(launch_finalize_narrow(d_table, bits, k, balance, static_cast<uint16_t *>(w->counts16.p),
+                                          try8 ? static_cast<uint8_t *>(w->counts8.p) : nullptr,
+                                          static_cast<int64_t *>(w->counts.p), split,
+                                          static_cast<unsigned int *>(w->overflow.p), st));
+        KPAL_CUDA(cudaMemcpyAsync(w->pflag.p, w->overflow.p, 8, cudaMemcpyDeviceToHost, st));
+        KPAL_CUDA(cudaEventRecord(w->flag_done, st));
+        // chunks of whole pieces, >= 1 MiB each (the last one may be shorter)
+        auto chunk_of = [&](int width) {
+            uint64_t per = 1;
+            while (per * piece * uint64_t(width) < (1ull << 20) && per < 16) per *= 2;
+            return per * piece;
+        };
+        auto copy_chunk = [&](int width, uint64_t chunk, uint64_t c) -> cudaError_t {
+            const unsigned char *src = static_cast<const unsigned char *>(width == 1 ? w->counts8.p : w->counts16.p);
+            const uint64_t at = c * chunk, len = std::min(chunk, split - at);
+            cudaError_t e = cudaMemcpyAsync(static_cast<unsigned char *>(w->pnarrow.p) + at * width, src + at * width,
+                                            len * width, cudaMemcpyDeviceToHost, st);
+            return e != cudaSuccess ? e : cudaEventRecord(w->d2h_done[c], st);
+        };
+        int width = try8 ? 1 : 2;
+        uint64_t chunk = chunk_of(width);
+        if (try8) KPAL_CUDA(copy_chunk(1, chunk, 0));               // speculative, behind the flags
+        g_trace.mark("queued");
+        KPAL_CUDA(cudaEventSynchronize(w->flag_done));
+        g_trace.mark("flags");
+        const volatile unsigned int *flag = static_cast<const volatile unsigned int *>(w->pflag.p);
+        if (pending && pending->flags) {
+            *text_flags = pending->flags;
+            KPAL_CUDA(cudaStreamSynchronize(st));
+            return KPAL_OK;
+        }
+        const bool over16 = flag[0] != 0, over8 = flag[1] != 0;
+        if (!over16) {
+            uint64_t first = 1;                                     // chunk 0 is already on its way
+            if (!try8 || over8) { width = 2; chunk = chunk_of(2); first = 0; }
+            const uint64_t n_chunks = (split + chunk - 1) / chunk;
+            for (uint64_t c = first; c < n_chunks; ++c) KPAL_CUDA(copy_chunk(width, chunk, c));
+            if (tail) KPAL_CUDA(cudaMemcpyAsync(counts_out + split, w->counts.p, tail * 8, cudaMemcpyDeviceToHost, st));
+            // from here on the workers are awake: every exit goes through widen_end
+            WidenHandle *h = widen_begin(w->pnarrow.p, width, counts_out, split, chunk);
+            cudaError_t err = cudaSuccess;
+            for (uint64_t c = 0; c < n_chunks; ++c) {
+                err = cudaEventSynchronize(w->d2h_done[c]);
+                if (err != cudaSuccess) break;
+                widen_publish(h, std::min((c + 1) * chunk, split));
+            }
+            g_trace.mark(width == 1 ? "d2h_u8" : "d2h_u16");
+            widen_end(h, err != cudaSuccess ? 1 : 0);
+            g_trace.mark("widened");
+            if (err == cudaSuccess && tail) err = cudaStreamSynchronize(st);
+            g_trace.mark("tail");
+            if (err != cudaSuccess) {
+                set_error("narrow D2H of the profile failed: %s", cudaGetErrorString(err));
+                cudaGetLastError();
+                return KPAL_ECUDA;
+            }
+            return KPAL_OK;
+        }
+        KPAL_CUDA(cudaStreamSynchronize(st));                       // drain the speculative chunk
+    } else if (pending) {
+        KPAL_CUDA(cudaStreamSynchronize(st));
+        if (pending->flags) { *text_flags = pending->flags; return KPAL_OK; }
     }
     KPAL_CHECK(w->counts.ensure(bins * 8));
     KPAL_CHECK(launch_finalize(d_table, bits, k, balance, static_cast<int64_t *>(w->counts.p), st));
     KPAL_CUDA(cudaMemcpyAsync(counts_out, w->counts.p, bins * 8, cudaMemcpyDeviceToHost, st));
     KPAL_CUDA(cudaStreamSynchronize(st));
+    g_trace.mark("d2h_i64");
     return KPAL_OK;
 }
 
@@ -512,16 +613,12 @@ extern "C" int kpal_count_sequences(const char *text, const uint64_t *offsets, u
     return count_packed_to_host(w, n_bases, k, balance, counts_out);
 }
 
-// Device scalars written by the GPU FASTA packer (fasta.cu: FastaScratch).
-struct FastaStatus {
-    unsigned long long first_header, total_bases;
-    unsigned int flags, pad;
-};
-
 // Raw FASTA bytes (host) -> device text -> GPU scan/pack -> windows accumulated
 // into d_table.  *flags gets bit 0 when the text holds bytes the GPU packer
 // does not handle (tabs & co on sequence lines): the caller then redoes the
-// file through the host packer.  Synchronises the stream.
+// file through the host packer.  Synchronises the stream -- unless `flags` is null:
+// then the status copy is only queued and the caller reads w->pstatus after its own
+// synchronisation (finalize_to_host does, together with its flag words).
 static int fasta_gpu_count(CountWorkspace *w, const char *fasta, uint64_t n_bytes, int k,
                            void *d_table, int bits, cudaStream_t st, unsigned *flags,
                            uint64_t *n_bases)
@@ -564,6 +661,8 @@ static int fasta_gpu_count(CountWorkspace *w, const char *fasta, uint64_t n_byte
                             n_bytes, k, d_table, bits, st));
     KPAL_CUDA(cudaMemcpyAsync(w->pstatus.p, w->fscratch.p, sizeof(FastaStatus),
                               cudaMemcpyDeviceToHost, st));
+    g_trace.mark("count_queued");
+    if (!flags) return KPAL_OK;
     KPAL_CUDA(cudaStreamSynchronize(st));
     const FastaStatus *fs = static_cast<const FastaStatus *>(w->pstatus.p);
     *flags = fs->flags;
@@ -598,9 +697,13 @@ extern "C" int kpal_count_fasta(const char *fasta, uint64_t n_bytes, int k, int 
         KPAL_CHECK(w->table.ensure(bins * (bits / 8)));
         cudaStream_t st = 0;
         KPAL_CUDA(cudaMemsetAsync(w->table.p, 0, bins * (bits / 8), st));
+        g_trace.begin();
+        KPAL_CHECK(fasta_gpu_count(w, fasta, n_bytes, k, w->table.p, bits, st, nullptr, nullptr));
         unsigned flags = 0;
-        KPAL_CHECK(fasta_gpu_count(w, fasta, n_bytes, k, w->table.p, bits, st, &flags, nullptr));
-        if (!flags) return finalize_to_host(w, w->table.p, bits, k, balance, counts_out, st);
+        const int rc = finalize_to_host(w, w->table.p, bits, k, balance, counts_out, st,
+                                        static_cast<const FastaStatus *>(w->pstatus.p), &flags);
+        g_trace.end();
+        if (rc != KPAL_OK || !flags) return rc;
         // exotic whitespace: fall through to the host packer (exact rstrip semantics)
     }
     uint64_t n_bases = 0;

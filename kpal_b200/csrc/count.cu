@@ -155,33 +155,46 @@ count_smem_kernel(const uint4 *__restrict__ codes, const uint2 *__restrict__ val
 // table -> int64 profile, fused with balance: out[i] = t[i] + t[rc(i)]
 // (pairs get the sum, palindromes are doubled: kpal/klib.py:293-298).
 // ---------------------------------------------------------------------------
-// OutT = int64_t: the API's profile.  OutT = uint16_t: the narrow form the host entry
-// points move over PCIe (a quarter of the bytes; widened to int64 by host threads while
-// the copy is still running) -- a count that does not fit raises *overflow and the caller
-// redoes the finalize in int64.
-template <typename OutT>
-__device__ __forceinline__ void put_count(OutT *__restrict__ out, uint64_t i, unsigned long long v,
-                                          unsigned int *__restrict__ overflow)
+// OutT = int64_t *: the API's profile.  OutT = NarrowOut: the forms the host entry points
+// move over PCIe -- bins below `split` as uint16 and (o8 != nullptr) also as uint8, a
+// quarter / an eighth of the bytes, widened to int64 by host threads while the copy is
+// still running; bins from `split` on as int64 (o64[i - split]), copied by the DMA engine
+// straight into the caller's array while the host threads are busy widening.  The host
+// copies the narrowest form that holds every count below `split`: flags[0] is raised by a
+// count above 65535 (the caller then redoes the finalize in int64), flags[1] by one above 255.
+struct NarrowOut {
+    uint16_t *o16;
+    uint8_t *o8;
+    int64_t *o64;
+    uint64_t split;
+    unsigned int *flags;
+};
+
+__device__ __forceinline__ void put_count(int64_t *__restrict__ out, uint64_t i, unsigned long long v)
 {
-    if constexpr (sizeof(OutT) == 8) {
-        out[i] = OutT(v);
-    } else {
-        if (v > 0xffffull) *overflow = 1u;      // same value from every writer: a plain store is enough
-        out[i] = OutT(v);
+    out[i] = int64_t(v);
+}
+__device__ __forceinline__ void put_count(const NarrowOut &out, uint64_t i, unsigned long long v)
+{
+    if (i >= out.split) { out.o64[i - out.split] = int64_t(v); return; }
+    if (v > 0xffull) {                          // same value from every writer: a plain store is enough
+        out.flags[1] = 1u;
+        if (v > 0xffffull) out.flags[0] = 1u;
     }
+    out.o16[i] = uint16_t(v);
+    if (out.o8) out.o8[i] = uint8_t(v);
 }
 
 template <typename CounterT, typename OutT>
 __global__ void __launch_bounds__(256)
-finalize_kernel(const CounterT *__restrict__ table, int k, int balance, OutT *__restrict__ out,
-                unsigned int *__restrict__ overflow)
+finalize_kernel(const CounterT *__restrict__ table, int k, int balance, const OutT out)
 {
     const uint32_t n = 1u << (2 * k);
     const int shift = 32 - 2 * k;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         unsigned long long v = table[i];
         if (balance) v += __ldg(table + rc_index(i, shift));
-        put_count(out, i, v, overflow);
+        put_count(out, i, v);
     }
 }
 
@@ -193,8 +206,7 @@ finalize_kernel(const CounterT *__restrict__ table, int k, int balance, OutT *__
 // per 32-byte sector for the partner).
 template <typename CounterT, typename OutT>
 __global__ void __launch_bounds__(256)
-finalize_balance_tiled_kernel(const CounterT *__restrict__ table, int k, OutT *__restrict__ out,
-                              unsigned int *__restrict__ overflow)
+finalize_balance_tiled_kernel(const CounterT *__restrict__ table, int k, const OutT out)
 {
     extern __shared__ __align__(16) unsigned char fin_smem[];
     CounterT *A = reinterpret_cast<CounterT *>(fin_smem);      // [64][65] tile of m
@@ -215,10 +227,10 @@ finalize_balance_tiled_kernel(const CounterT *__restrict__ table, int k, OutT *_
         const uint32_t h = e >> 6, l = e & 63u;
         const uint32_t t = rc_index(l, 26) * 65 + rc_index(h, 26);
         put_count(out, (uint64_t(h) << hshift) | (uint64_t(m) << 6) | l,
-                  (unsigned long long)(A[h * 65 + l]) + (unsigned long long)(partner[t]), overflow);
+                  (unsigned long long)(A[h * 65 + l]) + (unsigned long long)(partner[t]));
         if (m != mr)
             put_count(out, (uint64_t(h) << hshift) | (uint64_t(mr) << 6) | l,
-                      (unsigned long long)(B[h * 65 + l]) + (unsigned long long)(A[t]), overflow);
+                      (unsigned long long)(B[h * 65 + l]) + (unsigned long long)(A[t]));
     }
 }
 
@@ -390,8 +402,8 @@ int launch_count(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_ba
 }
 
 template <typename OutT>
-static int launch_finalize_as(const void *d_table, int counter_bits, int k, int balance, OutT *d_out,
-                              unsigned int *d_overflow, cudaStream_t stream)
+static int launch_finalize_as(const void *d_table, int counter_bits, int k, int balance, const OutT d_out,
+                              cudaStream_t stream)
 {
     KPAL_CHECK(check_k(k));
     if (counter_bits != 32 && counter_bits != 64) return bad_arg("counter_bits must be 32 or 64");
@@ -404,22 +416,22 @@ static int launch_finalize_as(const void *d_table, int counter_bits, int k, int 
         const size_t smem = size_t(2) * 64 * 65 * (counter_bits / 8);
         if (counter_bits == 32) {
             finalize_balance_tiled_kernel<uint32_t, OutT><<<tiles, 256, smem, stream>>>(
-                static_cast<const uint32_t *>(d_table), k, d_out, d_overflow);
+                static_cast<const uint32_t *>(d_table), k, d_out);
         } else {
             KPAL_CUDA(cudaFuncSetAttribute(finalize_balance_tiled_kernel<unsigned long long, OutT>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
             finalize_balance_tiled_kernel<unsigned long long, OutT><<<tiles, 256, smem, stream>>>(
-                static_cast<const unsigned long long *>(d_table), k, d_out, d_overflow);
+                static_cast<const unsigned long long *>(d_table), k, d_out);
         }
         KPAL_LAUNCH_CHECK("finalize_balance_tiled_kernel");
         return KPAL_OK;
     }
     if (counter_bits == 32)
         finalize_kernel<uint32_t, OutT><<<grid, 256, 0, stream>>>(
-            static_cast<const uint32_t *>(d_table), k, balance, d_out, d_overflow);
+            static_cast<const uint32_t *>(d_table), k, balance, d_out);
     else
         finalize_kernel<unsigned long long, OutT><<<grid, 256, 0, stream>>>(
-            static_cast<const unsigned long long *>(d_table), k, balance, d_out, d_overflow);
+            static_cast<const unsigned long long *>(d_table), k, balance, d_out);
     KPAL_LAUNCH_CHECK("finalize_kernel");
     return KPAL_OK;
 }
@@ -427,16 +439,21 @@ static int launch_finalize_as(const void *d_table, int counter_bits, int k, int 
 int launch_finalize(const void *d_table, int counter_bits, int k, int balance, int64_t *d_counts,
                     cudaStream_t stream)
 {
-    return launch_finalize_as<int64_t>(d_table, counter_bits, k, balance, d_counts, nullptr, stream);
+    return launch_finalize_as<int64_t *>(d_table, counter_bits, k, balance, d_counts, stream);
 }
 
-// Narrow form for the host entry points: uint16 counts + *d_overflow (a device word the
-// caller zeroed) set when a count exceeds 65535.
-int launch_finalize_u16(const void *d_table, int counter_bits, int k, int balance, uint16_t *d_counts16,
-                        unsigned int *d_overflow, cudaStream_t stream)
+// Narrow forms for the host entry points (see NarrowOut): bins [0, split) as uint16 and
+// optionally uint8, bins [split, 4^k) as int64 into d_tail64 (split = 4^k: none);
+// d_flags[2] are device words the caller zeroed.
+int launch_finalize_narrow(const void *d_table, int counter_bits, int k, int balance, uint16_t *d_counts16,
+                           uint8_t *d_counts8, int64_t *d_tail64, uint64_t split, unsigned int *d_flags,
+                           cudaStream_t stream)
 {
-    if (!d_overflow) return bad_arg("null overflow flag");
-    return launch_finalize_as<uint16_t>(d_table, counter_bits, k, balance, d_counts16, d_overflow, stream);
+    if (!d_flags || !d_counts16) return bad_arg("null narrow buffer");
+    if (split > (1ull << (2 * k)) || (split < (1ull << (2 * k)) && !d_tail64)) return bad_arg("bad split");
+    NarrowOut out;
+    out.o16 = d_counts16; out.o8 = d_counts8; out.o64 = d_tail64; out.split = split; out.flags = d_flags;
+    return launch_finalize_as<NarrowOut>(d_table, counter_bits, k, balance, out, stream);
 }
 
 int launch_balance(const int64_t *d_in, int64_t *d_out, int k, cudaStream_t stream)

@@ -160,25 +160,28 @@ def test_format_matrix_equals_python_format():
     assert L.kpal_format_matrix(_cabi.ptr(v), 3, 2, 2, None, 0, ctypes.byref(length)) == _cabi.KPAL_EINVAL
 
 
-@pytest.mark.skipif(_cabi.device_count() > 0, reason="a GPU is present")
-def test_widen_u16_stage_is_exact():
-    """The host stage of the narrow profile copy (kpal_widen_u16): uint16 -> the
-    int64 counts of Profile.counts (klib.py:170), chunked, any alignment / length."""
+@pytest.mark.parametrize("width", (2, 1))
+def test_widen_stage_is_exact(width):
+    """The host stage of the narrow profile copy (kpal_widen_u16 / kpal_widen_u8): narrow
+    counts -> the int64 counts of Profile.counts (klib.py:170), chunked, any alignment /
+    length."""
     L = _cabi.load()
+    fn = L.kpal_widen_u16 if width == 2 else L.kpal_widen_u8
+    dtype, top = (np.uint16, 65535) if width == 2 else (np.uint8, 255)
     rng = np.random.default_rng(11)
     for n, chunk, offset in ((1, 0, 0), (7, 3, 1), (1000, 0, 0), (2500, 1000, 1), (1 << 20, 1 << 17, 0),
                              ((1 << 22) + 5, 1 << 18, 1), (1 << 16, 1 << 20, 0)):
-        narrow = rng.integers(0, 65536, n, dtype=np.uint16)
-        narrow[:3] = (65535, 0, 1)[:min(3, n)]
+        narrow = rng.integers(0, top + 1, n, dtype=dtype)
+        narrow[:3] = (top, 0, 1)[:min(3, n)]
         backing = np.full(n + 2, -1, dtype=np.int64)
         out = backing[offset:offset + n]            # offset 1: only 8-byte aligned
         for _ in range(3):                          # the pool is reused from call to call
             out[:] = -1
-            assert L.kpal_widen_u16(_cabi.ptr(narrow), n, chunk, out.ctypes.data) == _cabi.KPAL_OK
+            assert fn(_cabi.ptr(narrow), n, chunk, out.ctypes.data) == _cabi.KPAL_OK
             assert np.array_equal(out, narrow.astype(np.int64))
         assert backing[offset + n] == -1 and (offset == 0 or backing[0] == -1)
-    assert L.kpal_widen_u16(None, 0, 0, None) == _cabi.KPAL_OK
-    assert L.kpal_widen_u16(None, 4, 0, None) == _cabi.KPAL_EINVAL
+    assert fn(None, 0, 0, None) == _cabi.KPAL_OK
+    assert fn(None, 4, 0, None) == _cabi.KPAL_EINVAL
 
 
 def test_widen_u16_from_many_threads():

@@ -495,10 +495,11 @@ def test_count_fasta_chunked_upload_pipeline(tutorial_texts):
 
 
 def test_narrow_profile_copy_and_its_overflow_path():
-    """From k = 10 on the host entry points move the profile over PCIe as uint16 and widen
-    it on the host (cabi.cu finalize_to_host).  Same bits as the plain int64 copy, for
-    counts that fit -- and for counts that do not (a repetitive input pushes one bin past
-    65535: the device flag sends the call down the int64 copy)."""
+    """From k = 10 on the host entry points move the profile over PCIe as uint8 or uint16
+    (whichever holds every count) and widen it on the host (cabi.cu finalize_to_host).
+    Same bits as the plain int64 copy, for counts that fit -- and for counts that do not
+    (a repetitive input pushes one bin past 65535: the device flags send the call down the
+    int64 copy).  narrow_d2h: 1 = uint8 / uint16, 2 = uint16 only, 0 = int64."""
     reads = random_reads(5, 20_000, 150)
     fasta = reads_to_fasta(reads)
     seqs = [r.tobytes().decode() for r in reads]
@@ -508,7 +509,8 @@ def test_narrow_profile_copy_and_its_overflow_path():
             want = ko.count_sequences(seqs, k)
             want_rep = ko.count_fasta(repetitive, k)
             assert want_rep.max() > 65535 and ko.balance(want_rep).max() > 65535
-            for narrow in (1, 0):
+            assert ko.balance(want).max() <= 255            # random reads: the uint8 copy under narrow_d2h = 1
+            for narrow in (1, 2, 0):
                 _set_option("narrow_d2h", narrow)
                 for balance in (False, True):
                     w = ko.balance(want) if balance else want
@@ -516,10 +518,40 @@ def test_narrow_profile_copy_and_its_overflow_path():
                     assert np.array_equal(_cabi.count_sequences(seqs, k, balance=balance), w), (k, narrow, balance)
                     wr = ko.balance(want_rep) if balance else want_rep
                     assert np.array_equal(_cabi.count_fasta(repetitive, k, balance=balance), wr), (k, narrow, balance)
-            # exactly 65535 fits, 65536 does not: both sides of the threshold
-            for n_a in (65535 + k - 1, 65536 + k - 1):
+            # exactly 255 / 65535 fits, 256 / 65536 does not: both sides of either threshold
+            for n_a in (255 + k - 1, 256 + k - 1, 65535 + k - 1, 65536 + k - 1):
                 _set_option("narrow_d2h", 1)
                 got = _cabi.count_sequences(["A" * n_a, "ACGT" * 50], k)
                 assert got[0] == n_a - k + 1 and np.array_equal(got, ko.count_sequences(["A" * n_a, "ACGT" * 50], k))
     finally:
         _set_option("narrow_d2h", 1)
+
+
+def test_narrow_copy_into_a_pinned_profile_with_dma_share():
+    """Pinned destination: the last dma_share/16 of the profile is copied as int64 by the DMA
+    engine behind the narrow chunks, the rest is widened by the host threads (cabi.cu
+    finalize_to_host).  Every share, every width, counts above 255 on either side of the
+    split, and the int64 fallback -- always the bits of the oracle."""
+    reads = random_reads(6, 20_000, 150)
+    fasta = reads_to_fasta(reads).decode()
+    low_rep = ">a\n" + "A" * 400 + "\n" + fasta                 # bin 0 (narrow side) above 255
+    high_rep = ">t\n" + "T" * 400 + "\n" + fasta                # last bin (int64 side) above 255
+    big_rep = ">t\n" + "T" * 70_000 + "\n" + fasta              # ... above 65535: stays narrow-copied
+    fallback = ">a\n" + "A" * 70_000 + "\n" + fasta             # narrow side above 65535: int64 copy
+    try:
+        for k in (10, 12):
+            pinned = _cabi.PinnedArray(4 ** k, np.int64)
+            for text in (fasta, low_rep, high_rep, big_rep, fallback):
+                want = ko.count_fasta(text, k)
+                for share in (0, 1, 3, 8):
+                    _set_option("dma_share", share)
+                    for narrow in (1, 2):
+                        _set_option("narrow_d2h", narrow)
+                        pinned.array[:] = -1
+                        got = _cabi.count_fasta(text, k, out=pinned.array)
+                        assert np.array_equal(got, want), (k, share, narrow)
+                        assert np.array_equal(_cabi.count_fasta(text, k), want), (k, share, narrow, "pageable")
+            pinned.free()
+    finally:
+        _set_option("narrow_d2h", 1)
+        _set_option("dma_share", 3)
