@@ -753,9 +753,10 @@ def main():
                     help="e2e leg: 1 = the profile leaves the device as uint8 / uint16 (the narrowest that "
                          "holds every count) and host threads widen it (library default), 2 = uint16 only, "
                          "0 = plain int64 copy")
-    ap.add_argument("--dma-share", type=int, default=3,
+    ap.add_argument("--dma-share", type=int, default=0,
                     help="e2e leg: sixteenths of the narrow-copied profile that the copy engine moves as int64 "
-                         "straight into the pinned result while the host threads widen the rest (library default 3)")
+                         "straight into the pinned result while the host threads widen the rest (library default 0: "
+                         "measured slower than widening everything, profiles/r01_e2e_trace.log)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

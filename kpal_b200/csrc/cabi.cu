@@ -64,7 +64,7 @@ static thread_local char t_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_host_fasta{-1};       // -1: from the environment (KPAL_HOST_FASTA=1)
 static std::atomic<int> g_fasta_chunks{0};      // 0 = automatic (one chunk per ~6 MB, at most 16)
-static std::atomic<int> g_dma_share{3};         // sixteenths of a narrow-copied profile the DMA engine moves as int64 (pinned destinations)
+static std::atomic<int> g_dma_share{0};         // sixteenths of a narrow-copied profile the DMA engine moves as int64 (pinned destinations)
 static std::atomic<int> g_narrow_d2h{1};        // 1: large profiles leave the device as uint8 / uint16, 2: uint16 only (see finalize_to_host)
 
 void set_error(const char *fmt, ...)
@@ -429,7 +429,27 @@ struct CallTrace {
         const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
         at += size_t(snprintf(line + at, sizeof line - at, " %s=%.0f", what, us));
     }
-    void end() { if (on) fprintf(stderr, "[kpal trace us]%s\n", line); }
+    // device side: timing events recorded on the streams of the call, printed relative to the first
+    cudaEvent_t dev[8] = {}; const char *dev_name[8] = {}; int n_dev = 0;
+    void dev_mark(const char *what, cudaStream_t st)
+    {
+        if (!on || n_dev >= 8) return;
+        if (!dev[n_dev] && cudaEventCreate(&dev[n_dev]) != cudaSuccess) return;
+        dev_name[n_dev] = what;
+        cudaEventRecord(dev[n_dev++], st);
+    }
+    void end()
+    {
+        if (!on) return;
+        for (int i = 1; i < n_dev && at + 48 <= sizeof line; ++i) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, dev[0], dev[i]) == cudaSuccess)
+                at += size_t(snprintf(line + at, sizeof line - at, " dev:%s=%.0f", dev_name[i], ms * 1e3));
+        }
+        cudaGetLastError();
+        n_dev = 0;
+        fprintf(stderr, "[kpal trace us]%s\n", line);
+    }
 };
 static CallTrace g_trace;       // used under g_count_mutex
 
@@ -487,6 +507,7 @@ static int finalize_to_host(CountWorkspace *w, const void *d_table, int bits, in
                                           try8 ? static_cast<uint8_t *>(w->counts8.p) : nullptr,
                                           static_cast<int64_t *>(w->counts.p), split,
                                           static_cast<unsigned int *>(w->overflow.p), st));
+        g_trace.dev_mark("finalized", st);
         KPAL_CUDA(cudaMemcpyAsync(w->pflag.p, w->overflow.p, 8, cudaMemcpyDeviceToHost, st));
         KPAL_CUDA(cudaEventRecord(w->flag_done, st));
         // chunks of whole pieces, >= 1 MiB each (the last one may be shorter)
@@ -644,6 +665,7 @@ static int fasta_gpu_count(CountWorkspace *w, const char *fasta, uint64_t n_byte
         for (auto &e : w->chunk_done) KPAL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     const uint64_t chunk = ((n_bytes + n_chunks - 1) / n_chunks + tile - 1) / tile * tile;
+    g_trace.dev_mark("start", n_chunks > 1 ? w->copy_stream : st);
     for (uint64_t c = 0, off = 0; off < n_bytes; ++c, off += chunk) {
         const uint64_t len = std::min(chunk, n_bytes - off);
         if (n_chunks > 1) {
@@ -656,9 +678,12 @@ static int fasta_gpu_count(CountWorkspace *w, const char *fasta, uint64_t n_byte
         KPAL_CHECK(launch_fasta_pack_tiles(d_text, n_bytes, off / tile, (off + len + tile - 1) / tile, d_codes,
                                            d_valid, w->fscratch.p, st));
     }
+    g_trace.dev_mark("h2d", n_chunks > 1 ? w->copy_stream : st);
+    g_trace.dev_mark("packed", st);
     // n_bytes is an upper bound of the packed length; the tail is all-invalid padding
     KPAL_CHECK(launch_count(static_cast<uint32_t *>(w->codes.p), static_cast<uint32_t *>(w->valid.p),
                             n_bytes, k, d_table, bits, st));
+    g_trace.dev_mark("counted", st);
     KPAL_CUDA(cudaMemcpyAsync(w->pstatus.p, w->fscratch.p, sizeof(FastaStatus),
                               cudaMemcpyDeviceToHost, st));
     g_trace.mark("count_queued");

@@ -554,4 +554,4 @@ def test_narrow_copy_into_a_pinned_profile_with_dma_share():
             pinned.free()
     finally:
         _set_option("narrow_d2h", 1)
-        _set_option("dma_share", 3)
+        _set_option("dma_share", 0)
