@@ -367,6 +367,11 @@ def bench_count(args):
 
     reducer = None
     reduce_note = None
+    if args.reduce == "auto":
+        # measured (profiles/README.md): at 2 GPUs the table sum fused into the count's histogram
+        # pass is on par with / ahead of the NCCL reduce (0.416 vs 0.421 ms per step), at 4 GPUs the
+        # peer stores slow pass 2 down and NCCL wins (0.473 vs 0.427 ms)
+        args.reduce = "fused" if world == 2 else "nccl"
     if world > 1 and args.reduce in ("peer", "fused"):
         from kpal_b200 import multigpu
         # CUDA IPC between the ranks can be refused by the box (container without a shared
@@ -744,7 +749,7 @@ def main():
     ap.add_argument("--radix-payload-bits", type=int, default=0)
     ap.add_argument("--radix-debug", type=int, default=0, help="timing experiments (results are wrong)")
     ap.add_argument("--radix-shape", type=int, default=0)
-    ap.add_argument("--reduce", default="fused", choices=["fused", "peer", "nccl"],
+    ap.add_argument("--reduce", default="auto", choices=["auto", "fused", "peer", "nccl"],
                     help="count workload at N > 1: table sum over NVLink peer memory fused into the count "
                          "(default), as separate push/collect kernels, or with dist.reduce")
     ap.add_argument("--no-e2e", action="store_true", help="matrix workload: skip the host-buffer end-to-end leg")

@@ -62,8 +62,8 @@ class ProfileFileType(object):
         try:
             import h5py
         except ImportError:
-            raise argparse.ArgumentTypeError(
-                "can't open '%s': the h5py package is needed for k-mer profile files" % string)
+            # no libhdf5 on this machine: the in-tree reader / writer of the same format
+            from . import h5lite as h5py
         try:
             if 'w' in self._mode and os.path.exists(string):
                 raise IOError('file exists')
@@ -337,6 +337,13 @@ def main(args=None):
                               if k not in ('func', 'subcommand')))
     except ValueError as error:
         parser.error(error)
+    finally:
+        # profile files are complete once closed (h5py does this at interpreter exit; here it
+        # happens as soon as the command is done, so main() can be called in-process)
+        for value in vars(arguments).values():
+            for handle in (value if isinstance(value, list) else [value]):
+                if hasattr(handle, 'create_dataset') and hasattr(handle, 'close'):
+                    handle.close()
 
 
 if __name__ == '__main__':

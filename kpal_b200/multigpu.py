@@ -97,16 +97,18 @@ def _gpu_finalize(table, k, balance):
 
 
 def count_fasta_distributed(fasta_shard, k, balance=False, group=None, device=None,
-                            count_shard=None, finalize=None, reduce='peer'):
+                            count_shard=None, finalize=None, reduce='nccl'):
     """
     ``Profile.from_fasta`` (+ ``balance``) over FASTA text that is sharded
     across the ranks of `group`: every rank passes ITS shard (cut at record
     boundaries, see :func:`split_fasta`); rank 0 gets the ``int64[4**k]``
     profile, the other ranks ``None``.
 
-    `reduce` = ``'peer'`` sums the tables over NVLink peer memory
-    (:class:`PeerReducer`; GPU ranks, u32 counters), ``'nccl'`` with
-    ``dist.reduce``.  `count_shard` / `finalize` are injection points for the
+    `reduce` = ``'nccl'`` (default) sums the tables with ``dist.reduce``,
+    ``'peer'`` over NVLink peer memory (:class:`PeerReducer`; GPU ranks, u32
+    counters).  For a single call the NCCL reduce is the faster one (the
+    peer path has to map its inboxes first; measured 0.455 vs 0.421 ms per
+    100 Mbp step at 2 GPUs even with the mapping kept, profiles/README.md).  `count_shard` / `finalize` are injection points for the
     CPU (gloo) tests of the sharding + reduce logic; by default both run on
     the GPU.
     """

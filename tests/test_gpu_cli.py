@@ -90,3 +90,69 @@ def test_balance_distance_matrix_commands(golden):
                          precision=6)
     want = ko.distance(left, right, do_balance=True, do_scale=True, metric='euclidean')
     assert out.getvalue().split('\n')[4] == '%.6f' % want
+
+
+def test_command_line_with_real_profile_files(golden, tutorial_texts, tmp_path, monkeypatch, capsys):
+    """`kpal count / balance / showbalance / distance / matrix` as a user runs them, on real
+    files: FASTA in, HDF5 profile files in between (kpal_b200.h5lite when h5py is absent),
+    the matrix text out.  Mirrors reference tests/test_kmer.py:83-125,185-202,373-382,455-467
+    and the tutorial (doc/tutorial.rst:36-146)."""
+    import sys
+    from kpal_b200 import h5lite
+    if 'h5py' not in sys.modules:
+        monkeypatch.setitem(sys.modules, 'h5py', None)       # make the fallback explicit
+    names = sorted(tutorial_texts)
+    paths = []
+    for name in names:
+        path = tmp_path / (name + '.fa')
+        path.write_text(tutorial_texts[name])
+        paths.append(str(path))
+    merged = str(tmp_path / 'merged.k9')
+    kmer.main(['count', '-k', '9'] + paths + [merged])
+    with h5lite.File(merged) as f:
+        assert f.attrs['format'] == 'kMer' and sorted(f['profiles']) == names
+        for name in names:
+            want = ko.count_fasta(tutorial_texts[name], 9)
+            assert np.array_equal(f['profiles/' + name][:], want)
+            assert f['profiles/' + name].attrs['total'] == want.sum()
+            assert f['profiles/' + name].attrs['non_zero'] == np.count_nonzero(want)
+
+    balanced = str(tmp_path / 'balanced.k9')
+    kmer.main(['balance', merged, balanced])
+    with h5lite.File(balanced) as f:
+        assert np.array_equal(f['profiles/' + names[0]][:],
+                              ko.balance(ko.count_fasta(tutorial_texts[names[0]], 9)))
+
+    capsys.readouterr()
+    kmer.main(['showbalance', merged, '-n', '3'])
+    lines = capsys.readouterr().out.strip().split('\n')
+    assert [line.split()[0] for line in lines] == names
+
+    kmer.main(['distance', merged, balanced, '-l', names[0], '-r', names[1]])
+    left, right, value = capsys.readouterr().out.split()
+    want = ko.distance(ko.count_fasta(tutorial_texts[names[0]], 9),
+                       ko.balance(ko.count_fasta(tutorial_texts[names[1]], 9)))
+    assert (left, right) == (names[0], names[1]) and float(value) == pytest.approx(want, abs=1.01e-10)
+
+    matrix = str(tmp_path / 'matrix.txt')
+    kmer.main(['matrix', merged, matrix, '-S', '-b', '-n', '6'])
+    rows = open(matrix).read().strip().split('\n')
+    assert rows[0] == str(len(names)) and rows[1:1 + len(names)] == names
+    counts = [ko.count_fasta(tutorial_texts[n], 9) for n in names]
+    for i in range(1, len(names)):
+        got = [float(x) for x in rows[len(names) + i].split()]
+        want = [ko.distance(counts[i], counts[j], do_balance=True, do_scale=True) for j in range(i)]
+        assert got == pytest.approx(want, abs=1.01e-6)
+
+    by_record = str(tmp_path / 'records.k4')
+    first = str(tmp_path / 'first.fa')
+    with open(first, 'w') as handle:
+        handle.write('\n'.join('>' + n + '\n' + s for n, s in zip('abcd', golden["fixtures"]["LENGTH_60"])) + '\n')
+    kmer.main(['count', '-k', '4', '--by-record', first, by_record])
+    with h5lite.File(by_record) as f:
+        assert sorted(f['profiles']) == ['a', 'b', 'c', 'd']
+        for name, seq in zip('abcd', golden["fixtures"]["LENGTH_60"]):
+            assert np.array_equal(f['profiles/' + name][:], ko.count_sequences([seq], 4))
+
+    with pytest.raises(SystemExit):                           # OUTPUT exists: argparse error, exit 2
+        kmer.main(['count', '-k', '4', first, by_record])
