@@ -370,7 +370,12 @@ int kpal_dev_fasta_pack(const void *d_text, uint64_t n_bytes, uint32_t *d_codes,
 
 /* run-time switches: "host_fasta" (1 = kpal_count_fasta uses the C++ packer
  * instead of the GPU one), "exact_div" (1 = IEEE division in the distance
- * kernels instead of MUFU.RCP64H + Newton). */
+ * kernels instead of MUFU.RCP64H + Newton), "narrow_d2h" (profile copy of the
+ * host entry points: 1 = uint8 / uint16, 2 = uint16 only, 0 = int64),
+ * "dma_share" (0..8 sixteenths of a narrow-copied profile that the copy engine
+ * moves as int64 into a pinned destination; default 0), "fasta_chunks" (0 = auto
+ * .. 32 chunks of the pipelined FASTA upload), and the tuning switches of the
+ * count path ("count_path", "radix_shape", "radix_payload_bits", "tiled_finalize"). */
 int kpal_set_option(const char *name, int value);
 
 /* counters for bench.py's "gpu_launches": kernels launched by this library

@@ -63,7 +63,7 @@ int launch_count_push(const uint32_t *, const uint32_t *, uint64_t, int, void *,
 static thread_local char t_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_host_fasta{-1};       // -1: from the environment (KPAL_HOST_FASTA=1)
-static std::atomic<int> g_fasta_chunks{0};      // 0 = automatic (one chunk per ~6 MB, at most 16)
+static std::atomic<int> g_fasta_chunks{0};      // 0 = automatic (one chunk per ~3 MB, at most 32)
 static std::atomic<int> g_dma_share{0};         // sixteenths of a narrow-copied profile the DMA engine moves as int64 (pinned destinations)
 static std::atomic<int> g_narrow_d2h{1};        // 1: large profiles leave the device as uint8 / uint16, 2: uint16 only (see finalize_to_host)
 
@@ -166,7 +166,7 @@ struct CountWorkspace {
     GrowDev codes, valid, table, counts, text, fscratch, counts16, counts8, overflow;
     GrowPin pcodes, pvalid, pstatus, pnarrow, pflag;
     cudaStream_t copy_stream = nullptr;          // H2D of the FASTA text, chunk by chunk
-    cudaEvent_t chunk_done[16] = {};
+    cudaEvent_t chunk_done[32] = {};
     cudaEvent_t d2h_done[16] = {};               // chunks of the narrow D2H of the profile
     cudaEvent_t flag_done = nullptr;             // ... and the flag words ahead of them
 };
@@ -316,7 +316,7 @@ extern "C" int kpal_set_option(const char *name, int value)
     if (!name) return bad_arg("null option name");
     if (!strcmp(name, "host_fasta")) { g_host_fasta.store(value ? 1 : 0); return KPAL_OK; }
     if (!strcmp(name, "fasta_chunks")) {
-        if (value < 0 || value > 16) return bad_arg("fasta_chunks must be 0 (auto) .. 16");
+        if (value < 0 || value > 32) return bad_arg("fasta_chunks must be 0 (auto) .. 32");
         g_fasta_chunks.store(value); return KPAL_OK;
     }
     if (!strcmp(name, "exact_div")) { set_exact_div(value != 0); return KPAL_OK; }
@@ -651,15 +651,18 @@ static int fasta_gpu_count(CountWorkspace *w, const char *fasta, uint64_t n_byte
     KPAL_CHECK(w->valid.ensure(vw * 4));
     KPAL_CHECK(w->fscratch.ensure(fasta_scratch_bytes(n_bytes)));
     KPAL_CHECK(w->pstatus.ensure(sizeof(FastaStatus)));
-    // The text goes up in up to 16 chunks on a copy stream; the packer runs on the tiles of
+    // The text goes up in up to 32 chunks on a copy stream; the packer runs on the tiles of
     // a chunk as soon as it has landed, so scan/pack hides behind the PCIe transfer.
     uint32_t *d_codes = static_cast<uint32_t *>(w->codes.p), *d_valid = static_cast<uint32_t *>(w->valid.p);
     const uint8_t *d_text = static_cast<const uint8_t *>(w->text.p);
     KPAL_CHECK(launch_fasta_pack_begin(n_bytes, d_codes, d_valid, w->fscratch.p, st));
     const uint64_t tile = fasta_tile_bytes();
-    uint64_t n_chunks = n_bytes / (6ull << 20);
-    n_chunks = std::min<uint64_t>(std::max<uint64_t>(n_chunks, 1), 16);
-    if (g_fasta_chunks.load() > 0) n_chunks = std::min<uint64_t>(uint64_t(g_fasta_chunks.load()), 16);
+    // (what remains after the last byte has landed is the scan/pack of ONE chunk: 80 us with 16
+    // chunks of the 109 MB of config 2, profiles/r01_e2e_trace.log; queuing a chunk costs the
+    // host ~25 us, far less than its 60 us on the bus)
+    uint64_t n_chunks = n_bytes / (3ull << 20);
+    n_chunks = std::min<uint64_t>(std::max<uint64_t>(n_chunks, 1), 32);
+    if (g_fasta_chunks.load() > 0) n_chunks = std::min<uint64_t>(uint64_t(g_fasta_chunks.load()), 32);
     if (n_chunks > 1 && !w->copy_stream) {
         KPAL_CUDA(cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
         for (auto &e : w->chunk_done) KPAL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

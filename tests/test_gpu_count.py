@@ -486,7 +486,7 @@ def test_count_fasta_chunked_upload_pipeline(tutorial_texts):
     try:
         for text in texts:
             want = {k: ko.balance(ko.count_fasta(text, k)) for k in (3, 9)}
-            for chunks in (1, 2, 7, 16):
+            for chunks in (1, 2, 7, 16, 32):
                 _set_option("fasta_chunks", chunks)
                 for k in (3, 9):
                     assert np.array_equal(_cabi.count_fasta(text, k, balance=True), want[k]), (chunks, k)
