@@ -63,7 +63,7 @@ int launch_count_push(const uint32_t *, const uint32_t *, uint64_t, int, void *,
 static thread_local char t_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_host_fasta{-1};       // -1: from the environment (KPAL_HOST_FASTA=1)
-static std::atomic<int> g_fasta_chunks{0};      // 0 = automatic (one chunk per ~3 MB, at most 32)
+static std::atomic<int> g_fasta_chunks{0};      // 0 = automatic (one chunk per ~6 MB, at most 16), else 1 .. 32
 static std::atomic<int> g_dma_share{0};         // sixteenths of a narrow-copied profile the DMA engine moves as int64 (pinned destinations)
 static std::atomic<int> g_narrow_d2h{1};        // 1: large profiles leave the device as uint8 / uint16, 2: uint16 only (see finalize_to_host)
 
@@ -658,10 +658,10 @@ static int fasta_gpu_count(CountWorkspace *w, const char *fasta, uint64_t n_byte
     KPAL_CHECK(launch_fasta_pack_begin(n_bytes, d_codes, d_valid, w->fscratch.p, st));
     const uint64_t tile = fasta_tile_bytes();
     // (what remains after the last byte has landed is the scan/pack of ONE chunk: 80 us with 16
-    // chunks of the 109 MB of config 2, profiles/r01_e2e_trace.log; queuing a chunk costs the
-    // host ~25 us, far less than its 60 us on the bus)
-    uint64_t n_chunks = n_bytes / (3ull << 20);
-    n_chunks = std::min<uint64_t>(std::max<uint64_t>(n_chunks, 1), 32);
+    // chunks of the 109 MB of config 2, 45 us with 32 -- but every chunk costs ~5 us on the
+    // bus, so 32 chunks end later than 16: profiles/r01_e2e_trace.log)
+    uint64_t n_chunks = n_bytes / (6ull << 20);
+    n_chunks = std::min<uint64_t>(std::max<uint64_t>(n_chunks, 1), 16);
     if (g_fasta_chunks.load() > 0) n_chunks = std::min<uint64_t>(uint64_t(g_fasta_chunks.load()), 32);
     if (n_chunks > 1 && !w->copy_stream) {
         KPAL_CUDA(cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));

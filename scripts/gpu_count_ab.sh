@@ -1,15 +1,16 @@
 #!/bin/bash
-# quick A/B of the count paths (value line only)
+# count bench A/B: payload bits of the radix path (15 = 512 buckets, one histogram CTA per SM;
+# 14 = 1024 buckets, three per SM) and the upload chunking of the end-to-end leg
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_count.py -x -q -m gpu -k "radix or tiled" 2>&1 | tail -5
-for args in "--count-path 1" "--count-path 2 --radix-shape 1" "--count-path 2 --radix-shape 2"; do
-  timeout 300 python bench.py --steps 10 --warmup 3 $args 2>/dev/null | python -c "
-import sys, json
-d = json.loads(sys.stdin.read())
-print('$args', 'step_ms', round(d['ms_per_step'], 4), 'kern_ms', round(d['roofline']['kernel_ms'], 4), 'e2e_ms', round(d['e2e']['ms_per_step'], 3), 'parity', d['parity_ok'])"
-done
-for sh in 1 2; do
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
-    --log-file gpurun_out/l.csv python bench.py --steps 2 --warmup 3 --count-path 2 --radix-shape $sh > gpurun_out/ncu_bench.log 2>&1
-echo "shape $sh: partition ns:" $(grep -E "radix_partition" gpurun_out/l.csv | awk -F'","' '{print $NF}' | tr -d '"' | sort -n | head -3 | tr '\n' ' ') "hist ns:" $(grep -E "radix_histogram" gpurun_out/l.csv | awk -F'","' '{print $NF}' | tr -d '"' | sort -n | head -3 | tr '\n' ' ')
-done
+run() {   # name, bench args
+  KPAL_TRACE=1 timeout 300 python bench.py --steps 20 $2 > gpurun_out/ab_$1.json 2> gpurun_out/ab_$1.err
+  python -c "
+import json; d=json.loads(open('gpurun_out/ab_$1.json').read().strip().splitlines()[-1])
+print('$1', 'ms/step', round(d['ms_per_step'],4), 'value', round(d['value'],1), 'kernel_ms', round(d['roofline']['kernel_ms'],4), 'e2e', round(d['e2e']['value'],2), round(d['e2e']['ms_per_step'],3), 'parity', d['parity_ok'])"
+  grep "kpal trace" gpurun_out/ab_$1.err | tail -1
+  grep -v "kpal trace" gpurun_out/ab_$1.err | tail -2
+}
+run p15_c32 ""
+run p14_c32 "--radix-payload-bits 14"
+run p15_c16 "--fasta-chunks 16"
+run p15_c24 "--fasta-chunks 24"
