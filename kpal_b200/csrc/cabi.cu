@@ -41,6 +41,7 @@ uint64_t fasta_scratch_bytes(uint64_t n_bytes);
 void set_exact_div(bool on);
 void set_count_path(int v);
 void set_tiled_finalize(int v);
+void set_by_record_path(int v);
 void set_radix_payload_bits(int bits);
 void set_radix_debug(int v);
 void set_radix_shape(int v);
@@ -333,6 +334,10 @@ extern "C" int kpal_set_option(const char *name, int value)
         set_count_path(value); return KPAL_OK;
     }
     if (!strcmp(name, "tiled_finalize")) { set_tiled_finalize(value != 0); return KPAL_OK; }
+    if (!strcmp(name, "by_record_path")) {
+        if (value < 0 || value > 1) return bad_arg("by_record_path must be 0 (shared-memory slabs) or 1 (RED rows)");
+        set_by_record_path(value); return KPAL_OK;
+    }
     if (!strcmp(name, "radix_shape")) {
         if (value < 0 || value > 2) return bad_arg("radix_shape must be 0 (auto), 1 (1024 x 1 CTA/SM) or 2 (512 x 2)");
         set_radix_shape(value); return KPAL_OK;

@@ -29,6 +29,8 @@ d_valid = torch.from_numpy(valid.view(np.int32)).to(dev)
 d_starts = torch.from_numpy(rec_starts.view(np.int64)).to(dev)
 rows = torch.empty((BATCH, 4 ** K), dtype=torch.int64, device=dev)
 sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+PATH = int(os.environ.get("KPAL_BY_RECORD_PATH", "0"))      # 1 = the zero-fill + RED rows, for comparison
+_cabi.check(L.kpal_set_option(b"by_record_path", PATH))
 for balance in (0, 1):
     times = []
     for rep in range(2):
@@ -51,7 +53,7 @@ for balance in (0, 1):
         ok &= bool(np.array_equal(got[i], want))
     ms = min(times)
     out_bytes = N_REC * 4 ** K * 8
-    print(json.dumps({"bench": "by_record", "k": K, "records": N_REC, "balance": balance,
+    print(json.dumps({"bench": "by_record", "path": "red rows" if PATH else "shared-memory slabs", "k": K, "records": N_REC, "balance": balance,
                       "ms": ms, "records_per_s": N_REC / ms * 1e3,
                       "write_GBps": out_bytes / ms / 1e6, "parity_ok": ok,
                       "host_pack_s": pack_s}))

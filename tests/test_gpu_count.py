@@ -202,6 +202,28 @@ def test_by_record_balance_and_long_records():
             assert np.array_equal(row, ko.count_sequences([seq], k))
 
 
+def test_by_record_slab_kernel_limits():
+    """by_record_kernel builds rows in 16-bit shared-memory slabs; records whose counts could
+    pass 65535 (>= 65536 bases, >= 32768 with balance: a palindrome counts twice) take the RED
+    rows instead.  Both sides of either limit, worst-case repeats, every slab count (k = 7: one
+    slab of 16384 bins, k = 8: two, k = 9: eight), and the RED rows for everything."""
+    seqs = ["A" * 65535, "A" * 65536, "AT" * 16383 + "A", "AT" * 16384, "T" * 32767, "ACGT" * 9000,
+            "", "ACG", "N" * 500 + "ACGTTGCAAC" * 40]
+    codes, valid, rec_starts, n_bases = _cabi.pack_sequences(seqs)
+    try:
+        for path in (0, 1):
+            _set_option("by_record_path", path)
+            for k in (1, 2, 7, 8, 9):
+                for balance in (False, True):
+                    rows = _cabi.count_by_record(codes, valid, n_bases, rec_starts, 0, len(seqs), k,
+                                                 balance=balance)
+                    for seq, row in zip(seqs, rows):
+                        want = ko.count_sequences([seq], k)
+                        assert np.array_equal(row, ko.balance(want) if balance else want), (path, k, balance, seq[:8])
+    finally:
+        _set_option("by_record_path", 0)
+
+
 def test_device_api_counter_widths():
     """kpal_dev_count_packed with 32- and 64-bit counters + finalize."""
     L = _cabi.load()
