@@ -319,6 +319,8 @@ def bench_count(args):
     _cabi.check(L.kpal_set_device(local))
     _cabi.check(L.kpal_set_option(b"count_path", args.count_path))
     _cabi.check(L.kpal_set_option(b"radix_payload_bits", args.radix_payload_bits))
+    if args.radix_max_buckets:
+        _cabi.check(L.kpal_set_option(b"radix_max_buckets", args.radix_max_buckets))
     _cabi.check(L.kpal_set_option(b"radix_debug", args.radix_debug))
     _cabi.check(L.kpal_set_option(b"radix_shape", args.radix_shape))
     _cabi.check(L.kpal_set_option(b"fasta_chunks", args.fasta_chunks))
@@ -570,7 +572,9 @@ def bench_count(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": count_kernel_name, "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": recorded_traffic(count_kernel_name.split("<")[0].split(" ")[0]),
+                         # the committed ncu capture is of the default workload (config 2, k = 12)
+                         "traffic": (recorded_traffic(count_kernel_name.split("<")[0].split(" ")[0])
+                                     if args.config == 2 and k == K_COUNT else None),
                          "algorithmic_bytes": alg_bytes, "kernel_ms": kern_ms, "peak_source": peak_src,
                          "windows_per_s": n_windows / (kern_ms * 1e-3)},
             "cpu_baseline": cpu, "clocks": clocks, "parity_ok": result_ok,
@@ -747,6 +751,8 @@ def main():
     ap.add_argument("--count-path", type=int, default=0, choices=[0, 1, 2],
                     help="0 = library default, 1 = scattered-RED kernel, 2 = radix-partitioned path")
     ap.add_argument("--radix-payload-bits", type=int, default=0)
+    ap.add_argument("--radix-max-buckets", type=int, default=0, choices=[0, 1024, 2048],
+                    help="buckets binned per pass-1 launch of the radix count (0 = library default)")
     ap.add_argument("--radix-debug", type=int, default=0, help="timing experiments (results are wrong)")
     ap.add_argument("--radix-shape", type=int, default=0)
     ap.add_argument("--reduce", default="auto", choices=["auto", "fused", "peer", "nccl"],

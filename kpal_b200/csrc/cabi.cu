@@ -45,6 +45,7 @@ void set_by_record_path(int v);
 void set_radix_payload_bits(int bits);
 void set_radix_debug(int v);
 void set_radix_shape(int v);
+void set_radix_max_buckets(int v);
 int launch_fasta_pack(const uint8_t *, uint64_t, uint32_t *, uint32_t *, void *, cudaStream_t);
 int launch_fasta_pack_begin(uint64_t, uint32_t *, uint32_t *, void *, cudaStream_t);
 int launch_fasta_pack_tiles(const uint8_t *, uint64_t, uint64_t, uint64_t, uint32_t *, uint32_t *, void *,
@@ -341,6 +342,10 @@ extern "C" int kpal_set_option(const char *name, int value)
     if (!strcmp(name, "radix_shape")) {
         if (value < 0 || value > 2) return bad_arg("radix_shape must be 0 (auto), 1 (1024 x 1 CTA/SM) or 2 (512 x 2)");
         set_radix_shape(value); return KPAL_OK;
+    }
+    if (!strcmp(name, "radix_max_buckets")) {
+        if (value != 1024 && value != 2048) return bad_arg("radix_max_buckets must be 1024 or 2048");
+        set_radix_max_buckets(value); return KPAL_OK;
     }
     if (!strcmp(name, "radix_debug")) { set_radix_debug(value); return KPAL_OK; }   // timing experiments
     if (!strcmp(name, "radix_payload_bits")) {

@@ -1,4 +1,4 @@
-// Two-pass radix-partitioned k-mer counting for large tables (9 <= k <= 13).
+// Two-pass radix-partitioned k-mer counting for large tables (9 <= k <= 15).
 //
 // Same contract as count_global_kernel (count.cu): accumulate the windows of a
 // packed stream (kpal/klib.py:154-168) into a table of 4^k counters.  A scattered
@@ -448,6 +448,8 @@ struct RadixWorkspace {
 static std::mutex g_radix_mutex;
 static std::vector<RadixWorkspace *> g_radix_ws;
 static std::atomic<int> g_radix_payload_bits{0};     // 0 = automatic
+static std::atomic<int> g_radix_max_buckets{2048};   // buckets binned by one pass-1 launch (1024 or 2048)
+void set_radix_max_buckets(int v) { g_radix_max_buckets.store(v); }
 static std::atomic<int> g_radix_shape{0};            // 0 = automatic
 void set_radix_shape(int v) { g_radix_shape.store(v); }
 static std::atomic<int> g_radix_debug{0};
@@ -488,10 +490,14 @@ static RadixGeometry radix_geometry(int k)
     if (p < 2 * k - 15) p = 2 * k - 15;                 // at most 32768 buckets
     g.P = p;
     g.nb = 1 << (2 * k - p);
-    // More than 1024 buckets do not fit the slots with a useful capacity: pass 1 then runs
-    // nb / 1024 times over the stream, each launch binning its own 1024 buckets (the stream
-    // is 0.375 B/base; re-reading it is cheap next to 5 B/base of RED traffic out of L2).
-    g.na = g.nb > 1024 ? 1024 : g.nb;
+    // Up to 2048 buckets fit the slots (40 payloads each: a slot keeps < 16 from tile to tile
+    // and gains 16 per tile on average, so ~2 % of the (slot, tile) pairs spill a few windows
+    // to the RED path).  Beyond that pass 1 runs nb / 2048 times over the stream, each launch
+    // binning its own buckets (the stream is 0.375 B/base; re-reading it is cheap next to
+    // 5 B/base of RED traffic out of L2).  Measured at k = 13, 375 Mbp: one launch of 2048
+    // buckets 1.06 ms for both passes, two launches of 1024 buckets 1.53 ms.
+    const int max_buckets = g_radix_max_buckets.load();
+    g.na = g.nb > max_buckets ? max_buckets : g.nb;
     int shape = g_radix_shape.load();                   // 1 = 1024 threads x 1 CTA/SM, 2 = 512 x 2
     if (shape == 0) shape = 1;      // measured: two half-size CTAs per SM do not beat one (147 vs 154 us)
     if (g.na > 512) shape = 1;
@@ -503,7 +509,7 @@ static RadixGeometry radix_geometry(int k)
     if (c > 1032) c = 1032;
     g.cap = c;
     // lanes per flush team ~ 16-byte pieces a slot gains per tile (2 per 16 payloads)
-    const int mean_pieces = g.threads * kUnitBases / g.nb / 8;
+    const int mean_pieces = g.threads * kUnitBases / g.na / 8;
     g.team = mean_pieces >= 8 ? 8 : 4;
     g.smem1 = size_t(g.na) * 8 + 128 + size_t(g.na) * c * 2 + 64;
     return g;

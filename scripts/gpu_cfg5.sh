@@ -1,10 +1,10 @@
 #!/bin/bash
+# config 5 shard (k=13, 375 Mbp per GPU): buckets per pass-1 launch 1024 (two sweeps) vs 2048 (one)
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_count.py -x -q -m gpu -k "radix or tiled" 2>&1 | tail -5
-for args in "--count-path 1" "--count-path 2"; do
-  timeout 600 python bench.py --config 5 --steps 5 --warmup 3 $args 2>gpurun_out/cfg5.err | tee gpurun_out/bench_cfg5_${args##* }.json | python -c "
-import sys, json
-d = json.loads(sys.stdin.read())
-print('$args', d['metric'], round(d['value'],1), 'step_ms', round(d['ms_per_step'], 4), 'kern_ms', round(d['roofline']['kernel_ms'], 4), 'e2e_ms', round(d['e2e']['ms_per_step'], 3), 'e2e', round(d['e2e']['value'],2), 'parity', d['parity_ok'], 'cpu', d['cpu_baseline']['value'])"
-  tail -3 gpurun_out/cfg5.err
+for mb in 1024 2048; do
+  timeout 400 python bench.py --config 5 --steps 5 --radix-max-buckets $mb > gpurun_out/bench_cfg5_mb$mb.json 2> gpurun_out/bench_cfg5_mb$mb.err
+  python -c "
+import json; d=json.loads(open('gpurun_out/bench_cfg5_mb$mb.json').read().strip().splitlines()[-1])
+print('max_buckets $mb', 'ms/step', round(d['ms_per_step'],4), 'value', round(d['value'],1), 'kernel_ms', round(d['roofline']['kernel_ms'],4), 'e2e', round(d['e2e']['value'],2), round(d['e2e']['ms_per_step'],3), 'parity', d['parity_ok'])"
+  tail -2 gpurun_out/bench_cfg5_mb$mb.err
 done

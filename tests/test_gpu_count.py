@@ -414,9 +414,9 @@ def _dev_count(text_bytes, k, bits, balance):
     (12, 3_000_000, "ACG", 0),         # skew: some slots and regions overflow into the RED path
     (12, 2_000_000, "AC", 0),          # 32 of 512 buckets used: heavy overflow
     (12, 1_000_000, "A", 0),           # one bin: everything overflows
-    (13, 6_000_000, "ACGTacgt", 0),    # 2048 buckets: pass 1 runs twice, 1024 buckets each
+    (13, 6_000_000, "ACGTacgt", 0),    # 2048 buckets: one pass-1 launch (or two of 1024 buckets each)
     (13, 1_000_000, "AT", 0),
-    (14, 3_000_000, "ACGT", 0),        # 8192 buckets, 8 sweeps
+    (14, 3_000_000, "ACGT", 0),        # 8192 buckets, 4 (or 8) sweeps
     (12, 2_000_000, "ACGT", 13),       # forced 2048 buckets at k = 12
     (11, 2_000_000, "ACGT", 0),
     (10, 2_000_000, "ACGT", 0),
@@ -432,12 +432,15 @@ def test_radix_count_path_bit_exact(k, n, letters, payload_bits):
     try:
         _set_option("count_path", 2)
         _set_option("radix_payload_bits", payload_bits)
-        for shape in (1, 2):           # one 1024-thread CTA per SM / two 512-thread CTAs per SM
-            _set_option("radix_shape", shape)
-            got32 = _dev_count(text, k, 32, False)
-            assert np.array_equal(got32, want), shape
-            got64 = _dev_count(text, k, 64, True)
-            assert np.array_equal(got64, ko.balance(want)), shape
+        many_buckets = k >= 13 or payload_bits == 13
+        for max_buckets in ((2048, 1024) if many_buckets else (2048,)):   # buckets per pass-1 launch
+            _set_option("radix_max_buckets", max_buckets)
+            for shape in (1, 2):           # one 1024-thread CTA per SM / two 512-thread CTAs per SM
+                _set_option("radix_shape", shape)
+                got32 = _dev_count(text, k, 32, False)
+                assert np.array_equal(got32, want), (max_buckets, shape)
+                got64 = _dev_count(text, k, 64, True)
+                assert np.array_equal(got64, ko.balance(want)), (max_buckets, shape)
         _set_option("count_path", 1)
         assert np.array_equal(_dev_count(text, k, 32, False), want)
     finally:
