@@ -28,6 +28,8 @@ void widen_publish(WidenHandle *h, uint64_t elements);
 void widen_end(WidenHandle *h, int abort);
 int launch_balance(const int64_t *, int64_t *, int, cudaStream_t);
 int launch_accumulate(const void *, void *, int, uint64_t, cudaStream_t);
+int launch_by_record_u16(const uint32_t *, const uint32_t *, const uint64_t *, uint64_t, uint64_t, int, int,
+                         uint16_t *, cudaStream_t);
 int launch_by_record(const uint32_t *, const uint32_t *, const uint64_t *, uint64_t, uint64_t, int,
                      int, int64_t *, cudaStream_t);
 int launch_prepare(const int64_t *, uint64_t, int, int, int, double *, double *, uint32_t *,
@@ -165,8 +167,9 @@ struct GrowPin {
 };
 struct CountWorkspace {
     int device = -1;
-    GrowDev codes, valid, table, counts, text, fscratch, counts16, counts8, overflow;
-    GrowPin pcodes, pvalid, pstatus, pnarrow, pflag;
+    GrowDev codes, valid, table, counts, text, fscratch, counts16, counts8, overflow, rows16[2];
+    GrowPin pcodes, pvalid, pstatus, pnarrow, pflag, prows16[2];
+    cudaEvent_t rows_done[2] = {};               // by-record: a batch of uint16 rows has landed
     cudaStream_t copy_stream = nullptr;          // H2D of the FASTA text, chunk by chunk
     cudaEvent_t chunk_done[32] = {};
     cudaEvent_t d2h_done[16] = {};               // chunks of the narrow D2H of the profile
@@ -801,6 +804,12 @@ extern "C" int kpal_dev_table_to_host(const void *d_table, int counter_bits, int
     return finalize_to_host(w, d_table, counter_bits, k, balance, counts_out, (cudaStream_t)stream);
 }
 
+// Dense int64 rows on the host for records [first, first + n).  When no record of the call can
+// overflow 16 bits (the usual case: reads, contigs below 65536 bases) the rows leave the device
+// as uint16 -- a quarter of the PCIe bytes -- in batches through two pinned buffers, and the
+// host threads of widen.cpp widen batch b into the caller's array while batch b + 1 is being
+// counted and copied; the caller's array may be pageable.  Otherwise: int64 rows, copied as
+// they are.
 extern "C" int kpal_count_by_record(const uint32_t *codes, const uint32_t *valid, uint64_t n_bases,
                                     const uint64_t *rec_starts, uint64_t first, uint64_t n, int k,
                                     int balance, int64_t *rows_out)
@@ -815,18 +824,64 @@ extern "C" int kpal_count_by_record(const uint32_t *codes, const uint32_t *valid
     if (b1 > n_bases || b0 > b1) return bad_arg("record starts outside the packed stream");
     const uint64_t c0 = b0 / 64, c1 = (b1 + 63) / 64 + 1;       // + halo chunk
     std::vector<uint64_t> rs(n + 1);
-    for (uint64_t r = 0; r <= n; ++r) rs[r] = rec_starts[first + r] - c0 * 64;
+    uint64_t longest = 0;
+    for (uint64_t r = 0; r <= n; ++r) {
+        rs[r] = rec_starts[first + r] - c0 * 64;
+        if (r) longest = std::max(longest, rs[r] - rs[r - 1]);
+    }
     DevBuf d_codes, d_valid, d_rs, d_rows;
     KPAL_CHECK(d_codes.alloc((c1 - c0) * 16));
     KPAL_CHECK(d_valid.alloc((c1 - c0) * 8));
     KPAL_CHECK(d_rs.alloc((n + 1) * 8));
-    // rows in batches that fit comfortably on the device
-    const uint64_t batch = std::max<uint64_t>(1, std::min<uint64_t>(n, (4ull << 30) / (bins * 8)));
-    KPAL_CHECK(d_rows.alloc(batch * bins * 8));
     cudaStream_t st = 0;
     KPAL_CUDA(cudaMemcpyAsync(d_codes.p, codes + c0 * 4, (c1 - c0) * 16, cudaMemcpyHostToDevice, st));
     KPAL_CUDA(cudaMemcpyAsync(d_valid.p, valid + c0 * 2, (c1 - c0) * 8, cudaMemcpyHostToDevice, st));
     KPAL_CUDA(cudaMemcpyAsync(d_rs.p, rs.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+
+    if (g_narrow_d2h.load() && k >= 2 && longest < (balance ? 32768ull : 65536ull)) {
+        std::lock_guard<std::mutex> lock(g_count_mutex);
+        CountWorkspace *w;
+        KPAL_CHECK(get_count_ws(&w));
+        // batches of ~128 MB of uint16 rows (1 GB of int64 on the host side)
+        const uint64_t batch = std::max<uint64_t>(1, std::min<uint64_t>(n, (128ull << 20) / (bins * 2)));
+        for (int i = 0; i < 2; ++i) {
+            KPAL_CHECK(w->rows16[i].ensure(batch * bins * 2));
+            KPAL_CHECK(w->prows16[i].ensure(batch * bins * 2));
+            if (!w->rows_done[i]) KPAL_CUDA(cudaEventCreateWithFlags(&w->rows_done[i], cudaEventDisableTiming));
+        }
+        const uint64_t n_batches = (n + batch - 1) / batch;
+        auto enqueue = [&](uint64_t b) -> int {
+            const uint64_t r = b * batch, m = std::min(batch, n - r);
+            uint16_t *d = static_cast<uint16_t *>(w->rows16[b & 1].p);
+            KPAL_CHECK(launch_by_record_u16(d_codes.as<uint32_t>(), d_valid.as<uint32_t>(), d_rs.as<uint64_t>(),
+                                            r, m, k, balance, d, st));
+            KPAL_CUDA(cudaMemcpyAsync(w->prows16[b & 1].p, d, m * bins * 2, cudaMemcpyDeviceToHost, st));
+            KPAL_CUDA(cudaEventRecord(w->rows_done[b & 1], st));
+            return KPAL_OK;
+        };
+        int rc = enqueue(0);
+        if (rc == KPAL_OK && n_batches > 1) rc = enqueue(1);
+        for (uint64_t b = 0; b < n_batches && rc == KPAL_OK; ++b) {
+            const uint64_t r = b * batch, m = std::min(batch, n - r);
+            cudaError_t e = cudaEventSynchronize(w->rows_done[b & 1]);
+            if (e != cudaSuccess) {
+                set_error("narrow D2H of the rows failed: %s", cudaGetErrorString(e));
+                cudaGetLastError();
+                rc = KPAL_ECUDA;
+                break;
+            }
+            WidenHandle *h = widen_begin(w->prows16[b & 1].p, 2, rows_out + r * bins, m * bins, m * bins);
+            widen_publish(h, m * bins);
+            widen_end(h, 0);
+            if (b + 2 < n_batches) rc = enqueue(b + 2);     // its buffers are free again
+        }
+        cudaStreamSynchronize(st);                           // nothing of this call stays queued
+        return rc;
+    }
+
+    // rows in batches that fit comfortably on the device
+    const uint64_t batch = std::max<uint64_t>(1, std::min<uint64_t>(n, (4ull << 30) / (bins * 8)));
+    KPAL_CHECK(d_rows.alloc(batch * bins * 8));
     for (uint64_t r = 0; r < n; r += batch) {
         const uint64_t m = std::min(batch, n - r);
         KPAL_CHECK(launch_by_record(d_codes.as<uint32_t>(), d_valid.as<uint32_t>(), d_rs.as<uint64_t>(),

@@ -295,22 +295,26 @@ __device__ __forceinline__ void by_record_red_row(const uint4 *__restrict__ code
     __syncthreads();
 }
 
-template <bool RED_ONLY>
+// RowT = int64_t: the API's rows.  RowT = uint16_t: the slab itself, for the host entry point's
+// narrow copy (kpal_count_by_record checks that no record of the call can overflow 16 bits).
+template <bool RED_ONLY, typename RowT>
 __global__ void __launch_bounds__(kRowThreads)
 by_record_kernel(const uint4 *__restrict__ codes, const uint2 *__restrict__ valid,
                  const uint64_t *__restrict__ rec_starts, uint64_t first_rec, uint64_t n_rec,
-                 int k, int balance, int64_t *__restrict__ rows)
+                 int k, int balance, RowT *__restrict__ rows)
 {
     extern __shared__ __align__(16) uint32_t slab[];            // 16-bit counters, two per word
     const uint64_t bins = 1ull << (2 * k);
     const int shift = 32 - 2 * k;
     const uint32_t slab_bins = bins < kSlabBins ? uint32_t(bins) : kSlabBins;
     for (uint64_t r = blockIdx.x; r < n_rec; r += gridDim.x) {
-        unsigned long long *row = reinterpret_cast<unsigned long long *>(rows + r * bins);
         const uint64_t b0 = rec_starts[first_rec + r], b1 = rec_starts[first_rec + r + 1];
-        if (RED_ONLY || (b1 - b0) >= (balance ? 32768ull : 65536ull)) {          // CTA-uniform
-            by_record_red_row(codes, valid, b0, b1, k, balance, row);
-            continue;
+        if constexpr (sizeof(RowT) == 8) {
+            if (RED_ONLY || (b1 - b0) >= (balance ? 32768ull : 65536ull)) {      // CTA-uniform
+                by_record_red_row(codes, valid, b0, b1, k, balance,
+                                  reinterpret_cast<unsigned long long *>(rows + r * bins));
+                continue;
+            }
         }
         for (uint64_t s0 = 0; s0 < bins; s0 += slab_bins) {
             if (slab_bins >= 8) {
@@ -331,10 +335,16 @@ by_record_kernel(const uint4 *__restrict__ codes, const uint2 *__restrict__ vali
             __syncthreads();
             // write-out: consecutive lanes write consecutive 16 bytes (two int64 counts from one
             // shared word), so every store instruction of a warp covers 512 contiguous bytes
-            ulonglong2 *out = reinterpret_cast<ulonglong2 *>(row + s0);
-            for (uint32_t i = threadIdx.x; i < slab_bins / 2; i += kRowThreads) {
-                const uint32_t w = slab[i];
-                __stcs(out + i, make_ulonglong2(w & 0xffffu, w >> 16));
+            if constexpr (sizeof(RowT) == 8) {
+                ulonglong2 *out = reinterpret_cast<ulonglong2 *>(rows + r * bins + s0);
+                for (uint32_t i = threadIdx.x; i < slab_bins / 2; i += kRowThreads) {
+                    const uint32_t w = slab[i];
+                    __stcs(out + i, make_ulonglong2(w & 0xffffu, w >> 16));
+                }
+            } else {                                    // 4^k >= 16: whole 16-byte pieces
+                uint4 *out = reinterpret_cast<uint4 *>(rows + r * bins + s0);
+                for (uint32_t i = threadIdx.x; i < slab_bins / 8; i += kRowThreads)
+                    __stcs(out + i, *reinterpret_cast<const uint4 *>(slab + 4 * i));
             }
             __syncthreads();
         }
@@ -547,16 +557,38 @@ int launch_by_record(const uint32_t *d_codes, const uint32_t *d_valid, const uin
     const auto vd = reinterpret_cast<const uint2 *>(d_valid);
     if (g_by_record_path.load() == 1) {                 // the RED path for every record (A/B measurements)
         const uint64_t cap = uint64_t(sm_count()) * 4;
-        by_record_kernel<true><<<unsigned(n < cap ? n : cap), kRowThreads, 0, stream>>>(
+        by_record_kernel<true, int64_t><<<unsigned(n < cap ? n : cap), kRowThreads, 0, stream>>>(
             cd, vd, d_rec_starts, first, n, k, balance, d_rows);
     } else {
-        KPAL_CUDA(cudaFuncSetAttribute(by_record_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        KPAL_CUDA(cudaFuncSetAttribute(by_record_kernel<false, int64_t>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         // resident CTAs per SM: three 64 KB slabs fit, and at most 2048 threads
         const uint64_t per_sm = smem > 32768 ? 3 : 4;
         const uint64_t cap = uint64_t(sm_count()) * per_sm;
-        by_record_kernel<false><<<unsigned(n < cap ? n : cap), kRowThreads, smem, stream>>>(
+        by_record_kernel<false, int64_t><<<unsigned(n < cap ? n : cap), kRowThreads, smem, stream>>>(
             cd, vd, d_rec_starts, first, n, k, balance, d_rows);
     }
+    KPAL_LAUNCH_CHECK("by_record_kernel");
+    return KPAL_OK;
+}
+
+// Rows as uint16 (k >= 2).  The caller guarantees that no record of [first, first + n) has
+// 65536 bases or more (32768 with balance): the counts then fit, see by_record_kernel.
+int launch_by_record_u16(const uint32_t *d_codes, const uint32_t *d_valid, const uint64_t *d_rec_starts,
+                         uint64_t first, uint64_t n, int k, int balance, uint16_t *d_rows,
+                         cudaStream_t stream)
+{
+    KPAL_CHECK(check_k(k));
+    if (k < 2) return bad_arg("uint16 rows need k >= 2");
+    if (n == 0) return KPAL_OK;
+    const uint64_t bins = 1ull << (2 * k);
+    const size_t smem = size_t(bins < kSlabBins ? bins : kSlabBins) * 2;
+    KPAL_CUDA(cudaFuncSetAttribute(by_record_kernel<false, uint16_t>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    const uint64_t cap = uint64_t(sm_count()) * (smem > 32768 ? 3 : 4);
+    by_record_kernel<false, uint16_t><<<unsigned(n < cap ? n : cap), kRowThreads, smem, stream>>>(
+        reinterpret_cast<const uint4 *>(d_codes), reinterpret_cast<const uint2 *>(d_valid),
+        d_rec_starts, first, n, k, balance, d_rows);
     KPAL_LAUNCH_CHECK("by_record_kernel");
     return KPAL_OK;
 }

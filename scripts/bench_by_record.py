@@ -57,3 +57,25 @@ for balance in (0, 1):
                       "ms": ms, "records_per_s": N_REC / ms * 1e3,
                       "write_GBps": out_bytes / ms / 1e6, "parity_ok": ok,
                       "host_pack_s": pack_s}))
+
+# ---- end to end through the host entry point (kpal_count_by_record: packed host stream ->
+# dense int64 rows in host memory), on the first E2E_REC records (10.5 GB of rows at 20 k)
+E2E_REC = int(os.environ.get("KPAL_BY_RECORD_E2E", "20000"))
+if E2E_REC:
+    out = np.empty((E2E_REC, 4 ** K), dtype=np.int64)
+    out[:] = -1                                              # touch the pages before timing
+    for narrow in (1, 0):
+        _cabi.check(L.kpal_set_option(b"narrow_d2h", narrow))
+        best = None
+        for rep in range(2):
+            t0 = time.perf_counter()
+            _cabi.check(L.kpal_count_by_record(_cabi.ptr(codes), _cabi.ptr(valid), int(n_bases), _cabi.ptr(rec_starts),
+                                               0, E2E_REC, K, 0, out.ctypes.data))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        ok = all(np.array_equal(out[i], c_oracle.count_bytes(reads[i].tobytes(), K)) for i in (0, 1, E2E_REC // 2, E2E_REC - 1))
+        print(json.dumps({"bench": "by_record_e2e", "k": K, "records": E2E_REC,
+                          "rows": "uint16 over PCIe, widened by host threads" if narrow else "int64 over PCIe",
+                          "s": best, "records_per_s": E2E_REC / best, "host_row_GBps": out.nbytes / best / 1e9,
+                          "parity_ok": bool(ok)}))
+    _cabi.check(L.kpal_set_option(b"narrow_d2h", 1))

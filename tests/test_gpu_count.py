@@ -220,8 +220,22 @@ def test_by_record_slab_kernel_limits():
                     for seq, row in zip(seqs, rows):
                         want = ko.count_sequences([seq], k)
                         assert np.array_equal(row, ko.balance(want) if balance else want), (path, k, balance, seq[:8])
+        # The host entry point copies the rows as uint16 when no record of the call can overflow
+        # 16 bits, as int64 otherwise (cabi.cu kpal_count_by_record): sub-ranges on either side,
+        # a count of exactly 65534 / 65535, and the narrow copy switched off.
+        _set_option("by_record_path", 0)
+        for narrow in (1, 0):
+            _set_option("narrow_d2h", narrow)
+            for k in (2, 8):
+                for first, n in ((0, 1), (2, 7), (4, 1), (6, 3), (1, 2)):
+                    for balance in (False, True):
+                        rows = _cabi.count_by_record(codes, valid, n_bases, rec_starts, first, n, k, balance=balance)
+                        for seq, row in zip(seqs[first:first + n], rows):
+                            want = ko.count_sequences([seq], k)
+                            assert np.array_equal(row, ko.balance(want) if balance else want), (narrow, k, first, balance)
     finally:
         _set_option("by_record_path", 0)
+        _set_option("narrow_d2h", 1)
 
 
 def test_device_api_counter_widths():
