@@ -275,6 +275,45 @@ __device__ __forceinline__ void for_record_windows(const uint4 *__restrict__ cod
     }
 }
 
+// The same walk with the windows of every chunk spread over the warp: a chunk's words are
+// broadcast from the lane that loaded it and lane l takes the windows starting at bases l and
+// l + 32.  A read of a few hundred bases occupies only a few lanes of one warp in the walk
+// above (64 windows in sequence per lane); here its windows are binned 32 at a time.
+template <typename F>
+__device__ __forceinline__ void for_record_windows_spread(const uint4 *__restrict__ codes,
+                                                          const uint2 *__restrict__ valid,
+                                                          uint64_t b0, uint64_t b1, int k, F &&f)
+{
+    const int shift = 32 - 2 * k;
+    const unsigned lane = threadIdx.x & 31u;
+    const bool upper = lane >= 16u;
+    const int rot = 2 * int(lane & 15u);
+    const uint64_t c0 = b0 / kChunkBases, c1 = (b1 + kChunkBases - 1) / kChunkBases;
+    for (uint64_t base = c0 + (threadIdx.x & ~31u); base < c1; base += blockDim.x) {
+        const uint64_t chunk = base + lane;
+        Chunk c = load_chunk(codes, valid, chunk, chunk < c1, k);
+        const uint64_t p0 = chunk * kChunkBases;
+        uint64_t keep = ~0ull;
+        if (p0 < b0) keep &= (b0 - p0 >= 64) ? 0ull : (~0ull >> (b0 - p0));
+        if (p0 + 64 > b1) keep &= (b1 <= p0) ? 0ull : ~(~0ull >> (b1 - p0));
+        c.starts &= keep;
+        unsigned todo = __ballot_sync(0xffffffffu, c.starts != 0ull);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const uint32_t w0 = __shfl_sync(0xffffffffu, c.w[0], src), w1 = __shfl_sync(0xffffffffu, c.w[1], src);
+            const uint32_t w2 = __shfl_sync(0xffffffffu, c.w[2], src), w3 = __shfl_sync(0xffffffffu, c.w[3], src);
+            const uint32_t w4 = __shfl_sync(0xffffffffu, c.w[4], src);
+            const uint32_t s_hi = __shfl_sync(0xffffffffu, uint32_t(c.starts >> 32), src);
+            const uint32_t s_lo = __shfl_sync(0xffffffffu, uint32_t(c.starts), src);
+            if ((s_hi >> (31u - lane)) & 1u)                                       // window at base `lane`
+                f(__funnelshift_l(upper ? w2 : w1, upper ? w1 : w0, rot) >> shift);
+            if ((s_lo >> (31u - lane)) & 1u)                                       // ... at base 32 + `lane`
+                f(__funnelshift_l(upper ? w4 : w3, upper ? w3 : w2, rot) >> shift);
+        }
+    }
+}
+
 __device__ __forceinline__ void by_record_red_row(const uint4 *__restrict__ codes, const uint2 *__restrict__ valid,
                                                   uint64_t b0, uint64_t b1, int k, int balance,
                                                   unsigned long long *__restrict__ row)
@@ -324,7 +363,7 @@ by_record_kernel(const uint4 *__restrict__ codes, const uint2 *__restrict__ vali
                 slab[threadIdx.x] = 0;
             }
             __syncthreads();
-            for_record_windows(codes, valid, b0, b1, k, [&](uint32_t idx) {
+            for_record_windows_spread(codes, valid, b0, b1, k, [&](uint32_t idx) {
                 const uint32_t a = idx - uint32_t(s0);
                 if (a < slab_bins) atomicAdd(slab + (a >> 1), 1u << (16 * (a & 1)));
                 if (balance) {
