@@ -566,8 +566,10 @@ def bench_count(args):
                              "count + balance kernels, " if world == 1 else
                              "per rank: pinned FASTA bytes -> kpal_count_fasta_to_dev (H2D in chunks, GPU scan/pack, "
                              "count); table sum onto rank 0; there kpal_dev_table_to_host (widen + balance, ") +
-                            ("D2H of the first %d/16 of the profile as uint%d in chunks, widened to int64 by host "
-                             "threads, the rest as int64 by the copy engine meanwhile)" % (16 - args.dma_share, 8 * narrow_width)
+                            (("D2H as uint%d in chunks, widened to the int64 profile by host threads)" % (8 * narrow_width)
+                              if args.dma_share == 0 else
+                              "D2H of the first %d/16 of the profile as uint%d in chunks, widened to int64 by host "
+                              "threads, the rest as int64 by the copy engine meanwhile)" % (16 - args.dma_share, 8 * narrow_width))
                              if narrow and narrow_width < 8 else "D2H int64)")},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": count_kernel_name, "achieved": achieved,
