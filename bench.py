@@ -326,6 +326,7 @@ def bench_count(args):
     _cabi.check(L.kpal_set_option(b"fasta_chunks", args.fasta_chunks))
     _cabi.check(L.kpal_set_option(b"narrow_d2h", args.narrow_d2h))
     _cabi.check(L.kpal_set_option(b"dma_share", args.dma_share))
+    _cabi.check(L.kpal_set_option(b"fasta_split", args.fasta_split))
     dev = torch.device("cuda", local)
 
     # ---- this rank's shard of records (same size on every rank: weak scaling)
@@ -766,6 +767,9 @@ def main():
                     help="e2e leg: 1 = the profile leaves the device as uint8 / uint16 (the narrowest that "
                          "holds every count) and host threads widen it (library default), 2 = uint16 only, "
                          "0 = plain int64 copy")
+    ap.add_argument("--fasta-split", type=int, default=0, choices=[0, 1],
+                    help="e2e leg: 1 = a large FASTA text is cut at a header line into two parts, the first counted "
+                         "while the second is uploaded, 0 = one part (library default: the cut measured no gain)")
     ap.add_argument("--dma-share", type=int, default=0,
                     help="e2e leg: sixteenths of the narrow-copied profile that the copy engine moves as int64 "
                          "straight into the pinned result while the host threads widen the rest (library default 0: "

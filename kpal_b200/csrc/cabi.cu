@@ -67,6 +67,7 @@ int launch_count_push(const uint32_t *, const uint32_t *, uint64_t, int, void *,
 static thread_local char t_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_host_fasta{-1};       // -1: from the environment (KPAL_HOST_FASTA=1)
+static std::atomic<int> g_fasta_split{0};         // 1: a large FASTA text is cut in two parts, the first counted while the second uploads (fasta_gpu_count; measured: no gain yet, so off)
 static std::atomic<int> g_fasta_chunks{0};      // 0 = automatic (one chunk per ~6 MB, at most 16), else 1 .. 32
 static std::atomic<int> g_dma_share{0};         // sixteenths of a narrow-copied profile the DMA engine moves as int64 (pinned destinations)
 static std::atomic<int> g_narrow_d2h{1};        // 1: large profiles leave the device as uint8 / uint16, 2: uint16 only (see finalize_to_host)
@@ -171,6 +172,8 @@ struct CountWorkspace {
     GrowPin pcodes, pvalid, pstatus, pnarrow, pflag, prows16[2];
     cudaEvent_t rows_done[2] = {};               // by-record: a batch of uint16 rows has landed
     cudaStream_t copy_stream = nullptr;          // H2D of the FASTA text, chunk by chunk
+    cudaStream_t count_stream = nullptr;         // count kernels of the first of two parts (fasta_gpu_count)
+    cudaEvent_t part_packed = nullptr, part_counted = nullptr;
     cudaEvent_t chunk_done[32] = {};
     cudaEvent_t d2h_done[16] = {};               // chunks of the narrow D2H of the profile
     cudaEvent_t flag_done = nullptr;             // ... and the flag words ahead of them
@@ -324,6 +327,7 @@ extern "C" int kpal_set_option(const char *name, int value)
         if (value < 0 || value > 32) return bad_arg("fasta_chunks must be 0 (auto) .. 32");
         g_fasta_chunks.store(value); return KPAL_OK;
     }
+    if (!strcmp(name, "fasta_split")) { g_fasta_split.store(value ? 1 : 0); return KPAL_OK; }
     if (!strcmp(name, "exact_div")) { set_exact_div(value != 0); return KPAL_OK; }
     if (!strcmp(name, "narrow_d2h")) {
         if (value < 0 || value > 2) return bad_arg("narrow_d2h must be 0 (int64), 1 (uint8 / uint16) or 2 (uint16)");
@@ -480,8 +484,8 @@ static CallTrace g_trace;       // used under g_count_mutex
 // the CPU.  A count above 65535 (a large table needs a very repetitive input for that)
 // sends the call down the int64 finalize + copy instead.  Exact either way.
 //
-// `pending` (optional): status words of the GPU FASTA packer whose D2H copy is already
-// queued on `st`.  They are looked at together with the flags; if the packer turned the
+// `pending` (optional): the two status slots of the GPU FASTA packer (one per part of the
+// text, fasta_gpu_count) whose D2H copies are already queued on `st`.  They are looked at together with the flags; if the packer turned the
 // text down (*text_flags != 0 on return) nothing is written and the caller redoes the
 // file through the host packer.
 static int finalize_to_host(CountWorkspace *w, const void *d_table, int bits, int k, int balance,
@@ -543,8 +547,8 @@ static int finalize_to_host(CountWorkspace *w, const void *d_table, int bits, in
         KPAL_CUDA(cudaEventSynchronize(w->flag_done));
         g_trace.mark("flags");
         const volatile unsigned int *flag = static_cast<const volatile unsigned int *>(w->pflag.p);
-        if (pending && pending->flags) {
-            *text_flags = pending->flags;
+        if (pending && (pending[0].flags | pending[1].flags)) {
+            *text_flags = pending[0].flags | pending[1].flags;
             KPAL_CUDA(cudaStreamSynchronize(st));
             return KPAL_OK;
         }
@@ -578,7 +582,7 @@ static int finalize_to_host(CountWorkspace *w, const void *d_table, int bits, in
         KPAL_CUDA(cudaStreamSynchronize(st));                       // drain the speculative chunk
     } else if (pending) {
         KPAL_CUDA(cudaStreamSynchronize(st));
-        if (pending->flags) { *text_flags = pending->flags; return KPAL_OK; }
+        if (pending[0].flags | pending[1].flags) { *text_flags = pending[0].flags | pending[1].flags; return KPAL_OK; }
     }
     KPAL_CHECK(w->counts.ensure(bins * 8));
     KPAL_CHECK(launch_finalize(d_table, bits, k, balance, static_cast<int64_t *>(w->counts.p), st));
@@ -647,28 +651,60 @@ extern "C" int kpal_count_sequences(const char *text, const uint64_t *offsets, u
     return count_packed_to_host(w, n_bases, k, balance, counts_out);
 }
 
+// A header line ('>' at a line start) near three quarters of the text, or 0: where
+// kpal_count_fasta cuts the file in two so that the first part is counted while the second
+// is still on the bus.  Looks at 1 MB only ('>' does not occur inside sequence lines, so
+// reads have one every few hundred bytes; a genome without a header there is not cut).
+static uint64_t fasta_split_point(const char *fasta, uint64_t n_bytes)
+{
+    if (g_fasta_split.load() == 0 || n_bytes < (16ull << 20)) return 0;
+    uint64_t at = n_bytes / 4 * 3;
+    const uint64_t end = std::min<uint64_t>(n_bytes, at + (1ull << 20));
+    while (at < end) {
+        const char *hit = static_cast<const char *>(memchr(fasta + at, '>', end - at));
+        if (!hit) return 0;
+        at = uint64_t(hit - fasta);
+        if (fasta[at - 1] == '\n') return at;
+        ++at;
+    }
+    return 0;
+}
+
 // Raw FASTA bytes (host) -> device text -> GPU scan/pack -> windows accumulated
 // into d_table.  *flags gets bit 0 when the text holds bytes the GPU packer
 // does not handle (tabs & co on sequence lines): the caller then redoes the
 // file through the host packer.  Synchronises the stream -- unless `flags` is null:
-// then the status copy is only queued and the caller reads w->pstatus after its own
-// synchronisation (finalize_to_host does, together with its flag words).
+// then the status copies are only queued and the caller reads the two FastaStatus
+// slots of w->pstatus after its own synchronisation (finalize_to_host does, together
+// with its flag words).
+//
+// The text goes up in chunks on a copy stream; the packer runs on the tiles of a chunk as
+// soon as it has landed, so scan/pack hides behind the PCIe transfer.  With the option
+// "fasta_split" a large text is cut at a header line into two parts that are packed and
+// counted independently (a part that begins with a header is a FASTA file of its own: no
+// window spans the cut): the first part's count kernels run while the second part is still
+// being uploaded, so only the last quarter of the counting is left once the last byte has
+// arrived.  Exact, but not faster yet (profiles/r01_e2e_trace.log: the count does leave
+// the critical path, 290 -> 125 us after the last pack, but the scan/pack chain of the
+// second part's chunks falls 150 us behind the first part's count kernels), hence off.
 static int fasta_gpu_count(CountWorkspace *w, const char *fasta, uint64_t n_bytes, int k,
                            void *d_table, int bits, cudaStream_t st, unsigned *flags,
                            uint64_t *n_bases)
 {
-    uint64_t cw, vw;
-    kpal_packed_words(n_bytes, &cw, &vw);           // capacity: one base per input byte
-    KPAL_CHECK(w->text.ensure(n_bytes + 32));
-    KPAL_CHECK(w->codes.ensure(cw * 4));
-    KPAL_CHECK(w->valid.ensure(vw * 4));
-    KPAL_CHECK(w->fscratch.ensure(fasta_scratch_bytes(n_bytes)));
-    KPAL_CHECK(w->pstatus.ensure(sizeof(FastaStatus)));
-    // The text goes up in up to 32 chunks on a copy stream; the packer runs on the tiles of
-    // a chunk as soon as it has landed, so scan/pack hides behind the PCIe transfer.
-    uint32_t *d_codes = static_cast<uint32_t *>(w->codes.p), *d_valid = static_cast<uint32_t *>(w->valid.p);
-    const uint8_t *d_text = static_cast<const uint8_t *>(w->text.p);
-    KPAL_CHECK(launch_fasta_pack_begin(n_bytes, d_codes, d_valid, w->fscratch.p, st));
+    const uint64_t split = fasta_split_point(fasta, n_bytes);
+    const uint64_t part_len[2] = {split ? split : n_bytes, split ? n_bytes - split : 0};
+    const uint64_t text_off[2] = {0, (part_len[0] + 255) / 256 * 256};      // 16-byte loads need alignment
+    uint64_t cw[2] = {0, 0}, vw[2] = {0, 0};
+    kpal_packed_words(part_len[0], &cw[0], &vw[0]);                          // capacity: one base per input byte
+    if (split) kpal_packed_words(part_len[1], &cw[1], &vw[1]);
+    KPAL_CHECK(w->text.ensure(text_off[1] + part_len[1] + 32));
+    KPAL_CHECK(w->codes.ensure((cw[0] + cw[1]) * 4));
+    KPAL_CHECK(w->valid.ensure((vw[0] + vw[1]) * 4));
+    const uint64_t scratch_off[2] = {0, (fasta_scratch_bytes(part_len[0]) + 255) / 256 * 256};
+    KPAL_CHECK(w->fscratch.ensure(scratch_off[1] + (split ? fasta_scratch_bytes(part_len[1]) : 0)));
+    KPAL_CHECK(w->pstatus.ensure(2 * sizeof(FastaStatus)));
+    FastaStatus *status = static_cast<FastaStatus *>(w->pstatus.p);
+    memset(status, 0, 2 * sizeof(FastaStatus));
     const uint64_t tile = fasta_tile_bytes();
     // (what remains after the last byte has landed is the scan/pack of ONE chunk: 80 us with 16
     // chunks of the 109 MB of config 2, 45 us with 32 -- but every chunk costs ~5 us on the
@@ -676,38 +712,80 @@ static int fasta_gpu_count(CountWorkspace *w, const char *fasta, uint64_t n_byte
     uint64_t n_chunks = n_bytes / (6ull << 20);
     n_chunks = std::min<uint64_t>(std::max<uint64_t>(n_chunks, 1), 16);
     if (g_fasta_chunks.load() > 0) n_chunks = std::min<uint64_t>(uint64_t(g_fasta_chunks.load()), 32);
-    if (n_chunks > 1 && !w->copy_stream) {
+    if (split) n_chunks = std::max<uint64_t>(n_chunks, 2);
+    const bool piped = n_chunks > 1;
+    if (piped && !w->copy_stream) {
         KPAL_CUDA(cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
         for (auto &e : w->chunk_done) KPAL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    const uint64_t chunk = ((n_bytes + n_chunks - 1) / n_chunks + tile - 1) / tile * tile;
-    g_trace.dev_mark("start", n_chunks > 1 ? w->copy_stream : st);
-    for (uint64_t c = 0, off = 0; off < n_bytes; ++c, off += chunk) {
-        const uint64_t len = std::min(chunk, n_bytes - off);
-        if (n_chunks > 1) {
-            KPAL_CUDA(cudaMemcpyAsync(w->text.as_bytes() + off, fasta + off, len, cudaMemcpyHostToDevice, w->copy_stream));
-            KPAL_CUDA(cudaEventRecord(w->chunk_done[c], w->copy_stream));
-            KPAL_CUDA(cudaStreamWaitEvent(st, w->chunk_done[c], 0));
-        } else {
-            KPAL_CUDA(cudaMemcpyAsync(w->text.as_bytes() + off, fasta + off, len, cudaMemcpyHostToDevice, st));
-        }
-        KPAL_CHECK(launch_fasta_pack_tiles(d_text, n_bytes, off / tile, (off + len + tile - 1) / tile, d_codes,
-                                           d_valid, w->fscratch.p, st));
+    if (split && !w->count_stream) {
+        KPAL_CUDA(cudaStreamCreateWithFlags(&w->count_stream, cudaStreamNonBlocking));
+        KPAL_CUDA(cudaEventCreateWithFlags(&w->part_packed, cudaEventDisableTiming));
+        KPAL_CUDA(cudaEventCreateWithFlags(&w->part_counted, cudaEventDisableTiming));
     }
-    g_trace.dev_mark("h2d", n_chunks > 1 ? w->copy_stream : st);
-    g_trace.dev_mark("packed", st);
-    // n_bytes is an upper bound of the packed length; the tail is all-invalid padding
-    KPAL_CHECK(launch_count(static_cast<uint32_t *>(w->codes.p), static_cast<uint32_t *>(w->valid.p),
-                            n_bytes, k, d_table, bits, st));
+    // the caller's work queued on `st` before this call (the table memset) comes first
+    if (split) {
+        KPAL_CUDA(cudaEventRecord(w->part_packed, st));
+        KPAL_CUDA(cudaStreamWaitEvent(w->count_stream, w->part_packed, 0));
+    }
+    // Both parts are initialised before the first byte is queued: the memsets may run on the
+    // copy engine, where they would wait behind every upload chunk already in its queue.
+    for (int part = 0; part < (split ? 2 : 1); ++part)
+        KPAL_CHECK(launch_fasta_pack_begin(part_len[part], static_cast<uint32_t *>(w->codes.p) + (part ? cw[0] : 0),
+                                           static_cast<uint32_t *>(w->valid.p) + (part ? vw[0] : 0),
+                                           w->fscratch.as_bytes() + scratch_off[part], st));
+    g_trace.dev_mark("start", piped ? w->copy_stream : st);
+    uint64_t event = 0;
+    for (int part = 0; part < (split ? 2 : 1); ++part) {
+        const char *src = fasta + (part ? split : 0);
+        const uint64_t len_p = part_len[part];
+        uint8_t *d_text = w->text.as_bytes() + text_off[part];
+        uint32_t *d_codes = static_cast<uint32_t *>(w->codes.p) + (part ? cw[0] : 0);
+        uint32_t *d_valid = static_cast<uint32_t *>(w->valid.p) + (part ? vw[0] : 0);
+        void *d_scratch = w->fscratch.as_bytes() + scratch_off[part];
+        // this part's share of the chunks, at least one
+        uint64_t chunks_p = split ? std::max<uint64_t>(1, (n_chunks * len_p + n_bytes / 2) / n_bytes) : n_chunks;
+        chunks_p = std::min<uint64_t>(chunks_p, 32 - event - (split && part == 0 ? 1 : 0));
+        const uint64_t chunk = ((len_p + chunks_p - 1) / chunks_p + tile - 1) / tile * tile;
+        for (uint64_t off = 0; off < len_p; off += chunk) {
+            const uint64_t len = std::min(chunk, len_p - off);
+            if (piped) {
+                KPAL_CUDA(cudaMemcpyAsync(d_text + off, src + off, len, cudaMemcpyHostToDevice, w->copy_stream));
+                KPAL_CUDA(cudaEventRecord(w->chunk_done[event], w->copy_stream));
+                KPAL_CUDA(cudaStreamWaitEvent(st, w->chunk_done[event], 0));
+                ++event;
+            } else {
+                KPAL_CUDA(cudaMemcpyAsync(d_text + off, src + off, len, cudaMemcpyHostToDevice, st));
+            }
+            KPAL_CHECK(launch_fasta_pack_tiles(d_text, len_p, off / tile, (off + len + tile - 1) / tile, d_codes,
+                                               d_valid, d_scratch, st));
+        }
+        if (part == (split ? 1 : 0)) {
+            g_trace.dev_mark("h2d", piped ? w->copy_stream : st);
+            g_trace.dev_mark("packed", st);
+        }
+        KPAL_CUDA(cudaMemcpyAsync(status + part, d_scratch, sizeof(FastaStatus), cudaMemcpyDeviceToHost, st));
+        // len_p is an upper bound of the packed length; the tail is all-invalid padding.
+        // The first of two parts is counted on a stream of its own: queued on `st` its
+        // count kernels would hold up the scan/pack of the second part's chunks, which then
+        // finish long after the last byte has arrived (measured: 290 instead of 80 us).
+        if (split && part == 0) {
+            KPAL_CUDA(cudaEventRecord(w->part_packed, st));
+            KPAL_CUDA(cudaStreamWaitEvent(w->count_stream, w->part_packed, 0));
+            KPAL_CHECK(launch_count(d_codes, d_valid, len_p, k, d_table, bits, w->count_stream));
+            KPAL_CUDA(cudaEventRecord(w->part_counted, w->count_stream));
+        } else {
+            // one table, one radix staging area: the second count follows the first
+            if (split) KPAL_CUDA(cudaStreamWaitEvent(st, w->part_counted, 0));
+            KPAL_CHECK(launch_count(d_codes, d_valid, len_p, k, d_table, bits, st));
+        }
+    }
     g_trace.dev_mark("counted", st);
-    KPAL_CUDA(cudaMemcpyAsync(w->pstatus.p, w->fscratch.p, sizeof(FastaStatus),
-                              cudaMemcpyDeviceToHost, st));
     g_trace.mark("count_queued");
     if (!flags) return KPAL_OK;
     KPAL_CUDA(cudaStreamSynchronize(st));
-    const FastaStatus *fs = static_cast<const FastaStatus *>(w->pstatus.p);
-    *flags = fs->flags;
-    if (n_bases) *n_bases = fs->total_bases;
+    *flags = status[0].flags | status[1].flags;
+    if (n_bases) *n_bases = status[0].total_bases + status[1].total_bases;
     return KPAL_OK;
 }
 

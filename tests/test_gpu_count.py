@@ -533,6 +533,40 @@ def test_count_fasta_chunked_upload_pipeline(tutorial_texts):
         _set_option("fasta_chunks", 0)
 
 
+def test_large_fasta_is_counted_in_two_overlapped_parts():
+    """With the option fasta_split, kpal_count_fasta cuts a text of 16 MB or more at a header
+    line near three quarters (cabi.cu fasta_gpu_count) and counts the first part while the
+    second is uploaded.  Same
+    bits with the cut, without it, for every chunking; '>' inside header lines is not a cut
+    point; a text without a header in the search window is not cut; exotic white space in
+    either part still sends the whole file through the host packer."""
+    reads = random_reads(21, 130_000, 150)
+    fasta = reads_to_fasta(reads)                                    # 20.9 MB, a header every 161 bytes
+    assert len(fasta) > (16 << 20)
+    want = {k: c_oracle.count_bytes(np.insert(reads, 150, ord("\n"), axis=1).tobytes(), k,
+                                    threads=c_oracle.max_threads()) for k in (6, 12)}
+    tricky = fasta.replace(b">r0097", b">r>>97")                      # '>' runs inside the header lines around 75 %
+    genome = b">chr\n" + reads[:120_000].tobytes() + b"\n>tail\nACGTACGTAC\n"      # no header near 75 %
+    want_genome = ko.count_fasta(genome.decode(), 12)
+    tab_late = fasta[:-20] + b"\tAC\t\n" + fasta[-20:]               # a tab in the second part
+    want_tab = ko.count_fasta(tab_late.decode(), 6)
+    try:
+        for split in (1, 0):
+            _set_option("fasta_split", split)
+            for chunks in (0, 2, 5, 32):
+                _set_option("fasta_chunks", chunks)
+                for k in (6, 12):
+                    assert np.array_equal(_cabi.count_fasta(fasta, k), want[k]), (split, chunks, k)
+                assert np.array_equal(_cabi.count_fasta(tricky, 12), want[12]), (split, chunks)
+            _set_option("fasta_chunks", 0)
+            assert np.array_equal(_cabi.count_fasta(fasta, 12, balance=True), ko.balance(want[12])), split
+            assert np.array_equal(_cabi.count_fasta(genome, 12), want_genome), split
+            assert np.array_equal(_cabi.count_fasta(tab_late, 6), want_tab), split
+    finally:
+        _set_option("fasta_split", 0)
+        _set_option("fasta_chunks", 0)
+
+
 def test_narrow_profile_copy_and_its_overflow_path():
     """From k = 10 on the host entry points move the profile over PCIe as uint8 or uint16
     (whichever holds every count) and widen it on the host (cabi.cu finalize_to_host).
