@@ -59,6 +59,8 @@ LEAF_K = 4              # symbol-table node holds up to 2 * LEAF_K entries
 GROUP_K = 16            # group B-tree node holds up to 2 * GROUP_K children
 CHUNK_K = 32            # chunk B-tree node holds up to 2 * CHUNK_K children (libhdf5 default)
 GZIP_LEVEL = 4          # h5py's default for compression='gzip'
+_DEFERRED_BYTES = 4 << 20       # datasets up to this size are deflated in the background (Dataset._write)
+_MAX_PENDING = 64               # ... at most this many at a time
 
 MSG_NIL, MSG_DATASPACE, MSG_DATATYPE, MSG_FILL_OLD, MSG_FILL = 0x0, 0x1, 0x3, 0x4, 0x5
 MSG_LAYOUT, MSG_FILTERS, MSG_ATTRIBUTE, MSG_CONTINUATION, MSG_SYMBOL_TABLE = 0x8, 0xB, 0xC, 0x10, 0x11
@@ -653,6 +655,8 @@ class Dataset(_Node):
     def _chunk_index(self):
         """[(offsets, address, stored bytes, filter mask)] from the chunk B-tree."""
         meta = self._load()
+        if 'index' not in meta and getattr(self, '_future', None) is not None:
+            self._file._drain(0)                                # still being deflated in the background
         if 'index' in meta:
             return meta['index']
         reader = self._file._reader
@@ -763,16 +767,32 @@ class Dataset(_Node):
                 origins = [o + (x,) for o in origins for x in axis]
 
             def encode(origin):
-                block = np.zeros(chunks, data.dtype)            # edge chunks are stored whole
                 where = tuple(slice(o, min(o + c, s)) for o, c, s in zip(origin, chunks, data.shape))
-                block[tuple(slice(0, w.stop - w.start) for w in where)] = data[where]
+                block = data[where]
+                if block.shape != chunks:                       # edge chunks are stored whole
+                    whole = np.zeros(chunks, data.dtype)
+                    whole[tuple(slice(0, w.stop - w.start) for w in where)] = block
+                    block = whole
                 raw = block.tobytes()
                 return zlib.compress(raw, gzip_level) if gzip_level is not None else raw
+            meta['layout'] = ('chunked', None)
+            if data.nbytes <= _DEFERRED_BYTES and gzip_level is not None:
+                # A small dataset (one profile of a --by-record run: 100 k of them) is deflated
+                # as ONE background task on a private copy, and its chunks reach the file when
+                # the task is done (File._drain): the caller goes on to the next profile, and
+                # the parallelism is across datasets instead of inside one.
+                data = np.array(data, copy=True)
+                self._future = _workers().submit(lambda: [encode(o) for o in origins])
+                self._origins = origins
+                file._pending.append(self)
+                self._meta = meta
+                file._drain(_MAX_PENDING)
+                return
             index = []
+            file._drain(0)                                       # keep the file in creation order
             for origin, raw in zip(origins, _workers().map(encode, origins)):
                 index.append((origin, file._append(raw), len(raw), 0))
             meta['index'] = index
-            meta['layout'] = ('chunked', None)
         self._meta = meta
 
 
@@ -800,6 +820,7 @@ class File(Group):
             self._handle = open(name, 'w+b')
             self._handle.write(b'\0' * 96)              # the superblock goes here on close()
             self._end = 96
+            self._pending = []                          # datasets whose chunks are still being deflated
             self._reader = _WriteSideReader(self)
             Group.__init__(self, self, '/')
             self._writable = True
@@ -839,9 +860,19 @@ class File(Group):
         self._end = address + len(raw)
         return address
 
+    def _drain(self, keep):
+        """Appends the chunks of pending datasets (oldest first) until at most `keep` are left."""
+        while len(self._pending) > keep:
+            dataset = self._pending.pop(0)
+            chunks = dataset._future.result()
+            dataset._meta['index'] = [(origin, self._append(raw), len(raw), 0)
+                                      for origin, raw in zip(dataset._origins, chunks)]
+            dataset._future = dataset._origins = None
+
     def flush(self):
-        """Pushes the data written so far to the OS.  The metadata (object headers, group
-        B-trees, superblock) is written by close()."""
+        """Pushes the data written so far to the OS.  Chunks still being deflated in the
+        background follow as they finish; the metadata (object headers, group B-trees,
+        superblock) is written by close()."""
         self._require_open()
         if self._writable:
             self._handle.flush()
@@ -858,6 +889,7 @@ class File(Group):
             return
         try:
             if self._writable:
+                self._drain(0)
                 _Serializer(self).run()
         finally:
             self._closed = True
