@@ -10,16 +10,20 @@ Default workload (BASELINE.json configs[1], the one `metric` is quoted on):
 A step = one pass of the hot path over the whole batch:
 
   value : packed sequence already resident in HBM -> int64 balanced profile in
-          HBM (memset + count kernel + [NCCL reduce] + widen/balance kernel),
-          timed with CUDA events on the launching stream, L2 flushed between
-          steps (untimed), max over ranks;
-  e2e   : the same job through the host-buffer C ABI: pinned FASTA bytes ->
-          C++ scan/pack -> H2D -> kernels -> [NCCL reduce] -> D2H of the int64
-          profile, wall clock around the call with device syncs.
+          HBM (memset + count kernels + [table sum over the ranks] + widen/balance
+          kernel), timed with CUDA events on the launching stream, L2 flushed
+          between steps (untimed), max over ranks;
+  e2e   : the same job through the host-buffer C ABI (kpal_count_fasta): pinned
+          FASTA bytes -> H2D in chunks -> GPU scan/pack -> count kernels ->
+          [table sum] -> narrow (uint8 / uint16) D2H of the profile, widened to
+          int64 by host threads; wall clock around the call with device syncs.
 
 Multi-GPU (weak scaling): every rank counts its own shard of records (same
-size per rank), the 4^k u32 tables are summed onto rank 0 with an NCCL reduce
-and finalised (widen + balance) once.
+size per rank), the 4^k u32 tables are summed onto rank 0 -- over NVLink peer
+memory fused into the count's histogram pass at 2 GPUs, with an NCCL reduce
+from 4 GPUs on (`--reduce auto`, chosen by measurement) -- and finalised
+(widen + balance) once.  `--config 5`: one GPU's shard of BASELINE configs[4]
+(k=13 genome-like records).
 
 `--workload matrix`: BASELINE.json configs[3], the 4096-profile k=10 scaled
 multiset distance matrix (profile-pairs/s); tiles sharded over the ranks.
