@@ -180,8 +180,8 @@ class _Reader(object):
         self._global_heaps = {}
 
     def read(self, address, size):
-        self.handle.seek(self.base + address)
-        data = self.handle.read(size)
+        # positional read: no shared file offset, so chunk tasks may read concurrently
+        data = os.pread(self.handle.fileno(), size, self.base + address)
         if len(data) != size:
             raise IOError('truncated HDF5 file (wanted %d bytes at %d)' % (size, address))
         return data
@@ -716,16 +716,29 @@ class Dataset(_Node):
                 return np.zeros(shape, dtype)
             return np.frombuffer(reader.read(address, size), dtype, int(np.prod(shape))).reshape(shape).copy()
         out = np.zeros(shape, dtype)
-        chunk = meta['chunks']
-        index = self._chunk_index()
-        raws = [reader.read(address, nbytes) for _o, address, nbytes, _m in index]
-        decoded = list(_workers().map(lambda rm: self._decode_chunk(rm[0], rm[1]),
-                                      zip(raws, (m for _o, _a, _n, m in index))))
-        for (offsets, _a, _n, _m), raw in zip(index, decoded):
-            block = np.frombuffer(raw, dtype, int(np.prod(chunk))).reshape(chunk)
+        self._read_chunks_into(out)
+        return out
+
+    def _read_chunks_into(self, out):
+        """Chunked layout: every chunk is read, decoded and placed by a pool task of its own
+        (positional reads and zlib both run without the GIL)."""
+        meta = self._meta
+        reader = self._file._reader
+        shape, dtype, chunk = meta['shape'], meta['dtype'], meta['chunks']
+        count = int(np.prod(chunk))
+
+        def place(entry):
+            offsets, address, nbytes, mask = entry
+            raw = self._decode_chunk(reader.read(address, nbytes), mask)
+            block = np.frombuffer(raw, dtype, count).reshape(chunk)
             where = tuple(slice(o, min(o + c, s)) for o, c, s in zip(offsets, chunk, shape))
             out[where] = block[tuple(slice(0, w.stop - w.start) for w in where)]
-        return out
+        index = self._chunk_index()
+        if len(index) > 1:
+            list(_workers().map(place, index))
+        else:
+            for entry in index:
+                place(entry)
 
     def __getitem__(self, key):
         self._file._require_open()
@@ -735,9 +748,19 @@ class Dataset(_Node):
         return data[key]
 
     def read_direct(self, dest):
-        """Read the whole dataset into the C-contiguous array `dest` (same shape)."""
+        """Read the whole dataset into the array `dest` (same shape)."""
         self._file._require_open()
-        dest[...] = self._read_all()
+        meta = self._load()
+        if (meta['layout'][0] == 'chunked' and isinstance(dest, np.ndarray) and dest.shape == meta['shape']
+                and dest.dtype == meta['dtype']):
+            n_chunks = 1
+            for s_, c_ in zip(meta['shape'], meta['chunks']):
+                n_chunks *= -(-s_ // c_)
+            if len(self._chunk_index()) < n_chunks:
+                dest[...] = 0                            # chunks that were never written read as the fill value
+            self._read_chunks_into(dest)                 # decoded straight into the caller's array
+        else:
+            dest[...] = self._read_all()
 
     def __array__(self, dtype=None, copy=None):
         data = self._read_all()
@@ -915,8 +938,7 @@ class _WriteSideReader(object):
     def read(self, address, size):
         handle = self._file._handle
         handle.flush()
-        handle.seek(address)
-        return handle.read(size)
+        return os.pread(handle.fileno(), size, address)
 
 
 # =========================================================================
