@@ -254,6 +254,40 @@ def test_large_profile_is_chunked_like_h5py(tmp_path):
     assert h5lite._guess_chunk((4 ** 6,), 8) == (1024,) and h5lite._guess_chunk((4,), 8) == (4,)
 
 
+def test_read_direct_into_slab_rows(tmp_path):
+    """The access pattern of kdistlib.distance_matrix_from_file: `group[name].shape`, then
+    `read_direct` into one row of a preallocated [rows][4^k] slab -- multi-chunk (k = 9),
+    single-chunk (k = 3) and uncompressed datasets, concurrently from several threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(5)
+    for k in (9, 3):
+        profiles = dict(('s%02d' % i, rng.poisson(2.0, 4 ** k).astype(np.int64)) for i in range(12))
+        path = str(tmp_path / ('slab%d.k' % k))
+        _profile_file(path, profiles)
+        with h5lite.File(path) as f:
+            group = f['profiles']
+            names = sorted(group)
+            slab = np.full((len(names), 4 ** k), -1, dtype=np.int64)
+            for row, name in enumerate(names):
+                assert int(group[name].shape[0]) == 4 ** k
+                group[name].read_direct(slab[row])
+            assert all(np.array_equal(slab[row], profiles[name]) for row, name in enumerate(names))
+            slab[:] = -1
+            with ThreadPoolExecutor(4) as pool:             # datasets in parallel: reads are positional
+                list(pool.map(lambda rn: group[rn[1]].read_direct(slab[rn[0]]), enumerate(names)))
+            assert all(np.array_equal(slab[row], profiles[name]) for row, name in enumerate(names))
+            wrong = np.empty(4 ** k, dtype=np.int32)         # other dtype: converted, not reinterpreted
+            group[names[0]].read_direct(wrong)
+            assert np.array_equal(wrong, profiles[names[0]])
+    plain = str(tmp_path / 'plain.h5')
+    with h5lite.File(plain, 'w') as f:
+        f.create_dataset('x', data=np.arange(100, dtype=np.int64))
+    with h5lite.File(plain) as f:
+        out = np.empty(100, dtype=np.int64)
+        f['x'].read_direct(out)
+        assert np.array_equal(out, np.arange(100))
+
+
 def test_values_and_layouts(tmp_path):
     path = str(tmp_path / 'misc.h5')
     matrix = np.arange(35 * 13, dtype=np.float64).reshape(35, 13)
