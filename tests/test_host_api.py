@@ -276,3 +276,34 @@ def test_cli_commands_with_handle_double(golden, tmp_path):
         kmer.main([])
     with pytest.raises(SystemExit):
         kmer.main(['matrix', str(tmp_path / 'missing.k'), '-'])
+
+
+def test_read_text_takes_ascii_files_as_bytes(tmp_path):
+    """klib._read_text: a text-mode FASTA file at its start is read through its binary buffer
+    when that cannot change the result (plain ASCII, no '\\r'); every other handle goes through
+    handle.read() and so keeps universal newlines, encodings and partial reads."""
+    from kpal_b200.klib import _read_text
+
+    def write(name, data):
+        path = tmp_path / name
+        path.write_bytes(data)
+        return str(path)
+    plain = write('plain.fa', b">r1 x\nACGT\nNN\n>r2\nTTGA")
+    with open(plain) as handle:
+        assert _read_text(handle) == b">r1 x\nACGT\nNN\n>r2\nTTGA"
+    with open(plain) as handle:
+        handle.readline()
+        assert _read_text(handle) == "ACGT\nNN\n>r2\nTTGA"          # partly consumed: the rest, as text
+    with open(plain, 'rb') as handle:
+        assert _read_text(handle) == b">r1 x\nACGT\nNN\n>r2\nTTGA"
+    with open(write('dos.fa', b">r1\r\nACGT\r\n")) as handle:
+        assert _read_text(handle) == ">r1\nACGT\n"
+    with open(write('mac.fa', b">r1\rACGT\r>r2\rTT\r")) as handle:
+        assert _read_text(handle) == ">r1\nACGT\n>r2\nTT\n"
+    with open(write('utf8.fa', u">ré\nACGT\n".encode('utf-8')), encoding='utf-8') as handle:
+        assert _read_text(handle) == u">ré\nACGT\n"
+    assert _read_text(io.StringIO(">x\nAC\n")) == ">x\nAC\n"
+    assert _read_text(io.BytesIO(b">x\nAC\n")) == b">x\nAC\n"
+    # either form parses to the same records
+    for text in (b">r1 x\nACGT\nNN\n>r2\nTTGA", ">r1 x\nACGT\nNN\n>r2\nTTGA"):
+        assert ko.parse_fasta(text) == [("r1", "ACGTNN"), ("r2", "TTGA")]
