@@ -2,11 +2,14 @@
 """
 bench.py -- headline benchmark of the kPAL hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload count|matrix]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload all|count|matrix]
                     [--impl ours|reference]
 
-Default workload (BASELINE.json configs[1], the one `metric` is quoted on):
-`kpal count` at k=12 over 100 Mbp of synthetic 150-bp reads, with balance.
+BASELINE.json's metric has two halves and the default run (`--workload all`) measures both
+and prints ONE JSON line: the count record (configs[1], the one `metric` is quoted on) with
+the matrix record (configs[3]) as its "matrix" sub-record.
+
+Count workload: `kpal count` at k=12 over 100 Mbp of synthetic 150-bp reads, with balance.
 A step = one pass of the hot path over the whole batch:
 
   value : packed sequence already resident in HBM -> int64 balanced profile in
@@ -25,8 +28,14 @@ from 4 GPUs on (`--reduce auto`, chosen by measurement) -- and finalised
 (widen + balance) once.  `--config 5`: one GPU's shard of BASELINE configs[4]
 (k=13 genome-like records).
 
-`--workload matrix`: BASELINE.json configs[3], the 4096-profile k=10 scaled
-multiset distance matrix (profile-pairs/s); tiles sharded over the ranks.
+Matrix workload: BASELINE.json configs[3], the 4096-profile k=10 scaled multiset distance
+matrix (profile-pairs/s), with its own small step count (<= 2).  At N > 1 (strong scaling)
+every rank generates / uploads and prepares 1/N of the profiles, the prepared set is
+all-gathered over NVLink, the upper-triangle tiles are dealt out in equal ranges and the
+finished tiles are gathered on rank 0 as compact tile arrays (kpal_b200/multigpu.py).
+
+`--config 1`: BASELINE configs[0] (k=6, one 1 Mbp record, no balance); `--config 5`: one
+GPU's shard of configs[4] (k=13; the full 3 Gbp job at --gpus 8).
 
 `--impl reference`: the CPU baseline -- the oracle's C port of the reference
 algorithm on all host threads (the reference itself is pure Python and cannot
@@ -217,66 +226,134 @@ def host_mem_available():
     return None
 
 
-def recorded_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture."""
+def host_threads():
+    """Threads for the CPU legs: every core this process may run on.  (torchrun exports
+    OMP_NUM_THREADS=1 to its workers; the C port takes its thread count as an argument, so
+    the reference arm and the oracle checks still use the whole host.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def traffic_record(kernel):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture, with the
+    file it came from (the bench does not run under a profiler)."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            return json.load(f).get(kernel)
+            table = json.load(f)
+        return table.get(kernel), table.get("_source", {}).get(kernel)
     except Exception:
-        return None
+        return None, None
+
+
+# ------------------------------------------------------- count workload inputs
+def count_shard_input(config, rank, k, mbp_per_gpu, composition="uniform"):
+    """(records as the oracle reads them [bytes, one record per line], FASTA bytes, sequence
+    bases, windows or None, description) of rank `rank`'s shard -- deterministic per rank, so
+    rank 0 can rebuild every shard for the oracle check."""
+    if config == 5:
+        rec_len = int(mbp_per_gpu * 1e6) // 3
+        records = synthetic_chromosomes(5000 + rank, 3, rec_len)
+        fasta = records_to_fasta(records, first=3 * rank)
+        oracle_text = np.concatenate([np.append(r, np.uint8(10)) for r in records])
+        bases = sum(len(r) for r in records)
+        what = ("kpal count k=%d, %d x %.1f Mbp records per GPU with N blocks and soft-masking, balance; "
+                "BASELINE configs[4]" % (k, 3, rec_len / 1e6))
+        return oracle_text, fasta, bases, None, what
+    if config == 1:
+        rng = np.random.default_rng(1 + rank)
+        seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 1_000_000, dtype=np.uint8)]
+        fasta = records_to_fasta([seq], first=rank)
+        oracle_text = np.append(seq, np.uint8(10))
+        return (oracle_text, fasta, seq.size, seq.size - (k - 1),
+                "kpal count k=%d, one 1 Mbp record, no balance; BASELINE configs[0]" % k)
+    reads = synthetic_reads(1000 + rank)
+    if composition == "skewed":
+        # 10 % of the reads are low-complexity: homopolymer runs and short tandem repeats
+        rng = np.random.default_rng(77 + rank)
+        low = np.flatnonzero(rng.random(N_READS) < 0.10)
+        units = [b"A", b"T", b"AC", b"AT", b"CAG", b"TTAGGG", b"AAAAT"]
+        for u in range(len(units)):
+            unit = np.frombuffer(units[u], dtype=np.uint8)
+            rows = low[u::len(units)]
+            reads[rows] = np.resize(unit, READ_LEN)
+    fasta = reads_to_fasta(reads)
+    oracle_text = np.insert(reads, READ_LEN, ord("\n"), axis=1).reshape(-1)
+    what = ("kpal count k=%d, 100 Mbp of 150-bp reads (666667 records/GPU)%s, balance; BASELINE configs[1]"
+            % (k, ", 10 %% low-complexity reads" if composition == "skewed" else ""))
+    return oracle_text, fasta, reads.size, reads.size - N_READS * (k - 1) if composition == "uniform" else None, what
 
 
 # ----------------------------------------------------------- reference arm
 def run_reference(args):
-    """CPU baseline: the oracle's C port on all host threads."""
+    """CPU baseline: the oracle's C port on all host threads, for both halves of the metric."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import c_oracle, kpal_oracle as ko
-    threads = c_oracle.max_threads()
-    if args.workload == "count":
-        reads = synthetic_reads(1000)
-        text = np.insert(reads, READ_LEN, ord("\n"), axis=1).reshape(-1)
-        n_bases = reads.size
-        rc = ko.reverse_complement_table(K_COUNT)
+    from oracle import c_oracle
+    threads = host_threads()
 
-        def step():
-            counts = c_oracle.count_bytes(text, K_COUNT, threads=threads)
-            return c_oracle.balance(counts)            # literal klib.py:285-298 loop in C
-        sample = "full workload: %d reads x %d bp, k=%d, balance (C port, OpenMP)" % (
-            N_READS, READ_LEN, K_COUNT)
-        units, unit, metric = n_bases / 1e9, "Gbases/s", "gbases_per_sec_counted_k12"
-        config = {"workload": "kpal count k=12, 100 Mbp of 150-bp reads, balance", "k": K_COUNT}
-    else:
+    def timed(step):
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        return (time.perf_counter() - t0) / args.steps
+
+    def matrix_leg():
         n = 48
         rng = np.random.default_rng(4)
         lam = np.exp(rng.uniform(np.log(0.5), np.log(8.0), n))
         profiles = np.stack([rng.poisson(l, 4 ** K_MATRIX) for l in lam]).astype(np.int64)
-
-        def step():
-            return c_oracle.distance_matrix(profiles, do_scale=True, threads=threads)
+        dt = timed(lambda: c_oracle.distance_matrix(profiles, do_scale=True, threads=threads))
         sample = "leading %d profiles (%d pairs) of the 4096-profile k=10 set (C port, OpenMP)" % (
             n, n * (n - 1) // 2)
-        units, unit, metric = n * (n - 1) / 2, "profile-pairs/s", "profile_pairs_per_sec_k10_multiset"
-        config = {"workload": "kpal matrix multiset/prod scaled, 4096 profiles k=10", "k": K_MATRIX}
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / args.steps
-    value = units / dt
-    print(json.dumps({
-        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int64" if args.workload == "count" else "f64", "data": "synthetic",
-        "config": config,
-        "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port",
-                         "sample": sample},
-        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }))
+        value = n * (n - 1) / 2 / dt
+        return {"impl": "reference", "metric": "profile_pairs_per_sec_k10_multiset", "value": value,
+                "unit": "profile-pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "kpal matrix multiset/prod scaled, 4096 profiles k=10", "k": K_MATRIX},
+                "cpu_baseline": {"value": value, "unit": "profile-pairs/s", "cores": threads, "kind": "port",
+                                 "sample": sample},
+                "e2e": {"value": value, "unit": "profile-pairs/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+
+    def count_leg():
+        k = args.k or (13 if args.config == 5 else 6 if args.config == 1 else K_COUNT)
+        balance = args.config != 1
+        mbp = min(args.mbp_per_gpu, 90.0) if args.config == 5 else args.mbp_per_gpu   # bounded sample
+        text, _, n_bases, _, what = count_shard_input(args.config, 0, k, mbp, args.composition)
+
+        def step():
+            counts = c_oracle.count_bytes(text, k, threads=threads)
+            return c_oracle.balance(counts) if balance else counts      # literal klib.py:285-298 loop in C
+        dt = timed(step)
+        value = n_bases / 1e9 / dt
+        sample = ("full workload of one GPU: %d bases, k=%d%s (C port, OpenMP)"
+                  % (n_bases, k, ", balance" if balance else ""))
+        if args.config == 5 and mbp < args.mbp_per_gpu:
+            sample = "bounded sample: 3 x %.0f Mbp records of the same generator, k=%d, balance (C port, OpenMP)" % (
+                mbp / 3, k)
+        return {"impl": "reference", "metric": "gbases_per_sec_counted_k%d" % k, "value": value,
+                "unit": "Gbases/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int64", "data": "synthetic", "config": {"workload": what, "k": k},
+                "cpu_baseline": {"value": value, "unit": "Gbases/s", "cores": threads, "kind": "port",
+                                 "sample": sample},
+                "e2e": {"value": value, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+
+    if args.workload == "matrix":
+        out = matrix_leg()
+    else:
+        out = count_leg()
+        if args.workload == "all":
+            out["matrix"] = matrix_leg()
+    print(json.dumps(out))
 
 
 # ------------------------------------------------------------------ our arm
@@ -313,16 +390,18 @@ def max_over_ranks(value, world):
     return float(t.item())
 
 
-def bench_count(args):
+def bench_count(args, world, rank, local):
     import torch
     import torch.distributed as dist
     from kpal_b200 import _cabi
 
-    world, rank, local = init_dist(args)
     L = _cabi.load()
     _cabi.check(L.kpal_set_device(local))
     _cabi.check(L.kpal_set_option(b"count_path", args.count_path))
     _cabi.check(L.kpal_set_option(b"radix_payload_bits", args.radix_payload_bits))
+    _cabi.check(L.kpal_set_option(b"pair_upt", args.pair_upt))
+    _cabi.check(L.kpal_set_option(b"pair_flush_every", args.pair_flush_every))
+    _cabi.check(L.kpal_set_option(b"pair_fused", args.pair_fused))
     if args.radix_max_buckets:
         _cabi.check(L.kpal_set_option(b"radix_max_buckets", args.radix_max_buckets))
     _cabi.check(L.kpal_set_option(b"radix_debug", args.radix_debug))
@@ -334,36 +413,19 @@ def bench_count(args):
     dev = torch.device("cuda", local)
 
     # ---- this rank's shard of records (same size on every rank: weak scaling)
-    if args.config == 5:
-        # BASELINE configs[4]: k = 13, human-genome-sized FASTA sharded over the GPUs
-        # (3 x 125 Mbp records per GPU at the full 8-GPU size)
-        k = args.k or 13
-        rec_len = int(args.mbp_per_gpu * 1e6) // 3
-        records = synthetic_chromosomes(5000 + rank, 3, rec_len)
-        fasta_np = records_to_fasta(records, first=3 * rank)
-        oracle_text = np.concatenate([np.append(r, np.uint8(10)) for r in records])
-        seq_bases_total = sum(len(r) for r in records)
-        n_windows = None
-        workload = ("kpal count k=%d, %d x %.1f Mbp records per GPU with N blocks and soft-masking, balance; "
-                    "BASELINE configs[4]" % (k, 3, rec_len / 1e6))
-        del records
-    else:
-        k = args.k or K_COUNT
-        reads = synthetic_reads(1000 + rank)
-        fasta_np = reads_to_fasta(reads)
-        oracle_text = np.insert(reads, READ_LEN, ord("\n"), axis=1).reshape(-1)
-        seq_bases_total = reads.size
-        n_windows = reads.size - N_READS * (k - 1)
-        workload = ("kpal count k=%d, 100 Mbp of 150-bp reads (666667 records/GPU), balance; "
-                    "BASELINE configs[1]" % k)
-        del reads
+    k = args.k or (13 if args.config == 5 else 6 if args.config == 1 else K_COUNT)
+    balance = 0 if args.config == 1 else 1
+    oracle_text, fasta_np, seq_bases, n_windows, workload = count_shard_input(
+        args.config, rank, k, args.mbp_per_gpu, args.composition)
+    if world > 1 or rank != 0:
+        oracle_text = None              # rank 0 rebuilds every shard for the check at the end
     bins = 4 ** k
     n_fasta = fasta_np.size
     pinned_fasta = _cabi.PinnedArray(n_fasta, np.uint8)
     pinned_fasta.array[:] = fasta_np
     pinned_out = _cabi.PinnedArray(bins, np.int64)
     codes, valid, _, _, n_bases = _cabi.fasta_pack(fasta_np.tobytes())
-    seq_bases = seq_bases_total
+    del fasta_np
     d_codes = torch.from_numpy(codes.view(np.int32)).to(dev)
     d_valid = torch.from_numpy(valid.view(np.int32)).to(dev)
     d_table = torch.zeros(bins, dtype=torch.int32, device=dev)
@@ -376,9 +438,9 @@ def bench_count(args):
     reduce_note = None
     if args.reduce == "auto":
         # measured (profiles/README.md): at 2 GPUs the table sum fused into the count's histogram
-        # pass is on par with / ahead of the NCCL reduce (0.416 vs 0.421 ms per step), at 4 GPUs the
-        # peer stores slow pass 2 down and NCCL wins (0.473 vs 0.427 ms)
-        args.reduce = "fused" if world == 2 else "nccl"
+        # pass is on par with / ahead of the NCCL reduce, at 4 GPUs the peer stores slow pass 2
+        # down and NCCL wins.  The fused form rides on the one-window radix path (k >= 13 here).
+        args.reduce = "fused" if (world == 2 and k >= 13) else "nccl"
     if world > 1 and args.reduce in ("peer", "fused"):
         from kpal_b200 import multigpu
         # CUDA IPC between the ranks can be refused by the box (container without a shared
@@ -417,7 +479,7 @@ def bench_count(args):
         """... + widen/balance there."""
         summed = reduce_tables()
         if rank == 0:
-            _cabi.check(L.kpal_dev_finalize_counts(summed, 32, k, 1, d_counts.data_ptr(), sp))
+            _cabi.check(L.kpal_dev_finalize_counts(summed, 32, k, balance, d_counts.data_ptr(), sp))
 
     def device_step(ev=None):
         d_table.zero_()
@@ -430,7 +492,7 @@ def bench_count(args):
             if ev:
                 ev[1].record(stream)
             if rank == 0:
-                _cabi.check(L.kpal_dev_finalize_counts(summed, 32, k, 1, d_counts.data_ptr(), sp))
+                _cabi.check(L.kpal_dev_finalize_counts(summed, 32, k, balance, d_counts.data_ptr(), sp))
             return
         _cabi.check(L.kpal_dev_count_packed(d_codes.data_ptr(), d_valid.data_ptr(), n_bases, k,
                                             d_table.data_ptr(), 32, sp))
@@ -440,7 +502,7 @@ def bench_count(args):
 
     def e2e_step():
         if world == 1:
-            _cabi.check(L.kpal_count_fasta(pinned_fasta._ptr, n_fasta, k, 1, pinned_out._ptr))
+            _cabi.check(L.kpal_count_fasta(pinned_fasta._ptr, n_fasta, k, balance, pinned_out._ptr))
         else:
             d_table.zero_()
             nb = ctypes.c_uint64()
@@ -448,7 +510,7 @@ def bench_count(args):
                                                   32, sp, ctypes.byref(nb)))
             summed = reduce_tables()
             if rank == 0:       # widen + balance + narrow D2H into the host profile
-                _cabi.check(L.kpal_dev_table_to_host(summed, 32, k, 1, pinned_out._ptr, sp))
+                _cabi.check(L.kpal_dev_table_to_host(summed, 32, k, balance, pinned_out._ptr, sp))
         torch.cuda.synchronize()
 
     # ---- warm-up (>= 3)
@@ -491,51 +553,66 @@ def bench_count(args):
     barrier_sync(world)
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps, world)
 
-    # ---- parity of what was just measured (rank 0, N=1: against the oracle)
-    result_ok = None
-    if rank == 0 and world == 1:
-        from oracle import c_oracle, kpal_oracle as ko
-        t0 = time.perf_counter()
-        want = c_oracle.count_bytes(oracle_text, k, threads=c_oracle.max_threads())
-        want = c_oracle.balance(want)                 # literal klib.py:285-298 loop in C
-        cpu_s = time.perf_counter() - t0
-        if n_windows is None:
-            n_windows = int(want.sum()) // 2
-        result_ok = bool(np.array_equal(d_counts.cpu().numpy(), want)
-                         and np.array_equal(pinned_out.array, want))
-        cpu = {"value": seq_bases / 1e9 / cpu_s, "unit": "Gbases/s", "cores": c_oracle.max_threads(),
-               "kind": "port",
-               "sample": "full workload once (C port of klib.py:149-170 + balance, OpenMP); the "
-                         "reference's pure-Python loop measured 0.001-0.0036 Gbases/s on 1 core "
-                         "(BASELINE.md)"}
-    else:
-        cpu = None
+    # ---- parity of what was just measured, against the ORACLE: the C port counts the
+    # concatenation of every rank's shard (rank 0 rebuilds the shards of the other ranks from
+    # their seeds; untimed).  At N > 1 the sum of the per-rank tables taken with a plain NCCL
+    # reduce is checked as well.
+    result_ok, cpu, parity = None, None, None
     if world > 1:
-        # N > 1: the job's result (rank 0) must equal, bit for bit, the sum of the per-rank
-        # tables taken with a plain NCCL reduce and finalised the same way; the host-buffer
-        # result of the e2e leg must equal it too.  (Each rank's own table is the N = 1 path,
-        # whose oracle parity is the N = 1 run's check.)
-        device_step()
+        device_step()                       # the result under test: rank 0's d_counts / pinned_out
         check = d_table.clone()
         d_table.zero_()
         _cabi.check(L.kpal_dev_count_packed(d_codes.data_ptr(), d_valid.data_ptr(), n_bases, k,
                                             d_table.data_ptr(), 32, sp))
         check.copy_(d_table)
         dist.reduce(check, dst=0, op=dist.ReduceOp.SUM)
-        if rank == 0:
+    if rank == 0:
+        from oracle import c_oracle
+        threads = host_threads()
+        want = np.zeros(bins, dtype=np.int64)
+        cpu_s = 0.0
+        for r in range(world):
+            text = oracle_text if world == 1 else count_shard_input(
+                args.config, r, k, args.mbp_per_gpu, args.composition)[0]
+            t0 = time.perf_counter()
+            part = c_oracle.count_bytes(text, k, threads=threads)
+            if world == 1 and balance:
+                part = c_oracle.balance(part)             # literal klib.py:285-298 loop in C
+            cpu_s += time.perf_counter() - t0
+            want += part
+            del text
+        if world > 1 and balance:
+            want = c_oracle.balance(want)
+        if n_windows is None:
+            n_windows = int(want.sum()) // (2 if balance else 1) // world
+        dev_ok = bool(np.array_equal(d_counts.cpu().numpy(), want))
+        host_ok = bool(np.array_equal(pinned_out.array, want))
+        parity = {"checked_against": "C port of klib.py:149-170 + 285-298 on the concatenation of all %d shard(s)" % world,
+                  "device_result_equals_oracle": dev_ok, "host_result_equals_oracle": host_ok,
+                  "total_windows": int(want.sum()) // (2 if balance else 1)}
+        result_ok = dev_ok and host_ok
+        if world > 1:
             want_dev = torch.empty_like(d_counts)
-            _cabi.check(L.kpal_dev_finalize_counts(check.data_ptr(), 32, k, 1, want_dev.data_ptr(), sp))
+            _cabi.check(L.kpal_dev_finalize_counts(check.data_ptr(), 32, k, balance, want_dev.data_ptr(), sp))
             torch.cuda.synchronize()
-            result_ok = bool(torch.equal(want_dev, d_counts)
-                             and np.array_equal(pinned_out.array, want_dev.cpu().numpy()))
+            parity["device_result_equals_nccl_sum"] = bool(torch.equal(want_dev, d_counts))
+            result_ok = result_ok and parity["device_result_equals_nccl_sum"]
+        else:
+            cpu = {"value": seq_bases / 1e9 / cpu_s, "unit": "Gbases/s", "cores": threads, "kind": "port",
+                   "sample": "full workload once (C port of klib.py:149-170 + balance, OpenMP); the "
+                             "reference's pure-Python loop measured 0.001-0.0036 Gbases/s on 1 core "
+                             "(BASELINE.md)"}
 
+    out = None
     if rank == 0:
         total_bases = seq_bases * world
         peak, peak_src = measured_peak("hbm_gbs", 6650.0)
-        alg_bytes = 0.375 * n_bases + 4 * bins      # packed stream read once + u32 table written once
-        radix = args.count_path == 2 or (args.count_path == 0 and n_bases >= ((16 << 20) if k <= 12 else (4 << 20)))
-        if n_windows is None:
-            n_windows = seq_bases
+        # packed stream read once + the int64 table written once (the balance
+        # is fused, + 0).  The whole step is charged: memset + count kernels + widen/balance.
+        alg_bytes = 0.375 * n_bases + 8 * bins
+        radix = args.count_path >= 2 or (args.count_path == 0 and k >= 9 and
+                                         n_bases >= ((16 << 20) if k <= 12 else (4 << 20)))
+        pairs = radix and k <= 12 and args.count_path != 3
         narrow = bool(args.narrow_d2h and bins >= (1 << 20))
         # bytes of the narrow copy: uint8 when every count of the result fits, else uint16
         # (what finalize_to_host decides from the device's flag words), + the 8 flag bytes
@@ -545,9 +622,18 @@ def bench_count(args):
         top = int(pinned_out.array[:split].max())
         narrow_width = 8 if (not narrow or top > 65535) else (1 if (args.narrow_d2h == 1 and top <= 255) else 2)
         d2h_bytes = bins * 8 if narrow_width == 8 else split * narrow_width + (bins - split) * 8 + 8
-        count_kernel_name = ("radix_partition_kernel<u32> + radix_histogram_kernel<u32>" if radix
-                             else "count_global_kernel<u32>")
-        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        kernels = (["pair_partition_kernel", "pair_histogram_kernel"] if pairs else
+                   ["radix_partition_kernel", "radix_histogram_kernel"] if radix else
+                   ["count_smem_kernel" if k <= 7 else "count_global_kernel"])
+        step_kernels = ["memset(table)"] + kernels + [
+            "finalize_balance_tiled_kernel" if (balance and k >= 6) else "finalize_kernel"]
+        traffic, traffic_src = None, None
+        if args.config == 2 and k == K_COUNT and args.composition == "uniform":
+            parts = [traffic_record(name) for name in step_kernels]
+            if all(p[0] is not None for p in parts):
+                traffic = int(sum(p[0] for p in parts))
+                traffic_src = sorted(set(p[1] for p in parts if p[1]))
+        achieved = alg_bytes / (step_ms * 1e-3) / 1e9 if world == 1 else alg_bytes / (kern_ms * 1e-3) / 1e9
         out = {
             "metric": "gbases_per_sec_counted_k%d" % k, "value": total_bases / 1e9 / (step_ms * 1e-3),
             "unit": "Gbases/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -577,39 +663,52 @@ def bench_count(args):
                               "threads, the rest as int64 by the copy engine meanwhile)" % (16 - args.dma_share, 8 * narrow_width))
                              if narrow and narrow_width < 8 else "D2H int64)")},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": count_kernel_name, "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         # the committed ncu capture is of the default workload (config 2, k = 12)
-                         "traffic": (recorded_traffic(count_kernel_name.split("<")[0].split(" ")[0])
-                                     if args.config == 2 and k == K_COUNT else None),
-                         "algorithmic_bytes": alg_bytes, "kernel_ms": kern_ms, "peak_source": peak_src,
+            "roofline": {"bound": "hbm",
+                         "kernel": " + ".join(step_kernels if world == 1 else kernels),
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes": alg_bytes,
+                         "accounting": "0.375 B/base (2-bit codes + validity, read once) + 8 B x 4^k (int64 "
+                                       "profile written once, balance fused): SURVEY.md section 8d; time = "
+                                       + ("the whole step" if world == 1 else "this rank's count kernels"),
+                         "step_ms": step_ms, "count_kernels_ms": kern_ms, "peak_source": peak_src,
                          "windows_per_s": n_windows / (kern_ms * 1e-3)},
-            "cpu_baseline": cpu, "clocks": clocks, "parity_ok": result_ok,
+            "cpu_baseline": cpu, "clocks": clocks, "parity_ok": result_ok, "parity": parity,
             "wall_s_timed_region": wall,
         }
-        print(json.dumps(out))
     if reducer is not None:
         reducer.close()
-    if world > 1:
-        dist.destroy_process_group()
+    del d_codes, d_valid, d_table, d_counts, flush
+    torch.cuda.empty_cache()
+    return out
 
 
-def bench_matrix(args):
+def matrix_slab(torch, gen, lam, slab_index, slab, n, d, dev):
+    """int64 counts of profiles [slab_index * slab, ...) of the synthetic set (SURVEY.md 8d cfg 4:
+    Poisson(lambda_i) per bin): seeded per slab, so any rank can (re)build any slab."""
+    r0 = slab_index * slab
+    m = min(slab, n - r0)
+    gen.manual_seed(4000 + slab_index)
+    rates = lam[r0:r0 + m, None].expand(m, d).to(torch.float32)
+    return torch.poisson(rates, generator=gen).to(torch.int64)
+
+
+def bench_matrix(args, world, rank, local):
     import torch
     import torch.distributed as dist
-    from kpal_b200 import _cabi
+    from kpal_b200 import _cabi, multigpu
 
-    world, rank, local = init_dist(args)
     L = _cabi.load()
     _cabi.check(L.kpal_set_device(local))
     dev = torch.device("cuda", local)
     n, k = args.profiles, K_MATRIX
     d = 4 ** k
+    steps = max(1, min(args.steps, 2))
     stride = int(L.kpal_prepared_stride(k))
     stream = torch.cuda.current_stream()
     sp = ctypes.c_void_p(stream.cuda_stream)
 
-    # ---- synthetic profile set (SURVEY.md 8d cfg 4): Poisson(lambda_i), generated on device
+    # ---- synthetic profile set: rank r generates and prepares rows shard_rows(n, r, world) only
     gen = torch.Generator(device=dev)
     gen.manual_seed(4)
     lam = torch.exp(torch.empty(n, device=dev, dtype=torch.float64).uniform_(
@@ -620,46 +719,67 @@ def bench_matrix(args):
     totals = torch.empty(n, dtype=torch.float64, device=dev)
     norm2 = torch.empty(n, dtype=torch.float64, device=dev)
     order = torch.empty(n, dtype=torch.int32, device=dev)
-    out = torch.zeros((n, n), dtype=torch.float64, device=dev)
     slab = 256
-    first_rows = None
-    # end-to-end leg: the same profile set as int64 rows in pinned host memory (the array
-    # kmer.distance_matrix hands to kpal_distance_matrix); bounded by the host's free RAM
-    n_e2e = n if (world == 1 and not args.no_e2e) else 0
-    if n_e2e:
+    row_b, row_e = multigpu.shard_rows(n, rank, world)
+    # end-to-end leg: this rank's rows as int64 in pinned host memory (what kmer.distance_matrix
+    # reads from the profile file); at N = 1 bounded by the host's free RAM
+    n_e2e = 0 if args.no_e2e else n
+    if n_e2e and world == 1:
         avail = host_mem_available()
         while n_e2e > 64 and avail is not None and n_e2e * d * 8 * 2.5 > avail:
             n_e2e //= 2
-        host_profiles = _cabi.PinnedArray((n_e2e, d), np.int64)
-        host_out = _cabi.PinnedArray((n_e2e, n_e2e), np.float64)
-        h_t = torch.from_numpy(host_profiles.array)
-    for r0 in range(0, n, slab):
-        m = min(slab, n - r0)
-        rates = lam[r0:r0 + m, None].expand(m, d).to(torch.float32)
-        counts = torch.poisson(rates, generator=gen).to(torch.int64)
-        if r0 == 0:
-            first_rows = counts[:64].cpu().numpy()
-        if r0 < n_e2e:
-            mm = min(m, n_e2e - r0)
-            h_t[r0:r0 + mm].copy_(counts[:mm])
+    e2e_b, e2e_e = (row_b, row_e) if world > 1 else (0, n_e2e)
+    host_rows = _cabi.PinnedArray((max(e2e_e - e2e_b, 1), d), np.int64) if n_e2e else None
+    h_t = torch.from_numpy(host_rows.array) if n_e2e else None
+    for s_i in range(row_b // slab, (row_e + slab - 1) // slab):
+        counts = matrix_slab(torch, gen, lam, s_i, slab, n, d, dev)
+        r0 = s_i * slab
+        lo, hi = max(r0, row_b), min(r0 + len(counts), row_e)
+        part = counts[lo - r0:hi - r0]
+        if n_e2e:
+            a, b = max(lo, e2e_b), min(hi, e2e_e)
+            if b > a:
+                h_t[a - e2e_b:b - e2e_b].copy_(counts[a - r0:b - r0])
         _cabi.check(L.kpal_dev_profiles_prepare(
-            counts.data_ptr(), m, k, 0, 1, F[r0].data_ptr(), R[r0].data_ptr(),
-            bitmap[r0].data_ptr(), totals[r0:].data_ptr(), norm2[r0:].data_ptr(), sp))
-        del counts, rates
+            part.data_ptr(), hi - lo, k, 0, 1, F[lo].data_ptr(), R[lo].data_ptr(),
+            bitmap[lo].data_ptr(), totals[lo:].data_ptr(), norm2[lo:].data_ptr(), sp))
+        del counts, part
+    torch.cuda.synchronize()
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    multigpu.allgather_rows([F, R, bitmap, totals, norm2], n)
+    torch.cuda.synchronize()
+    allgather_s = max_over_ranks(time.perf_counter() - t0, world)
     _cabi.check(L.kpal_dev_order_by_total(totals.data_ptr(), n, 0, order.data_ptr(), sp))
     tiles = int(L.kpal_distance_num_tiles(n))
-    t_begin = tiles * rank // world
-    t_end = tiles * (rank + 1) // world
+    t_begin, t_end = multigpu.tile_range(tiles, rank, world)
+    tile_elems = int(L.kpal_distance_tile_elems())
+    out = torch.zeros((n, n), dtype=torch.float64, device=dev) if rank == 0 else None
+    if world > 1:
+        most = max(multigpu.tile_range(tiles, r, world)[1] - multigpu.tile_range(tiles, r, world)[0]
+                   for r in range(world))
+        packed = torch.zeros((most, tile_elems), dtype=torch.float64, device=dev)
+        parts = [torch.zeros((most, tile_elems), dtype=torch.float64, device=dev) for _ in range(world)] \
+            if rank == 0 else None
 
     def device_step():
-        _cabi.check(L.kpal_dev_distance_tiles(
+        if world == 1:
+            _cabi.check(L.kpal_dev_distance_tiles(
+                F.data_ptr(), R.data_ptr(), bitmap.data_ptr(), totals.data_ptr(), norm2.data_ptr(),
+                order.data_ptr(), n, k, 0, 0, 1, 0, t_begin, t_end, out.data_ptr(), sp))
+            return
+        _cabi.check(L.kpal_dev_distance_tiles_packed(
             F.data_ptr(), R.data_ptr(), bitmap.data_ptr(), totals.data_ptr(), norm2.data_ptr(),
-            order.data_ptr(), n, k, 0, 0, 1, 0, t_begin, t_end, out.data_ptr(), sp))
-        if world > 1:
-            dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
+            order.data_ptr(), n, k, 0, 0, 1, 0, t_begin, t_end, packed.data_ptr(), sp))
+        dist.gather(packed, parts, dst=0)
+        if rank == 0:
+            for r in range(world):
+                b, e = multigpu.tile_range(tiles, r, world)
+                _cabi.check(L.kpal_dev_distance_unpack_tiles(
+                    parts[r].data_ptr(), totals.data_ptr(), norm2.data_ptr(), order.data_ptr(), n, 0, 0, 1,
+                    b, e, int(r == 0), out.data_ptr(), sp))
 
-    for _ in range(max(args.warmup, 1)):
-        out.zero_()
+    for _ in range(max(min(args.warmup, 1), 1)):
         device_step()
     barrier_sync(world)
     sampler = ClockSampler(local)
@@ -667,80 +787,127 @@ def bench_matrix(args):
         sampler.start()
     L.kpal_reset_kernel_launches()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(args.steps)]
+           for _ in range(steps)]
     barrier_sync(world)
-    for i in range(args.steps):
-        out.zero_()
+    for i in range(steps):
+        if rank == 0:
+            out.zero_()
         evs[i][0].record(stream)
         device_step()
         evs[i][1].record(stream)
     barrier_sync(world)
     launches = int(L.kpal_kernel_launches())
-    step_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs) / args.steps, world)
+    step_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs) / steps, world)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end to end through the host-buffer C ABI (every rank on its own replica of the
-    # call at N>1 would only repeat rank 0: measured on rank 0 at N=1)
+    # ---- parity against the oracle (rank 0): the full leading 64 x 64 block and 2000 random
+    # pairs among 96 profiles drawn from the whole set
+    parity = None
+    if rank == 0:
+        from oracle import c_oracle
+        threads = host_threads()
+        rng = np.random.default_rng(44)
+        lead = min(64, n)
+        far = np.sort(rng.choice(n, size=min(96, n), replace=False))
+        need = sorted(set(range(lead)) | set(int(i) for i in far))
+        rows = {}
+        for s_i in sorted(set(i // slab for i in need)):
+            counts = matrix_slab(torch, gen, lam, s_i, slab, n, d, dev)
+            for i in need:
+                if i // slab == s_i:
+                    rows[i] = counts[i - s_i * slab].cpu().numpy()
+            del counts
+        got = out.cpu().numpy()
+        t0 = time.perf_counter()
+        block = c_oracle.distance_matrix(np.stack([rows[i] for i in range(lead)]), do_scale=True, threads=threads)
+        cpu_s = time.perf_counter() - t0
+        low = np.tril_indices(lead, -1)
+        rel_block = float(np.max(np.abs(got[:lead, :lead][low] - block[low]) / np.abs(block[low]))) if lead > 1 else 0.0
+        sub = c_oracle.distance_matrix(np.stack([rows[int(i)] for i in far]), do_scale=True, threads=threads)
+        ii, jj = np.tril_indices(len(far), -1)
+        pick = rng.choice(len(ii), size=min(2000, len(ii)), replace=False)
+        a, b = far[ii[pick]], far[jj[pick]]
+        rel_far = float(np.max(np.abs(got[a, b] - sub[ii[pick], jj[pick]]) / np.abs(sub[ii[pick], jj[pick]])))
+        sym = bool(np.array_equal(got[a, b], got[b, a]))
+        parity = {"checked_against": "C port of kdistlib.py:126-161 / metrics.py:49-123",
+                  "leading_block_pairs": int(len(low[0])), "max_rel_err_leading_block": rel_block,
+                  "random_pairs": int(len(pick)), "random_pairs_drawn_from_profiles": int(len(far)),
+                  "max_rel_err_random_pairs": rel_far, "symmetric": sym, "tolerance": 1e-9}
+        cpu = {"value": len(low[0]) / cpu_s, "unit": "profile-pairs/s", "cores": threads, "kind": "port",
+               "sample": "leading %d profiles (%d pairs), C port, OpenMP" % (lead, len(low[0]))}
+        check_block = got[:lead, :lead].copy()
+        del got
+
+    # ---- end to end through the public entry points, host buffers in, host matrix out
     e2e = None
-    got = out[:64, :64].cpu().numpy() if rank == 0 else None
-    if world == 1 and n_e2e:
-        check_block = out[:64, :64].clone()
+    if n_e2e:
         del F, R, bitmap, out
+        if world > 1:
+            del packed, parts
         torch.cuda.empty_cache()
+        host_out = _cabi.PinnedArray((n_e2e, n_e2e), np.float64) if (rank == 0 and world == 1) else None
 
         def e2e_step():
-            _cabi.check(L.kpal_distance_matrix(host_profiles._ptr, n_e2e, k, 0, 0, 0, 1, 0, host_out._ptr))
+            if world == 1:
+                _cabi.check(L.kpal_distance_matrix(host_rows._ptr, n_e2e, k, 0, 0, 0, 1, 0, host_out._ptr))
+                return host_out.array
+            return multigpu.distance_matrix_distributed(host_rows.array[:row_e - row_b], do_scale=True,
+                                                        sharded=True, n_total=n, device=dev)
         e2e_step()
-        e2e_steps = max(1, min(args.steps, 2))
+        e2e_steps = 1 if n_e2e >= 2048 else steps
+        barrier_sync(world)
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            e2e_step()
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
-        e2e_pairs = n_e2e * (n_e2e - 1) // 2
-        e2e_ok = None
-        if n_e2e == n:
-            a, b = host_out.array[:64, :64], check_block.cpu().numpy()
-            e2e_ok = bool(np.allclose(a, b, rtol=1e-12, atol=0))
-        e2e = {"value": e2e_pairs / e2e_s, "unit": "profile-pairs/s",
-               "h2d_bytes_per_step": int(n_e2e * d * 8), "d2h_bytes_per_step": int(n_e2e * n_e2e * 8),
-               "ms_per_step": e2e_s * 1e3, "profiles": n_e2e, "steps": e2e_steps,
-               "matches_device_result": e2e_ok,
-               "path": "pinned int64 profiles -> kpal_distance_matrix (H2D in 1 GiB slabs, prepare, order, "
-                       "tile kernel, D2H of the N x N float64 matrix)"}
+            res = e2e_step()
+        barrier_sync(world)
+        e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps, world)
+        if rank == 0:
+            e2e_pairs = n_e2e * (n_e2e - 1) // 2
+            e2e_ok = None
+            if n_e2e == n:
+                e2e_ok = bool(np.allclose(res[:lead, :lead], check_block, rtol=1e-12, atol=0))
+            h2d = int(n_e2e * d * 8)
+            e2e = {"value": e2e_pairs / e2e_s, "unit": "profile-pairs/s",
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(n_e2e * n_e2e * 8),
+                   "ms_per_step": e2e_s * 1e3, "profiles": n_e2e, "steps": e2e_steps,
+                   "matches_device_result": e2e_ok,
+                   "path": ("pinned int64 profiles -> kpal_distance_matrix (H2D in slabs, prepare, order, "
+                            "tile kernel, D2H of the N x N float64 matrix)" if world == 1 else
+                            "per rank: its 1/%d of the int64 profiles (pinned host) -> multigpu."
+                            "distance_matrix_distributed (H2D + prepare of the shard, NCCL all-gather of the "
+                            "prepared set, tile range, gather of packed tiles, scatter + D2H on rank 0); "
+                            "h2d bytes summed over the ranks" % world)}
 
+    rec = None
     if rank == 0:
         pairs = n * (n - 1) // 2
-        from oracle import c_oracle
-        t0 = time.perf_counter()
-        want = c_oracle.distance_matrix(first_rows[:24], do_scale=True, threads=c_oracle.max_threads())
-        cpu_s = time.perf_counter() - t0
-        low = np.tril_indices(24, -1)
-        rel = float(np.max(np.abs(got[:24, :24][low] - want[low]) / np.abs(want[low])))
         # per-GPU roofline: rank 0's share of the tiles (the tile kernel is >99 % of the step)
         flops = 8.0 * d * pairs * (t_end - t_begin) / max(tiles, 1)
         peak_tf, peak_src = measured_fp64_peak()
         achieved_tf = flops / (step_ms * 1e-3) / 1e12
-        print(json.dumps({
+        traffic, traffic_src = traffic_record("distance_tile_kernel")
+        rec = {
             "metric": "profile_pairs_per_sec_k10_multiset", "value": pairs / (step_ms * 1e-3),
-            "unit": "profile-pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 1), "ms_per_step": step_ms, "higher_is_better": True,
+            "unit": "profile-pairs/s", "n_gpus": world, "steps": steps,
+            "warmup": 1, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "kpal matrix, multiset/prod, scaled, %d profiles, k=10; BASELINE configs[3]" % n,
                        "profiles": n, "k": k, "l2": "68 GB working set >> L2",
-                       "parallelism": "upper-triangle tiles sharded over ranks, NCCL reduce of the result" if world > 1 else "1 GPU"},
+                       "parallelism": ("1/%d of the profiles prepared per rank, NCCL all-gather of the prepared set "
+                                       "(%.1f ms, outside the timed step), upper-triangle tiles in equal ranges, "
+                                       "gather of packed tiles onto rank 0 (inside the step)" % (world, allgather_s * 1e3))
+                       if world > 1 else "1 GPU"},
             "gpu_launches": launches,
             "roofline": {"bound": "fp64", "kernel": "distance_tile_kernel<prod>",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": recorded_traffic("distance_tile_kernel"),
+                         "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                          "flops_per_element_pair": 8, "peak_source": peak_src},
-            "e2e": e2e,
-            "cpu_baseline": {"value": 276 / cpu_s, "unit": "profile-pairs/s",
-                             "cores": c_oracle.max_threads(), "kind": "port",
-                             "sample": "leading 24 profiles (276 pairs), C port, OpenMP"},
-            "clocks": clocks, "max_rel_err_vs_oracle_276_pairs": rel, "parity_ok": bool(rel <= 1e-9),
-        }))
-    if world > 1:
-        dist.destroy_process_group()
+            "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
+            "parity": parity,
+            "parity_ok": bool(parity["max_rel_err_leading_block"] <= 1e-9 and
+                              parity["max_rel_err_random_pairs"] <= 1e-9 and parity["symmetric"]),
+        }
+    return rec
 
 
 def main():
@@ -749,22 +916,32 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="count", choices=["count", "matrix"])
+    ap.add_argument("--workload", default="all", choices=["all", "count", "matrix"],
+                    help="all (default) = the count line with the matrix record as its 'matrix' sub-record")
     ap.add_argument("--profiles", type=int, default=N_PROFILES)
-    ap.add_argument("--config", type=int, default=2, choices=[2, 5],
-                    help="count workload: 2 = BASELINE configs[1] (default), 5 = configs[4] (k=13 genome shards)")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 5],
+                    help="count workload: 2 = BASELINE configs[1] (default), 1 = configs[0] (k=6, 1 Mbp), "
+                         "5 = configs[4] (k=13 genome shards; the full 3 Gbp job at --gpus 8)")
+    ap.add_argument("--composition", default="uniform", choices=["uniform", "skewed"],
+                    help="config 2: 'skewed' makes 10 %% of the reads low-complexity repeats")
     ap.add_argument("--k", type=int, default=0, help="override the k-mer length of the count workload")
     ap.add_argument("--mbp-per-gpu", type=float, default=375.0, help="config 5: Mbp per GPU")
-    ap.add_argument("--count-path", type=int, default=0, choices=[0, 1, 2],
-                    help="0 = library default, 1 = scattered-RED kernel, 2 = radix-partitioned path")
+    ap.add_argument("--count-path", type=int, default=0, choices=[0, 1, 2, 3],
+                    help="0 = library default, 1 = scattered-RED kernel, 2 = radix-partitioned path "
+                         "(two windows per payload up to k = 12), 3 = one-window radix path")
+    ap.add_argument("--pair-upt", type=int, default=1, choices=[1, 2],
+                    help="pair path: 32-base units per thread and tile")
+    ap.add_argument("--pair-flush-every", type=int, default=0, help="pair path: tiles between slot flushes (0 = auto)")
+    ap.add_argument("--pair-fused", type=int, default=1, choices=[0, 1],
+                    help="pair path, pass 2: 1 = both roles in one launch, flushed with cp.reduce.async.bulk")
     ap.add_argument("--radix-payload-bits", type=int, default=0)
     ap.add_argument("--radix-max-buckets", type=int, default=0, choices=[0, 1024, 2048],
                     help="buckets binned per pass-1 launch of the radix count (0 = library default)")
     ap.add_argument("--radix-debug", type=int, default=0, help="timing experiments (results are wrong)")
     ap.add_argument("--radix-shape", type=int, default=0)
     ap.add_argument("--reduce", default="auto", choices=["auto", "fused", "peer", "nccl"],
-                    help="count workload at N > 1: table sum over NVLink peer memory fused into the count "
-                         "(default), as separate push/collect kernels, or with dist.reduce")
+                    help="count workload at N > 1: table sum over NVLink peer memory fused into the count, "
+                         "as separate push/collect kernels, or with dist.reduce")
     ap.add_argument("--no-e2e", action="store_true", help="matrix workload: skip the host-buffer end-to-end leg")
     ap.add_argument("--fasta-chunks", type=int, default=0, help="chunks of the pipelined FASTA upload (0 = auto)")
     ap.add_argument("--narrow-d2h", type=int, default=1, choices=[0, 1, 2],
@@ -782,10 +959,23 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
-    if args.workload == "count":
-        bench_count(args)
-    else:
-        bench_matrix(args)
+    world, rank, local = init_dist(args)
+    rec = None
+    if args.workload in ("all", "count"):
+        rec = bench_count(args, world, rank, local)
+    if args.workload in ("all", "matrix"):
+        mrec = bench_matrix(args, world, rank, local)
+        if rank == 0:
+            if rec is None:
+                rec = mrec
+            else:
+                rec["matrix"] = mrec
+                rec["gpu_launches"] += mrec["gpu_launches"]
+    if rank == 0:
+        print(json.dumps(rec))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -351,6 +351,29 @@ int kpal_dev_distance_tiles(const double *d_F, const double *d_P, const uint32_t
                             uint64_t tile_begin, uint64_t tile_end,
                             double *d_out, void *stream);
 
+/*
+ * Multi-GPU matrix (tiles of the upper triangle sharded over the GPUs
+ * after an all-gather of the prepared profile set; kpal/kdistlib.py:179-184 is the loop that
+ * is being cut up).  kpal_dev_distance_tiles_packed is kpal_dev_distance_tiles with the
+ * finished values of tiles [tile_begin, tile_end) written as a compact
+ * [tile_end - tile_begin][kpal_distance_tile_elems()] array (entries outside the triangle
+ * are 0), so that the ranks' results travel in ONE gather of N^2 / 2 doubles;
+ * kpal_dev_distance_unpack_tiles scatters such an array into the symmetric out[n][n] on the
+ * root (diagonal != 0: also writes d(p, p)).
+ */
+uint64_t kpal_distance_tile_elems(void);
+int kpal_dev_distance_tiles_packed(const double *d_F, const double *d_P, const uint32_t *d_bitmap,
+                                   const double *d_totals, const double *d_norm2,
+                                   const int32_t *d_order, uint64_t n, int k,
+                                   int metric, int pairwise, int do_scale, int down,
+                                   uint64_t tile_begin, uint64_t tile_end,
+                                   double *d_packed, void *stream);
+int kpal_dev_distance_unpack_tiles(const double *d_packed, const double *d_totals,
+                                   const double *d_norm2, const int32_t *d_order, uint64_t n,
+                                   int metric, int pairwise, int do_scale,
+                                   uint64_t tile_begin, uint64_t tile_end, int diagonal,
+                                   double *d_out, void *stream);
+
 /* ------------------------------------------------ FASTA scan/pack: device API
  *
  * GPU version of kpal_fasta_scan + kpal_fasta_pack for whole-file counting

@@ -36,6 +36,7 @@ SYMBOLS = (
     "kpal_dev_count_packed", "kpal_count_fasta_to_dev", "kpal_dev_finalize_counts", "kpal_dev_table_to_host", "kpal_dev_balance",
     "kpal_dev_count_by_record", "kpal_prepared_stride", "kpal_dev_profiles_prepare",
     "kpal_dev_order_by_total", "kpal_distance_num_tiles", "kpal_dev_distance_tiles",
+    "kpal_distance_tile_elems", "kpal_dev_distance_tiles_packed", "kpal_dev_distance_unpack_tiles",
     "kpal_fasta_scratch_bytes", "kpal_dev_fasta_pack", "kpal_set_option",
     "kpal_kernel_launches", "kpal_reset_kernel_launches",
 )
@@ -119,6 +120,10 @@ def load():
     sig("kpal_distance_num_tiles", u64, u64)
     sig("kpal_dev_distance_tiles", i32, vp, vp, vp, vp, vp, vp, u64, i32, i32, i32, i32, i32,
         u64, u64, vp, vp)
+    sig("kpal_distance_tile_elems", u64)
+    sig("kpal_dev_distance_tiles_packed", i32, vp, vp, vp, vp, vp, vp, u64, i32, i32, i32, i32, i32,
+        u64, u64, vp, vp)
+    sig("kpal_dev_distance_unpack_tiles", i32, vp, vp, vp, vp, u64, i32, i32, i32, u64, u64, i32, vp, vp)
     sig("kpal_fasta_scratch_bytes", u64, u64)
     sig("kpal_dev_fasta_pack", i32, vp, u64, vp, vp, vp, vp)
     sig("kpal_set_option", i32, c.c_char_p, i32)

@@ -36,8 +36,12 @@ int launch_prepare(const int64_t *, uint64_t, int, int, int, double *, double *,
                    double *, double *, unsigned long long *, cudaStream_t);
 int launch_distance_tiles(const double *, const double *, const uint32_t *, const double *,
                           const double *, const int32_t *, uint64_t, int, int, int, int, int,
-                          uint64_t, uint64_t, double *, uint32_t *, double *, cudaStream_t);
+                          uint64_t, uint64_t, double *, uint32_t *, double *, cudaStream_t,
+                          double *d_packed = nullptr);
+int launch_distance_unpack(const double *, const double *, const double *, const int32_t *, uint64_t, int, int,
+                           int, uint64_t, uint64_t, int, double *, cudaStream_t);
 uint64_t distance_num_tiles(uint64_t n);
+uint64_t distance_tile_elems();
 uint64_t prepared_stride_host(int k);
 uint64_t fasta_scratch_bytes(uint64_t n_bytes);
 void set_exact_div(bool on);
@@ -48,6 +52,9 @@ void set_radix_payload_bits(int bits);
 void set_radix_debug(int v);
 void set_radix_shape(int v);
 void set_radix_max_buckets(int v);
+void set_pair_upt(int v);
+void set_pair_fused(int v);
+void set_pair_flush_every(int v);
 int launch_fasta_pack(const uint8_t *, uint64_t, uint32_t *, uint32_t *, void *, cudaStream_t);
 int launch_fasta_pack_begin(uint64_t, uint32_t *, uint32_t *, void *, cudaStream_t);
 int launch_fasta_pack_tiles(const uint8_t *, uint64_t, uint64_t, uint64_t, uint32_t *, uint32_t *, void *,
@@ -206,10 +213,14 @@ static int require_device()
     return KPAL_OK;
 }
 
-// Scratch for the dev-level distance entry point (acc / cnt matrices), cached
-// per device and grown on demand.
+// Scratch of the dev-level distance entry point (acc / cnt matrices), cached per (device,
+// stream) and grown on demand.  Calls on one stream are ordered by the stream, calls on
+// different streams (other host threads) get buffers of their own, so no two calls in
+// flight ever share an accumulator; a buffer is only replaced after its stream has drained.
+// The host-level entry points (matrix sessions, pair distances) own their accumulators.
 struct DistScratch {
     int device = -1;
+    cudaStream_t stream = nullptr;
     uint64_t n = 0;
     double *acc = nullptr;
     uint32_t *cnt = nullptr;
@@ -217,15 +228,16 @@ struct DistScratch {
 static std::mutex g_scratch_mutex;
 static std::vector<DistScratch> g_scratch;
 
-static int get_dist_scratch(uint64_t n, double **acc, uint32_t **cnt)
+static int get_dist_scratch(uint64_t n, cudaStream_t stream, double **acc, uint32_t **cnt)
 {
     int dev = 0;
     KPAL_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(g_scratch_mutex);
     DistScratch *s = nullptr;
-    for (auto &x : g_scratch) if (x.device == dev) s = &x;
-    if (!s) { g_scratch.push_back(DistScratch()); s = &g_scratch.back(); s->device = dev; }
+    for (auto &x : g_scratch) if (x.device == dev && x.stream == stream) s = &x;
+    if (!s) { g_scratch.push_back(DistScratch()); s = &g_scratch.back(); s->device = dev; s->stream = stream; }
     if (s->n < n) {
+        if (s->acc || s->cnt) KPAL_CUDA(cudaStreamSynchronize(stream));     // earlier calls may still use them
         if (s->acc) cudaFree(s->acc);
         if (s->cnt) cudaFree(s->cnt);
         s->acc = nullptr; s->cnt = nullptr; s->n = 0;
@@ -338,7 +350,7 @@ extern "C" int kpal_set_option(const char *name, int value)
         g_dma_share.store(value); return KPAL_OK;
     }
     if (!strcmp(name, "count_path")) {
-        if (value < 0 || value > 2) return bad_arg("count_path must be 0 (auto), 1 (RED) or 2 (radix)");
+        if (value < 0 || value > 3) return bad_arg("count_path must be 0 (auto), 1 (RED), 2 (radix) or 3 (one-window radix)");
         set_count_path(value); return KPAL_OK;
     }
     if (!strcmp(name, "tiled_finalize")) { set_tiled_finalize(value != 0); return KPAL_OK; }
@@ -354,6 +366,15 @@ extern "C" int kpal_set_option(const char *name, int value)
         if (value != 1024 && value != 2048) return bad_arg("radix_max_buckets must be 1024 or 2048");
         set_radix_max_buckets(value); return KPAL_OK;
     }
+    if (!strcmp(name, "pair_upt")) {
+        if (value < 1 || value > 2) return bad_arg("pair_upt must be 1 or 2 (units per thread and tile)");
+        set_pair_upt(value); return KPAL_OK;
+    }
+    if (!strcmp(name, "pair_flush_every")) {
+        if (value < 0 || value > 6) return bad_arg("pair_flush_every must be 0 (auto) .. 6 tiles");
+        set_pair_flush_every(value); return KPAL_OK;
+    }
+    if (!strcmp(name, "pair_fused")) { set_pair_fused(value); return KPAL_OK; }
     if (!strcmp(name, "radix_debug")) { set_radix_debug(value); return KPAL_OK; }   // timing experiments
     if (!strcmp(name, "radix_payload_bits")) {
         if (value < 0 || value > 15) return bad_arg("radix_payload_bits must be 0 (auto) .. 15");
@@ -1019,10 +1040,38 @@ extern "C" int kpal_dev_distance_tiles(const double *d_F, const double *d_R, con
 {
     if (!d_F || !d_bitmap || !d_totals || !d_norm2 || !d_out) return bad_arg("null device pointer");
     double *acc; uint32_t *cnt;
-    KPAL_CHECK(get_dist_scratch(n, &acc, &cnt));
+    KPAL_CHECK(get_dist_scratch(n, (cudaStream_t)stream, &acc, &cnt));
     return launch_distance_tiles(d_F, d_R, d_bitmap, d_totals, d_norm2, d_order, n, k, metric, pairwise,
                                  do_scale, down, tile_begin, tile_end, acc, cnt, d_out,
                                  (cudaStream_t)stream);
+}
+
+// Multi-GPU form of kpal_dev_distance_tiles: the finished values of tiles [tile_begin,
+// tile_end) as a compact [tile][kpal_distance_tile_elems()] array, ready for one gather.
+extern "C" uint64_t kpal_distance_tile_elems(void) { return distance_tile_elems(); }
+
+extern "C" int kpal_dev_distance_tiles_packed(const double *d_F, const double *d_R, const uint32_t *d_bitmap,
+                                              const double *d_totals, const double *d_norm2,
+                                              const int32_t *d_order, uint64_t n, int k, int metric,
+                                              int pairwise, int do_scale, int down, uint64_t tile_begin,
+                                              uint64_t tile_end, double *d_packed, void *stream)
+{
+    if (!d_F || !d_bitmap || !d_totals || !d_norm2 || !d_packed) return bad_arg("null device pointer");
+    double *acc; uint32_t *cnt;
+    KPAL_CHECK(get_dist_scratch(n, (cudaStream_t)stream, &acc, &cnt));
+    return launch_distance_tiles(d_F, d_R, d_bitmap, d_totals, d_norm2, d_order, n, k, metric, pairwise,
+                                 do_scale, down, tile_begin, tile_end, acc, cnt, nullptr,
+                                 (cudaStream_t)stream, d_packed);
+}
+
+extern "C" int kpal_dev_distance_unpack_tiles(const double *d_packed, const double *d_totals,
+                                              const double *d_norm2, const int32_t *d_order, uint64_t n,
+                                              int metric, int pairwise, int do_scale, uint64_t tile_begin,
+                                              uint64_t tile_end, int diagonal, double *d_out, void *stream)
+{
+    if (!d_packed || !d_totals || !d_norm2 || !d_out) return bad_arg("null device pointer");
+    return launch_distance_unpack(d_packed, d_totals, d_norm2, d_order, n, metric, pairwise, do_scale,
+                                  tile_begin, tile_end, diagonal, d_out, (cudaStream_t)stream);
 }
 
 // ----------------------------------------------------- distances: host API
@@ -1037,7 +1086,7 @@ struct MatrixSession {
     int k = 0, metric = 0, pairwise = 0, do_balance = 0, do_scale = 0, down = 0;
     bool need_r = false;
     int cur = 0;
-    DevBuf F, R, bitmap, totals, norm2, order, tot_i64, slab[2], d_out;
+    DevBuf F, R, bitmap, totals, norm2, order, tot_i64, slab[2], d_out, acc, cnt;   // acc / cnt: this session's accumulators
     cudaStream_t copy = nullptr, compute = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr}, prepared[2] = {nullptr, nullptr};
     ~MatrixSession()
@@ -1115,8 +1164,10 @@ static int matrix_finish(MatrixSession *s, double *out)
         KPAL_CHECK(make_order(s->totals.as<double>(), n, s->down, s->order.as<int32_t>(), st));
         d_order = s->order.as<int32_t>();
     }
-    double *acc; uint32_t *cnt;
-    KPAL_CHECK(get_dist_scratch(n, &acc, &cnt));
+    if (!s->acc.p) KPAL_CHECK(s->acc.alloc(n * n * sizeof(double)));
+    if (!s->cnt.p) KPAL_CHECK(s->cnt.alloc(n * n * sizeof(uint32_t)));
+    double *acc = s->acc.as<double>();
+    uint32_t *cnt = s->cnt.as<uint32_t>();
     KPAL_CHECK(launch_distance_tiles(s->F.as<double>(), s->R.as<double>(), s->bitmap.as<uint32_t>(),
                                      s->totals.as<double>(), s->norm2.as<double>(), d_order, n, s->k,
                                      s->metric, s->pairwise, s->do_scale, s->down, 0,
@@ -1207,7 +1258,7 @@ extern "C" int kpal_pair_distance_positive(const int64_t *left, const int64_t *r
     KPAL_CHECK(require_device());
     const uint64_t d = 1ull << (2 * k), stride = prepared_stride_host(k);
     const bool need_r = (metric == KPAL_METRIC_MULTISET && pairwise == KPAL_PAIRWISE_PROD);
-    DevBuf raw, work, F, R, bitmap, totals, norm2, order, tot_i64, d_out;
+    DevBuf raw, work, F, R, bitmap, totals, norm2, order, tot_i64, d_out, d_acc, d_cnt;
     KPAL_CHECK(raw.alloc(2 * d * 8));
     KPAL_CHECK(work.alloc(2 * d * 8));
     KPAL_CHECK(F.alloc(2 * stride * 8));
@@ -1218,6 +1269,8 @@ extern "C" int kpal_pair_distance_positive(const int64_t *left, const int64_t *r
     KPAL_CHECK(order.alloc(8));
     KPAL_CHECK(tot_i64.alloc(16));
     KPAL_CHECK(d_out.alloc(4 * 8));
+    KPAL_CHECK(d_acc.alloc(4 * 8));
+    KPAL_CHECK(d_cnt.alloc(4 * 4));
     cudaStream_t st = 0;
     KPAL_CUDA(cudaMemcpyAsync(raw.p, left, d * 8, cudaMemcpyHostToDevice, st));
     KPAL_CUDA(cudaMemcpyAsync(raw.as<int64_t>() + d, right, d * 8, cudaMemcpyHostToDevice, st));
@@ -1236,11 +1289,10 @@ extern "C" int kpal_pair_distance_positive(const int64_t *left, const int64_t *r
         KPAL_CHECK(make_order(totals.as<double>(), 2, down, order.as<int32_t>(), st));
         d_order = order.as<int32_t>();
     }
-    double *acc; uint32_t *cnt;
-    KPAL_CHECK(get_dist_scratch(2, &acc, &cnt));
     KPAL_CHECK(launch_distance_tiles(F.as<double>(), R.as<double>(), bitmap.as<uint32_t>(),
                                      totals.as<double>(), norm2.as<double>(), d_order, 2, k, metric,
-                                     pairwise, do_scale, down, 0, distance_num_tiles(2), acc, cnt,
+                                     pairwise, do_scale, down, 0, distance_num_tiles(2), d_acc.as<double>(),
+                                     d_cnt.as<uint32_t>(),
                                      d_out.as<double>(), st));
     double m[4];
     KPAL_CUDA(cudaMemcpyAsync(m, d_out.p, 32, cudaMemcpyDeviceToHost, st));

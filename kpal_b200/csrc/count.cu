@@ -416,12 +416,16 @@ bool radix_supported(int k);
 int launch_count_radix(const uint32_t *, const uint32_t *, uint64_t, int, void *, int, cudaStream_t,
                        const PeerOut *peer = nullptr);
 bool radix_peer_supported(int k, int world);
+// count_pairs.cu
+bool pairs_supported(int k);
+int launch_count_pairs(const uint32_t *, const uint32_t *, uint64_t, int, void *, int, cudaStream_t);
 // peer_reduce.cu
 int launch_reduce_push(const void *, int, int, int, int, void *const *, cudaStream_t);
 int peer_check_args(int k, int counter_bits, int rank, int world);
 
 // run-time switches (kpal_set_option): "count_path" 0 = automatic, 1 = always the
-// scattered-RED kernel, 2 = the radix-partitioned path wherever it is supported;
+// scattered-RED kernel, 2 = the radix-partitioned path wherever it is supported (two windows
+// per payload for k <= 12, count_pairs.cu), 3 = the one-window radix path (count_radix.cu);
 // "tiled_finalize" 0 = plain gather kernel for the balanced finalize.
 static std::atomic<int> g_count_path{0};
 static std::atomic<int> g_tiled_finalize{1};
@@ -434,7 +438,7 @@ static bool use_radix_path(int k, uint64_t n_bases)
 {
     const int mode = g_count_path.load();
     if (mode == 1 || !radix_supported(k)) return false;
-    if (mode == 2) return true;
+    if (mode >= 2) return true;
     // The two passes cost a fixed ~2 x 4^k x 4 bytes of table traffic; below these sizes
     // the RED kernel wins.  From k = 13 on the table no longer fits in L2 and the RED
     // rate drops ~7x, so the switch comes earlier relative to the table size.
@@ -501,6 +505,8 @@ int launch_count(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_ba
         }
         KPAL_LAUNCH_CHECK("count_smem_kernel");
     } else if (use_radix_path(k, n_bases)) {
+        if (pairs_supported(k) && g_count_path.load() != 3)
+            return launch_count_pairs(d_codes, d_valid, n_bases, k, d_table, counter_bits, stream);
         return launch_count_radix(d_codes, d_valid, n_bases, k, d_table, counter_bits, stream);
     } else {
         uint64_t want = (n_chunks + 255) / 256;

@@ -26,7 +26,7 @@
 //
 // Staging memory: 3 x the mean region size, i.e. ~6 bytes per base, owned by a
 // grow-only per-device workspace (HBM is 180 GB; a 100 Mbp call takes 0.6 GB).
-#include "common.cuh"
+#include "radix_common.cuh"
 
 #include <mutex>
 #include <vector>
@@ -34,25 +34,10 @@
 namespace kpal {
 
 constexpr int kHistThreadsMax = 1024;
-constexpr int kUnitBases = 32;          // bases (= window starts) per thread and tile
-constexpr int kGroup = 16;              // payloads per 32-byte group
 
 // ---------------------------------------------------------------------------
 // pass 1
 // ---------------------------------------------------------------------------
-struct Unit {
-    uint32_t w[3];      // 32 bases of codes + 16 look-ahead bases
-    uint32_t starts;    // bit (31 - o) set <=> the window starting at base o is all-valid
-};
-
-template <int O>
-__device__ __forceinline__ uint32_t unit_window(const Unit &u, int shift)
-{
-    constexpr int j = O / 16, r = O % 16;
-    const uint32_t x = (r == 0) ? u.w[j] : __funnelshift_l(u.w[j + 1], u.w[j], 2 * r);
-    return x >> shift;
-}
-
 struct RadixParams {
     const uint2 *codes;         // 32 bases per uint2
     const uint32_t *valid;      // 32 bases per word
@@ -65,45 +50,6 @@ struct RadixParams {
     uint32_t *region_fill;      // [grid][nb] payloads stored per region
     int debug;                  // timing experiments only: 1 = no flush, 2 = no slot stores, 4 = no atomics
 };
-
-// Explicit shared-state-space accesses: through generic pointers the compiler
-// emitted generic ATOM / ST (+ QSPC checks) for the slot bookkeeping.
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-    return uint32_t(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v)
-{
-    uint32_t old;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
-    return old;
-}
-__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v)
-{
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
-}
-
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
-{
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint4 lds_v4(uint32_t addr)
-{
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4 &v)
-{
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 
 struct BinCtx {
     uint32_t cnt_s, slots_s;        // shared addresses of cnt[] and slots[]
@@ -472,6 +418,24 @@ static int grow(void **p, size_t *cap, size_t bytes)
     return KPAL_OK;
 }
 
+// Staging buffers of the current device, grown on demand (shared with count_pairs.cu).
+int radix_workspace(size_t staging_bytes, size_t fill_bytes, void **staging, uint32_t **fill)
+{
+    int dev = 0;
+    KPAL_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_radix_mutex);
+    RadixWorkspace *ws = nullptr;
+    for (auto *w : g_radix_ws) if (w->device == dev) ws = w;
+    if (!ws) { ws = new RadixWorkspace(); ws->device = dev; g_radix_ws.push_back(ws); }
+    KPAL_CHECK(grow(&ws->staging, &ws->staging_cap, staging_bytes));
+    void *f = ws->fill;
+    size_t fc = ws->fill_cap;
+    KPAL_CHECK(grow(&f, &fc, fill_bytes));
+    ws->fill = static_cast<uint32_t *>(f); ws->fill_cap = fc;
+    *staging = ws->staging; *fill = ws->fill;
+    return KPAL_OK;
+}
+
 bool radix_supported(int k) { return k >= 9 && k <= KPAL_MAX_K; }
 
 // Geometry for a given k: payload bits P, buckets nb = 4^k >> P, CTA shape and slot
@@ -571,13 +535,6 @@ int launch_count_radix(const uint32_t *d_codes, const uint32_t *d_valid, uint64_
     const size_t smem2 = size_t(4) << P;
     const int threads2 = P >= 15 ? 1024 : 512;
 
-    int dev = 0;
-    KPAL_CUDA(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(g_radix_mutex);
-    RadixWorkspace *ws = nullptr;
-    for (auto *w : g_radix_ws) if (w->device == dev) ws = w;
-    if (!ws) { ws = new RadixWorkspace(); ws->device = dev; g_radix_ws.push_back(ws); }
-
     // the stream is walked in segments so that the staging stays bounded (<= ~3 GB)
     const uint64_t n_units = 2 * n_chunks_of(n_bases);
     const uint64_t seg_units = (512ull << 20) / kUnitBases;
@@ -588,21 +545,17 @@ int launch_count_radix(const uint32_t *d_codes, const uint32_t *d_valid, uint64_
         const uint64_t windows_per_cta = per * kUnitBases;
         // 3 x the mean region plus slack, in groups
         const uint64_t groups = (3 * windows_per_cta / nb + 4 * kGroup + kGroup - 1) / kGroup;
-        KPAL_CHECK(grow(&ws->staging, &ws->staging_cap, size_t(grid1) * nb * groups * kGroup * 2));
-        {
-            void *f = ws->fill;
-            size_t fc = ws->fill_cap;
-            KPAL_CHECK(grow(&f, &fc, size_t(grid1) * nb * 4));
-            ws->fill = static_cast<uint32_t *>(f); ws->fill_cap = fc;
-        }
+        void *staging = nullptr;
+        uint32_t *fill = nullptr;
+        KPAL_CHECK(radix_workspace(size_t(grid1) * nb * groups * kGroup * 2, size_t(grid1) * nb * 4, &staging, &fill));
         RadixParams p;
         p.codes = reinterpret_cast<const uint2 *>(d_codes);
         p.valid = d_valid;
         p.unit_begin = s0; p.unit_end = s1; p.n_units = n_units;
         p.k = k; p.P = P; p.nb = nb; p.cap = g.cap;
         p.region_groups = uint32_t(groups);
-        p.staging = static_cast<uint16_t *>(ws->staging);
-        p.region_fill = ws->fill;
+        p.staging = static_cast<uint16_t *>(staging);
+        p.region_fill = fill;
         p.debug = g_radix_debug.load();
         const PeerOut *seg_peer = (s1 == n_units) ? peer : nullptr;      // last segment only
         if (counter_bits == 32)

@@ -551,6 +551,54 @@ distance_finalize_kernel(const double *__restrict__ acc, const uint32_t *__restr
     }
 }
 
+// Multi-GPU result exchange: a rank's tiles leave as a compact
+// [tile][TA x TB] array of finished values (one NCCL gather of N^2 / 2 doubles in total
+// instead of a zero-padded N x N reduce), and the root scatters them into the symmetric
+// matrix in profile-index space.  Entries of a tile outside the triangle are left as they are.
+__global__ void __launch_bounds__(256)
+distance_pack_kernel(const double *__restrict__ acc, const uint32_t *__restrict__ cnt,
+                     const double *__restrict__ totals, const double *__restrict__ norm2,
+                     const int32_t *__restrict__ order, uint64_t n, int metric, int do_scale,
+                     uint64_t tile_begin, uint64_t tile_end, double *__restrict__ packed)
+{
+    const uint64_t tile = tile_begin + blockIdx.x;
+    if (tile >= tile_end) return;
+    uint32_t I, J;
+    tile_coords(tile, n, I, J);
+    double *dst = packed + uint64_t(blockIdx.x) * (TA * TB);
+    for (uint32_t e = threadIdx.x; e < TA * TB; e += blockDim.x) {
+        const uint64_t p = uint64_t(I) * TA + e / TB, q = uint64_t(J) * TB + e % TB;
+        double v = 0.0;
+        if (p < q && q < n) {
+            const int32_t ip = order ? order[p] : int32_t(p), iq = order ? order[q] : int32_t(q);
+            const double s = acc[p * n + q];
+            if (metric == M_PROD || metric == M_SUM) v = s / double(cnt[p * n + q] + 1u);
+            else if (metric == M_EUCLID) { v = sqrt(s); if (do_scale) v *= totals[iq]; }
+            else v = s / (sqrt(norm2[ip]) * sqrt(norm2[iq]));
+        }
+        dst[e] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+distance_unpack_kernel(const double *__restrict__ packed, const int32_t *__restrict__ order, uint64_t n,
+                       uint64_t tile_begin, uint64_t tile_end, double *__restrict__ out)
+{
+    const uint64_t tile = tile_begin + blockIdx.x;
+    if (tile >= tile_end) return;
+    uint32_t I, J;
+    tile_coords(tile, n, I, J);
+    const double *src = packed + uint64_t(blockIdx.x) * (TA * TB);
+    for (uint32_t e = threadIdx.x; e < TA * TB; e += blockDim.x) {
+        const uint64_t p = uint64_t(I) * TA + e / TB, q = uint64_t(J) * TB + e % TB;
+        if (p >= q || q >= n) continue;
+        const int32_t ip = order ? order[p] : int32_t(p), iq = order ? order[q] : int32_t(q);
+        const double v = src[e];
+        out[uint64_t(ip) * n + iq] = v;
+        out[uint64_t(iq) * n + ip] = v;
+    }
+}
+
 // d(p, p): 0 for the distances (nan when scaling a zero-total profile, as the
 // reference), cosine similarity 1 (nan for an all-zero profile).
 __global__ void distance_diagonal_kernel(const double *__restrict__ totals,
@@ -633,7 +681,7 @@ int launch_distance_tiles(const double *d_F, const double *d_P, const uint32_t *
                           const double *d_totals, const double *d_norm2, const int32_t *d_order,
                           uint64_t n, int k, int metric, int pairwise, int do_scale, int down,
                           uint64_t tile_begin, uint64_t tile_end, double *d_acc, uint32_t *d_cnt,
-                          double *d_out, cudaStream_t stream)
+                          double *d_out, cudaStream_t stream, double *d_packed)
 {
     (void)down;   // the order array already encodes ascending / descending totals
     int m;
@@ -665,6 +713,12 @@ int launch_distance_tiles(const double *d_F, const double *d_P, const uint32_t *
     case M_EUCLID: KPAL_CHECK(launch_tiles_metric<M_EUCLID>(a, exact, unsigned(items), stream)); break;
     default: KPAL_CHECK(launch_tiles_metric<M_COSINE>(a, exact, unsigned(items), stream)); break;
     }
+    if (d_packed) {     // multi-GPU: finished values tile by tile, for the gather onto the root
+        distance_pack_kernel<<<unsigned(a.n_tiles_range), 256, 0, stream>>>(
+            d_acc, d_cnt, d_totals, d_norm2, d_order, n, m, do_scale, tile_begin, tile_end, d_packed);
+        KPAL_LAUNCH_CHECK("distance_pack_kernel");
+        return KPAL_OK;
+    }
     distance_finalize_kernel<<<unsigned(a.n_tiles_range), 256, 0, stream>>>(
         d_acc, d_cnt, d_totals, d_norm2, d_order, n, m, do_scale, tile_begin, tile_end, d_out);
     KPAL_LAUNCH_CHECK("distance_finalize_kernel");
@@ -676,7 +730,31 @@ int launch_distance_tiles(const double *d_F, const double *d_P, const uint32_t *
     return KPAL_OK;
 }
 
+// packed tiles [tile_begin, tile_end) -> symmetric out (+ the diagonal when asked to)
+int launch_distance_unpack(const double *d_packed, const double *d_totals, const double *d_norm2,
+                           const int32_t *d_order, uint64_t n, int metric, int pairwise, int do_scale,
+                           uint64_t tile_begin, uint64_t tile_end, int diagonal, double *d_out,
+                           cudaStream_t stream)
+{
+    int m;
+    KPAL_CHECK(metric_id(metric, pairwise, &m));
+    const uint64_t total_tiles = num_tiles(n);
+    if (tile_end > total_tiles) tile_end = total_tiles;
+    if (tile_begin < tile_end) {
+        distance_unpack_kernel<<<unsigned(tile_end - tile_begin), 256, 0, stream>>>(
+            d_packed, d_order, n, tile_begin, tile_end, d_out);
+        KPAL_LAUNCH_CHECK("distance_unpack_kernel");
+    }
+    if (diagonal) {
+        distance_diagonal_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(
+            d_totals, d_norm2, n, m, do_scale, d_out);
+        KPAL_LAUNCH_CHECK("distance_diagonal_kernel");
+    }
+    return KPAL_OK;
+}
+
 uint64_t distance_num_tiles(uint64_t n) { return num_tiles(n); }
+uint64_t distance_tile_elems() { return uint64_t(TA) * TB; }
 uint64_t prepared_stride_host(int k) { return prepared_stride(k); }
 
 }  // namespace kpal

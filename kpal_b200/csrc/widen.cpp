@@ -13,7 +13,12 @@
 // variable), so a call costs a wake-up, not a thread spawn per chunk.
 #include "../../include/kpal_b200.h"
 
+#if defined(__x86_64__) || defined(__i386__)
+#define KPAL_WIDEN_X86 1
 #include <immintrin.h>
+#else
+#define KPAL_WIDEN_X86 0        // e.g. the aarch64 host of a GB200: plain loops (the compiler emits NEON)
+#endif
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -26,6 +31,7 @@
 
 namespace kpal {
 
+#if KPAL_WIDEN_X86
 // src[0..n) uint16 -> dst[0..n) int64.  Streaming (non-temporal) stores where dst is
 // 16-byte aligned: the array is written once and is larger than the caches, so the
 // read-for-ownership of an ordinary store would double the memory traffic.
@@ -95,6 +101,21 @@ static const bool g_have_avx512 = [] {
     const char *e = getenv("KPAL_NO_AVX512");
     return __builtin_cpu_supports("avx512f") && !(e && e[0] == '1');
 }();
+
+#else
+// Portable form for non-x86 hosts: zero-extending loops the compiler vectorises.
+static void widen_u16_range(const uint16_t *src, int64_t *dst, uint64_t n)
+{
+    for (uint64_t i = 0; i < n; ++i) dst[i] = src[i];
+}
+static void widen_u8_range(const uint8_t *src, int64_t *dst, uint64_t n)
+{
+    for (uint64_t i = 0; i < n; ++i) dst[i] = src[i];
+}
+static void widen_u16_range_512(const uint16_t *src, int64_t *dst, uint64_t n) { widen_u16_range(src, dst, n); }
+static void widen_u8_range_512(const uint8_t *src, int64_t *dst, uint64_t n) { widen_u8_range(src, dst, n); }
+static const bool g_have_avx512 = false;
+#endif
 
 static void widen_range(const void *src, int width, uint64_t b, int64_t *dst, uint64_t n)
 {

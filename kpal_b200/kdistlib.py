@@ -133,9 +133,24 @@ class ProfileDistance(object):
         are never modified.
         """
         options = self._gpu_options()
-        if options is None:
+        if options is None or not (_integer_counts(left) and _integer_counts(right)):
+            # the device path works on int64 counts; anything else (float counts from a
+            # custom merger, say) keeps the reference's dtype-agnostic NumPy pipeline
             return self._host_distance(left, right)
         return np.float64(_cabi.pair_distance(left.counts, right.counts, **options))
+
+
+def _integer_counts(profile):
+    """True when `profile` holds integer counts that int64 represents exactly (the device
+    path never truncates: other dtypes are routed to the host pipeline)."""
+    counts = profile.counts
+    dtype = getattr(counts, 'dtype', None)
+    if dtype is None:
+        counts = np.asarray(counts)
+        dtype = counts.dtype
+    if dtype.kind == 'u' and dtype.itemsize == 8:
+        return bool(counts.size == 0 or counts.max() <= np.iinfo(np.int64).max)
+    return dtype.kind in 'iub'
 
 
 def distance_matrix_values(profiles, dist):
@@ -143,7 +158,8 @@ def distance_matrix_values(profiles, dist):
     GPU call when the options are in the fast path."""
     n = len(profiles)
     options = dist._gpu_options()
-    if options is not None and n > 0 and not options.get('do_positive'):
+    if (options is not None and n > 0 and not options.get('do_positive')
+            and all(_integer_counts(profile) for profile in profiles)):
         stacked = np.empty((n, profiles[0].number), dtype=np.int64)
         for i, profile in enumerate(profiles):
             if profile.number != stacked.shape[1]:

@@ -274,7 +274,9 @@ def _read_text(handle):
     bytes are plain ASCII without ``\\r``: decoding 100 MB to ``str`` and encoding it again
     for the C ABI costs ~50 times the GPU call it feeds.  Anything else (universal-newline
     translation, another encoding, a partly consumed or unseekable handle, ``StringIO``)
-    goes through ``handle.read()`` exactly as before.
+    goes through ``handle.read()`` exactly as before.  The shortcut is only taken when the
+    handle's encoding maps bytes below 0x80 to the same ASCII characters (UTF-16 / UTF-32
+    text without a BOM is all "ASCII bytes" too, but NUL-interleaved).
     """
     buffer = getattr(handle, 'buffer', None)
     if buffer is not None and hasattr(handle, 'encoding'):
@@ -282,9 +284,24 @@ def _read_text(handle):
             at_start = handle.seekable() and handle.tell() == 0
         except (OSError, ValueError):
             at_start = False
-        if at_start:
+        if at_start and _ascii_superset(getattr(handle, 'encoding', None)):
             data = buffer.read()
             if data.isascii() and b'\r' not in data:
                 return data
             handle.seek(0)                     # let the text layer do what it does
     return handle.read()
+
+
+#: codecs under which a byte below 0x80 decodes to the ASCII character of the same value
+_ASCII_SUPERSETS = frozenset((
+    'ascii', 'utf-8', 'utf-8-sig', 'latin-1', 'iso8859-1', 'iso8859-15', 'cp1252', 'cp1250',
+    'cp1251', 'cp437', 'cp850', 'mac-roman', 'iso8859-2', 'koi8-r', 'gbk', 'gb2312', 'gb18030',
+    'euc-jp', 'euc-kr', 'big5', 'shift_jis'))
+
+
+def _ascii_superset(encoding):
+    import codecs
+    try:
+        return codecs.lookup(encoding or '').name in _ASCII_SUPERSETS
+    except (LookupError, TypeError):
+        return False

@@ -64,6 +64,8 @@ class ProfileFileType(object):
         except ImportError:
             # no libhdf5 on this machine: the in-tree reader / writer of the same format
             from . import h5lite as h5py
+            if 'w' in self._mode:
+                _warn_h5lite_writer()
         try:
             if 'w' in self._mode and os.path.exists(string):
                 raise IOError('file exists')
@@ -83,6 +85,26 @@ class ProfileFileType(object):
             return handle
         except IOError as error:
             raise argparse.ArgumentTypeError("can't open '%s': %s" % (string, error))
+
+
+_h5lite_warned = False
+
+
+def _warn_h5lite_writer():
+    """One warning per process when a profile file is WRITTEN without h5py: the in-tree
+    writer follows the HDF5 specification for the subset kPAL uses and round-trips through
+    its own reader and the reference's test-suite, but its files have never been opened
+    by libhdf5 itself (there is none in this image).  ``KPAL_B200_H5LITE=1`` acknowledges
+    that and silences the warning."""
+    global _h5lite_warned
+    if _h5lite_warned or os.environ.get('KPAL_B200_H5LITE') == '1':
+        return
+    _h5lite_warned = True
+    import warnings
+    warnings.warn('h5py is not installed: writing the profile file with the in-tree HDF5 writer '
+                  '(kpal_b200.h5lite), whose interoperability with libhdf5 / upstream kPAL is '
+                  'unverified; install h5py for guaranteed-compatible files '
+                  '(set KPAL_B200_H5LITE=1 to silence this warning)', RuntimeWarning, stacklevel=3)
 
 
 def _text(value):

@@ -69,15 +69,18 @@ def tile_range(n_tiles, rank, world):
 
 # ------------------------------------------------------------------ counting
 def _gpu_count_shard(fasta_bytes, k, device):
-    """This rank's windows as a device ``int32`` tensor of ``4**k`` u32 counters."""
+    """This rank's windows as a device tensor of ``4**k`` counters: u32 (``int32``), or
+    u64 (``int64``) for a shard of 4 Gi bases or more."""
     import torch
     L = _cabi.load()
-    table = torch.zeros(4 ** k, dtype=torch.int32, device=device)
+    # 32-bit counters are exact while the shard has fewer than 2**32 bases (as kpal_count_fasta)
+    bits = 64 if len(fasta_bytes) >= 2 ** 32 else 32
+    table = torch.zeros(4 ** k, dtype=torch.int64 if bits == 64 else torch.int32, device=device)
     stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
     buf = np.frombuffer(fasta_bytes, dtype=np.uint8)
     n_bases = ctypes.c_uint64()
     _cabi.check(L.kpal_count_fasta_to_dev(_cabi.ptr(buf) if buf.size else None, buf.size, int(k),
-                                          table.data_ptr(), 32, stream, ctypes.byref(n_bases)))
+                                          table.data_ptr(), bits, stream, ctypes.byref(n_bases)))
     return table
 
 
@@ -129,7 +132,7 @@ def count_fasta_distributed(fasta_shard, k, balance=False, group=None, device=No
         # u32 counters are exact while the GLOBAL window total stays below 2**32
         total = torch.tensor([len(fasta_shard)], dtype=torch.int64, device=table.device)
         dist.all_reduce(total, group=group)
-        if int(total.item()) >= 2 ** 32:
+        if int(total.item()) >= 2 ** 32 and table.dtype == torch.int32:
             table = table.to(torch.int64) & 0xffffffff
         if reduce == 'peer' and table.is_cuda and table.dtype == torch.int32:
             reducer = PeerReducer(k, 32, group=group)
@@ -266,56 +269,239 @@ class PeerReducer(object):
             self._root_table = None
 
 
-# ------------------------------------------------------------------ distances
-def distance_matrix_distributed(profiles, metric='multiset', pairwise='prod', do_balance=False,
-                                do_scale=False, down=False, group=None, device=None):
+# ------------------------------------------------------------- per-record counting
+def count_by_record_distributed(fasta_text, k, balance=False, group=None, device=None,
+                                gather=False, count_rows=None):
     """
-    The symmetric ``[n][n]`` distance matrix of `profiles` (C-contiguous
-    ``[n][4**k]`` int64, the same array on every rank) with the upper-triangle
-    tiles sharded over the ranks of `group`.  Rank 0 gets the matrix.
+    ``Profile.from_fasta_by_record`` (reference kpal/klib.py:114-133) with the records of
+    `fasta_text` (the WHOLE file, the same bytes on every rank) sharded over the ranks of
+    `group`: rank r takes the r-th of `world` contiguous byte ranges cut at record
+    boundaries (:func:`split_fasta`, about equal bases per rank), counts its records on its
+    GPU and gets ``(first, names, rows)`` -- the global index of its first record, the
+    names of its records (``''`` for a nameless one: the caller numbers it ``first + i +
+    1``, kpal/klib.py:129-132) and the dense ``[n_r][4**k]`` int64 rows.  Rows are
+    independent, so there is no data-path collective: only the record
+    counts are exchanged, to number the records globally.
+
+    `gather` = True additionally concatenates all rows, in record order, on rank 0 (which
+    then gets ``(0, all_names, all_rows)``; the others ``(first, names, None)``) -- for
+    small inputs and tests; at scale every rank writes the profiles it counted.
+    `count_rows` is the injection point of the CPU (gloo) tests.
     """
     import torch
     import torch.distributed as dist
-    _cabi.require_gpu()
-    L = _cabi.load()
-    if device is None:
-        device = torch.device('cuda', torch.cuda.current_device())
-    profiles = np.ascontiguousarray(profiles, dtype=np.int64)
-    n, size = profiles.shape
-    k = _cabi._k_of(size)
-    stride = int(L.kpal_prepared_stride(k))
-    sp = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-    need_p = metric == 'multiset' and pairwise == 'prod'
-    F = torch.empty((n, stride), dtype=torch.float64, device=device)
-    P = torch.empty((n, stride), dtype=torch.float64, device=device) if need_p else None
-    bitmap = torch.empty((n, stride // 32), dtype=torch.int32, device=device)
-    totals = torch.empty(n, dtype=torch.float64, device=device)
-    norm2 = torch.empty(n, dtype=torch.float64, device=device)
-    slab = max(1, min(n, (1 << 28) // (size * 8)))
-    for r0 in range(0, n, slab):
-        m = min(slab, n - r0)
-        counts = torch.from_numpy(profiles[r0:r0 + m]).to(device)
-        _cabi.check(L.kpal_dev_profiles_prepare(
-            counts.data_ptr(), m, k, int(bool(do_balance)), int(bool(do_scale)), F[r0].data_ptr(),
-            P[r0].data_ptr() if need_p else None, bitmap[r0].data_ptr(), totals[r0:].data_ptr(),
-            norm2[r0:].data_ptr(), sp))
-    order = None
-    if do_scale:
-        order = torch.empty(n, dtype=torch.int32, device=device)
-        _cabi.check(L.kpal_dev_order_by_total(totals.data_ptr(), n, int(bool(down)),
-                                              order.data_ptr(), sp))
+    _cabi._check_k(k)
+    if isinstance(fasta_text, str):
+        fasta_text = fasta_text.encode('latin-1', 'replace')
     distributed = dist.is_available() and dist.is_initialized()
     world = dist.get_world_size(group) if distributed else 1
     rank = dist.get_rank(group) if distributed else 0
-    begin, end = tile_range(int(L.kpal_distance_num_tiles(n)), rank, world)
-    out = torch.zeros((n, n), dtype=torch.float64, device=device)
-    _cabi.check(L.kpal_dev_distance_tiles(
-        F.data_ptr(), P.data_ptr() if need_p else None, bitmap.data_ptr(), totals.data_ptr(),
-        norm2.data_ptr(), order.data_ptr() if order is not None else None, n, k,
-        _cabi.METRICS[metric], _cabi.PAIRWISE[pairwise], int(bool(do_scale)), int(bool(down)),
-        begin, end, out.data_ptr(), sp))
+    begin, end = split_fasta(fasta_text, world)[rank]
+    shard = fasta_text[begin:end]
+    if rank > 0 and begin > 0 and shard[:1] != b'>':
+        shard = b''                 # no record starts in this range (text without headers)
+    codes, valid, rec_starts, names, n_bases = _cabi.fasta_pack(shard)
+    n_local = len(names)
+    if count_rows is None:
+        _cabi.require_gpu()
+        if device is not None:
+            _cabi.check(_cabi.load().kpal_set_device(device.index if hasattr(device, 'index') else int(device)))
+        rows = np.empty((n_local, 4 ** k), dtype=np.int64)
+        batch = max(1, (256 << 20) // (8 * 4 ** k))
+        for first in range(0, n_local, batch):
+            n = min(batch, n_local - first)
+            rows[first:first + n] = _cabi.count_by_record(codes, valid, n_bases, rec_starts, first, n, k,
+                                                          balance=balance)
+    else:
+        rows = count_rows(shard, k, balance)
+    first_record = 0
     if world > 1:
-        dist.reduce(out, dst=0, group=group)
-        if rank != 0:
-            return None
-    return out.cpu().numpy()
+        counts = [None] * world
+        dist.all_gather_object(counts, n_local, group=group)
+        first_record = int(sum(counts[:rank]))
+    if not gather or world == 1:
+        return first_record, names, rows
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object((names, rows), parts, dst=0, group=group)
+    if rank != 0:
+        return first_record, names, None
+    all_names = [name for part in parts for name in part[0]]
+    return 0, all_names, np.concatenate([part[1] for part in parts], axis=0)
+
+
+# ------------------------------------------------------------------ distances
+def shard_rows(n, rank, world):
+    """Rows ``[begin, end)`` of an `n`-row profile set that rank `rank` uploads and
+    prepares: equal shares of ``ceil(n / world)`` rows (the last ones may be shorter)."""
+    per = (n + world - 1) // world
+    return min(rank * per, n), min((rank + 1) * per, n)
+
+
+class _GpuMatrixOps(object):
+    """The device side of :func:`distance_matrix_distributed` (CUDA library + torch
+    tensors); the CPU (gloo) tests substitute an oracle-backed double with the same methods."""
+
+    def __init__(self, n, k, options, device):
+        import torch
+        self.torch = torch
+        self.L = _cabi.load()
+        self.n, self.k, self.device = n, k, device
+        self.metric = _cabi.METRICS[options['metric']]
+        self.pairwise = _cabi.PAIRWISE[options['pairwise']]
+        self.do_balance = int(bool(options['do_balance']))
+        self.do_scale = int(bool(options['do_scale']))
+        self.down = int(bool(options['down']))
+        self.stride = int(self.L.kpal_prepared_stride(k))
+        self.need_p = options['metric'] == 'multiset' and options['pairwise'] == 'prod'
+        f64 = dict(dtype=torch.float64, device=device)
+        self.F = torch.empty((n, self.stride), **f64)
+        self.P = torch.empty((n, self.stride), **f64) if self.need_p else None
+        self.bitmap = torch.empty((n, self.stride // 32), dtype=torch.int32, device=device)
+        self.totals = torch.empty(n, **f64)
+        self.norm2 = torch.empty(n, **f64)
+        self.order = None
+        self.tile_elems = int(self.L.kpal_distance_tile_elems())
+
+    def _sp(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def arrays(self):
+        """The prepared per-profile arrays, row-sharded like the profiles."""
+        return [a for a in (self.F, self.P, self.bitmap, self.totals, self.norm2) if a is not None]
+
+    def prepare(self, rows, begin):
+        """Upload raw int64 `rows` (host) and prepare them as profiles begin, begin + 1, ..."""
+        torch, L = self.torch, self.L
+        size = 4 ** self.k
+        slab = max(1, min(len(rows), (1 << 28) // (size * 8))) if len(rows) else 1
+        for r0 in range(0, len(rows), slab):
+            m = min(slab, len(rows) - r0)
+            counts = torch.from_numpy(np.ascontiguousarray(rows[r0:r0 + m], dtype=np.int64)).to(self.device)
+            at = begin + r0
+            _cabi.check(L.kpal_dev_profiles_prepare(
+                counts.data_ptr(), m, self.k, self.do_balance, self.do_scale, self.F[at].data_ptr(),
+                self.P[at].data_ptr() if self.need_p else None, self.bitmap[at].data_ptr(),
+                self.totals[at:].data_ptr(), self.norm2[at:].data_ptr(), self._sp()))
+
+    def make_order(self):
+        if self.do_scale:
+            self.order = self.torch.empty(self.n, dtype=self.torch.int32, device=self.device)
+            _cabi.check(self.L.kpal_dev_order_by_total(self.totals.data_ptr(), self.n, self.down,
+                                                       self.order.data_ptr(), self._sp()))
+
+    def num_tiles(self):
+        return int(self.L.kpal_distance_num_tiles(self.n))
+
+    def new_packed(self, n_tiles):
+        return self.torch.zeros((max(n_tiles, 1), self.tile_elems), dtype=self.torch.float64, device=self.device)
+
+    def tiles_packed(self, begin, end, packed):
+        if end > begin:
+            _cabi.check(self.L.kpal_dev_distance_tiles_packed(
+                self.F.data_ptr(), self.P.data_ptr() if self.need_p else None, self.bitmap.data_ptr(),
+                self.totals.data_ptr(), self.norm2.data_ptr(),
+                self.order.data_ptr() if self.order is not None else None, self.n, self.k,
+                self.metric, self.pairwise, self.do_scale, self.down, begin, end, packed.data_ptr(),
+                self._sp()))
+
+    def new_out(self):
+        return self.torch.zeros((self.n, self.n), dtype=self.torch.float64, device=self.device)
+
+    def unpack(self, packed, begin, end, diagonal, out):
+        _cabi.check(self.L.kpal_dev_distance_unpack_tiles(
+            packed.data_ptr(), self.totals.data_ptr(), self.norm2.data_ptr(),
+            self.order.data_ptr() if self.order is not None else None, self.n, self.metric,
+            self.pairwise, self.do_scale, begin, end, int(bool(diagonal)), out.data_ptr(), self._sp()))
+
+    def to_host(self, out):
+        return out.cpu().numpy()
+
+
+def allgather_rows(arrays, n, group=None):
+    """All-gather of row-sharded arrays, in place: every array has `n` rows on every rank,
+    rank r holds valid data in rows :func:`shard_rows` ``(n, r, world)`` and receives the
+    others' (one ``all_gather_into_tensor`` per array when the shards are equal, which NCCL
+    runs in place over NVLink; one broadcast per rank and array otherwise)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world == 1:
+        return
+    per = (n + world - 1) // world
+    for a in arrays:
+        if n == per * world:
+            try:
+                dist.all_gather_into_tensor(a, a[rank * per:(rank + 1) * per], group=group)
+                continue
+            except (RuntimeError, NotImplementedError):      # backend without the in-place form
+                pass
+        for r in range(world):
+            b, e = shard_rows(n, r, world)
+            if e > b:
+                dist.broadcast(a[b:e], src=dist.get_global_rank(group, r) if group is not None else r,
+                               group=group)
+
+
+def distance_matrix_distributed(profiles, metric='multiset', pairwise='prod', do_balance=False,
+                                do_scale=False, down=False, group=None, device=None, sharded=False,
+                                n_total=None, ops=None):
+    """
+    The symmetric ``[n][n]`` distance matrix of a profile set over the ranks of `group`
+    (the loop being cut up is kpal/kdistlib.py:179-184):
+
+    1. rank r uploads and prepares only rows :func:`shard_rows` ``(n, r, world)`` -- 1/world of
+       the host-to-device traffic and of the pre-pass per GPU;
+    2. the prepared arrays (frequencies, ``x + 1``, non-zero bitmaps, totals, norms) are
+       all-gathered over NVLink (:func:`allgather_rows`), so every GPU holds the whole set;
+    3. the upper-triangle tiles are dealt out in contiguous, equal ranges (:func:`tile_range`);
+    4. every rank's finished tiles travel to rank 0 in ONE gather of compact tile arrays
+       (``N^2 / 2`` doubles in total) and are scattered into the matrix there.
+
+    `profiles`: C-contiguous ``[n][4**k]`` int64 -- the whole set on every rank (each rank
+    reads only its rows), or with ``sharded=True`` just this rank's rows (then `n_total` is
+    required).  Rank 0 gets the matrix, the other ranks ``None``.
+    """
+    import torch
+    import torch.distributed as dist
+    distributed = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if distributed else 1
+    rank = dist.get_rank(group) if distributed else 0
+    profiles = np.asarray(profiles)
+    if profiles.ndim != 2:
+        raise ValueError('profiles must be [rows][4**k]')
+    n = int(n_total) if sharded else profiles.shape[0]
+    if sharded and n_total is None:
+        raise ValueError('sharded=True needs n_total')
+    k = _cabi._k_of(profiles.shape[1])
+    begin, end = shard_rows(n, rank, world)
+    mine = profiles if sharded else profiles[begin:end]
+    if len(mine) != end - begin:
+        raise ValueError('rank %d must hold rows [%d, %d) of the profile set' % (rank, begin, end))
+    options = dict(metric=metric, pairwise=pairwise, do_balance=do_balance, do_scale=do_scale, down=down)
+    if ops is None:
+        _cabi.require_gpu()
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        ops = _GpuMatrixOps(n, k, options, device)
+    ops.prepare(mine, begin)
+    allgather_rows(ops.arrays(), n, group=group)
+    ops.make_order()
+    n_tiles = ops.num_tiles()
+    t_begin, t_end = tile_range(n_tiles, rank, world)
+    most = max(tile_range(n_tiles, r, world)[1] - tile_range(n_tiles, r, world)[0] for r in range(world))
+    packed = ops.new_packed(most)
+    ops.tiles_packed(t_begin, t_end, packed)
+    if world == 1:
+        out = ops.new_out()
+        ops.unpack(packed, t_begin, t_end, True, out)
+        return ops.to_host(out)
+    parts = [ops.new_packed(most) for _ in range(world)] if rank == 0 else None
+    dist.gather(packed, parts, dst=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    if rank != 0:
+        return None
+    out = ops.new_out()
+    for r in range(world):
+        b, e = tile_range(n_tiles, r, world)
+        ops.unpack(parts[r], b, e, r == 0, out)
+    return ops.to_host(out)

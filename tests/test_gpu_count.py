@@ -439,12 +439,12 @@ def _dev_count(text_bytes, k, bits, balance):
     (12, 70, "ACGT", 0),               # far less than one tile
 ])
 def test_radix_count_path_bit_exact(k, n, letters, payload_bits):
-    """The two-pass radix path (count_radix.cu) forced on: bit-exact against the C oracle
-    for uniform, skewed and degenerate compositions, 32- and 64-bit counters."""
+    """The one-window two-pass radix path (count_radix.cu) forced on: bit-exact against the C
+    oracle for uniform, skewed and degenerate compositions, 32- and 64-bit counters."""
     text = _composition_bytes(k * 7919 + n, n, letters)
     want = c_oracle.count_bytes(text, k, threads=c_oracle.max_threads())
     try:
-        _set_option("count_path", 2)
+        _set_option("count_path", 3)
         _set_option("radix_payload_bits", payload_bits)
         many_buckets = k >= 13 or payload_bits == 13
         for max_buckets in ((2048, 1024) if many_buckets else (2048,)):   # buckets per pass-1 launch
@@ -461,6 +461,55 @@ def test_radix_count_path_bit_exact(k, n, letters, payload_bits):
         _set_option("count_path", 0)
         _set_option("radix_payload_bits", 0)
         _set_option("radix_shape", 0)
+
+
+@pytest.mark.parametrize("k,n,letters,p_n", [
+    (12, 40_000_000, "ACGT", 0.0005),  # ~9 tiles per CTA, several flushes per slot
+    (12, 5_000_000, "ACGTacgt", 0.05), # short runs: many windows without a valid partner
+    (12, 3_000_000, "ACG", 0.0005),    # skew: slots and regions overflow into the RED path
+    (12, 2_000_000, "AC", 0.0005),     # 32 of 1024 buckets used: heavy overflow
+    (12, 1_000_000, "A", 0.0005),      # one bin
+    (12, 300_000, "AT", 0.3),          # runs barely longer than k
+    (11, 4_000_000, "ACGT", 0.001),
+    (10, 4_000_000, "ACGT", 0.001),
+    (9, 4_000_000, "ACGT", 0.001),
+    (9, 500_000, "CG", 0.001),
+    (12, 70, "ACGT", 0.0),             # far less than one tile
+    (12, 13, "ACGT", 0.0),             # one pair
+    (12, 12, "ACGT", 0.0),             # one window, no pair
+])
+def test_pair_count_path_bit_exact(k, n, letters, p_n):
+    """The two-windows-per-payload radix path (count_pairs.cu) forced on: bit-exact against
+    the C oracle, 32- and 64-bit counters, every tiling / flush / pass-2 variant."""
+    text = _composition_bytes(k * 104729 + n, n, letters, p_n=p_n)
+    want = c_oracle.count_bytes(text, k, threads=c_oracle.max_threads())
+    try:
+        _set_option("count_path", 2)
+        # units per thread and tile, tiles between two slot flushes (0 = automatic), pass 2 as one
+        # launch flushed by the TMA unit (cp.reduce.async.bulk) or as two launches per role
+        for upt, flush_every, fused in ((1, 0, 1), (2, 0, 1), (1, 1, 0), (1, 6, 1), (2, 1, 0)):
+            _set_option("pair_upt", upt)
+            _set_option("pair_flush_every", flush_every)
+            _set_option("pair_fused", fused)
+            got32 = _dev_count(text, k, 32, False)
+            assert np.array_equal(got32, want), (upt, flush_every, fused)
+            got64 = _dev_count(text, k, 64, True)
+            assert np.array_equal(got64, ko.balance(want)), (upt, flush_every, fused)
+    finally:
+        _set_option("count_path", 0)
+        _set_option("pair_upt", 1)
+        _set_option("pair_flush_every", 0)
+        _set_option("pair_fused", 1)
+
+
+def test_pair_count_path_reads():
+    """150-bp reads (every record ends a run: the windows without a partner go through
+    the RED path) at the default path selection, k = 12 and 10."""
+    reads = random_reads(78, 140_000, 150)
+    text = np.insert(reads, 150, ord("\n"), axis=1).tobytes()
+    for k in (12, 10):
+        want = c_oracle.count_bytes(text, k, threads=c_oracle.max_threads())
+        assert np.array_equal(_dev_count(text, k, 32, False), want)
 
 
 def test_radix_count_path_through_host_api():

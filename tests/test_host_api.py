@@ -304,6 +304,63 @@ def test_read_text_takes_ascii_files_as_bytes(tmp_path):
         assert _read_text(handle) == u">ré\nACGT\n"
     assert _read_text(io.StringIO(">x\nAC\n")) == ">x\nAC\n"
     assert _read_text(io.BytesIO(b">x\nAC\n")) == b">x\nAC\n"
+    # ASCII-incompatible encodings whose bytes are all below 0x80 are decoded by the text layer
+    for codec in ('utf-16-le', 'utf-32-be'):
+        with open(write(codec + '.fa', u">r1\nACGT\n".encode(codec)), encoding=codec) as handle:
+            assert _read_text(handle) == u">r1\nACGT\n"
+    with open(plain, encoding='latin-1') as handle:
+        assert _read_text(handle) == b">r1 x\nACGT\nNN\n>r2\nTTGA"
     # either form parses to the same records
     for text in (b">r1 x\nACGT\nNN\n>r2\nTTGA", ">r1 x\nACGT\nNN\n>r2\nTTGA"):
         assert ko.parse_fasta(text) == [("r1", "ACGTNN"), ("r2", "TTGA")]
+
+
+def test_non_integer_counts_take_the_host_pipeline(monkeypatch):
+    """The device path works on int64 counts.  Profiles holding anything else (float counts
+    from a custom merger, say) are never truncated: they run the reference's NumPy pipeline."""
+    def no_gpu(*args, **kwargs):
+        raise AssertionError('device path used for non-integer counts')
+    monkeypatch.setattr(kdistlib._cabi, 'pair_distance', no_gpu)
+    monkeypatch.setattr(kdistlib._cabi, 'distance_matrix', no_gpu)
+    rng = np.random.default_rng(5)
+    a = klib.Profile(rng.integers(0, 9, 256) + 0.5, 'a')
+    b = klib.Profile(rng.integers(0, 9, 256) * 1.25, 'b')
+    c = klib.Profile(rng.integers(0, 9, 256).astype(np.float32), 'c')
+    dist = kdistlib.ProfileDistance(do_scale=True)
+    # kpal/kdistlib.py:150-161 + kpal/metrics.py:49-72,101-123 on the float counts themselves
+    x, y = a.counts * (b.counts.sum() / a.counts.sum()), b.counts * 1.0
+    if a.counts.sum() >= b.counts.sum():
+        x, y = a.counts * 1.0, b.counts * (a.counts.sum() / b.counts.sum())
+    nz = np.where(np.logical_or(x, y))
+    want = (np.abs(x[nz] - y[nz]) / ((x[nz] + 1) * (y[nz] + 1))).sum() / (len(nz[0]) + 1)
+    assert abs(dist.distance(a, b) - want) <= 1e-12 * abs(want)
+    values = kdistlib.distance_matrix_values([a, b, c], dist)
+    assert abs(values[1, 0] - want) <= 1e-12 * abs(want) and values[1, 0] == values[0, 1]
+    assert kdistlib._integer_counts(klib.Profile(np.zeros(16, dtype=np.uint16)))
+    assert kdistlib._integer_counts(klib.Profile([0] * 16))
+    assert not kdistlib._integer_counts(klib.Profile(np.zeros(16)))
+    big = np.zeros(16, dtype=np.uint64)
+    big[3] = 2 ** 63
+    assert not kdistlib._integer_counts(klib.Profile(big))
+
+
+def test_h5lite_writer_warns_once(tmp_path, monkeypatch):
+    """Without h5py, writing a profile file with the in-tree HDF5 writer says so (once)."""
+    import builtins
+    import warnings
+    from kpal_b200 import kmer
+    real_import = builtins.__import__
+
+    def no_h5py(name, *args, **kwargs):
+        if name == 'h5py':
+            raise ImportError('no h5py')
+        return real_import(name, *args, **kwargs)
+    monkeypatch.setattr(builtins, '__import__', no_h5py)
+    monkeypatch.setattr(kmer, '_h5lite_warned', False)
+    monkeypatch.delenv('KPAL_B200_H5LITE', raising=False)
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter('always')
+        kmer.ProfileFileType('w')(str(tmp_path / 'a.k')).close()
+        kmer.ProfileFileType('w')(str(tmp_path / 'b.k')).close()
+        kmer.ProfileFileType('r')(str(tmp_path / 'a.k')).close()
+    assert len([w for w in caught if 'h5lite' in str(w.message)]) == 1

@@ -107,6 +107,142 @@ def test_count_distributed_gloo(tmp_path, world):
     assert np.array_equal(np.load(out), ko.balance(ko.count_fasta(text, k)))
 
 
+class _OracleMatrixOps(object):
+    """CPU stand-in for multigpu._GpuMatrixOps (test only): the 'prepared arrays' are the raw
+    counts, a 'tile' is a run of 7 pairs of the lower triangle, the distances come from the
+    oracle.  What is under test is the host logic around it: who prepares which rows, the
+    all-gather, the tile ranges, the gather of packed tiles and their scatter on rank 0."""
+    TILE = 7
+
+    def __init__(self, n, size, options):
+        import torch
+        self.torch, self.n, self.options = torch, n, options
+        self.counts = torch.full((n, size), -1, dtype=torch.int64)
+        self.pairs = [(i, j) for i in range(1, n) for j in range(i)]
+
+    def arrays(self):
+        return [self.counts]
+
+    def prepare(self, rows, begin):
+        if len(rows):
+            self.counts[begin:begin + len(rows)] = self.torch.from_numpy(np.ascontiguousarray(rows))
+
+    def make_order(self):
+        assert int(self.counts.min()) >= 0, "rows missing after the all-gather"
+
+    def num_tiles(self):
+        return (len(self.pairs) + self.TILE - 1) // self.TILE
+
+    def new_packed(self, n_tiles):
+        return self.torch.zeros((max(n_tiles, 1), self.TILE), dtype=self.torch.float64)
+
+    def tiles_packed(self, begin, end, packed):
+        c = self.counts.numpy()
+        for t in range(begin, end):
+            for e, (i, j) in enumerate(self.pairs[t * self.TILE:(t + 1) * self.TILE]):
+                packed[t - begin, e] = ko.distance(c[i], c[j], **self.options)
+
+    def new_out(self):
+        return self.torch.full((self.n, self.n), np.nan, dtype=self.torch.float64)
+
+    def unpack(self, packed, begin, end, diagonal, out):
+        for t in range(begin, end):
+            for e, (i, j) in enumerate(self.pairs[t * self.TILE:(t + 1) * self.TILE]):
+                out[i, j] = out[j, i] = packed[t - begin, e]
+        if diagonal:
+            for i in range(self.n):
+                out[i, i] = 0.0
+
+    def to_host(self, out):
+        return out.numpy()
+
+
+def _gloo_matrix_worker(rank, world, port, profiles, sharded, out_path):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = len(profiles)
+        options = dict(do_scale=True, metric="multiset", pairwise="sum")
+        ops = _OracleMatrixOps(n, profiles.shape[1], options)
+        b, e = multigpu.shard_rows(n, rank, world)
+        # every rank may only ever look at its own rows
+        mine = profiles[b:e] if sharded else np.where(
+            ((np.arange(n) >= b) & (np.arange(n) < e))[:, None], profiles, -7)
+        got = multigpu.distance_matrix_distributed(mine, sharded=sharded, n_total=n, ops=ops, **options)
+        if rank == 0:
+            np.save(out_path, got)
+        else:
+            assert got is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,sharded", [(2, 8, False), (3, 9, True), (3, 10, True), (4, 3, True)])
+def test_matrix_distributed_gloo(tmp_path, world, n, sharded):
+    """Shard -> all-gather -> tile ranges -> gather of packed tiles, on CPU with gloo: equal and
+    unequal shards (the in-place all-gather and the broadcast route), fewer rows than ranks."""
+    import torch.multiprocessing as mp
+    rng = np.random.default_rng(n)
+    profiles = rng.poisson(rng.uniform(0.5, 4, (n, 1)), (n, 64)).astype(np.int64)
+    out = str(tmp_path / "matrix.npy")
+    mp.spawn(_gloo_matrix_worker, args=(world, _free_port(), profiles, sharded, out), nprocs=world, join=True)
+    got = np.load(out)
+    for i in range(1, n):
+        for j in range(i):
+            want = ko.distance(profiles[i], profiles[j], do_scale=True, pairwise="sum")
+            assert abs(got[i, j] - want) <= 1e-12 * abs(want), (i, j)
+    assert np.array_equal(got, got.T) and not np.isnan(got).any()
+
+
+def _gloo_by_record_worker(rank, world, port, text, k, out_path):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        def count_rows(shard, kk, balance):      # stand-in for by_record_kernel (test only)
+            rows = [ko.count_sequences([seq], kk) for _, seq in ko.parse_fasta(shard)]
+            rows = [ko.balance(r) if balance else r for r in rows]
+            return np.array(rows, dtype=np.int64).reshape(len(rows), 4 ** kk)
+
+        first, names, rows = multigpu.count_by_record_distributed(text, k, balance=True, count_rows=count_rows)
+        np.savez(out_path % rank, first=first, names=np.array(names, dtype=object), rows=rows, allow_pickle=True)
+        first, names, rows = multigpu.count_by_record_distributed(text, k, gather=True, count_rows=count_rows)
+        if rank == 0:
+            np.savez(out_path % 99, first=first, names=np.array(names, dtype=object), rows=rows, allow_pickle=True)
+        else:
+            assert rows is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_by_record_distributed_gloo(tmp_path, world):
+    """Records sharded over the ranks by byte range; the rows come back with the global
+    index of the rank's first record, so record order is restored by index."""
+    import torch.multiprocessing as mp
+    text = make_fasta(12, 41)
+    k = 4
+    out = str(tmp_path / "rows_%d.npz")
+    mp.spawn(_gloo_by_record_worker, args=(world, _free_port(), text, k, out), nprocs=world, join=True)
+    records = ko.parse_fasta(text)
+    want = np.array([ko.balance(ko.count_sequences([seq], k)) for _, seq in records])
+    seen = 0
+    for rank in range(world):
+        part = np.load(out % rank, allow_pickle=True)
+        first, rows = int(part["first"]), part["rows"]
+        assert first == seen
+        assert list(part["names"]) == [name for name, _ in records[first:first + len(rows)]]
+        assert np.array_equal(rows, want[first:first + len(rows)])
+        seen += len(rows)
+    assert seen == len(records)
+    whole = np.load(out % 99, allow_pickle=True)
+    assert int(whole["first"]) == 0 and list(whole["names"]) == [name for name, _ in records]
+    assert np.array_equal(whole["rows"], np.array([ko.count_sequences([seq], k) for _, seq in records]))
+
+
 # ---------------------------------------------------------------------- GPU
 def _nccl_worker(rank, world, port, text, k, profiles, out_dir):
     import torch
@@ -122,10 +258,18 @@ def _nccl_worker(rank, world, port, text, k, profiles, out_dir):
         counts = multigpu.count_fasta_distributed(text[b:e], k, balance=True)        # peer-memory reduce
         counts_nccl = multigpu.count_fasta_distributed(text[b:e], k, balance=True, reduce='nccl')
         matrix = multigpu.distance_matrix_distributed(profiles, do_scale=True)
+        # unequal shards (301 rows): the broadcast route; this rank hands over its rows only
+        rb, re_ = multigpu.shard_rows(len(profiles), rank, world)
+        matrix_sharded = multigpu.distance_matrix_distributed(
+            profiles[rb:re_], do_scale=True, pairwise='sum', sharded=True, n_total=len(profiles))
+        first, names, rows = multigpu.count_by_record_distributed(text, 6, balance=True)
+        np.savez(os.path.join(out_dir, "rows_%d.npz" % rank), first=first, rows=rows,
+                 names=np.array(names, dtype=object), allow_pickle=True)
         if rank == 0:
             assert np.array_equal(counts, counts_nccl)
             np.save(os.path.join(out_dir, "counts.npy"), counts)
             np.save(os.path.join(out_dir, "matrix.npy"), matrix)
+            np.save(os.path.join(out_dir, "matrix_sharded.npy"), matrix_sharded)
     finally:
         dist.destroy_process_group()
 
@@ -141,7 +285,7 @@ def test_distributed_nccl(tmp_path):
     text = make_fasta(21, 5000, max_len=1500)
     k = 11
     rng = np.random.default_rng(3)
-    lam = np.exp(rng.uniform(np.log(0.5), np.log(8.0), 300))
+    lam = np.exp(rng.uniform(np.log(0.5), np.log(8.0), 301))
     profiles = np.stack([rng.poisson(l, 4 ** 6) for l in lam]).astype(np.int64)
     mp.spawn(_nccl_worker, args=(world, _free_port(), text, k, profiles, str(tmp_path)),
              nprocs=world, join=True)
@@ -152,6 +296,54 @@ def test_distributed_nccl(tmp_path):
     low = np.tril_indices(len(profiles), -1)
     np.testing.assert_allclose(matrix[low], want[low], rtol=1e-9, atol=0)
     assert np.array_equal(matrix, matrix.T)
+    matrix = np.load(str(tmp_path / "matrix_sharded.npy"))
+    want = c_oracle.distance_matrix(profiles, do_scale=True, pairwise="sum", threads=c_oracle.max_threads())
+    np.testing.assert_allclose(matrix[low], want[low], rtol=1e-9, atol=0)
+    # per-record rows: every rank's rows, put back in record order by the global index
+    records = ko.parse_fasta(text)
+    seen = 0
+    for rank in range(world):
+        part = np.load(str(tmp_path / ("rows_%d.npz" % rank)), allow_pickle=True)
+        first, rows = int(part["first"]), part["rows"]
+        assert first == seen
+        for i in range(0, len(rows), 97):
+            assert part["names"][i] == records[first + i][0]
+            assert np.array_equal(rows[i], ko.balance(ko.count_sequences([records[first + i][1]], 6)))
+        seen += len(rows)
+    assert seen == len(records)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 3, 8])
+def test_matrix_packed_tiles_virtual_world(world):
+    """The multi-GPU matrix route on ONE GPU: the tile ranges of `world` virtual ranks are
+    computed one after the other as packed tile arrays and scattered into one matrix, exactly
+    as rank 0 does with the gathered arrays.  Against the C oracle."""
+    import torch
+    from oracle import c_oracle
+    rng = np.random.default_rng(world)
+    n, k = 333, 7
+    lam = np.exp(rng.uniform(np.log(0.5), np.log(8.0), n))
+    profiles = np.stack([rng.poisson(l, 4 ** k) for l in lam]).astype(np.int64)
+    options = dict(metric='multiset', pairwise='prod', do_balance=True, do_scale=True, down=False)
+    ops = multigpu._GpuMatrixOps(n, k, options, torch.device('cuda', 0))
+    ops.prepare(profiles, 0)
+    ops.make_order()
+    n_tiles = ops.num_tiles()
+    out = ops.new_out()
+    for r in range(world):
+        b, e = multigpu.tile_range(n_tiles, r, world)
+        packed = ops.new_packed(e - b)
+        ops.tiles_packed(b, e, packed)
+        ops.unpack(packed, b, e, r == 0, out)
+    got = ops.to_host(out)
+    want = c_oracle.distance_matrix(profiles, do_balance=True, do_scale=True, threads=c_oracle.max_threads())
+    low = np.tril_indices(n, -1)
+    np.testing.assert_allclose(got[low], want[low], rtol=1e-9, atol=0)
+    assert np.array_equal(got, got.T) and not got.diagonal().any()
+    # the single-process call of the public function takes the same route
+    one = multigpu.distance_matrix_distributed(profiles, **options)
+    assert np.array_equal(one, got)
 
 
 @pytest.mark.gpu
