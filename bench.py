@@ -482,10 +482,10 @@ def bench_count(args, world, rank, local):
             _cabi.check(L.kpal_dev_finalize_counts(summed, 32, k, balance, d_counts.data_ptr(), sp))
 
     def device_step(ev=None):
-        d_table.zero_()
         if ev:
             ev[0].record(stream)
         if reducer is not None and args.reduce == "fused":
+            d_table.zero_()
             # count + all-to-all in one call: pass 2 of the radix count stores into the inboxes
             summed = reducer.count_and_reduce(d_codes.data_ptr(), d_valid.data_ptr(), n_bases,
                                               d_table.data_ptr(), sp)
@@ -494,8 +494,15 @@ def bench_count(args, world, rank, local):
             if rank == 0:
                 _cabi.check(L.kpal_dev_finalize_counts(summed, 32, k, balance, d_counts.data_ptr(), sp))
             return
-        _cabi.check(L.kpal_dev_count_packed(d_codes.data_ptr(), d_valid.data_ptr(), n_bases, k,
-                                            d_table.data_ptr(), 32, sp))
+        # the table is zeroed by the call: inside the first count kernel on the pair path (its
+        # CTAs zero their shares while they bin), with a memset before the kernels otherwise
+        if args.fresh:
+            _cabi.check(L.kpal_dev_count_packed_fresh(d_codes.data_ptr(), d_valid.data_ptr(), n_bases, k,
+                                                      d_table.data_ptr(), 32, sp))
+        else:           # A/B: memset + count into the zeroed table
+            d_table.zero_()
+            _cabi.check(L.kpal_dev_count_packed(d_codes.data_ptr(), d_valid.data_ptr(), n_bases, k,
+                                                d_table.data_ptr(), 32, sp))
         if ev:
             ev[1].record(stream)
         reduce_and_finalize()
@@ -625,7 +632,7 @@ def bench_count(args, world, rank, local):
         kernels = (["pair_partition_kernel", "pair_histogram_kernel"] if pairs else
                    ["radix_partition_kernel", "radix_histogram_kernel"] if radix else
                    ["count_smem_kernel" if k <= 7 else "count_global_kernel"])
-        step_kernels = ["memset(table)"] + kernels + [
+        step_kernels = ([] if pairs else ["memset(table)"]) + kernels + [
             "finalize_balance_tiled_kernel" if (balance and k >= 6) else "finalize_kernel"]
         traffic, traffic_src = None, None
         if args.config == 2 and k == K_COUNT and args.composition == "uniform":
@@ -641,7 +648,8 @@ def bench_count(args, world, rank, local):
             "vs_baseline": None, "dtype": "u32 counters -> int64", "data": "synthetic",
             "config": {"workload": workload,
                        "k": k, "bases_per_gpu": int(seq_bases), "packed_bases_per_gpu": int(n_bases),
-                       "l2": "512 MB memset between steps (untimed); table memset is inside the step",
+                       "l2": "512 MB memset between steps (untimed); zeroing the table is inside the step "
+                             "(folded into the first count kernel on the pair path)",
                        "parallelism": ("records sharded per GPU, u32 tables summed onto rank 0 " +
                                        ("over NVLink peer memory (all-to-all fused into the count's histogram pass + collect kernel)"
                                         if (reducer is not None and args.reduce == "fused") else
@@ -838,6 +846,73 @@ def bench_matrix(args, world, rank, local):
         check_block = got[:lead, :lead].copy()
         del got
 
+    # ---- euclidean distances of the same set through the exact integer Gram matrix on the
+    # tensor cores (tcgen05 kind::i8), next to the element-wise fp64 tile kernel (N = 1 only)
+    gram_rec = None
+    if world == 1 and not args.no_gram:
+        dp = int(L.kpal_gram_row_stride(k))
+        x8 = torch.zeros((n, dp), dtype=torch.uint8, device=dev)
+        g_tot = torch.zeros(n, dtype=torch.int64, device=dev)
+        g_norm = torch.zeros(n, dtype=torch.int64, device=dev)
+        g_flags = torch.zeros(4, dtype=torch.int32, device=dev)
+        for s_i in range((n + slab - 1) // slab):
+            counts = matrix_slab(torch, gen, lam, s_i, slab, n, d, dev)
+            r0 = s_i * slab
+            _cabi.check(L.kpal_dev_gram_prepare(counts.data_ptr(), len(counts), k, 0, x8[r0].data_ptr(),
+                                                g_tot[r0:].data_ptr(), g_norm[r0:].data_ptr(), g_flags.data_ptr(), sp))
+            del counts
+        torch.cuda.synchronize()
+        if int(g_flags[0].item()) == 0:
+            norm_max = int(g_norm.max().item())
+            g_mat = torch.empty((n, n), dtype=torch.int64, device=dev)
+            g_out = torch.empty((n, n), dtype=torch.float64, device=dev)
+
+            def gram_step():
+                _cabi.check(L.kpal_dev_gram_distances(x8.data_ptr(), g_tot.data_ptr(), g_norm.data_ptr(), norm_max,
+                                                      n, k, 1, 1, 0, g_mat.data_ptr(), g_out.data_ptr(), sp))
+            gram_step()
+            torch.cuda.synchronize()
+            g_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+            for a_ev, b_ev in g_ev:
+                a_ev.record(stream)
+                gram_step()
+                b_ev.record(stream)
+            torch.cuda.synchronize()
+            gram_ms = sum(x.elapsed_time(y) for x, y in g_ev) / len(g_ev)
+            # the same matrix from the element-wise fp64 tile kernel, once
+            t_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            t_ev[0].record(stream)
+            _cabi.check(L.kpal_dev_distance_tiles(
+                F.data_ptr(), R.data_ptr(), bitmap.data_ptr(), totals.data_ptr(), norm2.data_ptr(),
+                order.data_ptr(), n, k, 1, 0, 1, 0, 0, tiles, out.data_ptr(), sp))
+            t_ev[1].record(stream)
+            torch.cuda.synchronize()
+            tile_ms = t_ev[0].elapsed_time(t_ev[1])
+            g_host, t_host = g_out.cpu().numpy(), out.cpu().numpy()
+            from oracle import c_oracle
+            want = c_oracle.distance_matrix(np.stack([rows[i] for i in range(lead)]), metric="euclidean",
+                                            do_scale=True, threads=host_threads())
+            lowb = np.tril_indices(lead, -1)
+            rel_gram = float(np.max(np.abs(g_host[:lead, :lead][lowb] - want[lowb]) / np.abs(want[lowb])))
+            iu = np.triu_indices(n, 1)
+            rel_tile = float(np.max(np.abs(g_host[iu] - t_host[iu]) / np.abs(t_host[iu])))
+            pairs_all = n * (n - 1) // 2
+            tensor_peak, tensor_src = measured_peak("bf16_tflops", 1590.0)
+            ops = 2.0 * d * (n * n / 2.0)            # multiply-adds of the triangle
+            gram_rec = {"metric": "profile_pairs_per_sec_k10_euclidean_scaled", "value": pairs_all / (gram_ms * 1e-3),
+                        "unit": "profile-pairs/s", "ms_per_step": gram_ms, "steps": len(g_ev),
+                        "kernel": "gram_u8_kernel (tcgen05.mma kind::i8, TMEM accumulators, TMA 128B-swizzled loads) "
+                                  "+ gram_finalize_kernel",
+                        "fp64_tile_kernel_ms": tile_ms, "speedup_vs_fp64_tile_kernel": tile_ms / gram_ms,
+                        "roofline": {"bound": "tensor", "achieved": ops / (gram_ms * 1e-3) / 1e12, "unit": "TOP/s",
+                                     "peak": 2 * tensor_peak, "frac": ops / (gram_ms * 1e-3) / 1e12 / (2 * tensor_peak),
+                                     "peak_source": "2 x the bf16 figure (int8 runs at twice the bf16 rate): " + tensor_src,
+                                     "ops": ops},
+                        "max_rel_err_vs_oracle_leading_block": rel_gram, "max_rel_diff_vs_fp64_tile_kernel": rel_tile,
+                        "tolerance": 1e-9, "parity_ok": bool(rel_gram <= 1e-9 and rel_tile <= 1e-9)}
+            del g_mat, g_out
+        del x8
+
     # ---- end to end through the public entry points, host buffers in, host matrix out
     e2e = None
     if n_e2e:
@@ -903,6 +978,7 @@ def bench_matrix(args, world, rank, local):
                          "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                          "flops_per_element_pair": 8, "peak_source": peak_src},
             "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
+            "euclidean_gram": gram_rec,
             "parity": parity,
             "parity_ok": bool(parity["max_rel_err_leading_block"] <= 1e-9 and
                               parity["max_rel_err_random_pairs"] <= 1e-9 and parity["symmetric"]),
@@ -931,6 +1007,9 @@ def main():
                          "(two windows per payload up to k = 12), 3 = one-window radix path")
     ap.add_argument("--pair-upt", type=int, default=1, choices=[1, 2],
                     help="pair path: 32-base units per thread and tile")
+    ap.add_argument("--fresh", type=int, default=1, choices=[0, 1],
+                    help="device step: 1 = the count call zeroes the table itself (inside the first kernel on "
+                         "the pair path), 0 = memset, then count")
     ap.add_argument("--pair-flush-every", type=int, default=0, help="pair path: tiles between slot flushes (0 = auto)")
     ap.add_argument("--pair-fused", type=int, default=1, choices=[0, 1],
                     help="pair path, pass 2: 1 = both roles in one launch, flushed with cp.reduce.async.bulk")
@@ -943,6 +1022,8 @@ def main():
                     help="count workload at N > 1: table sum over NVLink peer memory fused into the count, "
                          "as separate push/collect kernels, or with dist.reduce")
     ap.add_argument("--no-e2e", action="store_true", help="matrix workload: skip the host-buffer end-to-end leg")
+    ap.add_argument("--no-gram", action="store_true",
+                    help="matrix workload: skip the euclidean (tensor-core Gram form) measurement")
     ap.add_argument("--fasta-chunks", type=int, default=0, help="chunks of the pipelined FASTA upload (0 = auto)")
     ap.add_argument("--narrow-d2h", type=int, default=1, choices=[0, 1, 2],
                     help="e2e leg: 1 = the profile leaves the device as uint8 / uint16 (the narrowest that "

@@ -236,6 +236,15 @@ int kpal_dev_count_packed(const uint32_t *d_codes, const uint32_t *d_valid, uint
                           int k, void *d_table, int counter_bits, void *stream);
 
 /*
+ * The same for a table in ANY state: the call zeroes it first.  On the radix path for
+ * 9 <= k <= 12 the memset is folded into the first count kernel (every CTA zeroes its
+ * share with stores that drain while it works; REDs wait for all shares), which takes
+ * the 4 * 4^k byte memset off the step.
+ */
+int kpal_dev_count_packed_fresh(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_bases,
+                                int k, void *d_table, int counter_bits, void *stream);
+
+/*
  * Host FASTA bytes -> windows accumulated into a caller-owned DEVICE table
  * (Profile.from_fasta, kpal/klib.py:97-112, split for the multi-GPU driver:
  * every rank counts its shard of records, the tables are then summed with an
@@ -374,6 +383,30 @@ int kpal_dev_distance_unpack_tiles(const double *d_packed, const double *d_total
                                    uint64_t tile_begin, uint64_t tile_end, int diagonal,
                                    double *d_out, void *stream);
 
+/*
+ * Euclidean distance / cosine similarity (kpal/metrics.py:126-147, after the scale step of
+ * kpal/kdistlib.py:150-157) through an EXACT integer Gram matrix on the tensor cores
+ * (tcgen05.mma kind::i8, accumulators in tensor memory; csrc/distance_gram.cu).  Usable when
+ * every (balanced) count fits 8 bits: kpal_dev_gram_prepare raises d_flags[0] otherwise and
+ * the caller takes kpal_dev_distance_tiles.  The host entry points (kpal_distance_matrix,
+ * matrix sessions) do this by themselves unless kpal_set_option("gram", 0).
+ *   d_rows_u8  [n][kpal_gram_row_stride(k)] uint8 (zero padded rows)
+ *   d_totals   [n] exact sums of the counts, d_norms [n] exact sums of their squares
+ *   d_flags    [1] zeroed by the caller; bit 0 <- a count above 255
+ *   norm_max   max of d_norms (host value): one accumulation is exact below 2^31, else the
+ *              profile is accumulated in chunks of 32768 elements
+ *   d_gram     [n][n] int64 scratch, d_out [n][n] float64 symmetric result (diagonal included)
+ * Tolerance: the Gram matrix and the numerators are exact integers; the result carries the
+ * rounding of one conversion, one division and one square root (tests state 1e-9 relative,
+ * the same as for the fp64 form).
+ */
+uint64_t kpal_gram_row_stride(int k);
+int kpal_dev_gram_prepare(const int64_t *d_counts, uint64_t n, int k, int do_balance, uint8_t *d_rows_u8,
+                          uint64_t *d_totals, uint64_t *d_norms, uint32_t *d_flags, void *stream);
+int kpal_dev_gram_distances(const uint8_t *d_rows_u8, const uint64_t *d_totals, const uint64_t *d_norms,
+                            uint64_t norm_max, uint64_t n, int k, int metric, int do_scale, int down,
+                            int64_t *d_gram, double *d_out, void *stream);
+
 /* ------------------------------------------------ FASTA scan/pack: device API
  *
  * GPU version of kpal_fasta_scan + kpal_fasta_pack for whole-file counting
@@ -393,7 +426,8 @@ int kpal_dev_fasta_pack(const void *d_text, uint64_t n_bytes, uint32_t *d_codes,
 
 /* run-time switches: "host_fasta" (1 = kpal_count_fasta uses the C++ packer
  * instead of the GPU one), "exact_div" (1 = IEEE division in the distance
- * kernels instead of MUFU.RCP64H + Newton), "narrow_d2h" (profile copy of the
+ * kernels instead of MUFU.RCP64H + Newton), "gram" (0 = euclidean / cosine matrices
+ * always take the element-wise fp64 kernel), "narrow_d2h" (profile copy of the
  * host entry points: 1 = uint8 / uint16, 2 = uint16 only, 0 = int64),
  * "dma_share" (0..8 sixteenths of a narrow-copied profile that the copy engine
  * moves as int64 into a pinned destination; default 0), "fasta_chunks" (0 = auto

@@ -33,10 +33,11 @@ SYMBOLS = (
     "kpal_split_length", "kpal_split", "kpal_show_balance",
     "kpal_ipc_export", "kpal_ipc_open", "kpal_ipc_close", "kpal_peer_inbox_bytes",
     "kpal_dev_reduce_push", "kpal_dev_reduce_collect", "kpal_dev_count_packed_push",
-    "kpal_dev_count_packed", "kpal_count_fasta_to_dev", "kpal_dev_finalize_counts", "kpal_dev_table_to_host", "kpal_dev_balance",
+    "kpal_dev_count_packed", "kpal_dev_count_packed_fresh", "kpal_count_fasta_to_dev", "kpal_dev_finalize_counts", "kpal_dev_table_to_host", "kpal_dev_balance",
     "kpal_dev_count_by_record", "kpal_prepared_stride", "kpal_dev_profiles_prepare",
     "kpal_dev_order_by_total", "kpal_distance_num_tiles", "kpal_dev_distance_tiles",
     "kpal_distance_tile_elems", "kpal_dev_distance_tiles_packed", "kpal_dev_distance_unpack_tiles",
+    "kpal_gram_row_stride", "kpal_dev_gram_prepare", "kpal_dev_gram_distances",
     "kpal_fasta_scratch_bytes", "kpal_dev_fasta_pack", "kpal_set_option",
     "kpal_kernel_launches", "kpal_reset_kernel_launches",
 )
@@ -109,6 +110,7 @@ def load():
     sig("kpal_dev_count_packed_push", i32, vp, vp, u64, i32, vp, i32, i32, i32, c.POINTER(vp), vp,
         c.POINTER(i32))
     sig("kpal_dev_count_packed", i32, vp, vp, u64, i32, vp, i32, vp)
+    sig("kpal_dev_count_packed_fresh", i32, vp, vp, u64, i32, vp, i32, vp)
     sig("kpal_count_fasta_to_dev", i32, vp, u64, i32, vp, i32, vp, pu64)
     sig("kpal_dev_finalize_counts", i32, vp, i32, i32, i32, vp, vp)
     sig("kpal_dev_table_to_host", i32, vp, i32, i32, i32, vp, vp)
@@ -124,6 +126,9 @@ def load():
     sig("kpal_dev_distance_tiles_packed", i32, vp, vp, vp, vp, vp, vp, u64, i32, i32, i32, i32, i32,
         u64, u64, vp, vp)
     sig("kpal_dev_distance_unpack_tiles", i32, vp, vp, vp, vp, u64, i32, i32, i32, u64, u64, i32, vp, vp)
+    sig("kpal_gram_row_stride", u64, i32)
+    sig("kpal_dev_gram_prepare", i32, vp, u64, i32, i32, vp, vp, vp, vp, vp)
+    sig("kpal_dev_gram_distances", i32, vp, vp, vp, u64, u64, i32, i32, i32, i32, vp, vp, vp)
     sig("kpal_fasta_scratch_bytes", u64, u64)
     sig("kpal_dev_fasta_pack", i32, vp, u64, vp, vp, vp, vp)
     sig("kpal_set_option", i32, c.c_char_p, i32)

@@ -17,7 +17,7 @@
 namespace kpal {
 
 // launchers (count.cu / distance.cu)
-int launch_count(const uint32_t *, const uint32_t *, uint64_t, int, void *, int, cudaStream_t);
+int launch_count(const uint32_t *, const uint32_t *, uint64_t, int, void *, int, cudaStream_t, bool zero_table = false);
 int launch_finalize(const void *, int, int, int, int64_t *, cudaStream_t);
 int launch_finalize_narrow(const void *, int, int, int, uint16_t *, uint8_t *, int64_t *, uint64_t, unsigned int *,
                            cudaStream_t);
@@ -42,6 +42,13 @@ int launch_distance_unpack(const double *, const double *, const double *, const
                            int, uint64_t, uint64_t, int, double *, cudaStream_t);
 uint64_t distance_num_tiles(uint64_t n);
 uint64_t distance_tile_elems();
+// distance_gram.cu: euclidean / cosine through an exact integer Gram matrix on the tensor cores
+uint64_t gram_row_stride(int k);
+int launch_gram_prepare(const int64_t *, uint64_t, int, int, uint8_t *, unsigned long long *, unsigned long long *,
+                        unsigned int *, cudaStream_t);
+int launch_gram_norm_max(const unsigned long long *, uint64_t, unsigned long long *, cudaStream_t);
+int launch_gram_distances(const uint8_t *, const unsigned long long *, const unsigned long long *, unsigned long long,
+                          uint64_t, int, int, int, int, long long *, double *, cudaStream_t);
 uint64_t prepared_stride_host(int k);
 uint64_t fasta_scratch_bytes(uint64_t n_bytes);
 void set_exact_div(bool on);
@@ -77,6 +84,7 @@ static std::atomic<int> g_host_fasta{-1};       // -1: from the environment (KPA
 static std::atomic<int> g_fasta_split{0};         // 1: a large FASTA text is cut in two parts, the first counted while the second uploads (fasta_gpu_count; measured: no gain yet, so off)
 static std::atomic<int> g_fasta_chunks{0};      // 0 = automatic (one chunk per ~6 MB, at most 16), else 1 .. 32
 static std::atomic<int> g_dma_share{0};         // sixteenths of a narrow-copied profile the DMA engine moves as int64 (pinned destinations)
+static std::atomic<int> g_gram{1};              // 1: euclidean / cosine matrices take the tensor-core Gram form when the counts allow it
 static std::atomic<int> g_narrow_d2h{1};        // 1: large profiles leave the device as uint8 / uint16, 2: uint16 only (see finalize_to_host)
 
 void set_error(const char *fmt, ...)
@@ -341,6 +349,7 @@ extern "C" int kpal_set_option(const char *name, int value)
     }
     if (!strcmp(name, "fasta_split")) { g_fasta_split.store(value ? 1 : 0); return KPAL_OK; }
     if (!strcmp(name, "exact_div")) { set_exact_div(value != 0); return KPAL_OK; }
+    if (!strcmp(name, "gram")) { g_gram.store(value ? 1 : 0); return KPAL_OK; }
     if (!strcmp(name, "narrow_d2h")) {
         if (value < 0 || value > 2) return bad_arg("narrow_d2h must be 0 (int64), 1 (uint8 / uint16) or 2 (uint16)");
         g_narrow_d2h.store(value); return KPAL_OK;
@@ -404,6 +413,14 @@ extern "C" int kpal_dev_count_packed(const uint32_t *d_codes, const uint32_t *d_
 {
     if (!d_table || ((!d_codes || !d_valid) && n_bases)) return bad_arg("null device pointer");
     return launch_count(d_codes, d_valid, n_bases, k, d_table, counter_bits, (cudaStream_t)stream);
+}
+
+extern "C" int kpal_dev_count_packed_fresh(const uint32_t *d_codes, const uint32_t *d_valid,
+                                           uint64_t n_bases, int k, void *d_table, int counter_bits,
+                                           void *stream)
+{
+    if (!d_table || ((!d_codes || !d_valid) && n_bases)) return bad_arg("null device pointer");
+    return launch_count(d_codes, d_valid, n_bases, k, d_table, counter_bits, (cudaStream_t)stream, true);
 }
 
 extern "C" int kpal_dev_finalize_counts(const void *d_table, int counter_bits, int k, int balance,
@@ -1074,6 +1091,28 @@ extern "C" int kpal_dev_distance_unpack_tiles(const double *d_packed, const doub
                                   tile_begin, tile_end, diagonal, d_out, (cudaStream_t)stream);
 }
 
+// Euclidean / cosine through the exact integer Gram matrix (distance_gram.cu), device API.
+extern "C" uint64_t kpal_gram_row_stride(int k) { return (k < 1 || k > KPAL_MAX_K) ? 0 : gram_row_stride(k); }
+
+extern "C" int kpal_dev_gram_prepare(const int64_t *d_counts, uint64_t n, int k, int do_balance, uint8_t *d_rows_u8,
+                                     uint64_t *d_totals, uint64_t *d_norms, uint32_t *d_flags, void *stream)
+{
+    if (n && (!d_counts || !d_rows_u8 || !d_totals || !d_norms || !d_flags)) return bad_arg("null device pointer");
+    return launch_gram_prepare(d_counts, n, k, do_balance, d_rows_u8,
+                               reinterpret_cast<unsigned long long *>(d_totals),
+                               reinterpret_cast<unsigned long long *>(d_norms), d_flags, (cudaStream_t)stream);
+}
+
+extern "C" int kpal_dev_gram_distances(const uint8_t *d_rows_u8, const uint64_t *d_totals, const uint64_t *d_norms,
+                                       uint64_t norm_max, uint64_t n, int k, int metric, int do_scale, int down,
+                                       int64_t *d_gram, double *d_out, void *stream)
+{
+    if (!d_rows_u8 || !d_totals || !d_norms || !d_gram || !d_out) return bad_arg("null device pointer");
+    return launch_gram_distances(d_rows_u8, reinterpret_cast<const unsigned long long *>(d_totals),
+                                 reinterpret_cast<const unsigned long long *>(d_norms), norm_max, n, k, metric,
+                                 do_scale, down, reinterpret_cast<long long *>(d_gram), d_out, (cudaStream_t)stream);
+}
+
 // ----------------------------------------------------- distances: host API
 // A matrix session takes the profile set in slabs (kpal_matrix_push) so the caller never
 // has to hold all N x 4^k int64 counts in host memory the way kpal/kmer.py:694-698 does:
@@ -1087,6 +1126,9 @@ struct MatrixSession {
     bool need_r = false;
     int cur = 0;
     DevBuf F, R, bitmap, totals, norm2, order, tot_i64, slab[2], d_out, acc, cnt;   // acc / cnt: this session's accumulators
+    // euclidean / cosine with option "gram": u8 rows, exact totals / norms, range flags { flags, pad, norm_max }
+    bool gram = false;
+    DevBuf x8, g_totals, g_norms, g_flags, g_matrix;
     cudaStream_t copy = nullptr, compute = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr}, prepared[2] = {nullptr, nullptr};
     ~MatrixSession()
@@ -1115,6 +1157,15 @@ static int matrix_open(MatrixSession *s)
     KPAL_CHECK(s->norm2.alloc(n * 8));
     KPAL_CHECK(s->order.alloc(n * 4));
     KPAL_CHECK(s->d_out.alloc(n * n * 8));
+    s->gram = g_gram.load() != 0 && n > 12 &&
+              (s->metric == KPAL_METRIC_EUCLIDEAN || s->metric == KPAL_METRIC_COSINE);
+    if (s->gram) {
+        KPAL_CHECK(s->x8.alloc(n * gram_row_stride(s->k)));
+        KPAL_CHECK(s->g_totals.alloc(n * 8));
+        KPAL_CHECK(s->g_norms.alloc(n * 8));
+        KPAL_CHECK(s->g_flags.alloc(16));
+        KPAL_CUDA(cudaMemset(s->g_flags.p, 0, 16));
+    }
     // raw int64 profiles pass through two bounded slabs (<= 512 MiB each)
     s->slab_rows = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(n, 65535), (512ull << 20) / (s->d * 8)));
     for (int i = 0; i < 2; ++i) KPAL_CHECK(s->slab[i].alloc(s->slab_rows * s->d * 8));
@@ -1145,6 +1196,12 @@ static int matrix_push(MatrixSession *s, const int64_t *rows, uint64_t m)
                                   s->bitmap.as<uint32_t>() + at * (s->stride / 32),
                                   s->totals.as<double>() + at, s->norm2.as<double>() + at,
                                   s->tot_i64.as<unsigned long long>(), s->compute));
+        if (s->gram)
+            KPAL_CHECK(launch_gram_prepare(s->slab[b].as<int64_t>(), c, s->k, s->do_balance,
+                                           s->x8.as<uint8_t>() + at * gram_row_stride(s->k),
+                                           s->g_totals.as<unsigned long long>() + at,
+                                           s->g_norms.as<unsigned long long>() + at,
+                                           s->g_flags.as<unsigned int>(), s->compute));
         KPAL_CUDA(cudaEventRecord(s->prepared[b], s->compute));
         s->pushed += c;
         s->cur ^= 1;
@@ -1159,6 +1216,25 @@ static int matrix_finish(MatrixSession *s, double *out)
     if (s->pushed != s->n) return bad_arg("fewer profiles pushed than the session was opened for");
     const uint64_t n = s->n;
     cudaStream_t st = s->compute;
+    if (s->gram) {
+        // the Gram form is exact while every count fits 8 bits; the device says whether it does
+        struct { unsigned int flags, pad; unsigned long long norm_max; } h;
+        KPAL_CHECK(launch_gram_norm_max(s->g_norms.as<unsigned long long>(), n,
+                                        reinterpret_cast<unsigned long long *>(s->g_flags.as<unsigned char>() + 8), st));
+        KPAL_CUDA(cudaMemcpyAsync(&h, s->g_flags.p, 16, cudaMemcpyDeviceToHost, st));
+        KPAL_CUDA(cudaStreamSynchronize(st));
+        if (h.flags == 0) {
+            if (!s->g_matrix.p) KPAL_CHECK(s->g_matrix.alloc(n * n * 8));
+            KPAL_CHECK(launch_gram_distances(s->x8.as<uint8_t>(), s->g_totals.as<unsigned long long>(),
+                                             s->g_norms.as<unsigned long long>(), h.norm_max, n, s->k, s->metric,
+                                             s->do_scale, s->down, s->g_matrix.as<long long>(),
+                                             s->d_out.as<double>(), st));
+            KPAL_CUDA(cudaMemcpyAsync(out, s->d_out.p, n * n * 8, cudaMemcpyDeviceToHost, st));
+            KPAL_CUDA(cudaStreamSynchronize(st));
+            return KPAL_OK;
+        }
+        // a count above 255: the element-wise fp64 kernel below
+    }
     const int32_t *d_order = nullptr;
     if (s->do_scale) {
         KPAL_CHECK(make_order(s->totals.as<double>(), n, s->down, s->order.as<int32_t>(), st));

@@ -205,6 +205,19 @@ finalize_kernel(const CounterT *__restrict__ table, int k, int balance, const Ou
 // rows, transposed through shared memory and written once as int64 -- table
 // read once, profile written once (the plain kernel reads 4 scattered bytes
 // per 32-byte sector for the partner).
+// two neighbouring counts: one 16-byte store for the int64 profile
+__device__ __forceinline__ void put_count2(int64_t *__restrict__ out, uint64_t i, unsigned long long v0,
+                                           unsigned long long v1)
+{
+    *reinterpret_cast<ulonglong2 *>(out + i) = make_ulonglong2(v0, v1);
+}
+__device__ __forceinline__ void put_count2(const NarrowOut &out, uint64_t i, unsigned long long v0,
+                                           unsigned long long v1)
+{
+    put_count(out, i, v0);
+    put_count(out, i + 1, v1);
+}
+
 template <typename CounterT, typename OutT>
 __global__ void __launch_bounds__(256)
 finalize_balance_tiled_kernel(const CounterT *__restrict__ table, int k, const OutT out)
@@ -217,21 +230,47 @@ finalize_balance_tiled_kernel(const CounterT *__restrict__ table, int k, const O
     const uint32_t mr = mid_bits ? ((~rev2(m)) >> (32 - mid_bits)) : 0u;
     if (m > mr) return;                                         // done by the CTA of rc(m)
     const int hshift = 2 * k - 6;
-    for (uint32_t e = threadIdx.x; e < 4096; e += 256) {
-        const uint32_t h = e >> 6, l = e & 63u;
-        A[h * 65 + l] = table[(uint64_t(h) << hshift) | (uint64_t(m) << 6) | l];
-        if (m != mr) B[h * 65 + l] = table[(uint64_t(h) << hshift) | (uint64_t(mr) << 6) | l];
+    // Both tiles are read with 16-byte loads, ALL of them issued before the first use (8 per
+    // thread with 32-bit counters: 32 KB in flight per CTA) -- the first form of this kernel
+    // waited for one 4-byte load per loop trip and ran at a third of the HBM rate.
+    constexpr int V = 16 / int(sizeof(CounterT));               // counters per 16-byte vector
+    constexpr int NV = 4096 / V / 256;                          // vectors per thread and tile
+    uint4 va[NV], vb[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        const uint32_t v = threadIdx.x + 256u * q, h = v / (64 / V), l = (v % (64 / V)) * V;
+        va[q] = *reinterpret_cast<const uint4 *>(table + ((uint64_t(h) << hshift) | (uint64_t(m) << 6) | l));
+    }
+    if (m != mr) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const uint32_t v = threadIdx.x + 256u * q, h = v / (64 / V), l = (v % (64 / V)) * V;
+            vb[q] = *reinterpret_cast<const uint4 *>(table + ((uint64_t(h) << hshift) | (uint64_t(mr) << 6) | l));
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        const uint32_t v = threadIdx.x + 256u * q, h = v / (64 / V), l = (v % (64 / V)) * V;
+        const CounterT *ea = reinterpret_cast<const CounterT *>(&va[q]), *eb = reinterpret_cast<const CounterT *>(&vb[q]);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            A[h * 65 + l + j] = ea[j];
+            if (m != mr) B[h * 65 + l + j] = eb[j];
+        }
     }
     __syncthreads();
     const CounterT *partner = (m != mr) ? B : A;
-    for (uint32_t e = threadIdx.x; e < 4096; e += 256) {
-        const uint32_t h = e >> 6, l = e & 63u;
-        const uint32_t t = rc_index(l, 26) * 65 + rc_index(h, 26);
-        put_count(out, (uint64_t(h) << hshift) | (uint64_t(m) << 6) | l,
-                  (unsigned long long)(A[h * 65 + l]) + (unsigned long long)(partner[t]));
+    for (uint32_t e = threadIdx.x; e < 2048; e += 256) {        // two neighbouring counts per thread
+        const uint32_t h = e >> 5, l = (e & 31u) * 2;
+        const uint32_t rh = rc_index(h, 26);
+        const uint32_t t0 = rc_index(l, 26) * 65 + rh, t1 = rc_index(l + 1, 26) * 65 + rh;
+        put_count2(out, (uint64_t(h) << hshift) | (uint64_t(m) << 6) | l,
+                   (unsigned long long)(A[h * 65 + l]) + (unsigned long long)(partner[t0]),
+                   (unsigned long long)(A[h * 65 + l + 1]) + (unsigned long long)(partner[t1]));
         if (m != mr)
-            put_count(out, (uint64_t(h) << hshift) | (uint64_t(mr) << 6) | l,
-                      (unsigned long long)(B[h * 65 + l]) + (unsigned long long)(A[t]));
+            put_count2(out, (uint64_t(h) << hshift) | (uint64_t(mr) << 6) | l,
+                       (unsigned long long)(B[h * 65 + l]) + (unsigned long long)(A[t0]),
+                       (unsigned long long)(B[h * 65 + l + 1]) + (unsigned long long)(A[t1]));
     }
 }
 
@@ -418,7 +457,7 @@ int launch_count_radix(const uint32_t *, const uint32_t *, uint64_t, int, void *
 bool radix_peer_supported(int k, int world);
 // count_pairs.cu
 bool pairs_supported(int k);
-int launch_count_pairs(const uint32_t *, const uint32_t *, uint64_t, int, void *, int, cudaStream_t);
+int launch_count_pairs(const uint32_t *, const uint32_t *, uint64_t, int, void *, int, cudaStream_t, bool zero_table);
 // peer_reduce.cu
 int launch_reduce_push(const void *, int, int, int, int, void *const *, cudaStream_t);
 int peer_check_args(int k, int counter_bits, int rank, int world);
@@ -470,11 +509,17 @@ static int check_k(int k)
     return KPAL_OK;
 }
 
+// zero_table: the table is zeroed first -- inside the first count kernel on the pair path
+// (count_pairs.cu), with a memset otherwise -- instead of by the caller.
 int launch_count(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_bases, int k,
-                 void *d_table, int counter_bits, cudaStream_t stream)
+                 void *d_table, int counter_bits, cudaStream_t stream, bool zero_table)
 {
     KPAL_CHECK(check_k(k));
     if (counter_bits != 32 && counter_bits != 64) return bad_arg("counter_bits must be 32 or 64");
+    const bool pairs = n_bases > 0 && k > 7 && use_radix_path(k, n_bases) && pairs_supported(k) &&
+                       g_count_path.load() != 3 && !(counter_bits == 32 && n_bases >= (1ull << 32));
+    if (zero_table && !pairs)
+        KPAL_CUDA(cudaMemsetAsync(d_table, 0, (size_t(1) << (2 * k)) * size_t(counter_bits / 8), stream));
     if (n_bases == 0) return KPAL_OK;
     if (counter_bits == 32 && n_bases >= (1ull << 32)) {
         set_error("%llu bases would overflow 32-bit counters; use counter_bits=64",
@@ -505,8 +550,8 @@ int launch_count(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_ba
         }
         KPAL_LAUNCH_CHECK("count_smem_kernel");
     } else if (use_radix_path(k, n_bases)) {
-        if (pairs_supported(k) && g_count_path.load() != 3)
-            return launch_count_pairs(d_codes, d_valid, n_bases, k, d_table, counter_bits, stream);
+        if (pairs)
+            return launch_count_pairs(d_codes, d_valid, n_bases, k, d_table, counter_bits, stream, zero_table);
         return launch_count_radix(d_codes, d_valid, n_bases, k, d_table, counter_bits, stream);
     } else {
         uint64_t want = (n_chunks + 255) / 256;
@@ -666,7 +711,7 @@ int launch_count_push(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t
         for (int i = 0; i < world; ++i) if (!peer.inbox[i]) return bad_arg("null inbox pointer");
         return launch_count_radix(d_codes, d_valid, n_bases, k, d_table, counter_bits, stream, &peer);
     }
-    KPAL_CHECK(launch_count(d_codes, d_valid, n_bases, k, d_table, counter_bits, stream));
+    KPAL_CHECK(launch_count(d_codes, d_valid, n_bases, k, d_table, counter_bits, stream, false));
     return launch_reduce_push(d_table, counter_bits, k, rank, world, inbox_ptrs, stream);
 }
 

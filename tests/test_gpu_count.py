@@ -189,6 +189,38 @@ def test_by_record_many_records():
         np.insert(reads, 1000, ord("\n"), axis=1).tobytes(), k).sum())
 
 
+def test_by_record_20k_records_every_row():
+    """BASELINE configs[2] at a fifth of its size: 20 000 records of 300 - 1200 bp at k = 8
+    through Profile.from_fasta_by_record (80 device batches); EVERY row is compared with the
+    oracle, names included."""
+    k = 8
+    rng = np.random.default_rng(20)
+    lengths = rng.integers(300, 1201, 20_000)
+    letters = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)
+    parts, seqs = [], []
+    for i, n in enumerate(lengths):
+        seq = letters[rng.choice(9, n, p=[.24, .24, .24, .24, .01, .01, .005, .005, .01])]
+        seqs.append(seq)
+        parts.append(b">rec%05d extra words\n" % i)
+        parts.append(seq.tobytes())
+        parts.append(b"\n")
+    lut = np.full(256, -1, dtype=np.int64)
+    for c, v in zip(b"ACGTacgt", (0, 1, 2, 3, 0, 1, 2, 3)):
+        lut[c] = v
+    n_seen = 0
+    for i, profile in enumerate(klib.Profile.from_fasta_by_record(io.BytesIO(b"".join(parts)), k)):
+        assert profile.name == "rec%05d" % i
+        codes = lut[seqs[i]]
+        ok = np.convolve((codes >= 0).astype(np.int64), np.ones(k, dtype=np.int64), "valid") == k
+        index = np.zeros(len(codes) - k + 1, dtype=np.int64)
+        for j in range(k):
+            index = index * 4 + np.maximum(codes[j:len(codes) - k + 1 + j], 0)
+        want = np.bincount(index[ok], minlength=4 ** k)          # klib.py:160-168, vectorised
+        assert np.array_equal(profile.counts, want), i
+        n_seen += 1
+    assert n_seen == 20_000
+
+
 def test_by_record_balance_and_long_records():
     rng = random.Random(9)
     seqs = ["".join(rng.choice("ACGTN") for _ in range(n)) for n in (0, 5, 64, 65, 100_000, 3, 12_345)]
@@ -500,6 +532,36 @@ def test_pair_count_path_bit_exact(k, n, letters, p_n):
         _set_option("pair_upt", 1)
         _set_option("pair_flush_every", 0)
         _set_option("pair_fused", 1)
+
+
+@pytest.mark.parametrize("k,n", [(12, 30_000_000), (12, 3_000), (10, 20_000_000), (6, 100_000), (13, 9_000_000)])
+def test_count_packed_fresh_zeroes_the_table(k, n):
+    """kpal_dev_count_packed_fresh on a table full of garbage: the pair path zeroes it inside
+    its first kernel (CTAs zero their shares while they bin; the windows that go to the table
+    directly are parked until every share is done), the other paths with a memset.  Repeated
+    calls reuse the arrival counter."""
+    L = _cabi.load()
+    text = _composition_bytes(k + n, n, "ACGTacgt", p_n=0.01)
+    want = c_oracle.count_bytes(text, k, threads=c_oracle.max_threads())
+    codes, valid, _, n_bases = _cabi.pack_sequences(bytes(text).split(b"\n"))
+    bins = 4 ** k
+    d_codes, d_valid = L.kpal_dev_alloc(codes.nbytes), L.kpal_dev_alloc(valid.nbytes)
+    d_table, d_counts = L.kpal_dev_alloc(bins * 4), L.kpal_dev_alloc(bins * 8)
+    try:
+        _cabi.check(L.kpal_memcpy_h2d(d_codes, _cabi.ptr(codes), codes.nbytes, None))
+        _cabi.check(L.kpal_memcpy_h2d(d_valid, _cabi.ptr(valid), valid.nbytes, None))
+        garbage = np.full(bins, 0xdeadbeef, dtype=np.uint32)
+        for round_ in range(3):
+            _cabi.check(L.kpal_memcpy_h2d(d_table, _cabi.ptr(garbage), garbage.nbytes, None))
+            _cabi.check(L.kpal_dev_count_packed_fresh(d_codes, d_valid, n_bases, k, d_table, 32, None))
+            _cabi.check(L.kpal_dev_finalize_counts(d_table, 32, k, 0, d_counts, None))
+            out = np.empty(bins, dtype=np.int64)
+            _cabi.check(L.kpal_memcpy_d2h(_cabi.ptr(out), d_counts, out.nbytes, None))
+            _cabi.check(L.kpal_stream_sync(None))
+            assert np.array_equal(out, want), round_
+    finally:
+        for ptr in (d_codes, d_valid, d_table, d_counts):
+            L.kpal_dev_free(ptr)
 
 
 def test_pair_count_path_reads():

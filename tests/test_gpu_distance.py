@@ -199,6 +199,152 @@ def test_matrix_256_k9_sampled_pairs():
     assert not np.diag(got).any()
 
 
+def test_matrix_600_k10_many_tiles_and_slices():
+    """The BASELINE length (k = 10: 16 slices of 65536 elements per tile) with 600 profiles:
+    5 tile rows x 10 tile columns, ragged last tiles, 18 000 sampled pairs of 190 profiles
+    spread over every tile row and column, against the C oracle."""
+    n, k = 600, 10
+    rng = np.random.default_rng(10)
+    highs = rng.integers(2, 18, n)
+    profiles = np.empty((n, 4 ** k), dtype=np.int64)
+    for i in range(n):
+        profiles[i] = rng.integers(0, highs[i], 4 ** k, dtype=np.int64)
+    profiles[17, ::3] = 0                        # more zeros: the union counts differ from 4^k
+    profiles[411] *= 1000
+    got = _cabi.distance_matrix(profiles, do_scale=True)
+    assert np.array_equal(got, got.T) and not np.diag(got).any()
+    pick = np.sort(rng.choice(n, 190, replace=False))
+    pick[:4] = [0, 17, 127, 128]
+    pick[-3:] = [411, 598, 599]
+    pick = np.unique(pick)
+    want = c_oracle.distance_matrix(profiles[pick], do_scale=True, threads=c_oracle.max_threads())
+    low = np.tril_indices(len(pick), -1)
+    sub = got[np.ix_(pick, pick)]
+    rel = np.abs(sub[low] - want[low]) / np.abs(want[low])
+    assert rel.max() <= RTOL, (rel.max(), len(low[0]))
+    # the other fast-path metrics on the same set, a handful of pairs each
+    for options in (dict(pairwise="sum", do_scale=True, down=True), dict(metric="euclidean", do_scale=True),
+                    dict(metric="cosine"), dict(do_balance=True)):
+        got = _cabi.distance_matrix(profiles[:200], **options)
+        for i, j in ((1, 0), (199, 3), (128, 127), (77, 64), (150, 149)):
+            want_ij = c_oracle.distance(profiles[i], profiles[j], **options)
+            assert got[i, j] == pytest.approx(want_ij, rel=RTOL), (options, i, j)
+
+
+def test_concurrent_matrices_do_not_share_accumulators():
+    """Two host threads computing distance matrices on one device at the same time (ctypes
+    drops the GIL): every call owns its accumulators, so both get the sequential results."""
+    import threading
+    sets = [synthetic_profiles(seed, 150, 7) for seed in (1, 2, 3, 4)]
+    want = [_cabi.distance_matrix(p, do_scale=True) for p in sets]
+    results = [None] * len(sets)
+
+    def work(i):
+        for _ in range(3):
+            results[i] = _cabi.distance_matrix(sets[i], do_scale=True)
+            assert np.array_equal(results[i], want[i])
+            pair = _cabi.pair_distance(sets[i][0], sets[i][1], do_scale=True)
+            assert pair == pytest.approx(want[i][1, 0], rel=1e-12)      # another kernel: other summation order
+    errors = []
+
+    def guarded(i):
+        try:
+            work(i)
+        except Exception as exc:            # surfaces in the main thread
+            errors.append((i, exc))
+    threads = [threading.Thread(target=guarded, args=(i,)) for i in range(len(sets))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
+# ------------------------------------------- tensor-core Gram form (distance_gram.cu)
+def _gram_option(value):
+    _cabi.check(_cabi.load().kpal_set_option(b"gram", int(value)))
+
+
+#: tolerance of the Gram form for euclidean / cosine: the Gram matrix and the numerators are
+#: exact integers (tcgen05 kind::i8 into 32-bit accumulators, 128-bit numerators); what is left
+#: is one int -> double conversion, one division and one square root
+GRAM_RTOL = 1e-9
+
+
+@pytest.mark.parametrize("n,k,lam_hi", [(13, 4, 6.0), (129, 5, 8.0), (300, 7, 8.0), (257, 8, 3.0), (40, 9, 20.0)])
+def test_gram_euclidean_cosine_vs_oracle(n, k, lam_hi):
+    """Euclidean distance and cosine similarity matrices through the exact integer Gram matrix
+    on the tensor cores: every scale / down / balance combination against the C oracle, ragged
+    tile edges (n not a multiple of 128 / 256), one to 2048 K blocks, several K ranges per tile."""
+    profiles = synthetic_profiles(n * 31 + k, n, k, lam_hi=lam_hi)
+    assert profiles.max() <= 255
+    low = np.tril_indices(n, -1)
+    try:
+        for metric in ("euclidean", "cosine"):
+            for opts in (dict(), dict(do_scale=True), dict(do_scale=True, down=True), dict(do_balance=True),
+                         dict(do_balance=True, do_scale=True)):
+                if 2 * profiles.max() > 255 and opts.get("do_balance"):
+                    continue
+                _gram_option(1)
+                got = _cabi.distance_matrix(profiles, metric=metric, **opts)
+                want = c_oracle.distance_matrix(profiles, metric=metric, threads=c_oracle.max_threads(), **opts)
+                rel = np.abs(got[low] - want[low]) / np.maximum(np.abs(want[low]), 1e-300)
+                assert rel.max() <= GRAM_RTOL, (metric, opts, rel.max())
+                assert np.array_equal(got, got.T)
+                _gram_option(0)                      # the element-wise fp64 kernel agrees with it
+                plain = _cabi.distance_matrix(profiles, metric=metric, **opts)
+                assert np.allclose(plain[low], got[low], rtol=1e-9, atol=0), (metric, opts)
+                if metric == "euclidean":
+                    assert not np.diag(got).any()
+                else:
+                    assert np.allclose(np.diag(got), 1.0, rtol=1e-15)
+    finally:
+        _gram_option(1)
+
+
+def test_gram_identical_and_zero_profiles_and_fallback():
+    """Exactness shows where floating point cancels: identical profiles are at distance exactly 0
+    (scaled: proportional profiles too), an all-zero profile gives the reference's nan; counts
+    above 255 leave the 8-bit form and take the fp64 kernel, with the same results."""
+    rng = np.random.default_rng(8)
+    n, k = 64, 6
+    profiles = rng.poisson(3.0, (n, 4 ** k)).astype(np.int64)
+    profiles[5] = profiles[9]
+    profiles[11] = 3 * profiles[9]                   # proportional: scaled euclidean distance 0
+    profiles[20] = 0
+    got = _cabi.distance_matrix(profiles, metric="euclidean")
+    assert got[5, 9] == 0.0 and got[9, 5] == 0.0
+    scaled = _cabi.distance_matrix(profiles, metric="euclidean", do_scale=True)
+    assert scaled[11, 9] == 0.0 and scaled[5, 11] == 0.0
+    assert np.isnan(scaled[20, 3]) and np.isnan(scaled[3, 20]) and np.isnan(scaled[20, 20])
+    cos = _cabi.distance_matrix(profiles, metric="cosine")
+    assert np.isnan(cos[20, 3]) and cos[5, 9] == pytest.approx(1.0, rel=1e-15)
+    assert got[20, 3] == pytest.approx(np.sqrt(float((profiles[3] ** 2).sum())), rel=1e-15)
+    big = profiles.copy()
+    big[33, 17] = 70_000                              # no longer 8-bit: fp64 tile kernel
+    want = c_oracle.distance_matrix(big, metric="euclidean", do_scale=True, threads=c_oracle.max_threads())
+    fallback = _cabi.distance_matrix(big, metric="euclidean", do_scale=True)
+    low = np.tril_indices(n, -1)
+    ok = ~np.isnan(want[low])
+    assert np.allclose(fallback[low][ok], want[low][ok], rtol=RTOL, atol=0)
+    assert np.array_equal(np.isnan(fallback[low]), np.isnan(want[low]))
+
+
+def test_gram_accumulation_chunks():
+    """Norms of 2^31 and more: one 32-bit accumulation over the whole profile could overflow, so
+    the profile is accumulated in chunks of 32768 elements added in 64-bit integers."""
+    rng = np.random.default_rng(9)
+    n, k = 20, 9
+    profiles = rng.integers(200, 256, (n, 4 ** k)).astype(np.int64)     # norms ~ 1.4e10 >> 2^31
+    profiles[:, ::5] = 0
+    got = _cabi.distance_matrix(profiles, metric="euclidean", do_scale=True)
+    cos = _cabi.distance_matrix(profiles, metric="cosine")
+    for i, j in ((1, 0), (19, 3), (10, 9)):
+        assert got[i, j] == pytest.approx(c_oracle.distance(profiles[i], profiles[j], metric="euclidean", do_scale=True),
+                                          rel=GRAM_RTOL)
+        assert cos[i, j] == pytest.approx(c_oracle.distance(profiles[i], profiles[j], metric="cosine"), rel=GRAM_RTOL)
+
+
 def test_host_path_options_still_work(golden):
     """do_positive / do_smooth / custom pairwise stay on the host pipeline."""
     left = klib.Profile(ko.count_sequences(golden["fixtures"]["LENGTH_60"], 4))
