@@ -435,12 +435,33 @@ def bench_count(args, world, rank, local):
     sp = ctypes.c_void_p(stream.cuda_stream)
 
     reducer = None
+    slicer, shared, d_slice = None, None, None
     reduce_note = None
     if args.reduce == "auto":
-        # measured (profiles/README.md): at 2 GPUs the table sum fused into the count's histogram
-        # pass is on par with / ahead of the NCCL reduce, at 4 GPUs the peer stores slow pass 2
-        # down and NCCL wins.  The fused form rides on the one-window radix path (k >= 13 here).
-        args.reduce = "fused" if (world == 2 and k >= 13) else "nccl"
+        # balance + narrow reduce-scatter + distributed finalize over NVLink peer memory
+        # (multigpu.SliceReducer) whenever the step balances; else the NCCL reduce
+        args.reduce = "slices" if (balance and k >= 6) else "nccl"
+    if world > 1 and args.reduce == "slices":
+        from kpal_b200 import multigpu
+        peer_ok = torch.ones(1, dtype=torch.int32, device=dev)
+        for a in range(world):
+            if a != local and not torch.cuda.can_device_access_peer(local, a):
+                peer_ok.zero_()
+        dist.all_reduce(peer_ok, op=dist.ReduceOp.MIN)
+        if int(peer_ok.item()):
+            try:
+                slicer = multigpu.SliceReducer(k)
+            except Exception as exc:        # all ranks fail together (collective decision inside)
+                slicer = None
+                reduce_note = "sliced peer reduce unavailable (%s): NCCL reduce used" % (exc,)
+        else:
+            reduce_note = "no peer access between all GPU pairs: NCCL reduce used"
+        if slicer is not None:
+            shared = multigpu.SharedProfile(k)
+            sb, se = slicer.slice_range()
+            d_slice = torch.zeros(max(se - sb, 1), dtype=torch.int64, device=dev)
+        else:
+            args.reduce = "nccl"
     if world > 1 and args.reduce in ("peer", "fused"):
         from kpal_b200 import multigpu
         # CUDA IPC between the ranks can be refused by the box (container without a shared
@@ -484,6 +505,15 @@ def bench_count(args, world, rank, local):
     def device_step(ev=None):
         if ev:
             ev[0].record(stream)
+        if slicer is not None:
+            # count, then balance + narrow push into the owners' inboxes, then this rank's slice
+            _cabi.check(L.kpal_dev_count_packed_fresh(d_codes.data_ptr(), d_valid.data_ptr(), n_bases, k,
+                                                      d_table.data_ptr(), 32, sp))
+            if ev:
+                ev[1].record(stream)
+            slicer.push(d_table.data_ptr(), 32, sp)
+            slicer.collect(d_slice.data_ptr(), sp)
+            return
         if reducer is not None and args.reduce == "fused":
             d_table.zero_()
             # count + all-to-all in one call: pass 2 of the radix count stores into the inboxes
@@ -494,8 +524,7 @@ def bench_count(args, world, rank, local):
             if rank == 0:
                 _cabi.check(L.kpal_dev_finalize_counts(summed, 32, k, balance, d_counts.data_ptr(), sp))
             return
-        # the table is zeroed by the call: inside the first count kernel on the pair path (its
-        # CTAs zero their shares while they bin), with a memset before the kernels otherwise
+        # the table is zeroed by the call (a memset on the stream, inside the timed step)
         if args.fresh:
             _cabi.check(L.kpal_dev_count_packed_fresh(d_codes.data_ptr(), d_valid.data_ptr(), n_bases, k,
                                                       d_table.data_ptr(), 32, sp))
@@ -510,6 +539,12 @@ def bench_count(args, world, rank, local):
     def e2e_step():
         if world == 1:
             _cabi.check(L.kpal_count_fasta(pinned_fasta._ptr, n_fasta, k, balance, pinned_out._ptr))
+        elif slicer is not None:
+            table, bits = ctypes.c_void_p(), ctypes.c_int()
+            _cabi.check(L.kpal_count_fasta_dev_table(pinned_fasta._ptr, n_fasta, k, ctypes.byref(table),
+                                                     ctypes.byref(bits), sp))
+            slicer.push(table, bits.value, sp)
+            slicer.collect_to_host(shared.array[sb:se], sp)      # this rank's slice, into shared host memory
         else:
             d_table.zero_()
             nb = ctypes.c_uint64()
@@ -565,6 +600,17 @@ def bench_count(args, world, rank, local):
     # their seeds; untimed).  At N > 1 the sum of the per-rank tables taken with a plain NCCL
     # reduce is checked as well.
     result_ok, cpu, parity = None, None, None
+    gathered = None
+    if world > 1 and slicer is not None:
+        device_step()
+        cap = max(slicer.slice_range(r)[1] - slicer.slice_range(r)[0] for r in range(world))
+        mine = torch.zeros(cap, dtype=torch.int64, device=dev)
+        mine[:se - sb].copy_(d_slice[:se - sb])
+        parts = [torch.zeros(cap, dtype=torch.int64, device=dev) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, parts, dst=0)
+        if rank == 0:
+            gathered = torch.cat([parts[r][:slicer.slice_range(r)[1] - slicer.slice_range(r)[0]]
+                                  for r in range(world)]).cpu().numpy()
     if world > 1:
         device_step()                       # the result under test: rank 0's d_counts / pinned_out
         check = d_table.clone()
@@ -592,8 +638,8 @@ def bench_count(args, world, rank, local):
             want = c_oracle.balance(want)
         if n_windows is None:
             n_windows = int(want.sum()) // (2 if balance else 1) // world
-        dev_ok = bool(np.array_equal(d_counts.cpu().numpy(), want))
-        host_ok = bool(np.array_equal(pinned_out.array, want))
+        dev_ok = bool(np.array_equal(gathered if gathered is not None else d_counts.cpu().numpy(), want))
+        host_ok = bool(np.array_equal(shared.array if shared is not None else pinned_out.array, want))
         parity = {"checked_against": "C port of klib.py:149-170 + 285-298 on the concatenation of all %d shard(s)" % world,
                   "device_result_equals_oracle": dev_ok, "host_result_equals_oracle": host_ok,
                   "total_windows": int(want.sum()) // (2 if balance else 1)}
@@ -602,7 +648,8 @@ def bench_count(args, world, rank, local):
             want_dev = torch.empty_like(d_counts)
             _cabi.check(L.kpal_dev_finalize_counts(check.data_ptr(), 32, k, balance, want_dev.data_ptr(), sp))
             torch.cuda.synchronize()
-            parity["device_result_equals_nccl_sum"] = bool(torch.equal(want_dev, d_counts))
+            parity["device_result_equals_nccl_sum"] = bool(
+                np.array_equal(want_dev.cpu().numpy(), gathered) if gathered is not None else torch.equal(want_dev, d_counts))
             result_ok = result_ok and parity["device_result_equals_nccl_sum"]
         else:
             cpu = {"value": seq_bases / 1e9 / cpu_s, "unit": "Gbases/s", "cores": threads, "kind": "port",
@@ -626,13 +673,24 @@ def bench_count(args, world, rank, local):
         # -- for the bins below the split; the last dma_share/16 of the (pinned) profile is
         # copied as int64 by the DMA engine
         split = bins // 16 * (16 - args.dma_share)
-        top = int(pinned_out.array[:split].max())
-        narrow_width = 8 if (not narrow or top > 65535) else (1 if (args.narrow_d2h == 1 and top <= 255) else 2)
-        d2h_bytes = bins * 8 if narrow_width == 8 else split * narrow_width + (bins - split) * 8 + 8
+        host_result = (shared.array if shared is not None else pinned_out.array)[:split]
+        n_over8, n_over16 = int((host_result > 255).sum()), int((host_result > 65535).sum())
+        cap8, cap16 = max(4096, bins // 32), max(4096, bins // 256)       # side lists (cabi.cu finalize_to_host)
+        listed = 0
+        if not narrow:
+            narrow_width = 8
+        elif args.narrow_d2h == 1 and n_over8 <= cap8:
+            narrow_width, listed = 1, n_over8
+        elif n_over16 <= cap16:
+            narrow_width, listed = 2, n_over16
+        else:
+            narrow_width = 8
+        d2h_bytes = (bins * 8 if narrow_width == 8 else
+                     split * narrow_width + (bins - split) * 8 + 16 + listed * 16)
         kernels = (["pair_partition_kernel", "pair_histogram_kernel"] if pairs else
                    ["radix_partition_kernel", "radix_histogram_kernel"] if radix else
                    ["count_smem_kernel" if k <= 7 else "count_global_kernel"])
-        step_kernels = ([] if pairs else ["memset(table)"]) + kernels + [
+        step_kernels = ["memset(table)"] + kernels + [
             "finalize_balance_tiled_kernel" if (balance and k >= 6) else "finalize_kernel"]
         traffic, traffic_src = None, None
         if args.config == 2 and k == K_COUNT and args.composition == "uniform":
@@ -648,9 +706,13 @@ def bench_count(args, world, rank, local):
             "vs_baseline": None, "dtype": "u32 counters -> int64", "data": "synthetic",
             "config": {"workload": workload,
                        "k": k, "bases_per_gpu": int(seq_bases), "packed_bases_per_gpu": int(n_bases),
-                       "l2": "512 MB memset between steps (untimed); zeroing the table is inside the step "
-                             "(folded into the first count kernel on the pair path)",
-                       "parallelism": ("records sharded per GPU, u32 tables summed onto rank 0 " +
+                       "l2": "512 MB memset between steps (untimed); the table memset is inside the step",
+                       "parallelism": ("records sharded per GPU; every rank balances its table and stores it, 1 byte per "
+                                       "bin, into the slice owners' inboxes over NVLink peer memory; every rank sums "
+                                       "the rows it received into its int64 slice of the profile (result sharded by "
+                                       "slice over the GPUs; e2e: the slices meet in shared host memory)"
+                                       if slicer is not None else
+                                       "records sharded per GPU, u32 tables summed onto rank 0 " +
                                        ("over NVLink peer memory (all-to-all fused into the count's histogram pass + collect kernel)"
                                         if (reducer is not None and args.reduce == "fused") else
                                         "over NVLink peer memory (all-to-all push + collect kernels)"
@@ -663,9 +725,13 @@ def bench_count(args, world, rank, local):
                     "ms_per_step": e2e_s * 1e3,
                     "path": ("pinned FASTA bytes -> kpal_count_fasta (H2D of the raw text in chunks, GPU scan/pack, "
                              "count + balance kernels, " if world == 1 else
+                             "per rank: pinned FASTA bytes -> kpal_count_fasta_dev_table (H2D in chunks, GPU scan/pack, "
+                             "count), kpal_dev_slice_push, kpal_dev_slice_collect_to_host (this rank's slice: "
+                             if slicer is not None else
                              "per rank: pinned FASTA bytes -> kpal_count_fasta_to_dev (H2D in chunks, GPU scan/pack, "
                              "count); table sum onto rank 0; there kpal_dev_table_to_host (widen + balance, ") +
-                            (("D2H as uint%d in chunks, widened to the int64 profile by host threads)" % (8 * narrow_width)
+                            (("D2H as uint%d in chunks%s, widened to the int64 profile by host threads)" % (
+                                8 * narrow_width, " + a side list of the %d larger counts" % listed if listed else "")
                               if args.dma_share == 0 else
                               "D2H of the first %d/16 of the profile as uint%d in chunks, widened to int64 by host "
                               "threads, the rest as int64 by the copy engine meanwhile)" % (16 - args.dma_share, 8 * narrow_width))
@@ -686,6 +752,10 @@ def bench_count(args, world, rank, local):
         }
     if reducer is not None:
         reducer.close()
+    if shared is not None:
+        shared.close()
+    if slicer is not None:
+        slicer.close()
     del d_codes, d_valid, d_table, d_counts, flush
     torch.cuda.empty_cache()
     return out
@@ -1018,9 +1088,10 @@ def main():
                     help="buckets binned per pass-1 launch of the radix count (0 = library default)")
     ap.add_argument("--radix-debug", type=int, default=0, help="timing experiments (results are wrong)")
     ap.add_argument("--radix-shape", type=int, default=0)
-    ap.add_argument("--reduce", default="auto", choices=["auto", "fused", "peer", "nccl"],
-                    help="count workload at N > 1: table sum over NVLink peer memory fused into the count, "
-                         "as separate push/collect kernels, or with dist.reduce")
+    ap.add_argument("--reduce", default="auto", choices=["auto", "slices", "fused", "peer", "nccl"],
+                    help="count workload at N > 1: slices (default) = balance + narrow reduce-scatter + distributed "
+                         "finalize over NVLink peer memory; fused / peer = u32 table all-to-all onto rank 0 (fused "
+                         "into the one-window radix count / as push + collect kernels); nccl = dist.reduce")
     ap.add_argument("--no-e2e", action="store_true", help="matrix workload: skip the host-buffer end-to-end leg")
     ap.add_argument("--no-gram", action="store_true",
                     help="matrix workload: skip the euclidean (tensor-core Gram form) measurement")

@@ -68,6 +68,7 @@ void       *kpal_dev_alloc(size_t bytes);
 void        kpal_dev_free(void *p);
 int         kpal_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, void *stream);
 int         kpal_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes, void *stream);
+int         kpal_dev_memset(void *dst_dev, int value, size_t bytes, void *stream);
 int         kpal_stream_sync(void *stream);
 
 /* ------------------------------------------------- packed sequence format
@@ -190,6 +191,23 @@ int kpal_format_matrix(const double *values, uint64_t n, uint64_t ld, int precis
 int kpal_widen_u16(const uint16_t *narrow, uint64_t n, uint64_t chunk, int64_t *counts_out);
 int kpal_widen_u8(const uint8_t *narrow, uint64_t n, uint64_t chunk, int64_t *counts_out);
 
+/*
+ * Host stages of writing many per-record profiles (Profile.save, kpal/klib.py:227-256, called
+ * once per record by kpal count --by-record, kpal/kmer.py:137-146); host only, multi-threaded.
+ * kpal_row_stats: stats_out[r][0..4] = total, non_zero, mean, median, std of row r
+ * (kpal/klib.py:192-225), bit-identical to the NumPy calls of the reference (same operations
+ * in the same order, NumPy's pairwise summation included).  kpal_deflate_chunks: chunk c of
+ * `data` (chunk_bytes each) -> a zlib stream of sizes[c] bytes at out + c * slot_bytes
+ * (slot_bytes >= kpal_deflate_bound(chunk_bytes)): what the HDF5 deflate filter stores.
+ */
+int      kpal_row_stats(const int64_t *rows, uint64_t n_rows, uint64_t n_cols, double *stats_out);
+uint64_t kpal_deflate_bound(uint64_t chunk_bytes);
+int      kpal_deflate_chunks(const void *data, uint64_t n_chunks, uint64_t chunk_bytes, int level,
+                             void *out, uint64_t slot_bytes, uint32_t *sizes);
+/* the streams packed back to back into out (NULL: only their total size, which is returned) */
+uint64_t kpal_compact_slots(const void *slots, uint64_t slot_bytes, const uint32_t *sizes,
+                            uint64_t n_chunks, void *out);
+
 /* ProfileDistance.distance for one pair (kpal/kdistlib.py:126-161). */
 int kpal_pair_distance(const int64_t *left, const int64_t *right, int k,
                        int metric, int pairwise, int do_balance, int do_scale, int down,
@@ -235,12 +253,7 @@ int kpal_show_balance(const int64_t *counts, int k, double *out);
 int kpal_dev_count_packed(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_bases,
                           int k, void *d_table, int counter_bits, void *stream);
 
-/*
- * The same for a table in ANY state: the call zeroes it first.  On the radix path for
- * 9 <= k <= 12 the memset is folded into the first count kernel (every CTA zeroes its
- * share with stores that drain while it works; REDs wait for all shares), which takes
- * the 4 * 4^k byte memset off the step.
- */
+/* The same for a table in ANY state: the call zeroes it first (a memset on the stream). */
 int kpal_dev_count_packed_fresh(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_bases,
                                 int k, void *d_table, int counter_bits, void *stream);
 
@@ -252,6 +265,14 @@ int kpal_dev_count_packed_fresh(const uint32_t *d_codes, const uint32_t *d_valid
  */
 int kpal_count_fasta_to_dev(const char *fasta, uint64_t n_bytes, int k, void *d_table,
                             int counter_bits, void *stream, uint64_t *n_bases_out);
+
+/*
+ * The same count into the library's own table (no copy into a caller-owned one): *d_table_out
+ * stays valid until the next host-level counting call on this device.  For the multi-GPU
+ * driver, which hands the table to kpal_dev_slice_push.  Synchronises `stream`.
+ */
+int kpal_count_fasta_dev_table(const char *fasta, uint64_t n_bytes, int k, void **d_table_out,
+                               int *counter_bits_out, void *stream);
 
 /* table (u32/u64) -> int64 counts, optionally fused with balance
  * (out[i] = t[i] + t[rc(i)], kpal/klib.py:290-298). */
@@ -315,6 +336,33 @@ int      kpal_dev_count_packed_push(const uint32_t *d_codes, const uint32_t *d_v
                                     uint64_t n_bases, int k, void *d_table, int counter_bits,
                                     int rank, int world, void *const *inbox_ptrs, void *stream,
                                     int *fused_out);
+
+/*
+ * The fused form of the multi-GPU table sum (csrc/peer_reduce.cu): balance is linear
+ * (kpal/klib.py:285-298), so every rank balances ITS table and sends the result narrow --
+ *   kpal_dev_slice_push     balanced counts of the local table, as 1 byte per bin, straight into
+ *                           the inbox of the rank that owns the bin's slice (u32 rows as well when
+ *                           a count exceeds 255), then one release store per peer ("epoch landed");
+ *   kpal_dev_slice_collect  on every rank: waits for the world's signals in its own inbox, sums
+ *                           the senders' rows and writes the int64 slice
+ *                           [kpal_slice_begin(k, rank, world), kpal_slice_begin(k, rank + 1, world))
+ *                           of the final balanced profile;
+ *   kpal_dev_slice_collect_to_host  the same followed by the narrow device->host copy of the
+ *                           slice (slice_out: host memory, e.g. this rank's part of a profile in
+ *                           memory shared between the processes).  Synchronises the stream.
+ * The profile stays sharded by slice, so no NVLink or PCIe link carries more than its share.
+ * Inboxes: kpal_slice_inbox_bytes() of kpal_dev_alloc memory per rank, ZEROED once, exchanged with
+ * kpal_ipc_export / kpal_ipc_open as above; inbox_ptrs[rank] is the local one.  `epoch` counts the
+ * steps from 1, the same on every rank (the two parities of an inbox alternate).  k >= 6.
+ */
+uint64_t kpal_slice_inbox_bytes(int k, int world);
+uint64_t kpal_slice_begin(int k, int rank, int world);
+int      kpal_dev_slice_push(const void *d_table, int counter_bits, int k, int rank, int world,
+                             void *const *inbox_ptrs, uint64_t epoch, void *stream);
+int      kpal_dev_slice_collect(const void *d_inbox, int k, int rank, int world, uint64_t epoch,
+                                int64_t *d_slice_out, void *stream);
+int      kpal_dev_slice_collect_to_host(const void *d_inbox, int k, int rank, int world, uint64_t epoch,
+                                        int64_t *slice_out, void *stream);
 
 /* --------------------------------------------------- distances: device API */
 

@@ -24,16 +24,20 @@ MAX_K = 15
 SYMBOLS = (
     "kpal_abi_version", "kpal_last_error", "kpal_device_count", "kpal_set_device",
     "kpal_host_alloc", "kpal_host_free", "kpal_dev_alloc", "kpal_dev_free",
-    "kpal_memcpy_h2d", "kpal_memcpy_d2h", "kpal_stream_sync",
+    "kpal_memcpy_h2d", "kpal_memcpy_d2h", "kpal_dev_memset", "kpal_stream_sync",
     "kpal_packed_words", "kpal_pack_sequences", "kpal_fasta_scan", "kpal_fasta_pack",
     "kpal_count_sequences", "kpal_count_fasta", "kpal_count_by_record", "kpal_balance",
     "kpal_distance_matrix", "kpal_pair_distance",
     "kpal_matrix_open", "kpal_matrix_push", "kpal_matrix_finish", "kpal_matrix_close",
     "kpal_format_matrix", "kpal_widen_u16", "kpal_widen_u8", "kpal_pair_distance_positive",
+    "kpal_row_stats", "kpal_deflate_bound", "kpal_deflate_chunks", "kpal_compact_slots",
     "kpal_split_length", "kpal_split", "kpal_show_balance",
     "kpal_ipc_export", "kpal_ipc_open", "kpal_ipc_close", "kpal_peer_inbox_bytes",
     "kpal_dev_reduce_push", "kpal_dev_reduce_collect", "kpal_dev_count_packed_push",
-    "kpal_dev_count_packed", "kpal_dev_count_packed_fresh", "kpal_count_fasta_to_dev", "kpal_dev_finalize_counts", "kpal_dev_table_to_host", "kpal_dev_balance",
+    "kpal_slice_inbox_bytes", "kpal_slice_begin", "kpal_dev_slice_push", "kpal_dev_slice_collect",
+    "kpal_dev_slice_collect_to_host",
+    "kpal_dev_count_packed", "kpal_dev_count_packed_fresh", "kpal_count_fasta_to_dev",
+    "kpal_count_fasta_dev_table", "kpal_dev_finalize_counts", "kpal_dev_table_to_host", "kpal_dev_balance",
     "kpal_dev_count_by_record", "kpal_prepared_stride", "kpal_dev_profiles_prepare",
     "kpal_dev_order_by_total", "kpal_distance_num_tiles", "kpal_dev_distance_tiles",
     "kpal_distance_tile_elems", "kpal_dev_distance_tiles_packed", "kpal_dev_distance_unpack_tiles",
@@ -79,6 +83,7 @@ def load():
     sig("kpal_dev_free", None, vp)
     sig("kpal_memcpy_h2d", i32, vp, vp, c.c_size_t, vp)
     sig("kpal_memcpy_d2h", i32, vp, vp, c.c_size_t, vp)
+    sig("kpal_dev_memset", i32, vp, i32, c.c_size_t, vp)
     sig("kpal_stream_sync", i32, vp)
     sig("kpal_packed_words", None, u64, pu64, pu64)
     sig("kpal_pack_sequences", i32, vp, vp, u64, vp, vp, vp, pu64)
@@ -98,6 +103,10 @@ def load():
     sig("kpal_widen_u16", i32, vp, u64, u64, vp)
     sig("kpal_widen_u8", i32, vp, u64, u64, vp)
     sig("kpal_pair_distance_positive", i32, vp, vp, i32, i32, i32, i32, i32, i32, vp)
+    sig("kpal_row_stats", i32, vp, u64, u64, vp)
+    sig("kpal_deflate_bound", u64, u64)
+    sig("kpal_deflate_chunks", i32, vp, u64, u64, i32, vp, u64, vp)
+    sig("kpal_compact_slots", u64, vp, u64, vp, u64, vp)
     sig("kpal_split_length", u64, i32)
     sig("kpal_split", i32, vp, i32, vp, vp)
     sig("kpal_show_balance", i32, vp, i32, vp)
@@ -109,9 +118,15 @@ def load():
     sig("kpal_dev_reduce_collect", i32, vp, i32, i32, i32, i32, vp, vp)
     sig("kpal_dev_count_packed_push", i32, vp, vp, u64, i32, vp, i32, i32, i32, c.POINTER(vp), vp,
         c.POINTER(i32))
+    sig("kpal_slice_inbox_bytes", u64, i32, i32)
+    sig("kpal_slice_begin", u64, i32, i32, i32)
+    sig("kpal_dev_slice_push", i32, vp, i32, i32, i32, i32, c.POINTER(vp), u64, vp)
+    sig("kpal_dev_slice_collect", i32, vp, i32, i32, i32, u64, vp, vp)
+    sig("kpal_dev_slice_collect_to_host", i32, vp, i32, i32, i32, u64, vp, vp)
     sig("kpal_dev_count_packed", i32, vp, vp, u64, i32, vp, i32, vp)
     sig("kpal_dev_count_packed_fresh", i32, vp, vp, u64, i32, vp, i32, vp)
     sig("kpal_count_fasta_to_dev", i32, vp, u64, i32, vp, i32, vp, pu64)
+    sig("kpal_count_fasta_dev_table", i32, vp, u64, i32, c.POINTER(vp), c.POINTER(i32), vp)
     sig("kpal_dev_finalize_counts", i32, vp, i32, i32, i32, vp, vp)
     sig("kpal_dev_table_to_host", i32, vp, i32, i32, i32, vp, vp)
     sig("kpal_dev_balance", i32, vp, vp, i32, vp)
@@ -377,6 +392,44 @@ class MatrixSession(object):
             self.close()
         except Exception:
             pass
+
+
+def row_stats(rows):
+    """``[n][5]`` float64: total, non_zero, mean, median, std of every row of a C-contiguous
+    ``[n][m]`` int64 array, bit-identical to the NumPy calls (host, multi-threaded)."""
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    if rows.ndim != 2 or rows.shape[1] == 0:
+        raise ValueError("rows must be [n][m] with m > 0")
+    out = np.empty((rows.shape[0], 5), dtype=np.float64)
+    check(load().kpal_row_stats(ptr(rows), rows.shape[0], rows.shape[1], ptr(out)))
+    return out
+
+
+def deflate_chunks(data, chunk_bytes, level):
+    """zlib streams of the equal-sized chunks of `data` (a C-contiguous array whose size is a
+    multiple of `chunk_bytes`): ``(buffer, slot_bytes, sizes)`` -- chunk ``c`` is
+    ``buffer[c * slot_bytes : c * slot_bytes + sizes[c]]``.  Host, multi-threaded."""
+    L = load()
+    raw = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+    if chunk_bytes < 1 or raw.size % chunk_bytes:
+        raise ValueError("data must be whole chunks")
+    n_chunks = raw.size // chunk_bytes
+    slot = int(L.kpal_deflate_bound(chunk_bytes))
+    buffer = np.empty(n_chunks * slot, dtype=np.uint8)
+    sizes = np.empty(n_chunks, dtype=np.uint32)
+    check(L.kpal_deflate_chunks(ptr(raw), n_chunks, int(chunk_bytes), int(level), ptr(buffer), slot, ptr(sizes)))
+    return buffer, slot, sizes
+
+
+def deflate_chunks_packed(data, chunk_bytes, level):
+    """The same streams back to back: ``(blob, sizes)`` (chunk ``c`` starts at
+    ``sizes[:c].sum()``)."""
+    buffer, slot, sizes = deflate_chunks(data, chunk_bytes, level)
+    L = load()
+    total = int(L.kpal_compact_slots(ptr(buffer), slot, ptr(sizes), sizes.size, None))
+    blob = np.empty(total, dtype=np.uint8)
+    L.kpal_compact_slots(ptr(buffer), slot, ptr(sizes), sizes.size, ptr(blob))
+    return blob, sizes
 
 
 def format_matrix(values, precision):

@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <mutex>
 #include <numeric>
+#include <thread>
 #include <string.h>
 #include <stdlib.h>
 #include <vector>
@@ -20,7 +21,8 @@ namespace kpal {
 int launch_count(const uint32_t *, const uint32_t *, uint64_t, int, void *, int, cudaStream_t, bool zero_table = false);
 int launch_finalize(const void *, int, int, int, int64_t *, cudaStream_t);
 int launch_finalize_narrow(const void *, int, int, int, uint16_t *, uint8_t *, int64_t *, uint64_t, unsigned int *,
-                           cudaStream_t);
+                           cudaStream_t, void *d_list8 = nullptr, unsigned int cap8 = 0, void *d_list16 = nullptr,
+                           unsigned int cap16 = 0);
 // widen.cpp: host workers that widen the uint16 form of a profile to int64
 struct WidenHandle;
 WidenHandle *widen_begin(const void *src, int width, int64_t *dst, uint64_t n, uint64_t chunk);
@@ -77,6 +79,11 @@ int launch_reduce_push(const void *, int, int, int, int, void *const *, cudaStre
 int launch_reduce_collect(const void *, int, int, int, int, void *, cudaStream_t);
 int launch_count_push(const uint32_t *, const uint32_t *, uint64_t, int, void *, int, int, int,
                       void *const *, cudaStream_t, int *);
+uint64_t slice_inbox_bytes(int k, int world);
+uint64_t slice_begin_host(int k, int o, int world);
+int launch_slice_push(const void *, int, int, int, int, void *const *, unsigned long long, unsigned int *, cudaStream_t);
+int launch_slice_collect(const void *, int, int, int, unsigned long long, int64_t *, uint16_t *, uint8_t *,
+                         unsigned int *, cudaStream_t);
 
 static thread_local char t_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
@@ -85,6 +92,7 @@ static std::atomic<int> g_fasta_split{0};         // 1: a large FASTA text is cu
 static std::atomic<int> g_fasta_chunks{0};      // 0 = automatic (one chunk per ~6 MB, at most 16), else 1 .. 32
 static std::atomic<int> g_dma_share{0};         // sixteenths of a narrow-copied profile the DMA engine moves as int64 (pinned destinations)
 static std::atomic<int> g_gram{1};              // 1: euclidean / cosine matrices take the tensor-core Gram form when the counts allow it
+static std::atomic<int> g_narrow_lists{1};      // 1: counts that do not fit the narrow form travel in a side list (0: all-or-nothing, as before)
 static std::atomic<int> g_narrow_d2h{1};        // 1: large profiles leave the device as uint8 / uint16, 2: uint16 only (see finalize_to_host)
 
 void set_error(const char *fmt, ...)
@@ -183,8 +191,9 @@ struct GrowPin {
 };
 struct CountWorkspace {
     int device = -1;
-    GrowDev codes, valid, table, counts, text, fscratch, counts16, counts8, overflow, rows16[2];
-    GrowPin pcodes, pvalid, pstatus, pnarrow, pflag, prows16[2];
+    GrowDev codes, valid, table, counts, text, fscratch, counts16, counts8, overflow, rows16[2], wide_flag;
+    GrowDev list8, list16;                       // side lists of the narrow profile copy: (index, value) of the large counts
+    GrowPin pcodes, pvalid, pstatus, pnarrow, pflag, prows16[2], plist;
     cudaEvent_t rows_done[2] = {};               // by-record: a batch of uint16 rows has landed
     cudaStream_t copy_stream = nullptr;          // H2D of the FASTA text, chunk by chunk
     cudaStream_t count_stream = nullptr;         // count kernels of the first of two parts (fasta_gpu_count)
@@ -333,6 +342,11 @@ extern "C" int kpal_memcpy_d2h(void *dst, const void *src, size_t bytes, void *s
     KPAL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return KPAL_OK;
 }
+extern "C" int kpal_dev_memset(void *dst, int value, size_t bytes, void *stream)
+{
+    KPAL_CUDA(cudaMemsetAsync(dst, value, bytes, (cudaStream_t)stream));
+    return KPAL_OK;
+}
 extern "C" int kpal_stream_sync(void *stream)
 {
     KPAL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
@@ -350,6 +364,7 @@ extern "C" int kpal_set_option(const char *name, int value)
     if (!strcmp(name, "fasta_split")) { g_fasta_split.store(value ? 1 : 0); return KPAL_OK; }
     if (!strcmp(name, "exact_div")) { set_exact_div(value != 0); return KPAL_OK; }
     if (!strcmp(name, "gram")) { g_gram.store(value ? 1 : 0); return KPAL_OK; }
+    if (!strcmp(name, "narrow_lists")) { g_narrow_lists.store(value ? 1 : 0); return KPAL_OK; }
     if (!strcmp(name, "narrow_d2h")) {
         if (value < 0 || value > 2) return bad_arg("narrow_d2h must be 0 (int64), 1 (uint8 / uint16) or 2 (uint16)");
         g_narrow_d2h.store(value); return KPAL_OK;
@@ -508,6 +523,101 @@ struct CallTrace {
 };
 static CallTrace g_trace;       // used under g_count_mutex
 
+// The narrow forms of `split` counts (w->counts8 / w->counts16, flags in w->overflow, an int64
+// tail of `tail` counts in w->counts) -> counts_out on the host: flags first, the first uint8
+// chunk speculatively behind them, then the chunks of the narrowest form that holds every
+// count, widened by the host workers while the next chunk is in flight.  *done = false when a
+// count exceeds 65535 (nothing usable was written: the caller copies int64) or when the FASTA
+// packer turned the text down (*text_flags).
+struct NarrowListEntry { unsigned long long index, value; };
+
+// counts_out[index] = value for the n listed bins (a few threads when the list is long)
+static void apply_narrow_list(const NarrowListEntry *list, uint64_t n, int64_t *counts_out)
+{
+    auto run = [&](uint64_t a, uint64_t b) { for (uint64_t i = a; i < b; ++i) counts_out[list[i].index] = int64_t(list[i].value); };
+    if (n < 16384) { run(0, n); return; }
+    const unsigned n_threads = 8;
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < n_threads; ++t) pool.emplace_back(run, n * t / n_threads, n * (t + 1) / n_threads);
+    for (auto &t : pool) t.join();
+}
+
+static int narrow_copy_out(CountWorkspace *w, uint64_t split, uint64_t tail, uint64_t piece, bool try8,
+                       int64_t *counts_out, cudaStream_t st, const FastaStatus *pending, unsigned *text_flags,
+                       bool *done, unsigned int cap8 = 0, unsigned int cap16 = 0)
+{
+    *done = false;
+    KPAL_CUDA(cudaMemcpyAsync(w->pflag.p, w->overflow.p, 16, cudaMemcpyDeviceToHost, st));
+    KPAL_CUDA(cudaEventRecord(w->flag_done, st));
+    // chunks of whole pieces, >= 1 MiB each (the last one may be shorter)
+    auto chunk_of = [&](int width) {
+        uint64_t per = 1;
+        while (per * piece * uint64_t(width) < (1ull << 20) && per < 16) per *= 2;
+        return per * piece;
+    };
+    auto copy_chunk = [&](int width, uint64_t chunk, uint64_t c) -> cudaError_t {
+        const unsigned char *src = static_cast<const unsigned char *>(width == 1 ? w->counts8.p : w->counts16.p);
+        const uint64_t at = c * chunk, len = std::min(chunk, split - at);
+        cudaError_t e = cudaMemcpyAsync(static_cast<unsigned char *>(w->pnarrow.p) + at * width, src + at * width,
+                                        len * width, cudaMemcpyDeviceToHost, st);
+        return e != cudaSuccess ? e : cudaEventRecord(w->d2h_done[c], st);
+    };
+    int width = try8 ? 1 : 2;
+    uint64_t chunk = chunk_of(width);
+    if (try8) KPAL_CUDA(copy_chunk(1, chunk, 0));               // speculative, behind the flags
+    g_trace.mark("queued");
+    KPAL_CUDA(cudaEventSynchronize(w->flag_done));
+    g_trace.mark("flags");
+    const volatile unsigned int *flag = static_cast<const volatile unsigned int *>(w->pflag.p);
+    if (pending && (pending[0].flags | pending[1].flags)) {
+        *text_flags = pending[0].flags | pending[1].flags;
+        KPAL_CUDA(cudaStreamSynchronize(st));
+        *done = true;                                               // (nothing to copy: the caller re-packs)
+        return KPAL_OK;
+    }
+    // the narrowest form that holds every count, or holds all but a short list of them
+    const unsigned int n8 = flag[2], n16 = flag[3];
+    const bool fits8 = try8 && (flag[1] == 0 || (cap8 && n8 <= cap8));
+    const bool fits16 = flag[0] == 0 || (cap16 && n16 <= cap16);
+    if (fits8 || fits16) {
+        uint64_t first = 1;                                     // chunk 0 is already on its way
+        if (!fits8) { width = 2; chunk = chunk_of(2); first = 0; }
+        if (!try8) first = 0;
+        const uint64_t n_listed = fits8 ? (flag[1] ? n8 : 0) : (flag[0] ? n16 : 0);
+        const uint64_t n_chunks = (split + chunk - 1) / chunk;
+        for (uint64_t c = first; c < n_chunks; ++c) KPAL_CUDA(copy_chunk(width, chunk, c));
+        if (n_listed) {
+            KPAL_CHECK(w->plist.ensure(n_listed * sizeof(NarrowListEntry)));
+            KPAL_CUDA(cudaMemcpyAsync(w->plist.p, fits8 ? w->list8.p : w->list16.p, n_listed * sizeof(NarrowListEntry),
+                                      cudaMemcpyDeviceToHost, st));
+        }
+        if (tail) KPAL_CUDA(cudaMemcpyAsync(counts_out + split, w->counts.p, tail * 8, cudaMemcpyDeviceToHost, st));
+        // from here on the workers are awake: every exit goes through widen_end
+        WidenHandle *h = widen_begin(w->pnarrow.p, width, counts_out, split, chunk);
+        cudaError_t err = cudaSuccess;
+        for (uint64_t c = 0; c < n_chunks; ++c) {
+            err = cudaEventSynchronize(w->d2h_done[c]);
+            if (err != cudaSuccess) break;
+            widen_publish(h, std::min((c + 1) * chunk, split));
+        }
+        g_trace.mark(width == 1 ? "d2h_u8" : "d2h_u16");
+        widen_end(h, err != cudaSuccess ? 1 : 0);
+        g_trace.mark("widened");
+        if (err == cudaSuccess && (tail || n_listed)) err = cudaStreamSynchronize(st);
+        if (err == cudaSuccess && n_listed)
+            apply_narrow_list(static_cast<const NarrowListEntry *>(w->plist.p), n_listed, counts_out);
+        g_trace.mark("tail");
+        if (err != cudaSuccess) {
+            set_error("narrow D2H of the profile failed: %s", cudaGetErrorString(err));
+            cudaGetLastError();
+            return KPAL_ECUDA;
+        }
+        *done = true;
+        return KPAL_OK;
+    }
+    return KPAL_OK;
+}
+
 // Counter table on the device -> the caller's int64 profile on the host
 // (widen + optional balance, then D2H).
 //
@@ -557,66 +667,22 @@ static int finalize_to_host(CountWorkspace *w, const void *d_table, int bits, in
             for (auto &e : w->d2h_done) KPAL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             KPAL_CUDA(cudaEventCreateWithFlags(&w->flag_done, cudaEventDisableTiming));
         }
-        KPAL_CUDA(cudaMemsetAsync(w->overflow.p, 0, 8, st));
+        // side lists: up to 1/32 of the bins above 255 (uint8 form), 1/256 above 65535 (uint16 form)
+        const bool lists = g_narrow_lists.load() != 0;
+        const unsigned int cap8 = lists ? unsigned(std::max<uint64_t>(4096, bins / 32)) : 0u;
+        const unsigned int cap16 = lists ? unsigned(std::max<uint64_t>(4096, bins / 256)) : 0u;
+        KPAL_CHECK(w->list8.ensure(size_t(cap8) * sizeof(NarrowListEntry)));
+        KPAL_CHECK(w->list16.ensure(size_t(cap16) * sizeof(NarrowListEntry)));
+        KPAL_CUDA(cudaMemsetAsync(w->overflow.p, 0, 16, st));
         KPAL_CHECK(launch_finalize_narrow(d_table, bits, k, balance, static_cast<uint16_t *>(w->counts16.p),
                                           try8 ? static_cast<uint8_t *>(w->counts8.p) : nullptr,
                                           static_cast<int64_t *>(w->counts.p), split,
-                                          static_cast<unsigned int *>(w->overflow.p), st));
+                                          static_cast<unsigned int *>(w->overflow.p), st, lists ? w->list8.p : nullptr,
+                                          cap8, lists ? w->list16.p : nullptr, cap16));
         g_trace.dev_mark("finalized", st);
-        KPAL_CUDA(cudaMemcpyAsync(w->pflag.p, w->overflow.p, 8, cudaMemcpyDeviceToHost, st));
-        KPAL_CUDA(cudaEventRecord(w->flag_done, st));
-        // chunks of whole pieces, >= 1 MiB each (the last one may be shorter)
-        auto chunk_of = [&](int width) {
-            uint64_t per = 1;
-            while (per * piece * uint64_t(width) < (1ull << 20) && per < 16) per *= 2;
-            return per * piece;
-        };
-        auto copy_chunk = [&](int width, uint64_t chunk, uint64_t c) -> cudaError_t {
-            const unsigned char *src = static_cast<const unsigned char *>(width == 1 ? w->counts8.p : w->counts16.p);
-            const uint64_t at = c * chunk, len = std::min(chunk, split - at);
-            cudaError_t e = cudaMemcpyAsync(static_cast<unsigned char *>(w->pnarrow.p) + at * width, src + at * width,
-                                            len * width, cudaMemcpyDeviceToHost, st);
-            return e != cudaSuccess ? e : cudaEventRecord(w->d2h_done[c], st);
-        };
-        int width = try8 ? 1 : 2;
-        uint64_t chunk = chunk_of(width);
-        if (try8) KPAL_CUDA(copy_chunk(1, chunk, 0));               // speculative, behind the flags
-        g_trace.mark("queued");
-        KPAL_CUDA(cudaEventSynchronize(w->flag_done));
-        g_trace.mark("flags");
-        const volatile unsigned int *flag = static_cast<const volatile unsigned int *>(w->pflag.p);
-        if (pending && (pending[0].flags | pending[1].flags)) {
-            *text_flags = pending[0].flags | pending[1].flags;
-            KPAL_CUDA(cudaStreamSynchronize(st));
-            return KPAL_OK;
-        }
-        const bool over16 = flag[0] != 0, over8 = flag[1] != 0;
-        if (!over16) {
-            uint64_t first = 1;                                     // chunk 0 is already on its way
-            if (!try8 || over8) { width = 2; chunk = chunk_of(2); first = 0; }
-            const uint64_t n_chunks = (split + chunk - 1) / chunk;
-            for (uint64_t c = first; c < n_chunks; ++c) KPAL_CUDA(copy_chunk(width, chunk, c));
-            if (tail) KPAL_CUDA(cudaMemcpyAsync(counts_out + split, w->counts.p, tail * 8, cudaMemcpyDeviceToHost, st));
-            // from here on the workers are awake: every exit goes through widen_end
-            WidenHandle *h = widen_begin(w->pnarrow.p, width, counts_out, split, chunk);
-            cudaError_t err = cudaSuccess;
-            for (uint64_t c = 0; c < n_chunks; ++c) {
-                err = cudaEventSynchronize(w->d2h_done[c]);
-                if (err != cudaSuccess) break;
-                widen_publish(h, std::min((c + 1) * chunk, split));
-            }
-            g_trace.mark(width == 1 ? "d2h_u8" : "d2h_u16");
-            widen_end(h, err != cudaSuccess ? 1 : 0);
-            g_trace.mark("widened");
-            if (err == cudaSuccess && tail) err = cudaStreamSynchronize(st);
-            g_trace.mark("tail");
-            if (err != cudaSuccess) {
-                set_error("narrow D2H of the profile failed: %s", cudaGetErrorString(err));
-                cudaGetLastError();
-                return KPAL_ECUDA;
-            }
-            return KPAL_OK;
-        }
+        bool done = false;
+        KPAL_CHECK(narrow_copy_out(w, split, tail, piece, try8, counts_out, st, pending, text_flags, &done, cap8, cap16));
+        if (done) return KPAL_OK;
         KPAL_CUDA(cudaStreamSynchronize(st));                       // drain the speculative chunk
     } else if (pending) {
         KPAL_CUDA(cudaStreamSynchronize(st));
@@ -901,6 +967,39 @@ extern "C" int kpal_count_fasta_to_dev(const char *fasta, uint64_t n_bytes, int 
     KPAL_CHECK(upload_and_count(w, n_bases, k, d_table, counter_bits, (cudaStream_t)stream));
     // the pinned staging buffers are reused by the next call: wait for the copies
     KPAL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return KPAL_OK;
+}
+
+// Host FASTA bytes -> this call's counter table in the library's workspace (no copy into a
+// caller-owned table): what the multi-GPU driver hands to kpal_dev_slice_push.  The pointer
+// stays valid until the next host-level counting call on this device.  Synchronises the stream.
+extern "C" int kpal_count_fasta_dev_table(const char *fasta, uint64_t n_bytes, int k, void **d_table_out,
+                                          int *counter_bits_out, void *stream)
+{
+    if (!d_table_out || !counter_bits_out || (!fasta && n_bytes)) return bad_arg("null pointer");
+    KPAL_CHECK(check_k_host(k));
+    KPAL_CHECK(require_device());
+    std::lock_guard<std::mutex> lock(g_count_mutex);
+    CountWorkspace *w;
+    KPAL_CHECK(get_count_ws(&w));
+    const uint64_t bins = 1ull << (2 * k);
+    const int bits = (n_bytes >= (1ull << 32)) ? 64 : 32;
+    KPAL_CHECK(w->table.ensure(bins * (bits / 8)));
+    cudaStream_t st = (cudaStream_t)stream;
+    *d_table_out = w->table.p;
+    *counter_bits_out = bits;
+    if (use_gpu_fasta() && n_bytes > 0) {
+        KPAL_CUDA(cudaMemsetAsync(w->table.p, 0, bins * (bits / 8), st));
+        unsigned flags = 0;
+        uint64_t n_bases = 0;
+        KPAL_CHECK(fasta_gpu_count(w, fasta, n_bytes, k, w->table.p, bits, st, &flags, &n_bases));
+        if (!flags) return KPAL_OK;
+    }
+    uint64_t n_bases = 0;
+    KPAL_CUDA(cudaMemsetAsync(w->table.p, 0, bins * (bits / 8), st));
+    KPAL_CHECK(pack_fasta_ws(w, fasta, n_bytes, &n_bases));
+    KPAL_CHECK(upload_and_count(w, n_bases, k, w->table.p, bits, st));
+    KPAL_CUDA(cudaStreamSynchronize(st));
     return KPAL_OK;
 }
 
@@ -1477,4 +1576,85 @@ extern "C" int kpal_dev_count_packed_push(const uint32_t *d_codes, const uint32_
     if (!d_table || (n_bases && (!d_codes || !d_valid))) return bad_arg("null device pointer");
     return launch_count_push(d_codes, d_valid, n_bases, k, d_table, counter_bits, rank, world,
                              inbox_ptrs, (cudaStream_t)stream, fused_out);
+}
+
+// ------------------------- multi-GPU: balance + narrow reduce-scatter + distributed finalize
+extern "C" uint64_t kpal_slice_inbox_bytes(int k, int world)
+{
+    if (k < 6 || k > KPAL_MAX_K || world < 1 || world > 16) return 0;
+    return slice_inbox_bytes(k, world);
+}
+
+extern "C" uint64_t kpal_slice_begin(int k, int rank, int world)
+{
+    if (k < 1 || k > KPAL_MAX_K || world < 1 || rank < 0) return 0;
+    return slice_begin_host(k, rank, world);
+}
+
+extern "C" int kpal_dev_slice_push(const void *d_table, int counter_bits, int k, int rank, int world,
+                                   void *const *inbox_ptrs, uint64_t epoch, void *stream)
+{
+    if (!d_table) return bad_arg("null device pointer");
+    if (epoch < 1) return bad_arg("epochs count from 1 (a zeroed inbox means epoch 0)");
+    KPAL_CHECK(require_device());
+    CountWorkspace *w;
+    {
+        std::lock_guard<std::mutex> lock(g_count_mutex);
+        KPAL_CHECK(get_count_ws(&w));
+        KPAL_CHECK(w->wide_flag.ensure(16));
+    }
+    return launch_slice_push(d_table, counter_bits, k, rank, world, inbox_ptrs, epoch,
+                             static_cast<unsigned int *>(w->wide_flag.p), (cudaStream_t)stream);
+}
+
+extern "C" int kpal_dev_slice_collect(const void *d_inbox, int k, int rank, int world, uint64_t epoch,
+                                      int64_t *d_slice_out, void *stream)
+{
+    return launch_slice_collect(d_inbox, k, rank, world, epoch, d_slice_out, nullptr, nullptr, nullptr,
+                                (cudaStream_t)stream);
+}
+
+// kpal_dev_slice_collect + the device->host copy of the slice in the narrow form of finalize_to_host
+// (uint8 / uint16 over PCIe, widened into slice_out by the host workers).  slice_out may be any host
+// memory, e.g. this rank's part of a profile in memory shared between the ranks' processes.
+extern "C" int kpal_dev_slice_collect_to_host(const void *d_inbox, int k, int rank, int world, uint64_t epoch,
+                                              int64_t *slice_out, void *stream)
+{
+    if (!d_inbox || !slice_out) return bad_arg("null pointer");
+    KPAL_CHECK(check_k_host(k));
+    KPAL_CHECK(require_device());
+    if (rank < 0 || rank >= world) return bad_arg("rank outside the world");
+    std::lock_guard<std::mutex> lock(g_count_mutex);
+    CountWorkspace *w;
+    KPAL_CHECK(get_count_ws(&w));
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t n = slice_begin_host(k, rank + 1, world) - slice_begin_host(k, rank, world);
+    KPAL_CHECK(w->counts.ensure(n * 8));
+    const int narrow = g_narrow_d2h.load();
+    if (narrow && n >= (1ull << 16)) {
+        const bool try8 = narrow == 1;
+        KPAL_CHECK(w->counts16.ensure(n * 2));
+        if (try8) KPAL_CHECK(w->counts8.ensure(n));
+        KPAL_CHECK(w->overflow.ensure(16));
+        KPAL_CHECK(w->pnarrow.ensure(n * 2));
+        KPAL_CHECK(w->pflag.ensure(16));
+        if (!w->d2h_done[0]) {
+            for (auto &e : w->d2h_done) KPAL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            KPAL_CUDA(cudaEventCreateWithFlags(&w->flag_done, cudaEventDisableTiming));
+        }
+        KPAL_CHECK(launch_slice_collect(d_inbox, k, rank, world, epoch, static_cast<int64_t *>(w->counts.p),
+                                        static_cast<uint16_t *>(w->counts16.p),
+                                        try8 ? static_cast<uint8_t *>(w->counts8.p) : nullptr,
+                                        static_cast<unsigned int *>(w->overflow.p), st));
+        bool done = false;
+        KPAL_CHECK(narrow_copy_out(w, n, 0, ((n + 15) / 16 + 15) / 16 * 16, try8, slice_out, st, nullptr, nullptr, &done));
+        if (done) return KPAL_OK;
+        KPAL_CUDA(cudaStreamSynchronize(st));
+    } else {
+        KPAL_CHECK(launch_slice_collect(d_inbox, k, rank, world, epoch, static_cast<int64_t *>(w->counts.p), nullptr,
+                                        nullptr, nullptr, st));
+    }
+    KPAL_CUDA(cudaMemcpyAsync(slice_out, w->counts.p, n * 8, cudaMemcpyDeviceToHost, st));
+    KPAL_CUDA(cudaStreamSynchronize(st));
+    return KPAL_OK;
 }

@@ -163,12 +163,20 @@ count_smem_kernel(const uint4 *__restrict__ codes, const uint2 *__restrict__ val
 // straight into the caller's array while the host threads are busy widening.  The host
 // copies the narrowest form that holds every count below `split`: flags[0] is raised by a
 // count above 65535 (the caller then redoes the finalize in int64), flags[1] by one above 255.
+// A count that does not fit its narrow form is ALSO appended to a side list (index, value):
+// a profile with a few large counts (poly-A, satellites) still travels narrow and the host
+// patches the listed bins after widening.  flags[2] / flags[3] count the entries of the two
+// lists (for the uint8 form: counts above 255; for the uint16 form: above 65535); entries
+// beyond a list's capacity are dropped, the host then takes the next wider form.
+struct NarrowEntry { unsigned long long index, value; };
 struct NarrowOut {
     uint16_t *o16;
     uint8_t *o8;
     int64_t *o64;
     uint64_t split;
     unsigned int *flags;
+    NarrowEntry *list8, *list16;
+    unsigned int cap8, cap16;
 };
 
 __device__ __forceinline__ void put_count(int64_t *__restrict__ out, uint64_t i, unsigned long long v)
@@ -180,7 +188,17 @@ __device__ __forceinline__ void put_count(const NarrowOut &out, uint64_t i, unsi
     if (i >= out.split) { out.o64[i - out.split] = int64_t(v); return; }
     if (v > 0xffull) {                          // same value from every writer: a plain store is enough
         out.flags[1] = 1u;
-        if (v > 0xffffull) out.flags[0] = 1u;
+        if (out.list8) {
+            const unsigned int at = atomicAdd(out.flags + 2, 1u);
+            if (at < out.cap8) out.list8[at] = NarrowEntry{i, v};
+        }
+        if (v > 0xffffull) {
+            out.flags[0] = 1u;
+            if (out.list16) {
+                const unsigned int at = atomicAdd(out.flags + 3, 1u);
+                if (at < out.cap16) out.list16[at] = NarrowEntry{i, v};
+            }
+        }
     }
     out.o16[i] = uint16_t(v);
     if (out.o8) out.o8[i] = uint8_t(v);
@@ -457,7 +475,7 @@ int launch_count_radix(const uint32_t *, const uint32_t *, uint64_t, int, void *
 bool radix_peer_supported(int k, int world);
 // count_pairs.cu
 bool pairs_supported(int k);
-int launch_count_pairs(const uint32_t *, const uint32_t *, uint64_t, int, void *, int, cudaStream_t, bool zero_table);
+int launch_count_pairs(const uint32_t *, const uint32_t *, uint64_t, int, void *, int, cudaStream_t);
 // peer_reduce.cu
 int launch_reduce_push(const void *, int, int, int, int, void *const *, cudaStream_t);
 int peer_check_args(int k, int counter_bits, int rank, int world);
@@ -509,8 +527,9 @@ static int check_k(int k)
     return KPAL_OK;
 }
 
-// zero_table: the table is zeroed first -- inside the first count kernel on the pair path
-// (count_pairs.cu), with a memset otherwise -- instead of by the caller.
+// zero_table: the table is zeroed first (a memset on the stream) instead of by the caller.
+// (Folding the memset into the first count kernel -- every CTA zeroing its share while it
+// bins -- was built and measured: 0.2703 vs 0.2706 ms per step, no gain, so it went again.)
 int launch_count(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_bases, int k,
                  void *d_table, int counter_bits, cudaStream_t stream, bool zero_table)
 {
@@ -518,7 +537,7 @@ int launch_count(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_ba
     if (counter_bits != 32 && counter_bits != 64) return bad_arg("counter_bits must be 32 or 64");
     const bool pairs = n_bases > 0 && k > 7 && use_radix_path(k, n_bases) && pairs_supported(k) &&
                        g_count_path.load() != 3 && !(counter_bits == 32 && n_bases >= (1ull << 32));
-    if (zero_table && !pairs)
+    if (zero_table)
         KPAL_CUDA(cudaMemsetAsync(d_table, 0, (size_t(1) << (2 * k)) * size_t(counter_bits / 8), stream));
     if (n_bases == 0) return KPAL_OK;
     if (counter_bits == 32 && n_bases >= (1ull << 32)) {
@@ -551,7 +570,7 @@ int launch_count(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_ba
         KPAL_LAUNCH_CHECK("count_smem_kernel");
     } else if (use_radix_path(k, n_bases)) {
         if (pairs)
-            return launch_count_pairs(d_codes, d_valid, n_bases, k, d_table, counter_bits, stream, zero_table);
+            return launch_count_pairs(d_codes, d_valid, n_bases, k, d_table, counter_bits, stream);
         return launch_count_radix(d_codes, d_valid, n_bases, k, d_table, counter_bits, stream);
     } else {
         uint64_t want = (n_chunks + 255) / 256;
@@ -614,12 +633,14 @@ int launch_finalize(const void *d_table, int counter_bits, int k, int balance, i
 // d_flags[2] are device words the caller zeroed.
 int launch_finalize_narrow(const void *d_table, int counter_bits, int k, int balance, uint16_t *d_counts16,
                            uint8_t *d_counts8, int64_t *d_tail64, uint64_t split, unsigned int *d_flags,
-                           cudaStream_t stream)
+                           cudaStream_t stream, void *d_list8, unsigned int cap8, void *d_list16, unsigned int cap16)
 {
     if (!d_flags || !d_counts16) return bad_arg("null narrow buffer");
     if (split > (1ull << (2 * k)) || (split < (1ull << (2 * k)) && !d_tail64)) return bad_arg("bad split");
     NarrowOut out;
     out.o16 = d_counts16; out.o8 = d_counts8; out.o64 = d_tail64; out.split = split; out.flags = d_flags;
+    out.list8 = d_counts8 ? static_cast<NarrowEntry *>(d_list8) : nullptr; out.cap8 = cap8;
+    out.list16 = static_cast<NarrowEntry *>(d_list16); out.cap16 = cap16;
     return launch_finalize_as<NarrowOut>(d_table, counter_bits, k, balance, out, stream);
 }
 

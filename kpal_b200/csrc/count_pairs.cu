@@ -39,7 +39,6 @@ constexpr int kPairThreads = 1024;
 constexpr int kPairHistThreads = 512;
 
 constexpr int kSlotTrash = 8;           // halfwords behind a slot's `cap` places that absorb stores of unbinned pairs
-constexpr int kQueue = 2048;            // windows waiting for the table to be zeroed (in-kernel memset)
 
 struct PairParams {
     const uint2 *codes;         // 32 bases per uint2
@@ -51,13 +50,6 @@ struct PairParams {
     uint16_t *staging;          // [grid][1024][region_groups * 16]
     uint32_t *region_fill;      // [grid][1024] payloads stored per region
     int flush_every;            // tiles binned between two flushes of the slots
-    // In-kernel memset (zero_table != 0): every CTA zeroes its share of the table with
-    // streaming stores that drain while it bins, then adds 1 to *zero_done; a RED on the
-    // table is only issued once *zero_done has reached zero_target (all CTAs of the launch).
-    int zero_table;
-    unsigned long long *zero_done;
-    unsigned long long zero_target;
-    uint64_t table_bytes;
 };
 
 struct PairCtx {
@@ -71,27 +63,12 @@ struct PairCtx {
     uint32_t kmask;                 // 4^k - 1
 };
 
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// spin until every CTA of the launch has zeroed its share of the table (rare paths only)
-__device__ __noinline__ void wait_table_zeroed(const unsigned long long *zero_done, unsigned long long zero_target)
-{
-    if (!zero_done) return;
-    while (ld_acquire_u64(zero_done) < zero_target) __nanosleep(200);
-}
-
 // Eight pairs (16 windows) at a time, branch-free as bin_eight in count_radix.cu.
 // A pair takes a returning shared atomic (its rank in the bucket's slot) and a 16-bit store at
 // slot[min(rank, cap)] -- the places from `cap` on are trash, so a full slot needs no branch;
 // the batch checks once whether any rank reached `cap` and then counts those pairs with REDs.
 template <typename CounterT, int O0>
-__device__ __forceinline__ void bin_eight_pairs(const Unit &u, uint32_t both, const PairCtx &c, CounterT *table,
-                                                const PairParams &p)
+__device__ __forceinline__ void bin_eight_pairs(const Unit &u, uint32_t both, const PairCtx &c, CounterT *table)
 {
     uint32_t m[8], rank[8];
     m[0] = unit_window<O0 + 0>(u, c.shift); m[1] = unit_window<O0 + 2>(u, c.shift);
@@ -117,13 +94,22 @@ __device__ __forceinline__ void bin_eight_pairs(const Unit &u, uint32_t both, co
         sts_u16(c.slots_s + bl4 * c.slot_words + 2u * pos, pay);
     }
     if (top >= c.cap) {             // slot full (skewed / repetitive sequence): count both windows directly
-        wait_table_zeroed(p.zero_table ? p.zero_done : nullptr, p.zero_target);
+        // Low-complexity sequence sends thousands of windows to ONE bin (poly-A reads: every
+        // lane, every pair), and same-address REDs serialise in L2: the lanes that are here
+        // with the same index add their number with one RED.
+        const unsigned here = __activemask();
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (((both << (O0 + 2 * j)) & 0x80000000u) && rank[j] >= c.cap) {
-                atomicAdd(table + (m[j] >> 2), CounterT(1));
-                atomicAdd(table + (m[j] & c.kmask), CounterT(1));
+        for (int j = 0; j < 8; ++j) {
+            const bool spill = ((both << (O0 + 2 * j)) & 0x80000000u) && rank[j] >= c.cap;
+            const unsigned voters = __ballot_sync(here, spill);
+            if (spill) {
+                const uint32_t w0 = m[j] >> 2, w1 = m[j] & c.kmask;
+                const unsigned same0 = __match_any_sync(voters, w0);
+                if ((threadIdx.x & 31u) == unsigned(__ffs(same0) - 1)) atomicAdd(table + w0, CounterT(__popc(same0)));
+                const unsigned same1 = __match_any_sync(voters, w1);
+                if ((threadIdx.x & 31u) == unsigned(__ffs(same1) - 1)) atomicAdd(table + w1, CounterT(__popc(same1)));
             }
+        }
     }
 }
 
@@ -151,29 +137,14 @@ pair_partition_kernel(const PairParams p, CounterT *__restrict__ table)
     constexpr int na = kPairBuckets;
     uint32_t *cnt = reinterpret_cast<uint32_t *>(pair_smem);            // [na] payloads in the slot (+32 dummies)
     uint32_t *fillg = cnt + na + 32;                                     // [na] groups already stored
-    uint32_t *queue = fillg + na;                                        // [kQueue] windows waiting for the zeroed table
-    uint32_t *queue_n = queue + kQueue;                                  // [4]: entries, table-is-zero flag
-    uint16_t *slots = reinterpret_cast<uint16_t *>(queue_n + 4);         // [na][cap + kSlotTrash]
+    uint16_t *slots = reinterpret_cast<uint16_t *>(fillg + na);          // [na][cap + kSlotTrash]
 
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31u;
     for (int b = tid; b < na + 32; b += kPairThreads) cnt[b] = 0;
     for (int b = tid; b < na; b += kPairThreads) fillg[b] = 0;
-    if (tid < 4) queue_n[tid] = 0;
 
-    // ---- in-kernel memset: this CTA's share of the table, streaming stores that drain while
-    // the first tiles are binned (pass 1 leaves the HBM write path idle otherwise)
-    if (p.zero_table) {
-        const uint64_t total_v4 = p.table_bytes / 16;
-        const uint64_t share = (total_v4 + gridDim.x - 1) / gridDim.x;
-        const uint64_t v0 = uint64_t(blockIdx.x) * share, v1 = min(v0 + share, total_v4);
-        uint4 *t4 = reinterpret_cast<uint4 *>(table);
-        for (uint64_t i = v0 + tid; i < v1; i += kPairThreads) __stcg(t4 + i, make_uint4(0, 0, 0, 0));
-        __threadfence();
-    }
     __syncthreads();
-    if (p.zero_table && tid == 0) { __threadfence(); atomicAdd(p.zero_done, 1ull); }   // after every thread's fence
-    bool table_ready = !p.zero_table;                                    // CTA-uniform, refreshed at the flush points
 
     constexpr uint64_t kTile = uint64_t(kPairThreads) * UPT;
     const uint64_t total = p.unit_end - p.unit_begin;
@@ -193,7 +164,6 @@ pair_partition_kernel(const PairParams p, CounterT *__restrict__ table)
     ctx.rmask = (1u << ctx.rshift) - 1u;
     ctx.kmask = (p.k == 16) ? ~0u : ((1u << (2 * p.k)) - 1u);
     const int kshift = 32 - 2 * p.k;
-    const uint32_t queue_s = smem_u32(queue), queue_n_s = smem_u32(queue_n);
 
     uint16_t *my_regions = p.staging + uint64_t(blockIdx.x) * na * p.region_groups * kGroup;
 
@@ -255,19 +225,13 @@ pair_partition_kernel(const PairParams p, CounterT *__restrict__ table)
                 // (a mask-free variant for batches of eight valid pairs only pays when it is taken
                 // by whole warps: with reads every warp holds record ends, and executing both
                 // variants cost 45 us -- measured, profiles/README.md)
-                if (both & 0xFFFF0000u) bin_eight_pairs<CounterT, 0>(u, both, ctx, table, p);
-                if (both & 0x0000FFFFu) bin_eight_pairs<CounterT, 16>(u, both, ctx, table, p);
+                if (both & 0xFFFF0000u) bin_eight_pairs<CounterT, 0>(u, both, ctx, table);
+                if (both & 0x0000FFFFu) bin_eight_pairs<CounterT, 16>(u, both, ctx, table);
                 while (singles) {                   // run ends: ~1 window per run of valid windows
                     const int o = __clz(singles);
                     singles &= ~(0x80000000u >> o);
                     const uint32_t lo = (o & 16) ? u.w[1] : u.w[0], hi = (o & 16) ? u.w[2] : u.w[1];
-                    const uint32_t idx = __funnelshift_l(hi, lo, 2 * (o & 15)) >> kshift;
-                    if (!table_ready) {             // the table may not be zero yet: park the window
-                        const uint32_t at = atoms_add(queue_n_s, 1u);
-                        if (at < uint32_t(kQueue)) { sts_u32(queue_s + 4u * at, idx); continue; }
-                        wait_table_zeroed(p.zero_table ? p.zero_done : nullptr, p.zero_target);       // queue full
-                    }
-                    atomicAdd(table + idx, CounterT(1));
+                    atomicAdd(table + (__funnelshift_l(hi, lo, 2 * (o & 15)) >> kshift), CounterT(1));
                 }
             }
         }
@@ -278,7 +242,6 @@ pair_partition_kernel(const PairParams p, CounterT *__restrict__ table)
         ++since_flush;
         if (since_flush < p.flush_every && t0 + kTile < u1) continue;
         since_flush = 0;
-        if (!table_ready && tid == 0 && ld_acquire_u64(p.zero_done) >= p.zero_target) sts_u32(queue_n_s + 4u, 1u);
         __syncthreads();
         {
             static_assert(kPairBuckets == kPairThreads, "one bucket per thread");
@@ -289,7 +252,6 @@ pair_partition_kernel(const PairParams p, CounterT *__restrict__ table)
             if (g) {
                 const uint32_t slot_a = ctx.slots_s + b * slot_bytes;
                 uint4 *dst = my_regions4 + b * region_v4 + 2u * f;
-                if (f + g > p.region_groups) wait_table_zeroed(p.zero_table ? p.zero_done : nullptr, p.zero_target);             // region full: REDs below
                 for (uint32_t q = 0; q < g; ++q) {
                     const uint4 x0 = lds_v4(slot_a + 32u * q), x1 = lds_v4(slot_a + 32u * q + 16u);
                     if (f + q < p.region_groups) { __stcs(dst + 2u * q, x0); __stcs(dst + 2u * q + 1u, x1); }
@@ -300,25 +262,11 @@ pair_partition_kernel(const PairParams p, CounterT *__restrict__ table)
                 sts_u32(cnt_a, n - g * kGroup);
                 sts_u32(fill_a, min(f + g, p.region_groups));
             }
-            // the parked windows, once the whole table is known to be zero
-            if (!table_ready && lds_u32(queue_n_s + 4u)) {
-                const uint32_t parked = min(lds_u32(queue_n_s), uint32_t(kQueue));
-                for (uint32_t i = tid; i < parked; i += kPairThreads)
-                    atomicAdd(table + lds_u32(queue_s + 4u * i), CounterT(1));
-                table_ready = true;
-            }
         }
         __syncthreads();
-        if (table_ready && tid == 0) sts_u32(queue_n_s, 0u);     // (parks nothing any more)
     }
 
     // ---- remainders (< 16 per bucket after the last flush) and the per-region totals
-    if (!table_ready) {                 // no flush point saw the flag (very short input): wait for it now
-        wait_table_zeroed(p.zero_table ? p.zero_done : nullptr, p.zero_target);
-        const uint32_t parked = min(lds_u32(queue_n_s), uint32_t(kQueue));
-        for (uint32_t i = tid; i < parked; i += kPairThreads)
-            atomicAdd(table + lds_u32(queue_s + 4u * i), CounterT(1));
-    }
     {
         const uint32_t b = uint32_t(tid);
         const uint32_t n = min(cnt[b], ctx.cap), f = fillg[b];
@@ -514,7 +462,7 @@ static int launch_pair_passes(const PairParams &p, int grid1, size_t smem1, int 
 }
 
 int launch_count_pairs(const uint32_t *d_codes, const uint32_t *d_valid, uint64_t n_bases, int k,
-                       void *d_table, int counter_bits, cudaStream_t stream, bool zero_table)
+                       void *d_table, int counter_bits, cudaStream_t stream)
 {
     if (!pairs_supported(k)) return bad_arg("the pair path covers 9 <= k <= 12");
     const int grid1 = sm_count();
@@ -524,16 +472,15 @@ int launch_count_pairs(const uint32_t *d_codes, const uint32_t *d_valid, uint64_
     // (the surplus of a fuller slot takes the RED path: exact, only slower).
     int flush_every = g_pair_flush_every.load();
     if (flush_every <= 0) flush_every = upt == 1 ? 3 : 1;
-    // shared memory: counters, fill, the queue of parked windows, then the slots.  cap + 8 trash
+    // shared memory: counters, fill, then the slots.  cap + 8 trash
     // places = 8 x odd halfwords keeps the 16-byte slot reads of neighbouring buckets on
     // distinct bank groups.
-    const size_t fixed = size_t(kPairBuckets + 32) * 4 + size_t(kPairBuckets) * 4 + size_t(kQueue) * 4 + 16;
+    const size_t fixed = size_t(kPairBuckets + 32) * 4 + size_t(kPairBuckets) * 4 + 64;     // + pad: the flush reads one piece past a full last slot
     int stride = int((232448 - fixed) / (2u * unsigned(kPairBuckets)));       // halfwords per slot
     stride = (stride - 8) / 16 * 16 + 8;
     const int cap = stride - kSlotTrash;
-    const size_t smem1 = fixed + size_t(kPairBuckets) * stride * 2;
+    const size_t smem1 = fixed + size_t(kPairBuckets) * stride * 2;     // (the pad sits behind the slots)
 
-    unsigned long long *zero_done = nullptr, zero_target = 0;
     const uint64_t tile = uint64_t(kPairThreads) * upt;
     const uint64_t n_units = 2 * n_chunks_of(n_bases);
     const uint64_t seg_units = (512ull << 20) / kUnitBases;
@@ -557,13 +504,6 @@ int launch_count_pairs(const uint32_t *d_codes, const uint32_t *d_valid, uint64_
         p.staging = static_cast<uint16_t *>(staging);
         p.region_fill = fill;
         p.flush_every = flush_every;
-        p.zero_table = (zero_table && s0 == 0) ? 1 : 0;         // the first segment's launch zeroes the table
-        p.zero_done = nullptr; p.zero_target = 0;
-        p.table_bytes = (uint64_t(1) << (2 * k)) * uint64_t(counter_bits / 8);
-        if (p.zero_table) {
-            KPAL_CHECK(radix_zero_counter(uint64_t(grid1), &zero_done, &zero_target));
-            p.zero_done = zero_done; p.zero_target = zero_target;
-        }
         if (counter_bits == 32)
             KPAL_CHECK(launch_pair_passes<uint32_t>(p, grid1, smem1, upt, static_cast<uint32_t *>(d_table), stream));
         else

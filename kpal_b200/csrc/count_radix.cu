@@ -390,8 +390,6 @@ struct RadixWorkspace {
     int device = -1;
     void *staging = nullptr; size_t staging_cap = 0;
     uint32_t *fill = nullptr; size_t fill_cap = 0;
-    unsigned long long *arrivals = nullptr;     // device counter of the in-kernel memset (count_pairs.cu)
-    unsigned long long expected = 0;            // ... and the total the launches so far will bring it to
 };
 static std::mutex g_radix_mutex;
 static std::vector<RadixWorkspace *> g_radix_ws;
@@ -435,25 +433,6 @@ int radix_workspace(size_t staging_bytes, size_t fill_bytes, void **staging, uin
     KPAL_CHECK(grow(&f, &fc, fill_bytes));
     ws->fill = static_cast<uint32_t *>(f); ws->fill_cap = fc;
     *staging = ws->staging; *fill = ws->fill;
-    return KPAL_OK;
-}
-
-int radix_zero_counter(uint64_t arrivals, unsigned long long **counter, unsigned long long *target)
-{
-    int dev = 0;
-    KPAL_CUDA(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(g_radix_mutex);
-    RadixWorkspace *ws = nullptr;
-    for (auto *w : g_radix_ws) if (w->device == dev) ws = w;
-    if (!ws) { ws = new RadixWorkspace(); ws->device = dev; g_radix_ws.push_back(ws); }
-    if (!ws->arrivals) {
-        KPAL_CUDA(cudaMalloc(&ws->arrivals, sizeof(unsigned long long)));
-        KPAL_CUDA(cudaMemset(ws->arrivals, 0, sizeof(unsigned long long)));
-        ws->expected = 0;
-    }
-    ws->expected += arrivals;
-    *counter = ws->arrivals;
-    *target = ws->expected;
     return KPAL_OK;
 }
 

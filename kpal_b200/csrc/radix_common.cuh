@@ -63,9 +63,5 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, const uint4 &v)
 
 // grow-only per-device staging of the radix paths (count_radix.cu); call under no lock
 int radix_workspace(size_t staging_bytes, size_t fill_bytes, void **staging, uint32_t **fill);
-// A monotonic device counter for launches whose CTAs signal each other (the in-kernel memset of
-// count_pairs.cu): adds `arrivals` to the expected total and returns the counter and the new total.
-// Launches that use it must be ordered on one stream per device (as for the staging buffers).
-int radix_zero_counter(uint64_t arrivals, unsigned long long **counter, unsigned long long *target);
 
 }  // namespace kpal

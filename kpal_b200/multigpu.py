@@ -107,7 +107,10 @@ def count_fasta_distributed(fasta_shard, k, balance=False, group=None, device=No
     boundaries, see :func:`split_fasta`); rank 0 gets the ``int64[4**k]``
     profile, the other ranks ``None``.
 
-    `reduce` = ``'nccl'`` (default) sums the tables with ``dist.reduce``,
+    `reduce` = ``'slices'`` (GPU ranks, ``balance=True``, k >= 6): the fused form --
+    balance + narrow reduce-scatter over NVLink peer memory + distributed finalize
+    (:class:`SliceReducer`), the slices meeting in shared host memory;
+    ``'nccl'`` (default) sums the tables with ``dist.reduce``,
     ``'peer'`` over NVLink peer memory (:class:`PeerReducer`; GPU ranks, u32
     counters).  For a single call the NCCL reduce is the faster one (the
     peer path has to map its inboxes first; measured 0.455 vs 0.421 ms per
@@ -120,6 +123,9 @@ def count_fasta_distributed(fasta_shard, k, balance=False, group=None, device=No
     _cabi._check_k(k)
     if isinstance(fasta_shard, str):
         fasta_shard = fasta_shard.encode('latin-1', 'replace')
+    distributed_now = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if reduce == 'slices' and count_shard is None and distributed_now and k >= 6 and balance:
+        return _count_fasta_slices(fasta_shard, k, group, device)
     if count_shard is None:
         _cabi.require_gpu()
         if device is None:
@@ -154,6 +160,34 @@ def count_fasta_distributed(fasta_shard, k, balance=False, group=None, device=No
             counts = _cabi.balance(work) if finalize is None else finalize(work, k, True)
         return counts
     return (finalize or _gpu_finalize)(table, k, balance)
+
+
+def _count_fasta_slices(fasta_shard, k, group, device):
+    """count_fasta_distributed(balance=True) through :class:`SliceReducer`: every rank counts its
+    shard, the balanced tables are reduce-scattered narrow over NVLink, every rank copies its
+    slice of the profile into shared host memory, rank 0 returns the whole."""
+    import torch
+    L = _cabi.load()
+    _cabi.require_gpu()
+    if device is None:
+        device = torch.device('cuda', torch.cuda.current_device())
+    stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    reducer = SliceReducer(k, group=group)
+    shared = SharedProfile(k, group=group)
+    try:
+        buf = np.frombuffer(fasta_shard, dtype=np.uint8)
+        table, bits = ctypes.c_void_p(), ctypes.c_int()
+        _cabi.check(L.kpal_count_fasta_dev_table(_cabi.ptr(buf) if buf.size else None, buf.size, int(k),
+                                                 ctypes.byref(table), ctypes.byref(bits), stream))
+        reducer.push(table, bits.value, stream)
+        begin, end = reducer.slice_range()
+        reducer.collect_to_host(shared.array[begin:end], stream)
+        import torch.distributed as dist
+        dist.barrier(group=group)
+        return shared.array.copy() if reducer.rank == 0 else None
+    finally:
+        shared.close()
+        reducer.close()
 
 
 class PeerReducer(object):
@@ -267,6 +301,128 @@ class PeerReducer(object):
         if self._root_table:
             self._L.kpal_dev_free(self._root_table)
             self._root_table = None
+
+
+class SliceReducer(object):
+    """
+    The fused form of the multi-GPU table sum (``csrc/peer_reduce.cu``): every rank balances
+    its own table and stores the result, one byte per bin, straight into the inbox of the
+    rank that owns the bin's slice (``push``: NVLink peer stores + one release flag per
+    peer); every rank then sums the rows it received into its int64 slice of the final
+    balanced profile (``collect`` / ``collect_to_host``: waits for the peers' flags in its own
+    inbox, no host round trip, no NCCL call).  The profile stays sharded by slice
+    ``[begin, end)`` = :meth:`slice_range`.
+
+    One process per GPU; inboxes are ``cudaMalloc`` buffers shared through CUDA IPC handles.
+    """
+
+    def __init__(self, k, group=None):
+        import torch
+        import torch.distributed as dist
+        self._L = L = _cabi.load()
+        self.k, self.group = int(k), group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        self.epoch = 0
+        self._opened = []
+        nbytes = int(L.kpal_slice_inbox_bytes(self.k, self.world))
+        if nbytes == 0:
+            raise ValueError('the sliced reduce needs 6 <= k <= 15 and at most 16 ranks')
+        self._inbox = L.kpal_dev_alloc(nbytes)
+        if not self._inbox:
+            raise MemoryError('kpal_dev_alloc failed for the slice inbox')
+        _cabi.check(L.kpal_dev_memset(self._inbox, 0, nbytes, None))
+        _cabi.check(L.kpal_stream_sync(None))
+        handle = ctypes.create_string_buffer(64)
+        _cabi.check(L.kpal_ipc_export(self._inbox, handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self._inboxes = (ctypes.c_void_p * self.world)()
+        error = None
+        try:
+            for r in range(self.world):
+                if r == self.rank:
+                    self._inboxes[r] = self._inbox
+                else:
+                    out = ctypes.c_void_p()
+                    _cabi.check(L.kpal_ipc_open(handles[r], ctypes.byref(out)))
+                    self._opened.append(out.value)
+                    self._inboxes[r] = out.value
+        except (RuntimeError, ValueError, MemoryError) as exc:
+            error = exc
+        flag = torch.tensor([0 if error is None else 1], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, group=group)
+        torch.cuda.synchronize()
+        if int(flag.item()):
+            self.close()
+            raise RuntimeError('sliced peer reduce unavailable: %d rank(s) could not map the peers (%s)'
+                               % (int(flag.item()), error if error is not None else 'failure on another rank'))
+
+    def slice_range(self, rank=None):
+        rank = self.rank if rank is None else rank
+        return (int(self._L.kpal_slice_begin(self.k, rank, self.world)),
+                int(self._L.kpal_slice_begin(self.k, rank + 1, self.world)))
+
+    def push(self, table_ptr, counter_bits, stream):
+        """Balance + narrow push of this rank's table; starts a new epoch."""
+        self.epoch += 1
+        _cabi.check(self._L.kpal_dev_slice_push(table_ptr, int(counter_bits), self.k, self.rank, self.world,
+                                                self._inboxes, self.epoch, stream))
+
+    def collect(self, slice_ptr, stream):
+        """This rank's int64 slice of the balanced profile -> device memory."""
+        _cabi.check(self._L.kpal_dev_slice_collect(self._inbox, self.k, self.rank, self.world, self.epoch,
+                                                   slice_ptr, stream))
+
+    def collect_to_host(self, host_slice, stream):
+        """... -> `host_slice` (a C-contiguous int64 array of the slice's length)."""
+        _cabi.check(self._L.kpal_dev_slice_collect_to_host(self._inbox, self.k, self.rank, self.world, self.epoch,
+                                                           _cabi.ptr(host_slice), stream))
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize()
+        for p in self._opened:
+            self._L.kpal_ipc_close(p)
+        self._opened = []
+        if self._inbox:
+            self._L.kpal_dev_free(self._inbox)
+            self._inbox = None
+
+
+class SharedProfile(object):
+    """An ``int64[4**k]`` profile in POSIX shared memory that every rank's process maps: the
+    owners of the slices write their parts side by side (each over its own PCIe link, widened by
+    its own host threads) and rank 0 reads the whole -- no gather through one process."""
+
+    def __init__(self, k, group=None):
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+        self.rank = dist.get_rank(group)
+        self.group = group
+        nbytes = 8 * 4 ** int(k)
+        names = [None]
+        if self.rank == 0:
+            self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            names[0] = self._shm.name
+        dist.broadcast_object_list(names, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        if self.rank != 0:
+            self._shm = shared_memory.SharedMemory(name=names[0])
+            try:                    # the creator unlinks it; keep this process's tracker out of it
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self._shm._name, 'shared_memory')
+            except Exception:
+                pass
+        self.array = np.ndarray((4 ** int(k),), dtype=np.int64, buffer=self._shm.buf)
+
+    def close(self):
+        import torch.distributed as dist
+        self.array = None
+        dist.barrier(group=self.group)
+        self._shm.close()
+        if self.rank == 0:
+            self._shm.unlink()
 
 
 # ------------------------------------------------------------- per-record counting

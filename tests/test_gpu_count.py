@@ -536,10 +536,8 @@ def test_pair_count_path_bit_exact(k, n, letters, p_n):
 
 @pytest.mark.parametrize("k,n", [(12, 30_000_000), (12, 3_000), (10, 20_000_000), (6, 100_000), (13, 9_000_000)])
 def test_count_packed_fresh_zeroes_the_table(k, n):
-    """kpal_dev_count_packed_fresh on a table full of garbage: the pair path zeroes it inside
-    its first kernel (CTAs zero their shares while they bin; the windows that go to the table
-    directly are parked until every share is done), the other paths with a memset.  Repeated
-    calls reuse the arrival counter."""
+    """kpal_dev_count_packed_fresh on a table full of garbage: the call zeroes it first, whichever
+    count path the input takes; repeated calls."""
     L = _cabi.load()
     text = _composition_bytes(k + n, n, "ACGTacgt", p_n=0.01)
     want = c_oracle.count_bytes(text, k, threads=c_oracle.max_threads())
@@ -683,19 +681,34 @@ def test_narrow_profile_copy_and_its_overflow_path():
     (whichever holds every count) and widen it on the host (cabi.cu finalize_to_host).
     Same bits as the plain int64 copy, for counts that fit -- and for counts that do not
     (a repetitive input pushes one bin past 65535: the device flags send the call down the
-    int64 copy).  narrow_d2h: 1 = uint8 / uint16, 2 = uint16 only, 0 = int64."""
+    int64 copy -- unless the counts that do not fit are few: they then travel in a side list and
+    the host patches their bins, option "narrow_lists").  narrow_d2h: 1 = uint8 / uint16,
+    2 = uint16 only, 0 = int64."""
     reads = random_reads(5, 20_000, 150)
     fasta = reads_to_fasta(reads)
     seqs = [r.tobytes().decode() for r in reads]
     repetitive = ">poly\n" + "A" * 70_000 + "\n>mix\n" + "ACGTTGCA" * 30_000 + "\n" + fasta.decode()
+    # 3000 different 120-mers, 300 copies each: ~330 000 bins above 255 at k = 10, 11 -- more than
+    # the side list of the uint8 form holds, so the profile travels as uint16
+    rng = np.random.default_rng(55)
+    units = ["".join("ACGT"[c] for c in rng.integers(0, 4, 120)) for _ in range(3000)]
+    many_big = "".join(">u%d\n%s\n" % (i, "N".join([u] * 300)) for i, u in enumerate(units))
     try:
+        for k in (10, 11):
+            want_big = ko.count_fasta(many_big, k)
+            assert (want_big > 255).sum() > 4 ** k // 32 and want_big.max() <= 65535
+            for lists in (1, 0):
+                _set_option("narrow_lists", lists)
+                assert np.array_equal(_cabi.count_fasta(many_big, k), want_big), (k, lists)
+                assert np.array_equal(_cabi.count_fasta(many_big, k, balance=True), ko.balance(want_big)), (k, lists)
         for k in (10, 11, 12):
             want = ko.count_sequences(seqs, k)
             want_rep = ko.count_fasta(repetitive, k)
             assert want_rep.max() > 65535 and ko.balance(want_rep).max() > 65535
             assert ko.balance(want).max() <= 255            # random reads: the uint8 copy under narrow_d2h = 1
-            for narrow in (1, 2, 0):
+            for narrow, lists in ((1, 1), (2, 1), (0, 1), (1, 0), (2, 0)):
                 _set_option("narrow_d2h", narrow)
+                _set_option("narrow_lists", lists)        # 0: a count that does not fit sends the whole profile wider
                 for balance in (False, True):
                     w = ko.balance(want) if balance else want
                     assert np.array_equal(_cabi.count_fasta(fasta, k, balance=balance), w), (k, narrow, balance)
@@ -709,6 +722,7 @@ def test_narrow_profile_copy_and_its_overflow_path():
                 assert got[0] == n_a - k + 1 and np.array_equal(got, ko.count_sequences(["A" * n_a, "ACGT" * 50], k))
     finally:
         _set_option("narrow_d2h", 1)
+        _set_option("narrow_lists", 1)
 
 
 def test_narrow_copy_into_a_pinned_profile_with_dma_share():

@@ -257,6 +257,7 @@ def _nccl_worker(rank, world, port, text, k, profiles, out_dir):
         b, e = multigpu.split_fasta(text, world)[rank]
         counts = multigpu.count_fasta_distributed(text[b:e], k, balance=True)        # peer-memory reduce
         counts_nccl = multigpu.count_fasta_distributed(text[b:e], k, balance=True, reduce='nccl')
+        counts_slices = multigpu.count_fasta_distributed(text[b:e], k, balance=True, reduce='slices')
         matrix = multigpu.distance_matrix_distributed(profiles, do_scale=True)
         # unequal shards (301 rows): the broadcast route; this rank hands over its rows only
         rb, re_ = multigpu.shard_rows(len(profiles), rank, world)
@@ -267,6 +268,7 @@ def _nccl_worker(rank, world, port, text, k, profiles, out_dir):
                  names=np.array(names, dtype=object), allow_pickle=True)
         if rank == 0:
             assert np.array_equal(counts, counts_nccl)
+            assert np.array_equal(counts, counts_slices)      # balance + narrow reduce-scatter + shared host memory
             np.save(os.path.join(out_dir, "counts.npy"), counts)
             np.save(os.path.join(out_dir, "matrix.npy"), matrix)
             np.save(os.path.join(out_dir, "matrix_sharded.npy"), matrix_sharded)
@@ -382,6 +384,50 @@ def test_peer_reduce_kernels_virtual_world(bits):
     assert L.kpal_dev_reduce_push(root.data_ptr(), bits, 2, 0, 5, ptrs, sp) == _cabi.KPAL_EINVAL
     assert L.kpal_dev_reduce_push(root.data_ptr(), 16, 6, 0, 2, ptrs, sp) == _cabi.KPAL_EINVAL
     assert L.kpal_dev_reduce_collect(root.data_ptr(), bits, 6, 2, 2, root.data_ptr(), sp) == _cabi.KPAL_EINVAL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits", [32, 64])
+def test_slice_push_collect_virtual_world(bits):
+    """The fused form of the table sum (balance + narrow reduce-scatter + distributed finalize,
+    csrc/peer_reduce.cu) with every "rank" on ONE device: the owners' int64 slices, put together,
+    equal balance(sum of the per-rank tables) -- for narrow (<= 255) and wide counts, world sizes
+    that do not divide 4^k, three epochs (both inbox parities), device slices and the narrow
+    device->host copy of a slice."""
+    import ctypes
+    import torch
+    L = _cabi.load()
+    dev = torch.device("cuda", 0)
+    dtype = torch.int32 if bits == 32 else torch.int64
+    sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rng = np.random.default_rng(bits)
+    for k, world in ((6, 1), (6, 3), (7, 2), (9, 8), (10, 5), (11, 16), (12, 8)):
+        bins = 4 ** k
+        inbox_bytes = int(L.kpal_slice_inbox_bytes(k, world))
+        inboxes = [torch.zeros(inbox_bytes, dtype=torch.uint8, device=dev) for _ in range(world)]
+        ptrs = (ctypes.c_void_p * world)(*[b.data_ptr() for b in inboxes])
+        begins = [int(L.kpal_slice_begin(k, r, world)) for r in range(world + 1)]
+        assert begins[0] == 0 and begins[-1] == bins and all(b % 64 == 0 for b in begins)
+        for epoch, high in ((1, 40), (2, 100_000), (3, 9)):
+            host = [rng.integers(0, high, bins).astype(np.int64) for _ in range(world)]
+            if epoch == 2:
+                for t in host[1:]:
+                    t[...] = rng.integers(0, 30, bins)          # only rank 0 sends wide rows
+            tables = [torch.from_numpy(t).to(dev).to(dtype) for t in host]
+            for r in range(world):
+                _cabi.check(L.kpal_dev_slice_push(tables[r].data_ptr(), bits, k, r, world, ptrs, epoch, sp))
+            want = ko.balance(np.sum(host, axis=0))
+            for r in range(world):
+                n = begins[r + 1] - begins[r]
+                piece = torch.full((max(n, 1),), -1, dtype=torch.int64, device=dev)
+                _cabi.check(L.kpal_dev_slice_collect(inboxes[r].data_ptr(), k, r, world, epoch, piece.data_ptr(), sp))
+                assert np.array_equal(piece[:n].cpu().numpy(), want[begins[r]:begins[r + 1]]), (k, world, epoch, r)
+                out = np.full(max(n, 1), -1, dtype=np.int64)
+                _cabi.check(L.kpal_dev_slice_collect_to_host(inboxes[r].data_ptr(), k, r, world, epoch, _cabi.ptr(out), sp))
+                assert np.array_equal(out[:n], want[begins[r]:begins[r + 1]]), (k, world, epoch, r, "host")
+    ptrs = (ctypes.c_void_p * 5)()
+    assert L.kpal_dev_slice_push(tables[0].data_ptr(), bits, 5, 0, 2, ptrs, 1, sp) == _cabi.KPAL_EINVAL     # k < 6
+    assert L.kpal_dev_slice_push(tables[0].data_ptr(), bits, 8, 0, 2, ptrs, 0, sp) == _cabi.KPAL_EINVAL     # epoch 0
 
 
 @pytest.mark.gpu
