@@ -120,98 +120,118 @@ __device__ __forceinline__ int owner_of(uint64_t index, uint64_t bins, int world
     return o;
 }
 
-// WIDE = false: u8 rows + overflow detection; WIDE = true: u32 rows, only when *wide_flag != 0.
-template <typename CounterT, bool WIDE>
-__global__ void __launch_bounds__(256)
-slice_push_kernel(const CounterT *__restrict__ table, int k, const SliceInbox peers, int parity,
-                  unsigned int *__restrict__ wide_flag)
-{
-    extern __shared__ __align__(16) unsigned char push_smem[];
-    if (WIDE && *reinterpret_cast<volatile unsigned int *>(wide_flag) == 0) return;
-    CounterT *A = reinterpret_cast<CounterT *>(push_smem);      // [64][65] tile of m
-    CounterT *B = A + 64 * 65;                                  // [64][65] tile of rc(m)
-    const uint32_t m = blockIdx.x;
-    const int mid_bits = 2 * (k - 6);
-    const uint32_t mr = mid_bits ? ((~rev2(m)) >> (32 - mid_bits)) : 0u;
-    if (m > mr) return;                                         // done by the CTA of rc(m)
-    const int hshift = 2 * k - 6;
-    const uint64_t bins = 1ull << (2 * k);
-    constexpr int V = 16 / int(sizeof(CounterT));
-    constexpr int NV = 4096 / V / 256;
-    uint4 va[NV], vb[NV];
-#pragma unroll
-    for (int q = 0; q < NV; ++q) {
-        const uint32_t v = threadIdx.x + 256u * q, h = v / (64 / V), l = (v % (64 / V)) * V;
-        va[q] = *reinterpret_cast<const uint4 *>(table + ((uint64_t(h) << hshift) | (uint64_t(m) << 6) | l));
-    }
-    if (m != mr) {
-#pragma unroll
-        for (int q = 0; q < NV; ++q) {
-            const uint32_t v = threadIdx.x + 256u * q, h = v / (64 / V), l = (v % (64 / V)) * V;
-            vb[q] = *reinterpret_cast<const uint4 *>(table + ((uint64_t(h) << hshift) | (uint64_t(mr) << 6) | l));
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < NV; ++q) {
-        const uint32_t v = threadIdx.x + 256u * q, h = v / (64 / V), l = (v % (64 / V)) * V;
-        const CounterT *ea = reinterpret_cast<const CounterT *>(&va[q]), *eb = reinterpret_cast<const CounterT *>(&vb[q]);
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-            A[h * 65 + l + j] = ea[j];
-            if (m != mr) B[h * 65 + l + j] = eb[j];
-        }
-    }
-    __syncthreads();
-    const CounterT *partner = (m != mr) ? B : A;
-    const uint64_t cap = slice64_cap(bins, peers.world);
-    const uint64_t par_off = uint64_t(parity) * inbox_parity_bytes(bins, peers.world);
-    bool big = false;
-    // eight neighbouring counts per thread: one 8-byte (narrow) or two 16-byte (wide) peer stores
-    for (uint32_t e = threadIdx.x; e < 512; e += 256) {
-        const uint32_t h = e >> 3, l = (e & 7u) * 8;
-        const uint32_t rh = rc_index(h, 26);
-        for (int tile = 0; tile < (m != mr ? 2 : 1); ++tile) {
-            const CounterT *own = tile ? B : A, *other = tile ? A : partner;
-            const uint64_t index = (uint64_t(h) << hshift) | (uint64_t(tile ? mr : m) << 6) | l;
-            unsigned long long v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                v[j] = (unsigned long long)(own[h * 65 + l + j]) + (unsigned long long)(other[rc_index(l + j, 26) * 65 + rh]);
-            const int o = owner_of(index, bins, peers.world);
-            unsigned char *inbox = static_cast<unsigned char *>(peers.base[o]) + par_off;
-            const uint64_t at = uint64_t(peers.rank) * cap + (index - slice64_begin(bins, o, peers.world));
-            if constexpr (!WIDE) {
-                unsigned long long packed = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    big |= v[j] > 0xffull;
-                    packed |= (v[j] & 0xffull) << (8 * j);
-                }
-                *reinterpret_cast<unsigned long long *>(inbox + 256 + at) = packed;
-            } else {
-                uint4 *dst = reinterpret_cast<uint4 *>(inbox + 256 + uint64_t(peers.world) * cap) + at / 4;
-                dst[0] = make_uint4(uint32_t(v[0]), uint32_t(v[1]), uint32_t(v[2]), uint32_t(v[3]));
-                dst[1] = make_uint4(uint32_t(v[4]), uint32_t(v[5]), uint32_t(v[6]), uint32_t(v[7]));
-#pragma unroll
-                for (int j = 0; j < 8; ++j) big |= v[j] > 0xffffffffull;
-            }
-        }
-    }
-    if (!WIDE && __any_sync(0xffffffffu, big) && (threadIdx.x & 31) == 0) *wide_flag = 1u;
-    if (WIDE && __any_sync(0xffffffffu, big) && (threadIdx.x & 31) == 0) wide_flag[1] = 1u;    // > 32 bits: caller's error
-}
-
-// "my rows of epoch e have landed in your inbox": one release store per peer
-__global__ void slice_signal_kernel(const SliceInbox peers, int parity, unsigned long long epoch, uint64_t bins,
-                                    const unsigned int *__restrict__ wide_flag)
+// "my rows of epoch e have landed in your inbox": one release store per peer (threads 0 .. world-1)
+__device__ __forceinline__ void slice_signal(const SliceInbox &peers, int parity, unsigned long long epoch,
+                                             uint64_t bins, bool wide)
 {
     const int o = threadIdx.x;
     if (o >= peers.world) return;
-    const unsigned long long value = (epoch << 1) | (wide_flag[0] ? 1ull : 0ull);
+    const unsigned long long value = (epoch << 1) | (wide ? 1ull : 0ull);
     unsigned long long *flag = reinterpret_cast<unsigned long long *>(
         static_cast<unsigned char *>(peers.base[o]) + uint64_t(parity) * inbox_parity_bytes(bins, peers.world)) + peers.rank;
     __threadfence_system();
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(value) : "memory");
+}
+
+// WIDE = false: u8 rows + overflow detection; WIDE = true: u32 rows, only when wide_flag[0] != 0.
+// state = { wide needed, count above 32 bits (caller's error), CTAs done (narrow), CTAs done (wide) }.
+// The last CTA to finish sends the signal: of the narrow launch when no count exceeded 255,
+// else of the wide launch (threadfence-reduction pattern: every CTA fences its peer stores
+// system-wide before it counts itself done).
+template <typename CounterT, bool WIDE>
+__global__ void __launch_bounds__(256)
+slice_push_kernel(const CounterT *__restrict__ table, int k, const SliceInbox peers, int parity,
+                  unsigned long long epoch, unsigned int *__restrict__ state)
+{
+    extern __shared__ __align__(16) unsigned char push_smem[];
+    __shared__ unsigned int last_s;
+    if (WIDE && *reinterpret_cast<volatile unsigned int *>(state) == 0) return;
+    CounterT *A = reinterpret_cast<CounterT *>(push_smem);      // [64][65] tile of m
+    CounterT *B = A + 64 * 65;                                  // [64][65] tile of rc(m)
+    const int mid_bits = 2 * (k - 6);
+    const int hshift = 2 * k - 6;
+    const uint64_t bins = 1ull << (2 * k);
+    const uint32_t tiles = 1u << mid_bits;
+    const uint64_t cap = slice64_cap(bins, peers.world);
+    const uint64_t par_off = uint64_t(parity) * inbox_parity_bytes(bins, peers.world);
+    bool big = false;
+    for (uint32_t m = blockIdx.x; m < tiles; m += gridDim.x) {
+        const uint32_t mr = mid_bits ? ((~rev2(m)) >> (32 - mid_bits)) : 0u;
+        if (m > mr) continue;                                   // done together with rc(m)
+        constexpr int V = 16 / int(sizeof(CounterT));
+        constexpr int NV = 4096 / V / 256;
+        uint4 va[NV], vb[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const uint32_t v = threadIdx.x + 256u * q, h = v / (64 / V), l = (v % (64 / V)) * V;
+            va[q] = *reinterpret_cast<const uint4 *>(table + ((uint64_t(h) << hshift) | (uint64_t(m) << 6) | l));
+        }
+        if (m != mr) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const uint32_t v = threadIdx.x + 256u * q, h = v / (64 / V), l = (v % (64 / V)) * V;
+                vb[q] = *reinterpret_cast<const uint4 *>(table + ((uint64_t(h) << hshift) | (uint64_t(mr) << 6) | l));
+            }
+        }
+        __syncthreads();                                        // the previous tile pair has been pushed
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const uint32_t v = threadIdx.x + 256u * q, h = v / (64 / V), l = (v % (64 / V)) * V;
+            const CounterT *ea = reinterpret_cast<const CounterT *>(&va[q]), *eb = reinterpret_cast<const CounterT *>(&vb[q]);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                A[h * 65 + l + j] = ea[j];
+                if (m != mr) B[h * 65 + l + j] = eb[j];
+            }
+        }
+        __syncthreads();
+        const CounterT *partner = (m != mr) ? B : A;
+        // eight neighbouring counts per thread: one 8-byte (narrow) or two 16-byte (wide) peer stores
+        for (uint32_t e = threadIdx.x; e < 512; e += 256) {
+            const uint32_t h = e >> 3, l = (e & 7u) * 8;
+            const uint32_t rh = rc_index(h, 26);
+            for (int tile = 0; tile < (m != mr ? 2 : 1); ++tile) {
+                const CounterT *own = tile ? B : A, *other = tile ? A : partner;
+                const uint64_t index = (uint64_t(h) << hshift) | (uint64_t(tile ? mr : m) << 6) | l;
+                unsigned long long v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    v[j] = (unsigned long long)(own[h * 65 + l + j]) + (unsigned long long)(other[rc_index(l + j, 26) * 65 + rh]);
+                const int o = owner_of(index, bins, peers.world);
+                unsigned char *inbox = static_cast<unsigned char *>(peers.base[o]) + par_off;
+                const uint64_t at = uint64_t(peers.rank) * cap + (index - slice64_begin(bins, o, peers.world));
+                if constexpr (!WIDE) {
+                    unsigned long long packed = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        big |= v[j] > 0xffull;
+                        packed |= (v[j] & 0xffull) << (8 * j);
+                    }
+                    *reinterpret_cast<unsigned long long *>(inbox + 256 + at) = packed;
+                } else {
+                    uint4 *dst = reinterpret_cast<uint4 *>(inbox + 256 + uint64_t(peers.world) * cap) + at / 4;
+                    dst[0] = make_uint4(uint32_t(v[0]), uint32_t(v[1]), uint32_t(v[2]), uint32_t(v[3]));
+                    dst[1] = make_uint4(uint32_t(v[4]), uint32_t(v[5]), uint32_t(v[6]), uint32_t(v[7]));
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) big |= v[j] > 0xffffffffull;
+                }
+            }
+        }
+    }
+    if (big) state[WIDE ? 1 : 0] = 1u;
+    // ---- done: fence the peer stores, count this CTA; the last one signals the peers
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last_s = atomicAdd(state + (WIDE ? 3 : 2), 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (last_s) {
+        __threadfence();
+        const bool wide_needed = *reinterpret_cast<volatile unsigned int *>(state) != 0;
+        if (WIDE || !wide_needed) slice_signal(peers, parity, epoch, bins, WIDE);
+    }
 }
 
 // Owner side.  out64: this rank's slice of the final profile (int64); o16 / o8 / flags (optional):
@@ -298,7 +318,7 @@ static int slice_args(int k, int counter_bits, int rank, int world, void *const 
     return KPAL_OK;
 }
 
-// balance + narrow push of this rank's table, then the signal.  d_wide_flag: 2 device words.
+// balance + narrow push of this rank's table (the last CTA signals the peers).  d_wide_flag: 4 device words.
 int launch_slice_push(const void *d_table, int counter_bits, int k, int rank, int world, void *const *inbox_ptrs,
                       unsigned long long epoch, unsigned int *d_wide_flag, cudaStream_t stream)
 {
@@ -308,22 +328,22 @@ int launch_slice_push(const void *d_table, int counter_bits, int k, int rank, in
     const int parity = int(epoch & 1ull);
     const unsigned tiles = 1u << (2 * (k - 6));
     const size_t smem = size_t(2) * 64 * 65 * (counter_bits / 8);
-    KPAL_CUDA(cudaMemsetAsync(d_wide_flag, 0, 8, stream));
+    KPAL_CUDA(cudaMemsetAsync(d_wide_flag, 0, 16, stream));
+    // the wide launch is a no-op unless a count exceeded 255: a small grid that loops over the tiles
+    const unsigned wide_grid = std::min<unsigned>(tiles, unsigned(sm_count()) * 2);
     if (counter_bits == 32) {
-        slice_push_kernel<uint32_t, false><<<tiles, 256, smem, stream>>>(static_cast<const uint32_t *>(d_table), k, peers, parity, d_wide_flag);
+        slice_push_kernel<uint32_t, false><<<tiles, 256, smem, stream>>>(static_cast<const uint32_t *>(d_table), k, peers, parity, epoch, d_wide_flag);
         KPAL_LAUNCH_CHECK("slice_push_kernel");
-        slice_push_kernel<uint32_t, true><<<tiles, 256, smem, stream>>>(static_cast<const uint32_t *>(d_table), k, peers, parity, d_wide_flag);
+        slice_push_kernel<uint32_t, true><<<wide_grid, 256, smem, stream>>>(static_cast<const uint32_t *>(d_table), k, peers, parity, epoch, d_wide_flag);
         KPAL_LAUNCH_CHECK("slice_push_kernel");
     } else {
         KPAL_CUDA(cudaFuncSetAttribute(slice_push_kernel<unsigned long long, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         KPAL_CUDA(cudaFuncSetAttribute(slice_push_kernel<unsigned long long, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        slice_push_kernel<unsigned long long, false><<<tiles, 256, smem, stream>>>(static_cast<const unsigned long long *>(d_table), k, peers, parity, d_wide_flag);
+        slice_push_kernel<unsigned long long, false><<<tiles, 256, smem, stream>>>(static_cast<const unsigned long long *>(d_table), k, peers, parity, epoch, d_wide_flag);
         KPAL_LAUNCH_CHECK("slice_push_kernel");
-        slice_push_kernel<unsigned long long, true><<<tiles, 256, smem, stream>>>(static_cast<const unsigned long long *>(d_table), k, peers, parity, d_wide_flag);
+        slice_push_kernel<unsigned long long, true><<<wide_grid, 256, smem, stream>>>(static_cast<const unsigned long long *>(d_table), k, peers, parity, epoch, d_wide_flag);
         KPAL_LAUNCH_CHECK("slice_push_kernel");
     }
-    slice_signal_kernel<<<1, 32, 0, stream>>>(peers, parity, epoch, 1ull << (2 * k), d_wide_flag);
-    KPAL_LAUNCH_CHECK("slice_signal_kernel");
     return KPAL_OK;
 }
 

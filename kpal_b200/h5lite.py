@@ -371,7 +371,7 @@ class AttributeManager(object):
                 if value.dtype.kind not in 'iufS':
                     raise TypeError('h5lite cannot store an attribute of type %r' % (value.dtype,))
                 value = value[()] if value.shape == () else value
-        self._owner._attrs[name] = value
+        self._owner._attributes()[name] = value
 
 
 class _Node(object):
@@ -529,6 +529,73 @@ class Group(_Node):
         parent._children[name] = dataset
         return dataset
 
+    def create_datasets(self, names, rows, compression_opts=None, attrs=None):
+        """
+        ``create_dataset(name, data=row, dtype=rows.dtype, compression='gzip')`` for every row
+        of the C-contiguous 2-D array `rows`, plus ``dataset.attrs[key] = values[i]`` for every
+        ``key: values`` of `attrs` (arrays of one int64 / float64 scalar per row) -- the bulk
+        form behind ``klib.save_profiles``.  Same file content as the loop; the chunks of all
+        rows are deflated by the native library on all host threads (``kpal_deflate_chunks``)
+        and written with one call, the metadata is laid out in bulk on ``close()``.
+        (h5lite extension: h5py has no such call.)
+        """
+        self._file._require_writable()
+        rows = np.ascontiguousarray(rows)
+        if rows.ndim != 2 or rows.dtype.kind not in 'iuf' or len(names) != rows.shape[0]:
+            raise ValueError('rows must be a 2-D numeric array with one row per name')
+        attrs = dict((key, np.ascontiguousarray(values)) for key, values in (attrs or {}).items())
+        level = GZIP_LEVEL if compression_opts is None else int(compression_opts)
+        links = self._links()
+        if len(set(names)) != len(names) or any(name in links or '/' in name for name in names):
+            raise ValueError('Unable to create dataset (name already exists)')
+        n, m = rows.shape
+        chunk = _guess_chunk((m,), rows.dtype.itemsize)[0] if m else 0
+        native = None
+        try:
+            from . import _cabi as native
+            native.load()
+        except Exception:
+            native = None
+        simple = all(v.shape == (n,) and v.dtype in (np.dtype('int64'), np.dtype('float64')) for v in attrs.values())
+        if native is None or not n or not m or m % chunk or m // chunk > 2 * CHUNK_K or not simple:
+            for i, name in enumerate(names):                    # the general path, one at a time
+                dataset = self.create_dataset(name, data=rows[i], dtype=rows.dtype, compression='gzip',
+                                              compression_opts=level)
+                for key, values in attrs.items():
+                    dataset.attrs[key] = values[i]
+            return
+        per = m // chunk
+        blob, sizes = native.deflate_chunks_packed(rows, chunk * rows.dtype.itemsize, level)
+        self._file._drain(0)                                    # keep the file in creation order
+        base = self._file._append(blob)
+        ends = np.cumsum(sizes, dtype=np.uint64)
+        addresses = (np.uint64(base) + ends - sizes.astype(np.uint64)).reshape(n, per)
+        bulk = _Bulk((m,), rows.dtype, (chunk,), level, addresses, sizes.reshape(n, per), attrs)
+        for i, name in enumerate(names):
+            dataset = Dataset(self._file, self._child_path(name))
+            dataset._bulk = (bulk, i)
+            dataset._attrs = None                               # built from the bulk arrays on demand
+            links[name] = dataset
+
+
+class _Bulk(object):
+    """The common part of the equally shaped, gzip-compressed 1-D datasets that one
+    ``Group.create_datasets`` call writes (the profiles of a ``kpal count --by-record`` run:
+    100 000 of them).  Their chunks are already in the file; addresses, stored sizes and
+    attribute values are kept as arrays, and the serializer lays out all their chunk B-trees
+    and object headers with a few array operations instead of a Python loop per dataset."""
+
+    def __init__(self, shape, dtype, chunks, level, addresses, sizes, attrs):
+        self.shape, self.dtype, self.chunks, self.level = shape, dtype, chunks, level
+        self.addresses, self.sizes, self.attrs = addresses, sizes, attrs
+        self.headers = None                 # object header addresses, set by the serializer
+
+    def meta(self, i):
+        per = self.addresses.shape[1]
+        index = [((c * self.chunks[0],), int(self.addresses[i, c]), int(self.sizes[i, c]), 0) for c in range(per)]
+        return {'shape': self.shape, 'dtype': self.dtype, 'filters': [(1, (self.level,))], 'chunks': self.chunks,
+                'layout': ('chunked', None), 'index': index}
+
 
 def _guess_chunk(shape, itemsize):
     """Chunk shape for a dataset whose chunking is left to the library: the rule h5py
@@ -555,10 +622,24 @@ class Dataset(_Node):
     def __init__(self, file, name, header=None):
         super(Dataset, self).__init__(file, name, header)
         self._meta = None
+        self._bulk = None                   # (_Bulk, row) for a dataset written by Group.create_datasets
+
+    def _attributes(self):
+        if self._attrs is None and self._bulk is not None:
+            # somebody looks at (or is about to change) the attributes: from here on this is an
+            # ordinary dataset, serialised on its own
+            bulk, i = self._bulk
+            self._meta = bulk.meta(i)
+            self._attrs = dict((key, values[i]) for key, values in bulk.attrs.items())
+            self._bulk = None
+        return super(Dataset, self)._attributes()
 
     # ---- metadata
     def _load(self):
         if self._meta is not None:
+            return self._meta
+        if self._bulk is not None:
+            self._meta = self._bulk[0].meta(self._bulk[1])
             return self._meta
         self._file._require_open()
         meta = {'filters': [], 'chunks': None, 'layout': None}
@@ -657,6 +738,8 @@ class Dataset(_Node):
         meta = self._load()
         if 'index' not in meta and getattr(self, '_future', None) is not None:
             self._file._drain(0)                                # still being deflated in the background
+        if self._meta is None:
+            self._meta = meta                                   # (a bulk dataset: keep what was built)
         if 'index' in meta:
             return meta['index']
         reader = self._file._reader
@@ -977,6 +1060,8 @@ class _Serializer(object):
         return len(data), len(self.heap_objects)
 
     def _collect_strings(self, node):
+        if isinstance(node, Dataset) and node._bulk is not None:
+            return                                      # written in bulk: numeric attributes only
         for value in node._attributes().values():
             if isinstance(value, str):
                 self.n_strings += 1
@@ -1065,12 +1150,65 @@ class _Serializer(object):
             entries = parents
             level += 1
 
+    def _write_bulk(self, bulk):
+        """Chunk B-trees and object headers of all datasets of a Group.create_datasets call:
+        the same bytes _write_dataset produces, built as two arrays (one leaf node and one
+        header per dataset) from a template whose variable fields are patched column-wise."""
+        file = self.file
+        n, per = bulk.addresses.shape
+        # ---- one leaf node per dataset (per <= 2 * CHUNK_K chunks, rank 1)
+        key = [('nbytes', '<u4'), ('mask', '<u4'), ('off0', '<u8'), ('off1', '<u8')]
+        used = 24 + per * 32 + 24
+        node_size = 24 + (2 * CHUNK_K + 1) * 24 + 2 * CHUNK_K * 8
+        node = np.dtype([('sig', 'S4'), ('type', 'u1'), ('level', 'u1'), ('used', '<u2'), ('left', '<u8'),
+                         ('right', '<u8'), ('entries', key + [('child', '<u8')], (per,)), ('last', key),
+                         ('pad', 'u1', (node_size - used,))])
+        assert node.itemsize == node_size
+        nodes = np.zeros(n, dtype=node)
+        nodes['sig'], nodes['type'], nodes['used'] = b'TREE', 1, per
+        nodes['left'] = nodes['right'] = UNDEF
+        nodes['entries']['nbytes'] = bulk.sizes
+        nodes['entries']['off0'] = (np.arange(per, dtype=np.uint64) * np.uint64(bulk.chunks[0]))[None, :]
+        nodes['entries']['child'] = bulk.addresses
+        nodes['last']['off0'] = -(-bulk.shape[0] // bulk.chunks[0]) * bulk.chunks[0]
+        base = file._append(nodes.tobytes())
+        btrees = np.uint64(base) + np.arange(n, dtype=np.uint64) * np.uint64(node_size)
+        # ---- one object header per dataset: a template with marked fields, then patched copies
+        marks = {}
+
+        def mark(label, dtype):
+            value = np.array([0x7E57A77B00000000 + len(marks)], dtype='<u8')
+            marks[label] = value.tobytes()
+            return value.view(dtype)[0]
+        template = Dataset(file, '/template')
+        template._meta = dict(bulk.meta(0), index=None)
+        template._attrs = dict((name, mark(('attr', name), values.dtype)) for name, values in bulk.attrs.items())
+        header = bytearray(self._dataset_header(template, int(mark('btree', '<u8'))))
+        offsets = {}
+        for label, pattern in marks.items():
+            at = bytes(header).find(pattern)
+            if at < 0 or bytes(header).find(pattern, at + 1) >= 0:
+                raise AssertionError('h5lite: cannot locate a field of the bulk object header')
+            offsets[label] = at
+        headers = np.tile(np.frombuffer(bytes(header), dtype=np.uint8), (n, 1))
+        headers[:, offsets['btree']:offsets['btree'] + 8] = btrees.astype('<u8').view(np.uint8).reshape(n, 8)
+        for name, values in bulk.attrs.items():
+            at = offsets[('attr', name)]
+            headers[:, at:at + 8] = np.ascontiguousarray(values).view(np.uint8).reshape(n, 8)
+        base = file._append(headers.tobytes())
+        bulk.headers = np.uint64(base) + np.arange(n, dtype=np.uint64) * np.uint64(len(header))
+
     def _write_dataset(self, dataset):
+        meta = dataset._load()
+        btree = self._chunk_btree(dataset) if meta['layout'][0] == 'chunked' else None
+        return self.file._append(self._dataset_header(dataset, btree))
+
+    def _dataset_header(self, dataset, btree):
+        """The object header of `dataset` (bytes) whose chunk B-tree, if any, is at `btree`."""
         meta = dataset._load()
         messages = [_message(MSG_DATASPACE, _dataspace_message(meta['shape']), 0),
                     _message(MSG_DATATYPE, _encode_datatype(meta['dtype']), 1)]
         if meta['layout'][0] == 'chunked':
-            btree = self._chunk_btree(dataset)
             rank = len(meta['shape'])
             # fill value v2: allocation incremental, written if set, no user-defined value
             messages.append(_message(MSG_FILL, struct.pack('<BBBB', 2, 3, 2, 0), 1))
@@ -1092,18 +1230,23 @@ class _Serializer(object):
             messages.append(_message(MSG_LAYOUT, struct.pack('<BBQQ', 3, 1, address, size)))
         for name, value in dataset._attributes().items():
             messages.append(self._attribute_message(name, value))
-        return self.file._append(_object_header(messages))
+        return _object_header(messages)
 
     # ---- groups
     def _write_group(self, group):
         """-> (object header address, B-tree address, local heap address)."""
         file = self.file
         children = []
+        for child in group._links().values():                   # datasets written in bulk: all at once
+            if isinstance(child, Dataset) and child._bulk is not None and child._bulk[0].headers is None:
+                self._write_bulk(child._bulk[0])
         for name in sorted(group._links(), key=lambda n: n.encode('utf-8')):
             child = group._links()[name]
             if isinstance(child, Group):
                 header, btree, heap = self._write_group(child)
                 children.append((name, header, 1, btree, heap))
+            elif child._bulk is not None:
+                children.append((name, int(child._bulk[0].headers[child._bulk[1]]), 0, 0, 0))
             else:
                 children.append((name, self._write_dataset(child), 0, 0, 0))
         # local heap: "" at offset 0, then the names, each padded to 8 bytes

@@ -124,6 +124,24 @@ class Profile(object):
                 yield cls(rows[i].copy(), name=prefix + (names[record] or str(record + 1)))
 
     @classmethod
+    def record_batches(cls, handle, length, prefix=None):
+        """
+        The same profiles as :meth:`from_fasta_by_record`, a device batch at a time: a
+        generator of ``(names, rows)`` with `rows` the dense ``[n][4**length]`` int64 counts of
+        `n` consecutive records.  What ``kpal count --by-record`` feeds to
+        :func:`save_profiles` (no Profile object, no row copy per record).
+        """
+        _cabi._check_k(length)
+        prefix = prefix + '_' if prefix else ''
+        codes, valid, rec_starts, names, n_bases = _cabi.fasta_pack(_read_text(handle))
+        n_records = len(names)
+        batch = max(1, cls._BY_RECORD_BATCH_BYTES // (8 * 4 ** length))
+        for first in range(0, n_records, batch):
+            n = min(batch, n_records - first)
+            rows = _cabi.count_by_record(codes, valid, n_bases, rec_starts, first, n, length)
+            yield [prefix + (names[first + i] or str(first + i + 1)) for i in range(n)], rows
+
+    @classmethod
     def from_sequences(cls, sequences, length, name=None):
         """
         Count all *k*-mers in an iterable of sequence strings
@@ -264,6 +282,34 @@ class Profile(object):
         """Print ``<k-mer> <count>`` lines (kpal/klib.py:460-465)."""
         for i in range(self.number):
             print(self.binary_to_dna(i), self.counts[i])
+
+
+def save_profiles(handle, names, rows):
+    """
+    ``Profile(rows[i], names[i]).save(handle)`` for every row (reference kpal/klib.py:227-256:
+    dataset ``/profiles/<name>``, int64, gzip, attributes ``length, total, non_zero, mean,
+    median, std``) -- for the 100 000 profiles of a ``--by-record`` run.  With the in-tree
+    HDF5 writer the statistics of all rows come from ``kpal_row_stats`` (host threads,
+    bit-identical to the NumPy calls behind the reference's properties), the chunks from
+    ``kpal_deflate_chunks``, and the datasets are created with one call; with h5py it is the
+    plain loop.
+    """
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    for name in names:
+        if not name or '/' in name or '.' in name:
+            raise ValueError('Profile name may not contain / or . characters.')
+    group = handle['profiles']
+    if not hasattr(group, 'create_datasets') or len(names) < 2:
+        for name, row in zip(names, rows):
+            Profile(row, name=name).save(handle)
+        return
+    stats = _cabi.row_stats(rows)
+    length = int(math.log(rows.shape[1], 4))
+    group.create_datasets(list(names), rows, attrs={
+        'length': np.full(len(names), length, dtype=np.int64),
+        'total': stats[:, 0].astype(np.int64), 'non_zero': stats[:, 1].astype(np.int64),
+        'mean': stats[:, 2].copy(), 'median': stats[:, 3].copy(), 'std': stats[:, 4].copy()})
+    handle.flush()
 
 
 def _read_text(handle):

@@ -155,12 +155,13 @@ def count(input_handles, output_handle, size, names=None, by_record=False):
         raise ValueError(NAMES_COUNT_ERROR)
     for input_handle, name in zip(input_handles, names):
         if by_record:
+            # a device batch of rows at a time: counted on the GPU, statistics and deflate on
+            # the host threads, all datasets of the batch created with one call
             prefix = name if len(input_handles) > 1 else None
-            profiles = klib.Profile.from_fasta_by_record(input_handle, size, prefix=prefix)
+            for batch_names, rows in klib.Profile.record_batches(input_handle, size, prefix=prefix):
+                klib.save_profiles(output_handle, batch_names, rows)
         else:
-            profiles = [klib.Profile.from_fasta(input_handle, size, name=name)]
-        for profile in profiles:
-            profile.save(output_handle)
+            klib.Profile.from_fasta(input_handle, size, name=name).save(output_handle)
 
 
 def balance(input_handle, output_handle, names=None):

@@ -204,6 +204,38 @@ def test_widen_u16_from_many_threads():
         assert np.array_equal(o, s.astype(np.int64))
 
 
+def test_row_stats_are_numpy_bit_for_bit():
+    """kpal_row_stats (host threads): total, non_zero, mean, median, std of every row, bit-identical
+    to the NumPy calls behind the reference's Profile properties (kpal/klib.py:192-225)."""
+    rng = np.random.default_rng(21)
+    for shape, high in (((40, 65536), 3), ((9, 4096), 50), ((5, 1024), 10 ** 6), ((12, 16), 4), ((3, 4 ** 9), 2)):
+        rows = rng.integers(0, high, shape).astype(np.int64)
+        rows[0] = 0
+        rows[-1, ::5] = 10 ** 10
+        stats = _cabi.row_stats(rows)
+        for r, x in enumerate(rows):
+            want = (float(x.sum()), float(np.count_nonzero(x)), x.mean(), np.median(x), x.std())
+            assert tuple(stats[r]) == want, (shape, r)
+
+
+def test_deflate_chunks_are_zlib_streams():
+    import zlib
+    rng = np.random.default_rng(22)
+    rows = rng.poisson(0.02, (33, 16384)).astype(np.int64)
+    for chunk_bytes, level in ((16384, 4), (131072, 1), (8 * 16384, 9)):
+        blob, sizes = _cabi.deflate_chunks_packed(rows, chunk_bytes, level)
+        raw = rows.view(np.uint8).reshape(-1)
+        at = 0
+        for c, size in enumerate(sizes):
+            stream = bytes(blob[at:at + size])
+            assert zlib.decompress(stream) == raw[c * chunk_bytes:(c + 1) * chunk_bytes].tobytes()
+            assert stream == zlib.compress(raw[c * chunk_bytes:(c + 1) * chunk_bytes].tobytes(), level)
+            at += size
+        assert at == blob.size
+    with pytest.raises(ValueError):
+        _cabi.deflate_chunks_packed(rows, 1000, 4)
+
+
 def test_no_cpu_fallback_without_gpu():
     """On a box without a GPU the product path must refuse, not emulate."""
     from kpal_b200 import klib, kdistlib

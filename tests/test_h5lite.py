@@ -408,3 +408,46 @@ def test_reference_test_suite_passes_on_h5lite(tmp_path):
     tail = result.stdout.strip().splitlines()[-1] if result.stdout.strip() else result.stderr[-400:]
     assert result.returncode == 0, result.stdout[-3000:]
     assert ' passed' in tail and 'failed' not in tail and int(tail.split()[0]) >= 105, tail
+
+
+def test_bulk_datasets_equal_the_loop(tmp_path):
+    """Group.create_datasets (one call for a batch of per-record profiles: native deflate of all
+    chunks, bulk chunk B-trees and object headers) writes the content the create_dataset loop
+    writes -- data, chunking, filter, attribute values and types -- and a structurally valid file;
+    datasets of both kinds mix in one group, and a bulk dataset whose attributes are touched
+    afterwards is serialised on its own."""
+    from kpal_b200 import klib
+    rng = np.random.default_rng(12)
+    n, k = 70, 7
+    rows = rng.poisson(0.05, (n, 4 ** k)).astype(np.int64)
+    rows[3] = 0
+    rows[5, ::11] = 10 ** 12
+    names = ['rec%03d' % i for i in range(n)]
+    bulk_path, loop_path = str(tmp_path / 'bulk.k'), str(tmp_path / 'loop.k')
+    with h5lite.File(bulk_path, 'w') as handle:
+        handle.create_group('profiles')
+        klib.Profile(rows[0], name='first').save(handle)                # an ordinary dataset before ...
+        klib.save_profiles(handle, names[:40], rows[:40])
+        klib.save_profiles(handle, names[40:], rows[40:])               # ... two bulk calls ...
+        handle['profiles/rec007'].attrs['note'] = 'touched'              # ... one of them modified ...
+        klib.Profile(rows[1], name='last').save(handle)                 # ... and one after
+        assert np.array_equal(handle['profiles/rec033'][:], rows[33])   # readable before close()
+    with h5lite.File(loop_path, 'w') as handle:
+        handle.create_group('profiles')
+        for name, row in zip(names, rows):
+            klib.Profile(row, name=name).save(handle)
+    _fsck(bulk_path)
+    with h5lite.File(bulk_path, 'r') as a, h5lite.File(loop_path, 'r') as b:
+        assert a['profiles'].keys() == sorted(names + ['first', 'last'])
+        assert a['profiles/rec007'].attrs['note'] == 'touched'
+        for name in names:
+            da, db = a['profiles/' + name], b['profiles/' + name]
+            assert np.array_equal(da[:], db[:]) and da.dtype == db.dtype
+            assert da.chunks == db.chunks and da.compression == db.compression
+            for key in ('length', 'total', 'non_zero', 'mean', 'median', 'std'):
+                va, vb = da.attrs[key], db.attrs[key]
+                assert va == vb and np.asarray(va).dtype == np.asarray(vb).dtype, (name, key)
+    with pytest.raises(ValueError):
+        with h5lite.File(str(tmp_path / 'dup.k'), 'w') as handle:
+            handle.create_group('profiles')
+            klib.save_profiles(handle, ['a', 'a'], rows[:2])
