@@ -399,7 +399,6 @@ def bench_count(args, world, rank, local):
     _cabi.check(L.kpal_set_device(local))
     _cabi.check(L.kpal_set_option(b"count_path", args.count_path))
     _cabi.check(L.kpal_set_option(b"radix_payload_bits", args.radix_payload_bits))
-    _cabi.check(L.kpal_set_option(b"pair_upt", args.pair_upt))
     _cabi.check(L.kpal_set_option(b"pair_flush_every", args.pair_flush_every))
     _cabi.check(L.kpal_set_option(b"pair_fused", args.pair_fused))
     if args.radix_max_buckets:
@@ -1075,8 +1074,6 @@ def main():
     ap.add_argument("--count-path", type=int, default=0, choices=[0, 1, 2, 3],
                     help="0 = library default, 1 = scattered-RED kernel, 2 = radix-partitioned path "
                          "(two windows per payload up to k = 12), 3 = one-window radix path")
-    ap.add_argument("--pair-upt", type=int, default=1, choices=[1, 2],
-                    help="pair path: 32-base units per thread and tile")
     ap.add_argument("--fresh", type=int, default=1, choices=[0, 1],
                     help="device step: 1 = the count call zeroes the table itself (inside the first kernel on "
                          "the pair path), 0 = memset, then count")

@@ -61,7 +61,6 @@ void set_radix_payload_bits(int bits);
 void set_radix_debug(int v);
 void set_radix_shape(int v);
 void set_radix_max_buckets(int v);
-void set_pair_upt(int v);
 void set_pair_fused(int v);
 void set_pair_flush_every(int v);
 int launch_fasta_pack(const uint8_t *, uint64_t, uint32_t *, uint32_t *, void *, cudaStream_t);
@@ -389,10 +388,6 @@ extern "C" int kpal_set_option(const char *name, int value)
     if (!strcmp(name, "radix_max_buckets")) {
         if (value != 1024 && value != 2048) return bad_arg("radix_max_buckets must be 1024 or 2048");
         set_radix_max_buckets(value); return KPAL_OK;
-    }
-    if (!strcmp(name, "pair_upt")) {
-        if (value < 1 || value > 2) return bad_arg("pair_upt must be 1 or 2 (units per thread and tile)");
-        set_pair_upt(value); return KPAL_OK;
     }
     if (!strcmp(name, "pair_flush_every")) {
         if (value < 0 || value > 6) return bad_arg("pair_flush_every must be 0 (auto) .. 6 tiles");

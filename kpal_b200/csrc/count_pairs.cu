@@ -31,6 +31,8 @@
 // both windows of the pair: exact for every input.
 #include "radix_common.cuh"
 
+#include <type_traits>
+
 namespace kpal {
 
 constexpr int kPairBucketBases = 5;                 // c: bucket = bases 1 .. c of the (k+1)-mer
@@ -39,77 +41,110 @@ constexpr int kPairThreads = 1024;
 constexpr int kPairHistThreads = 512;
 
 constexpr int kSlotTrash = 8;           // halfwords behind a slot's `cap` places that absorb stores of unbinned pairs
+constexpr int kPairCap = 96;            // places per slot; cap + trash = 8 x 13 halfwords = 208 bytes keeps the
+constexpr int kSlotHalfwords = kPairCap + kSlotTrash;       // 16-byte slot reads of neighbouring buckets on distinct bank groups
+constexpr size_t kPairSmem1 = size_t(kPairBuckets + 32) * 4 + size_t(kPairBuckets) * 4 +
+                              size_t(kPairBuckets) * kSlotHalfwords * 2 + 64;      // counters, fill, slots, pad
 
 struct PairParams {
     const uint2 *codes;         // 32 bases per uint2
     const uint32_t *valid;      // 32 bases per word
     uint64_t unit_begin, unit_end;   // units [begin, end) of this launch
     uint64_t n_units;           // units readable in the stream (loads are clamped to this)
-    int k, cap;                 // k-mer length, slot capacity (payloads); slot stride = cap + kSlotTrash
+    int k;
     uint32_t region_groups;     // capacity of one (CTA, bucket) region in groups of 16 payloads
     uint16_t *staging;          // [grid][1024][region_groups * 16]
     uint32_t *region_fill;      // [grid][1024] payloads stored per region
     int flush_every;            // tiles binned between two flushes of the slots
 };
 
-struct PairCtx {
-    uint32_t cnt_s, slots_s;        // shared addresses of cnt[] and slots[]
-    uint32_t dummy_cnt_s;           // per-lane counter that absorbs pairs that are not binned
-    uint32_t cap;
-    uint32_t slot_words;            // slot stride in 32-bit words (x 4 bl = byte offset / 4 ...)
-    int shift;                      // 32 - 2 (k + 1): funnel-shifted word -> M
-    int rshift;                     // 2 (k - c): M -> b0 : C
-    uint32_t rmask;                 // 4^(k-c) - 1
-    uint32_t kmask;                 // 4^k - 1
+// k is a template parameter of pass 1: every shift, mask and slot offset of the inner loop is an
+// immediate, which frees the registers the sixteen ranks in flight need (below).
+template <int K>
+struct PairGeom {
+    static constexpr int shift = 32 - 2 * (K + 1);                  // funnel-shifted word -> M
+    static constexpr int rshift = 2 * (K - kPairBucketBases);       // M -> b0 : C
+    static constexpr uint32_t rmask = (1u << rshift) - 1u;          // 4^(k-c) - 1
+    static constexpr uint32_t kmask = (1u << (2 * K)) - 1u;         // 4^k - 1
 };
 
-// Eight pairs (16 windows) at a time, branch-free as bin_eight in count_radix.cu.
+// The pairs of a unit in two batches (12 + 4), branch-free as bin_eight in count_radix.cu.
 // A pair takes a returning shared atomic (its rank in the bucket's slot) and a 16-bit store at
 // slot[min(rank, cap)] -- the places from `cap` on are trash, so a full slot needs no branch;
-// the batch checks once whether any rank reached `cap` and then counts those pairs with REDs.
-template <typename CounterT, int O0>
-__device__ __forceinline__ void bin_eight_pairs(const Unit &u, uint32_t both, const PairCtx &c, CounterT *table)
+// the unit checks once whether any rank reached `cap` and then counts those pairs with REDs.
+// All atomics of a batch are issued before the first rank is used: the kernel runs at the latency
+// of the shared atomics times the number a warp keeps in flight (ncu: 1.5 atomics per cycle
+// and SM with eight in flight per warp, issue slots 45 % busy), so the (k+1)-mers are not kept
+// in registers but extracted a second time for the stores -- registers for the ranks instead.
+template <int J, int JE, typename F>
+__device__ __forceinline__ void static_for(F &&f)
 {
-    uint32_t m[8], rank[8];
-    m[0] = unit_window<O0 + 0>(u, c.shift); m[1] = unit_window<O0 + 2>(u, c.shift);
-    m[2] = unit_window<O0 + 4>(u, c.shift); m[3] = unit_window<O0 + 6>(u, c.shift);
-    m[4] = unit_window<O0 + 8>(u, c.shift); m[5] = unit_window<O0 + 10>(u, c.shift);
-    m[6] = unit_window<O0 + 12>(u, c.shift); m[7] = unit_window<O0 + 14>(u, c.shift);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t okm = uint32_t(int32_t(both << (O0 + 2 * j)) >> 31);
-        const uint32_t bl4 = (m[j] >> (c.rshift - 2)) & uint32_t(4 * (kPairBuckets - 1));
-        const uint32_t real = c.cnt_s + bl4;
-        rank[j] = atoms_add(c.dummy_cnt_s ^ ((c.dummy_cnt_s ^ real) & okm), 1u);
+    if constexpr (J < JE) {
+        f(std::integral_constant<int, J>{});
+        static_for<J + 1, JE>(f);
     }
+}
+
+#ifndef KPAL_PAIR_BATCH
+#define KPAL_PAIR_BATCH 8           // pairs whose atomics are in flight together (of the 16 of a unit); B200: 8 -> 0.2456, 12 -> 0.2471, 14 -> 0.2503 ms/step
+#endif
+
+// pairs [J0, J1) of the unit
+template <typename CounterT, int K, int J0, int J1>
+__device__ __forceinline__ void bin_pairs(const Unit &u, uint32_t both, uint32_t cnt_s, uint32_t slots_s,
+                                          uint32_t dummy_cnt_s, CounterT *table)
+{
+    using G = PairGeom<K>;
+    uint32_t rank[J1 - J0];
+    static_for<J0, J1>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        const uint32_t m = unit_window<2 * j>(u, G::shift);
+        const uint32_t okm = uint32_t(int32_t(both << (2 * j)) >> 31);
+        const uint32_t bl4 = (m >> (G::rshift - 2)) & uint32_t(4 * (kPairBuckets - 1));
+        const uint32_t real = cnt_s + bl4;
+        rank[j - J0] = atoms_add(dummy_cnt_s ^ ((dummy_cnt_s ^ real) & okm), 1u);
+    });
     uint32_t top = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t okm = uint32_t(int32_t(both << (O0 + 2 * j)) >> 31);
-        const uint32_t bl4 = (m[j] >> (c.rshift - 2)) & uint32_t(4 * (kPairBuckets - 1));
-        const uint32_t pos = min(rank[j] | ~okm, c.cap);          // unbinned pair or full slot: the trash place
-        top = max(top, rank[j] & okm);
+    static_for<J0, J1>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        const uint32_t m = unit_window<2 * j>(u, G::shift);
+        const uint32_t okm = uint32_t(int32_t(both << (2 * j)) >> 31);
+        const uint32_t bl4 = (m >> (G::rshift - 2)) & uint32_t(4 * (kPairBuckets - 1));
+        const uint32_t pos = min(rank[j - J0] | ~okm, uint32_t(kPairCap));    // unbinned pair or full slot: the trash place
+        top = max(top, rank[j - J0] & okm);
         // payload = b0 : R  (b0 moved down over the bucket bits; the store keeps 16 bits)
-        const uint32_t pay = (m[j] & c.rmask) | ((m[j] >> (2 * kPairBucketBases)) & ~c.rmask);
-        sts_u16(c.slots_s + bl4 * c.slot_words + 2u * pos, pay);
-    }
-    if (top >= c.cap) {             // slot full (skewed / repetitive sequence): count both windows directly
+        const uint32_t pay = (m & G::rmask) | ((m >> (2 * kPairBucketBases)) & ~G::rmask);
+        sts_u16(slots_s + bl4 * uint32_t(kSlotHalfwords / 2) + 2u * pos, pay);
+    });
+    if (top >= uint32_t(kPairCap)) {    // slot full (skewed / repetitive sequence): count both windows directly
         // Low-complexity sequence sends thousands of windows to ONE bin (poly-A reads: every
         // lane, every pair), and same-address REDs serialise in L2: the lanes that are here
         // with the same index add their number with one RED.
         const unsigned here = __activemask();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const bool spill = ((both << (O0 + 2 * j)) & 0x80000000u) && rank[j] >= c.cap;
+        static_for<J0, J1>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            const uint32_t m = unit_window<2 * j>(u, G::shift);
+            const bool spill = ((both << (2 * j)) & 0x80000000u) && rank[j - J0] >= uint32_t(kPairCap);
             const unsigned voters = __ballot_sync(here, spill);
             if (spill) {
-                const uint32_t w0 = m[j] >> 2, w1 = m[j] & c.kmask;
+                const uint32_t w0 = m >> 2, w1 = m & G::kmask;
                 const unsigned same0 = __match_any_sync(voters, w0);
                 if ((threadIdx.x & 31u) == unsigned(__ffs(same0) - 1)) atomicAdd(table + w0, CounterT(__popc(same0)));
                 const unsigned same1 = __match_any_sync(voters, w1);
                 if ((threadIdx.x & 31u) == unsigned(__ffs(same1) - 1)) atomicAdd(table + w1, CounterT(__popc(same1)));
             }
-        }
+        });
+    }
+}
+
+template <typename CounterT, int K>
+__device__ __forceinline__ void bin_unit_pairs(const Unit &u, uint32_t both, uint32_t cnt_s, uint32_t slots_s,
+                                               uint32_t dummy_cnt_s, CounterT *table)
+{
+    constexpr int NB = KPAL_PAIR_BATCH;
+    bin_pairs<CounterT, K, 0, NB>(u, both, cnt_s, slots_s, dummy_cnt_s, table);
+    if constexpr (NB < 16) {
+        if (both & (0xFFFFFFFFu >> (2 * NB))) bin_pairs<CounterT, K, NB, 16>(u, both, cnt_s, slots_s, dummy_cnt_s, table);
     }
 }
 
@@ -128,8 +163,8 @@ __device__ __noinline__ void red_pairs(uint4 a, uint32_t C, int k, int n, Counte
     }
 }
 
-// One persistent 1024-thread CTA per SM; a tile is UPT units (of 32 bases) per thread.
-template <typename CounterT, int UPT>
+// One persistent 1024-thread CTA per SM; a tile is one unit (32 bases) per thread.
+template <typename CounterT, int K>
 __global__ void __launch_bounds__(kPairThreads, 1)
 pair_partition_kernel(const PairParams p, CounterT *__restrict__ table)
 {
@@ -137,84 +172,67 @@ pair_partition_kernel(const PairParams p, CounterT *__restrict__ table)
     constexpr int na = kPairBuckets;
     uint32_t *cnt = reinterpret_cast<uint32_t *>(pair_smem);            // [na] payloads in the slot (+32 dummies)
     uint32_t *fillg = cnt + na + 32;                                     // [na] groups already stored
-    uint16_t *slots = reinterpret_cast<uint16_t *>(fillg + na);          // [na][cap + kSlotTrash]
+    uint16_t *slots = reinterpret_cast<uint16_t *>(fillg + na);          // [na][cap + kSlotTrash] (+ 64 B pad)
 
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31u;
     for (int b = tid; b < na + 32; b += kPairThreads) cnt[b] = 0;
     for (int b = tid; b < na; b += kPairThreads) fillg[b] = 0;
-
     __syncthreads();
 
-    constexpr uint64_t kTile = uint64_t(kPairThreads) * UPT;
+    constexpr uint64_t kTile = kPairThreads;
     const uint64_t total = p.unit_end - p.unit_begin;
     uint64_t per = (total + gridDim.x - 1) / gridDim.x;
     per = (per + kTile - 1) / kTile * kTile;
     const uint64_t u0 = p.unit_begin + uint64_t(blockIdx.x) * per;
     const uint64_t u1 = (u0 + per < p.unit_end) ? u0 + per : p.unit_end;
 
-    PairCtx ctx;
-    ctx.cnt_s = smem_u32(cnt);
-    ctx.slots_s = smem_u32(slots);
-    ctx.dummy_cnt_s = ctx.cnt_s + 4u * (uint32_t(na) + lane);
-    ctx.cap = uint32_t(p.cap);
-    ctx.slot_words = uint32_t(p.cap + kSlotTrash) / 2u;
-    ctx.shift = 32 - 2 * (p.k + 1);
-    ctx.rshift = 2 * (p.k - kPairBucketBases);
-    ctx.rmask = (1u << ctx.rshift) - 1u;
-    ctx.kmask = (p.k == 16) ? ~0u : ((1u << (2 * p.k)) - 1u);
-    const int kshift = 32 - 2 * p.k;
+    const uint32_t cnt_s = smem_u32(cnt), slots_s = smem_u32(slots), fill_s = smem_u32(fillg);
+    const uint32_t dummy_cnt_s = cnt_s + 4u * (uint32_t(na) + lane);
+    constexpr int kshift = 32 - 2 * K;
+    constexpr uint32_t slot_bytes = uint32_t(kSlotHalfwords) * 2u;
 
-    uint16_t *my_regions = p.staging + uint64_t(blockIdx.x) * na * p.region_groups * kGroup;
+    uint4 *const my_regions4 = reinterpret_cast<uint4 *>(p.staging + uint64_t(blockIdx.x) * na * p.region_groups * kGroup);
+    const uint32_t region_v4 = p.region_groups * 2u;            // 16-byte pieces per region
 
     // software pipeline: the words of the next tile (and lane 31's halo words) are in flight
-    uint2 cw_next[UPT];
-    uint32_t vw_next[UPT], hc_next[UPT], hv_next[UPT];
+    uint2 cw_next = make_uint2(0, 0);
+    uint32_t vw_next = 0, hc_next = 0, hv_next = 0;
     auto prefetch = [&](uint64_t t0) {
-#pragma unroll
-        for (int q = 0; q < UPT; ++q) {
-            const uint64_t unit = t0 + uint64_t(q) * kPairThreads + tid;
-            cw_next[q] = make_uint2(0, 0); vw_next[q] = 0; hc_next[q] = 0; hv_next[q] = 0;
-            if (t0 < u1 && unit < p.n_units) {
-                cw_next[q] = __ldg(p.codes + unit);
-                vw_next[q] = __ldg(p.valid + unit);
-                if (lane == 31u) {                  // the stream is padded by one 64-base chunk
-                    hc_next[q] = __ldg(reinterpret_cast<const uint32_t *>(p.codes + unit + 1));
-                    hv_next[q] = __ldg(p.valid + unit + 1);
-                }
+        const uint64_t unit = t0 + tid;
+        cw_next = make_uint2(0, 0); vw_next = 0; hc_next = 0; hv_next = 0;
+        if (t0 < u1 && unit < p.n_units) {
+            cw_next = ldg_keep_v2(p.codes + unit);
+            vw_next = ldg_keep_u32(p.valid + unit);
+            if (lane == 31u) {                  // the stream is padded by one 64-base chunk
+                hc_next = ldg_keep_u32(reinterpret_cast<const uint32_t *>(p.codes + unit + 1));
+                hv_next = ldg_keep_u32(p.valid + unit + 1);
             }
         }
     };
     prefetch(u0);
 
-    const uint32_t fill_s = smem_u32(fillg);
-    const uint32_t slot_bytes = uint32_t(p.cap + kSlotTrash) * 2u;
-    uint4 *const my_regions4 = reinterpret_cast<uint4 *>(my_regions);
-    const uint32_t region_v4 = p.region_groups * 2u;            // 16-byte pieces per region
-
     int since_flush = 0;
     for (uint64_t t0 = u0; t0 < u1; t0 += kTile) {
         // ---- A: bin this tile's pairs into the bucket slots
-        uint2 cw[UPT];
-        uint32_t vw[UPT], hc[UPT], hv[UPT];
-#pragma unroll
-        for (int q = 0; q < UPT; ++q) { cw[q] = cw_next[q]; vw[q] = vw_next[q]; hc[q] = hc_next[q]; hv[q] = hv_next[q]; }
-        prefetch(t0 + kTile);
-#pragma unroll
-        for (int q = 0; q < UPT; ++q) {
-            const uint64_t unit = t0 + uint64_t(q) * kPairThreads + tid;
-            uint32_t next_c = __shfl_down_sync(0xffffffffu, cw[q].x, 1);
-            uint32_t next_v = __shfl_down_sync(0xffffffffu, vw[q], 1);
-            if (lane == 31u) { next_c = hc[q]; next_v = hv[q]; }
+        {
+            const uint64_t unit = t0 + tid;
+            const uint2 cw = cw_next;
+            const uint32_t vw = vw_next;
+            uint32_t next_c = __shfl_down_sync(0xffffffffu, cw.x, 1);
+            uint32_t next_v = __shfl_down_sync(0xffffffffu, vw, 1);
+            if (lane == 31u) { next_c = hc_next; next_v = hv_next; }
+            prefetch(t0 + kTile);
             Unit u;
-            u.w[0] = cw[q].x; u.w[1] = cw[q].y; u.w[2] = next_c;
+            u.w[0] = cw.x; u.w[1] = cw.y; u.w[2] = next_c;
             {   // run mask by the binary method on k (as load_chunk in count.cu)
-                const uint64_t v = (uint64_t(vw[q]) << 32) | next_v;
+                const uint64_t v = (uint64_t(vw) << 32) | next_v;
                 uint64_t a = v;
                 int len = 1;
-                for (int bit = 30 - __clz(p.k); bit >= 0; --bit) {
+#pragma unroll
+                for (int bit = 2; bit >= 0; --bit) {        // 9 <= K <= 12: top bit 3
                     a &= a << len; len <<= 1;
-                    if ((p.k >> bit) & 1) { a &= v << len; len += 1; }
+                    if ((K >> bit) & 1) { a &= v << len; len += 1; }
                 }
                 u.starts = (unit < u1) ? uint32_t(a >> 32) : 0u;
             }
@@ -222,11 +240,10 @@ pair_partition_kernel(const PairParams p, CounterT *__restrict__ table)
                 // pairs at the even bases whose two windows are both valid
                 const uint32_t both = u.starts & (u.starts << 1) & 0xAAAAAAAAu;
                 uint32_t singles = u.starts & ~(both | (both >> 1));
-                // (a mask-free variant for batches of eight valid pairs only pays when it is taken
-                // by whole warps: with reads every warp holds record ends, and executing both
+                // (a mask-free variant for units of sixteen valid pairs only pays when it is taken by
+                // whole warps: with reads every warp holds record ends, and executing both
                 // variants cost 45 us -- measured, profiles/README.md)
-                if (both & 0xFFFF0000u) bin_eight_pairs<CounterT, 0>(u, both, ctx, table);
-                if (both & 0x0000FFFFu) bin_eight_pairs<CounterT, 16>(u, both, ctx, table);
+                if (both) bin_unit_pairs<CounterT, K>(u, both, cnt_s, slots_s, dummy_cnt_s, table);
                 while (singles) {                   // run ends: ~1 window per run of valid windows
                     const int o = __clz(singles);
                     singles &= ~(0x80000000u >> o);
@@ -246,16 +263,16 @@ pair_partition_kernel(const PairParams p, CounterT *__restrict__ table)
         {
             static_assert(kPairBuckets == kPairThreads, "one bucket per thread");
             const uint32_t b = uint32_t(tid);
-            const uint32_t cnt_a = ctx.cnt_s + 4u * b, fill_a = fill_s + 4u * b;
-            const uint32_t n = min(lds_u32(cnt_a), ctx.cap), f = lds_u32(fill_a);
+            const uint32_t cnt_a = cnt_s + 4u * b, fill_a = fill_s + 4u * b;
+            const uint32_t n = min(lds_u32(cnt_a), uint32_t(kPairCap)), f = lds_u32(fill_a);
             const uint32_t g = n / kGroup;
             if (g) {
-                const uint32_t slot_a = ctx.slots_s + b * slot_bytes;
+                const uint32_t slot_a = slots_s + b * slot_bytes;
                 uint4 *dst = my_regions4 + b * region_v4 + 2u * f;
                 for (uint32_t q = 0; q < g; ++q) {
                     const uint4 x0 = lds_v4(slot_a + 32u * q), x1 = lds_v4(slot_a + 32u * q + 16u);
                     if (f + q < p.region_groups) { __stcs(dst + 2u * q, x0); __stcs(dst + 2u * q + 1u, x1); }
-                    else { red_pairs<CounterT>(x0, b, p.k, 8, table); red_pairs<CounterT>(x1, b, p.k, 8, table); }
+                    else { red_pairs<CounterT>(x0, b, K, 8, table); red_pairs<CounterT>(x1, b, K, 8, table); }
                 }
                 const uint4 r0 = lds_v4(slot_a + 32u * g), r1 = lds_v4(slot_a + 32u * g + 16u);   // the remainder
                 sts_v4(slot_a, r0); sts_v4(slot_a + 16u, r1);
@@ -269,10 +286,10 @@ pair_partition_kernel(const PairParams p, CounterT *__restrict__ table)
     // ---- remainders (< 16 per bucket after the last flush) and the per-region totals
     {
         const uint32_t b = uint32_t(tid);
-        const uint32_t n = min(cnt[b], ctx.cap), f = fillg[b];
+        const uint32_t n = min(cnt[b], uint32_t(kPairCap)), f = fillg[b];
         uint32_t stored = f * kGroup;
         if (n) {
-            const uint4 *slot = reinterpret_cast<const uint4 *>(slots + b * (p.cap + kSlotTrash));
+            const uint4 *slot = reinterpret_cast<const uint4 *>(slots + b * kSlotHalfwords);
             const uint4 x0 = slot[0], x1 = slot[1];
             if (f < p.region_groups) {
                 uint4 *dst = my_regions4 + b * region_v4 + 2u * f;
@@ -280,8 +297,8 @@ pair_partition_kernel(const PairParams p, CounterT *__restrict__ table)
                 if (n > 8) dst[1] = x1;
                 stored += n;
             } else {
-                red_pairs<CounterT>(x0, b, p.k, n < 8 ? int(n) : 8, table);
-                if (n > 8) red_pairs<CounterT>(x1, b, p.k, int(n) - 8, table);
+                red_pairs<CounterT>(x0, b, K, n < 8 ? int(n) : 8, table);
+                if (n > 8) red_pairs<CounterT>(x1, b, K, int(n) - 8, table);
             }
         }
         p.region_fill[uint64_t(blockIdx.x) * na + b] = stored;
@@ -306,6 +323,8 @@ pair_histogram_kernel(const uint16_t *__restrict__ staging, const uint32_t *__re
                       CounterT *__restrict__ table)
 {
     extern __shared__ __align__(128) uint32_t pair_hist[];
+    __shared__ unsigned int next_group;
+    if (threadIdx.x == 0) next_group = 0;
     const int rbits = 2 * (k - kPairBucketBases);
     const uint32_t bins = 1u << rbits;
     // fused: neighbouring CTAs are the two roles of one bucket, so the second read of the
@@ -324,24 +343,33 @@ pair_histogram_kernel(const uint16_t *__restrict__ staging, const uint32_t *__re
     const uint32_t hist_s = smem_u32(pair_hist);
     auto fill_of = [&](int g) -> uint32_t {
         const int c = g * 4 + (lane >> 3);
-        return c < n_part_ctas ? __ldg(region_fill + uint64_t(c) * kPairBuckets + C) : 0u;
+        return c < n_part_ctas ? ldg_keep_u32(region_fill + uint64_t(c) * kPairBuckets + C) : 0u;
     };
-    int g = warp;
+    // groups of four regions are handed out through a shared counter: with a fixed split
+    // (37 groups over 16 warps) a third of the warps walked three groups, the others two, and
+    // the CTA waited for them at the barrier (ncu: barrier + long scoreboard were the top stalls)
+    auto grab = [&]() -> int {
+        int v = 0;
+        if (lane == 0) v = int(atomicAdd(&next_group, 1u));
+        return __shfl_sync(0xffffffffu, v, 0);
+    };
+    int g = grab();
     uint32_t n_ahead = g * 4 < n_part_ctas ? fill_of(g) : 0u;
-    for (; g * 4 < n_part_ctas; g += n_warps) {
+    while (g * 4 < n_part_ctas) {
+        const int g_next = grab();
         const int c = g * 4 + (lane >> 3);
         const uint32_t n = n_ahead;
-        n_ahead = (g + n_warps) * 4 < n_part_ctas ? fill_of(g + n_warps) : 0u;
+        n_ahead = g_next * 4 < n_part_ctas ? fill_of(g_next) : 0u;
         const uint32_t nv = (n + 7u) / 8u;
         const uint4 *src = reinterpret_cast<const uint4 *>(
             staging + (uint64_t(c < n_part_ctas ? c : 0) * kPairBuckets + C) * region_groups * kGroup);
         uint32_t i = lane & 7u;
         uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
-        if (i < nv) cur = __ldg(src + i);
-        if (i + 8u < nv) nxt = __ldg(src + i + 8u);
+        if (i < nv) cur = ldg_keep_v4(src + i);
+        if (i + 8u < nv) nxt = ldg_keep_v4(src + i + 8u);
         while (__any_sync(0xffffffffu, i < nv)) {
             uint4 far = make_uint4(0, 0, 0, 0);
-            if (i + 16u < nv) far = __ldg(src + i + 16u);
+            if (i + 16u < nv) far = ldg_keep_v4(src + i + 16u);
             const uint32_t at = i * 8u;
             const uint32_t rem = at < n ? n - at : 0u;
             const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
@@ -355,6 +383,7 @@ pair_histogram_kernel(const uint16_t *__restrict__ staging, const uint32_t *__re
             cur = nxt; nxt = far;
             i += 8u;
         }
+        g = g_next;
     }
     __syncthreads();
 
@@ -417,8 +446,6 @@ pair_histogram_kernel(const uint16_t *__restrict__ staging, const uint32_t *__re
 // ---------------------------------------------------------------------------
 // launcher
 // ---------------------------------------------------------------------------
-static std::atomic<int> g_pair_upt{1};          // units per thread and tile (1 or 2; measured: 116 vs 129 us)
-void set_pair_upt(int v) { g_pair_upt.store(v == 2 ? 2 : 1); }
 static std::atomic<int> g_pair_flush_every{0};  // tiles between flushes of the pass-1 slots (0 = automatic)
 void set_pair_flush_every(int v) { g_pair_flush_every.store(v < 0 ? 0 : v); }
 static std::atomic<int> g_pair_fused{1};        // pass 2: 1 = both roles in one launch, flushed by the TMA unit
@@ -426,20 +453,25 @@ void set_pair_fused(int v) { g_pair_fused.store(v ? 1 : 0); }
 
 bool pairs_supported(int k) { return k >= 9 && k <= 12; }
 
-template <typename CounterT>
-static int launch_pair_passes(const PairParams &p, int grid1, size_t smem1, int upt, CounterT *table,
-                              cudaStream_t stream)
+template <typename CounterT, int K>
+static int launch_partition(const PairParams &p, int grid1, CounterT *table, cudaStream_t stream)
 {
-    if (upt == 1) {
-        KPAL_CUDA(cudaFuncSetAttribute(pair_partition_kernel<CounterT, 1>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
-        pair_partition_kernel<CounterT, 1><<<grid1, kPairThreads, smem1, stream>>>(p, table);
-    } else {
-        KPAL_CUDA(cudaFuncSetAttribute(pair_partition_kernel<CounterT, 2>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem1)));
-        pair_partition_kernel<CounterT, 2><<<grid1, kPairThreads, smem1, stream>>>(p, table);
-    }
+    KPAL_CUDA(cudaFuncSetAttribute(pair_partition_kernel<CounterT, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   int(kPairSmem1)));
+    pair_partition_kernel<CounterT, K><<<grid1, kPairThreads, kPairSmem1, stream>>>(p, table);
     KPAL_LAUNCH_CHECK("pair_partition_kernel");
+    return KPAL_OK;
+}
+
+template <typename CounterT>
+static int launch_pair_passes(const PairParams &p, int grid1, CounterT *table, cudaStream_t stream)
+{
+    switch (p.k) {
+    case 9: KPAL_CHECK((launch_partition<CounterT, 9>(p, grid1, table, stream))); break;
+    case 10: KPAL_CHECK((launch_partition<CounterT, 10>(p, grid1, table, stream))); break;
+    case 11: KPAL_CHECK((launch_partition<CounterT, 11>(p, grid1, table, stream))); break;
+    default: KPAL_CHECK((launch_partition<CounterT, 12>(p, grid1, table, stream))); break;
+    }
     const size_t smem2 = size_t(4) << (2 * (p.k - kPairBucketBases));
     if constexpr (sizeof(CounterT) == 4) {
         if (g_pair_fused.load()) {
@@ -466,22 +498,12 @@ int launch_count_pairs(const uint32_t *d_codes, const uint32_t *d_valid, uint64_
 {
     if (!pairs_supported(k)) return bad_arg("the pair path covers 9 <= k <= 12");
     const int grid1 = sm_count();
-    const int upt = g_pair_upt.load();
-    // A slot keeps < 16 payloads over a flush and gains 16 * upt per tile on average (uniform
-    // sequence): with 96 places, 3 tiles of one unit between flushes leave 5 sigma of headroom
-    // (the surplus of a fuller slot takes the RED path: exact, only slower).
+    // A slot keeps < 16 payloads over a flush and gains 16 per tile on average (uniform
+    // sequence): with 96 places, 3 tiles between flushes leave 5 sigma of headroom (the surplus
+    // of a fuller slot takes the RED path: exact, only slower).
     int flush_every = g_pair_flush_every.load();
-    if (flush_every <= 0) flush_every = upt == 1 ? 3 : 1;
-    // shared memory: counters, fill, then the slots.  cap + 8 trash
-    // places = 8 x odd halfwords keeps the 16-byte slot reads of neighbouring buckets on
-    // distinct bank groups.
-    const size_t fixed = size_t(kPairBuckets + 32) * 4 + size_t(kPairBuckets) * 4 + 64;     // + pad: the flush reads one piece past a full last slot
-    int stride = int((232448 - fixed) / (2u * unsigned(kPairBuckets)));       // halfwords per slot
-    stride = (stride - 8) / 16 * 16 + 8;
-    const int cap = stride - kSlotTrash;
-    const size_t smem1 = fixed + size_t(kPairBuckets) * stride * 2;     // (the pad sits behind the slots)
-
-    const uint64_t tile = uint64_t(kPairThreads) * upt;
+    if (flush_every <= 0) flush_every = 3;
+    const uint64_t tile = kPairThreads;
     const uint64_t n_units = 2 * n_chunks_of(n_bases);
     const uint64_t seg_units = (512ull << 20) / kUnitBases;
     for (uint64_t s0 = 0; s0 < n_units; s0 += seg_units) {
@@ -499,16 +521,15 @@ int launch_count_pairs(const uint32_t *d_codes, const uint32_t *d_valid, uint64_
         p.codes = reinterpret_cast<const uint2 *>(d_codes);
         p.valid = d_valid;
         p.unit_begin = s0; p.unit_end = s1; p.n_units = n_units;
-        p.k = k; p.cap = cap;
+        p.k = k;
         p.region_groups = uint32_t(groups);
         p.staging = static_cast<uint16_t *>(staging);
         p.region_fill = fill;
         p.flush_every = flush_every;
         if (counter_bits == 32)
-            KPAL_CHECK(launch_pair_passes<uint32_t>(p, grid1, smem1, upt, static_cast<uint32_t *>(d_table), stream));
+            KPAL_CHECK(launch_pair_passes<uint32_t>(p, grid1, static_cast<uint32_t *>(d_table), stream));
         else
-            KPAL_CHECK(launch_pair_passes<unsigned long long>(p, grid1, smem1, upt,
-                                                              static_cast<unsigned long long *>(d_table), stream));
+            KPAL_CHECK(launch_pair_passes<unsigned long long>(p, grid1, static_cast<unsigned long long *>(d_table), stream));
     }
     return KPAL_OK;
 }

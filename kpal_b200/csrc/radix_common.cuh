@@ -61,6 +61,31 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, const uint4 &v)
 }
 
 
+// Read-only global loads the compiler may not move: __ldg data is known to be immutable, so
+// nvcc sinks such loads to their first use -- which turns a software prefetch (load the next
+// tile's words, bin this tile, use them) back into a load-and-wait (ncu: the top stall of
+// pair_partition_kernel was the first use of the "prefetched" words).  Volatile asm statements
+// keep their order among themselves, and the shared-memory atomics / stores between are volatile too.
+__device__ __forceinline__ uint2 ldg_keep_v2(const uint2 *p)
+{
+    uint2 v;
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg_keep_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_keep_v4(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 // grow-only per-device staging of the radix paths (count_radix.cu); call under no lock
 int radix_workspace(size_t staging_bytes, size_t fill_bytes, void **staging, uint32_t **fill);
 

@@ -60,13 +60,13 @@ def test_product_arm_has_no_cpu_fallback():
 def test_set_option_knows_its_switches():
     L = _cabi.load()
     good = {"host_fasta": (0, 1), "fasta_chunks": (0, 16, 32), "fasta_split": (0, 1), "exact_div": (0, 1),
-            "narrow_d2h": (0, 1, 2), "dma_share": (0, 3, 8), "count_path": (0, 1, 2, 3), "pair_upt": (1, 2), "pair_flush_every": (0, 1, 6), "pair_fused": (0, 1), "gram": (0, 1), "narrow_lists": (0, 1), "tiled_finalize": (0, 1),
+            "narrow_d2h": (0, 1, 2), "dma_share": (0, 3, 8), "count_path": (0, 1, 2, 3), "pair_flush_every": (0, 1, 6), "pair_fused": (0, 1), "gram": (0, 1), "narrow_lists": (0, 1), "tiled_finalize": (0, 1),
             "by_record_path": (0, 1), "radix_shape": (0, 1, 2), "radix_max_buckets": (1024, 2048),
             "radix_payload_bits": (0, 13, 15), "radix_debug": (0,)}
     defaults = {"host_fasta": 0, "fasta_chunks": 0, "fasta_split": 0, "exact_div": 0, "narrow_d2h": 1,
-                "dma_share": 0, "count_path": 0, "pair_upt": 1, "pair_flush_every": 0, "pair_fused": 1, "gram": 1, "narrow_lists": 1, "tiled_finalize": 1, "by_record_path": 0, "radix_shape": 0,
+                "dma_share": 0, "count_path": 0, "pair_flush_every": 0, "pair_fused": 1, "gram": 1, "narrow_lists": 1, "tiled_finalize": 1, "by_record_path": 0, "radix_shape": 0,
                 "radix_max_buckets": 2048, "radix_payload_bits": 0, "radix_debug": 0}
-    bad = {"fasta_chunks": (-1, 33), "narrow_d2h": (-1, 3), "dma_share": (-1, 9), "count_path": (4,), "pair_upt": (0, 3), "pair_flush_every": (-1, 7),
+    bad = {"fasta_chunks": (-1, 33), "narrow_d2h": (-1, 3), "dma_share": (-1, 9), "count_path": (4,), "pair_flush_every": (-1, 7),
            "by_record_path": (2,), "radix_shape": (3,), "radix_max_buckets": (512, 4096), "radix_payload_bits": (16,)}
     try:
         for name, values in good.items():

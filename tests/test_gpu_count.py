@@ -517,19 +517,17 @@ def test_pair_count_path_bit_exact(k, n, letters, p_n):
     want = c_oracle.count_bytes(text, k, threads=c_oracle.max_threads())
     try:
         _set_option("count_path", 2)
-        # units per thread and tile, tiles between two slot flushes (0 = automatic), pass 2 as one
-        # launch flushed by the TMA unit (cp.reduce.async.bulk) or as two launches per role
-        for upt, flush_every, fused in ((1, 0, 1), (2, 0, 1), (1, 1, 0), (1, 6, 1), (2, 1, 0)):
-            _set_option("pair_upt", upt)
+        # tiles between two slot flushes (0 = automatic; 6 overflows the slots into the RED path),
+        # pass 2 as one launch flushed by the TMA unit (cp.reduce.async.bulk) or as two launches per role
+        for flush_every, fused in ((0, 1), (1, 0), (6, 1), (2, 0)):
             _set_option("pair_flush_every", flush_every)
             _set_option("pair_fused", fused)
             got32 = _dev_count(text, k, 32, False)
-            assert np.array_equal(got32, want), (upt, flush_every, fused)
+            assert np.array_equal(got32, want), (flush_every, fused)
             got64 = _dev_count(text, k, 64, True)
-            assert np.array_equal(got64, ko.balance(want)), (upt, flush_every, fused)
+            assert np.array_equal(got64, ko.balance(want)), (flush_every, fused)
     finally:
         _set_option("count_path", 0)
-        _set_option("pair_upt", 1)
         _set_option("pair_flush_every", 0)
         _set_option("pair_fused", 1)
 
