@@ -510,7 +510,9 @@ def bench_count(args, world, rank, local):
                                                       d_table.data_ptr(), 32, sp))
             if ev:
                 ev[1].record(stream)
-            slicer.push(d_table.data_ptr(), 32, sp)
+            slicer.push(d_table.data_ptr(), 32, sp, n_bases=n_bases)
+            if ev:
+                ev[2].record(stream)
             slicer.collect(d_slice.data_ptr(), sp)
             return
         if reducer is not None and args.reduce == "fused":
@@ -542,7 +544,7 @@ def bench_count(args, world, rank, local):
             table, bits = ctypes.c_void_p(), ctypes.c_int()
             _cabi.check(L.kpal_count_fasta_dev_table(pinned_fasta._ptr, n_fasta, k, ctypes.byref(table),
                                                      ctypes.byref(bits), sp))
-            slicer.push(table, bits.value, sp)
+            slicer.push(table, bits.value, sp, n_bases=n_bases)
             slicer.collect_to_host(shared.array[sb:se], sp)      # this rank's slice, into shared host memory
         else:
             d_table.zero_()
@@ -567,7 +569,8 @@ def bench_count(args, world, rank, local):
     L.kpal_reset_kernel_launches()
     step_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                for _ in range(args.steps)]
-    kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+                torch.cuda.Event(enable_timing=True))
                for _ in range(args.steps)]
     barrier_sync(world)
     wall0 = time.perf_counter()
@@ -580,7 +583,11 @@ def bench_count(args, world, rank, local):
     wall = time.perf_counter() - wall0
     launches = int(L.kpal_kernel_launches())
     step_ms = sum(a.elapsed_time(b) for a, b in step_ev) / args.steps
-    kern_ms = sum(a.elapsed_time(b) for a, b in kern_ev) / args.steps
+    kern_ms = sum(e[0].elapsed_time(e[1]) for e in kern_ev) / args.steps
+    tail_ms = None
+    if slicer is not None:      # this rank's view: count | balance + push | wait for the peers + collect
+        tail_ms = {"push_ms": sum(e[1].elapsed_time(e[2]) for e in kern_ev) / args.steps,
+                   "wait_collect_ms": sum(e[2].elapsed_time(s[1]) for e, s in zip(kern_ev, step_ev)) / args.steps}
     step_ms = max_over_ranks(step_ms, world)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -749,6 +756,9 @@ def bench_count(args, world, rank, local):
             "cpu_baseline": cpu, "clocks": clocks, "parity_ok": result_ok, "parity": parity,
             "wall_s_timed_region": wall,
         }
+        if tail_ms is not None:
+            out["reduce_tail"] = dict(tail_ms, note="rank 0's stream: balance + narrow push kernels | wait for "
+                                      "the peers' signals + collect of its slice (CUDA events)")
     if reducer is not None:
         reducer.close()
     if shared is not None:

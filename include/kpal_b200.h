@@ -341,12 +341,19 @@ int      kpal_dev_count_packed_push(const uint32_t *d_codes, const uint32_t *d_v
  * The fused form of the multi-GPU table sum (csrc/peer_reduce.cu): balance is linear
  * (kpal/klib.py:285-298), so every rank balances ITS table and sends the result narrow --
  *   kpal_dev_slice_push     balanced counts of the local table, as 1 byte per bin, straight into
- *                           the inbox of the rank that owns the bin's slice (u32 rows as well when
- *                           a count exceeds 255), then one release store per peer ("epoch landed");
+ *                           the inbox of the rank that owns the bin's slice (a count >= 255 is sent
+ *                           as the escape byte 255 plus a 4-byte store of its value; wide_rows != 0
+ *                           sends u32 rows instead -- for shards whose MEAN balanced count, about
+ *                           2 * bases / 4^k, is not small).  One kernel launch, peer stores only;
+ *   kpal_dev_slice_signal   one release store per peer: "the rows of `epoch` from `rank` have
+ *                           landed" (wide_rows as given to the push).  After the push, on its stream;
  *   kpal_dev_slice_collect  on every rank: waits for the world's signals in its own inbox, sums
  *                           the senders' rows and writes the int64 slice
  *                           [kpal_slice_begin(k, rank, world), kpal_slice_begin(k, rank + 1, world))
- *                           of the final balanced profile;
+ *                           of the final balanced profile.  signal = 0 / 1: the kernel first sends
+ *                           this rank's signal itself (the value = the wide_rows of its push, which
+ *                           must be the previous work on `stream`) -- no separate signal launch;
+ *                           signal = -1: kpal_dev_slice_signal has been called;
  *   kpal_dev_slice_collect_to_host  the same followed by the narrow device->host copy of the
  *                           slice (slice_out: host memory, e.g. this rank's part of a profile in
  *                           memory shared between the processes).  Synchronises the stream.
@@ -358,11 +365,13 @@ int      kpal_dev_count_packed_push(const uint32_t *d_codes, const uint32_t *d_v
 uint64_t kpal_slice_inbox_bytes(int k, int world);
 uint64_t kpal_slice_begin(int k, int rank, int world);
 int      kpal_dev_slice_push(const void *d_table, int counter_bits, int k, int rank, int world,
-                             void *const *inbox_ptrs, uint64_t epoch, void *stream);
-int      kpal_dev_slice_collect(const void *d_inbox, int k, int rank, int world, uint64_t epoch,
-                                int64_t *d_slice_out, void *stream);
-int      kpal_dev_slice_collect_to_host(const void *d_inbox, int k, int rank, int world, uint64_t epoch,
-                                        int64_t *slice_out, void *stream);
+                             void *const *inbox_ptrs, uint64_t epoch, int wide_rows, void *stream);
+int      kpal_dev_slice_signal(int k, int rank, int world, void *const *inbox_ptrs, uint64_t epoch,
+                               int wide_rows, void *stream);
+int      kpal_dev_slice_collect(void *const *inbox_ptrs, int k, int rank, int world, uint64_t epoch,
+                                int signal, int64_t *d_slice_out, void *stream);
+int      kpal_dev_slice_collect_to_host(void *const *inbox_ptrs, int k, int rank, int world, uint64_t epoch,
+                                        int signal, int64_t *slice_out, void *stream);
 
 /* --------------------------------------------------- distances: device API */
 

@@ -34,7 +34,7 @@ SYMBOLS = (
     "kpal_split_length", "kpal_split", "kpal_show_balance",
     "kpal_ipc_export", "kpal_ipc_open", "kpal_ipc_close", "kpal_peer_inbox_bytes",
     "kpal_dev_reduce_push", "kpal_dev_reduce_collect", "kpal_dev_count_packed_push",
-    "kpal_slice_inbox_bytes", "kpal_slice_begin", "kpal_dev_slice_push", "kpal_dev_slice_collect",
+    "kpal_slice_inbox_bytes", "kpal_slice_begin", "kpal_dev_slice_push", "kpal_dev_slice_signal", "kpal_dev_slice_collect",
     "kpal_dev_slice_collect_to_host",
     "kpal_dev_count_packed", "kpal_dev_count_packed_fresh", "kpal_count_fasta_to_dev",
     "kpal_count_fasta_dev_table", "kpal_dev_finalize_counts", "kpal_dev_table_to_host", "kpal_dev_balance",
@@ -120,9 +120,10 @@ def load():
         c.POINTER(i32))
     sig("kpal_slice_inbox_bytes", u64, i32, i32)
     sig("kpal_slice_begin", u64, i32, i32, i32)
-    sig("kpal_dev_slice_push", i32, vp, i32, i32, i32, i32, c.POINTER(vp), u64, vp)
-    sig("kpal_dev_slice_collect", i32, vp, i32, i32, i32, u64, vp, vp)
-    sig("kpal_dev_slice_collect_to_host", i32, vp, i32, i32, i32, u64, vp, vp)
+    sig("kpal_dev_slice_push", i32, vp, i32, i32, i32, i32, c.POINTER(vp), u64, i32, vp)
+    sig("kpal_dev_slice_signal", i32, i32, i32, i32, c.POINTER(vp), u64, i32, vp)
+    sig("kpal_dev_slice_collect", i32, c.POINTER(vp), i32, i32, i32, u64, i32, vp, vp)
+    sig("kpal_dev_slice_collect_to_host", i32, c.POINTER(vp), i32, i32, i32, u64, i32, vp, vp)
     sig("kpal_dev_count_packed", i32, vp, vp, u64, i32, vp, i32, vp)
     sig("kpal_dev_count_packed_fresh", i32, vp, vp, u64, i32, vp, i32, vp)
     sig("kpal_count_fasta_to_dev", i32, vp, u64, i32, vp, i32, vp, pu64)

@@ -80,8 +80,9 @@ int launch_count_push(const uint32_t *, const uint32_t *, uint64_t, int, void *,
                       void *const *, cudaStream_t, int *);
 uint64_t slice_inbox_bytes(int k, int world);
 uint64_t slice_begin_host(int k, int o, int world);
-int launch_slice_push(const void *, int, int, int, int, void *const *, unsigned long long, unsigned int *, cudaStream_t);
-int launch_slice_collect(const void *, int, int, int, unsigned long long, int64_t *, uint16_t *, uint8_t *,
+int launch_slice_push(const void *, int, int, int, int, void *const *, unsigned long long, int, unsigned int *, cudaStream_t);
+int launch_slice_signal(int, int, int, void *const *, unsigned long long, int, cudaStream_t);
+int launch_slice_collect(int, int, int, void *const *, unsigned long long, int, int64_t *, uint16_t *, uint8_t *,
                          unsigned int *, cudaStream_t);
 
 static thread_local char t_error[512] = "";
@@ -1587,7 +1588,7 @@ extern "C" uint64_t kpal_slice_begin(int k, int rank, int world)
 }
 
 extern "C" int kpal_dev_slice_push(const void *d_table, int counter_bits, int k, int rank, int world,
-                                   void *const *inbox_ptrs, uint64_t epoch, void *stream)
+                                   void *const *inbox_ptrs, uint64_t epoch, int wide_rows, void *stream)
 {
     if (!d_table) return bad_arg("null device pointer");
     if (epoch < 1) return bad_arg("epochs count from 1 (a zeroed inbox means epoch 0)");
@@ -1596,26 +1597,38 @@ extern "C" int kpal_dev_slice_push(const void *d_table, int counter_bits, int k,
     {
         std::lock_guard<std::mutex> lock(g_count_mutex);
         KPAL_CHECK(get_count_ws(&w));
-        KPAL_CHECK(w->wide_flag.ensure(16));
+        if (!w->wide_flag.p) {          // the kernel's counters: zero once, its last CTA resets them
+            KPAL_CHECK(w->wide_flag.ensure(32));
+            KPAL_CUDA(cudaMemset(w->wide_flag.p, 0, 32));
+        }
     }
-    return launch_slice_push(d_table, counter_bits, k, rank, world, inbox_ptrs, epoch,
+    return launch_slice_push(d_table, counter_bits, k, rank, world, inbox_ptrs, epoch, wide_rows,
                              static_cast<unsigned int *>(w->wide_flag.p), (cudaStream_t)stream);
 }
 
-extern "C" int kpal_dev_slice_collect(const void *d_inbox, int k, int rank, int world, uint64_t epoch,
-                                      int64_t *d_slice_out, void *stream)
+extern "C" int kpal_dev_slice_signal(int k, int rank, int world, void *const *inbox_ptrs, uint64_t epoch,
+                                     int wide_rows, void *stream)
 {
-    return launch_slice_collect(d_inbox, k, rank, world, epoch, d_slice_out, nullptr, nullptr, nullptr,
+    if (epoch < 1) return bad_arg("epochs count from 1 (a zeroed inbox means epoch 0)");
+    KPAL_CHECK(require_device());
+    return launch_slice_signal(k, rank, world, inbox_ptrs, epoch, wide_rows, (cudaStream_t)stream);
+}
+
+extern "C" int kpal_dev_slice_collect(void *const *inbox_ptrs, int k, int rank, int world, uint64_t epoch,
+                                      int signal, int64_t *d_slice_out, void *stream)
+{
+    KPAL_CHECK(require_device());
+    return launch_slice_collect(k, rank, world, inbox_ptrs, epoch, signal, d_slice_out, nullptr, nullptr, nullptr,
                                 (cudaStream_t)stream);
 }
 
 // kpal_dev_slice_collect + the device->host copy of the slice in the narrow form of finalize_to_host
 // (uint8 / uint16 over PCIe, widened into slice_out by the host workers).  slice_out may be any host
 // memory, e.g. this rank's part of a profile in memory shared between the ranks' processes.
-extern "C" int kpal_dev_slice_collect_to_host(const void *d_inbox, int k, int rank, int world, uint64_t epoch,
-                                              int64_t *slice_out, void *stream)
+extern "C" int kpal_dev_slice_collect_to_host(void *const *inbox_ptrs, int k, int rank, int world, uint64_t epoch,
+                                              int signal, int64_t *slice_out, void *stream)
 {
-    if (!d_inbox || !slice_out) return bad_arg("null pointer");
+    if (!inbox_ptrs || !slice_out) return bad_arg("null pointer");
     KPAL_CHECK(check_k_host(k));
     KPAL_CHECK(require_device());
     if (rank < 0 || rank >= world) return bad_arg("rank outside the world");
@@ -1637,7 +1650,7 @@ extern "C" int kpal_dev_slice_collect_to_host(const void *d_inbox, int k, int ra
             for (auto &e : w->d2h_done) KPAL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             KPAL_CUDA(cudaEventCreateWithFlags(&w->flag_done, cudaEventDisableTiming));
         }
-        KPAL_CHECK(launch_slice_collect(d_inbox, k, rank, world, epoch, static_cast<int64_t *>(w->counts.p),
+        KPAL_CHECK(launch_slice_collect(k, rank, world, inbox_ptrs, epoch, signal, static_cast<int64_t *>(w->counts.p),
                                         static_cast<uint16_t *>(w->counts16.p),
                                         try8 ? static_cast<uint8_t *>(w->counts8.p) : nullptr,
                                         static_cast<unsigned int *>(w->overflow.p), st));
@@ -1646,7 +1659,7 @@ extern "C" int kpal_dev_slice_collect_to_host(const void *d_inbox, int k, int ra
         if (done) return KPAL_OK;
         KPAL_CUDA(cudaStreamSynchronize(st));
     } else {
-        KPAL_CHECK(launch_slice_collect(d_inbox, k, rank, world, epoch, static_cast<int64_t *>(w->counts.p), nullptr,
+        KPAL_CHECK(launch_slice_collect(k, rank, world, inbox_ptrs, epoch, signal, static_cast<int64_t *>(w->counts.p), nullptr,
                                         nullptr, nullptr, st));
     }
     KPAL_CUDA(cudaMemcpyAsync(slice_out, w->counts.p, n * 8, cudaMemcpyDeviceToHost, st));

@@ -179,7 +179,7 @@ def _count_fasta_slices(fasta_shard, k, group, device):
         table, bits = ctypes.c_void_p(), ctypes.c_int()
         _cabi.check(L.kpal_count_fasta_dev_table(_cabi.ptr(buf) if buf.size else None, buf.size, int(k),
                                                  ctypes.byref(table), ctypes.byref(bits), stream))
-        reducer.push(table, bits.value, stream)
+        reducer.push(table, bits.value, stream, n_bases=buf.size)
         begin, end = reducer.slice_range()
         reducer.collect_to_host(shared.array[begin:end], stream)
         import torch.distributed as dist
@@ -325,6 +325,7 @@ class SliceReducer(object):
         self.rank = dist.get_rank(group)
         self.device = torch.device('cuda', torch.cuda.current_device())
         self.epoch = 0
+        self._wide = 0
         self._opened = []
         nbytes = int(L.kpal_slice_inbox_bytes(self.k, self.world))
         if nbytes == 0:
@@ -364,21 +365,25 @@ class SliceReducer(object):
         return (int(self._L.kpal_slice_begin(self.k, rank, self.world)),
                 int(self._L.kpal_slice_begin(self.k, rank + 1, self.world)))
 
-    def push(self, table_ptr, counter_bits, stream):
-        """Balance + narrow push of this rank's table; starts a new epoch."""
+    def push(self, table_ptr, counter_bits, stream, n_bases=None):
+        """Balance + narrow push of this rank's table; starts a new epoch.  `n_bases` (the bases
+        this rank counted) picks the row form: bytes with escapes for counts >= 255 while the mean
+        balanced count 2 * n_bases / 4^k stays below 64, else u32 rows.  The peers are told by
+        the collect that follows on the same stream."""
         self.epoch += 1
+        self._wide = 1 if (n_bases is not None and 2 * int(n_bases) >= 64 * 4 ** self.k) else 0
         _cabi.check(self._L.kpal_dev_slice_push(table_ptr, int(counter_bits), self.k, self.rank, self.world,
-                                                self._inboxes, self.epoch, stream))
+                                                self._inboxes, self.epoch, self._wide, stream))
 
     def collect(self, slice_ptr, stream):
-        """This rank's int64 slice of the balanced profile -> device memory."""
-        _cabi.check(self._L.kpal_dev_slice_collect(self._inbox, self.k, self.rank, self.world, self.epoch,
-                                                   slice_ptr, stream))
+        """Signal + this rank's int64 slice of the balanced profile -> device memory."""
+        _cabi.check(self._L.kpal_dev_slice_collect(self._inboxes, self.k, self.rank, self.world, self.epoch,
+                                                   self._wide, slice_ptr, stream))
 
     def collect_to_host(self, host_slice, stream):
         """... -> `host_slice` (a C-contiguous int64 array of the slice's length)."""
-        _cabi.check(self._L.kpal_dev_slice_collect_to_host(self._inbox, self.k, self.rank, self.world, self.epoch,
-                                                           _cabi.ptr(host_slice), stream))
+        _cabi.check(self._L.kpal_dev_slice_collect_to_host(self._inboxes, self.k, self.rank, self.world, self.epoch,
+                                                           self._wide, _cabi.ptr(host_slice), stream))
 
     def close(self):
         import torch

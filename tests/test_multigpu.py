@@ -414,20 +414,24 @@ def test_slice_push_collect_virtual_world(bits):
                 for t in host[1:]:
                     t[...] = rng.integers(0, 30, bins)          # only rank 0 sends wide rows
             tables = [torch.from_numpy(t).to(dev).to(dtype) for t in host]
+            # rows as bytes with escapes; the last rank of the last epoch sends u32 rows
+            wide_rows = [1 if (epoch == 3 and r == world - 1) else 0 for r in range(world)]
             for r in range(world):
-                _cabi.check(L.kpal_dev_slice_push(tables[r].data_ptr(), bits, k, r, world, ptrs, epoch, sp))
+                _cabi.check(L.kpal_dev_slice_push(tables[r].data_ptr(), bits, k, r, world, ptrs, epoch, wide_rows[r], sp))
+                if r:           # rank 0's signal is sent by its collect kernel below
+                    _cabi.check(L.kpal_dev_slice_signal(k, r, world, ptrs, epoch, wide_rows[r], sp))
             want = ko.balance(np.sum(host, axis=0))
             for r in range(world):
                 n = begins[r + 1] - begins[r]
                 piece = torch.full((max(n, 1),), -1, dtype=torch.int64, device=dev)
-                _cabi.check(L.kpal_dev_slice_collect(inboxes[r].data_ptr(), k, r, world, epoch, piece.data_ptr(), sp))
+                _cabi.check(L.kpal_dev_slice_collect(ptrs, k, r, world, epoch, wide_rows[0] if r == 0 else -1, piece.data_ptr(), sp))
                 assert np.array_equal(piece[:n].cpu().numpy(), want[begins[r]:begins[r + 1]]), (k, world, epoch, r)
                 out = np.full(max(n, 1), -1, dtype=np.int64)
-                _cabi.check(L.kpal_dev_slice_collect_to_host(inboxes[r].data_ptr(), k, r, world, epoch, _cabi.ptr(out), sp))
+                _cabi.check(L.kpal_dev_slice_collect_to_host(ptrs, k, r, world, epoch, -1, _cabi.ptr(out), sp))
                 assert np.array_equal(out[:n], want[begins[r]:begins[r + 1]]), (k, world, epoch, r, "host")
     ptrs = (ctypes.c_void_p * 5)()
-    assert L.kpal_dev_slice_push(tables[0].data_ptr(), bits, 5, 0, 2, ptrs, 1, sp) == _cabi.KPAL_EINVAL     # k < 6
-    assert L.kpal_dev_slice_push(tables[0].data_ptr(), bits, 8, 0, 2, ptrs, 0, sp) == _cabi.KPAL_EINVAL     # epoch 0
+    assert L.kpal_dev_slice_push(tables[0].data_ptr(), bits, 5, 0, 2, ptrs, 1, 0, sp) == _cabi.KPAL_EINVAL     # k < 6
+    assert L.kpal_dev_slice_push(tables[0].data_ptr(), bits, 8, 0, 2, ptrs, 0, 0, sp) == _cabi.KPAL_EINVAL     # epoch 0
 
 
 @pytest.mark.gpu
