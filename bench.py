@@ -231,7 +231,7 @@ def host_threads():
     OMP_NUM_THREADS=1 to its workers; the C port takes its thread count as an argument, so
     the reference arm and the oracle checks still use the whole host.)"""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        return max(1, len(_FULL_AFFINITY if _FULL_AFFINITY is not None else os.sched_getaffinity(0)))
     except AttributeError:
         return max(1, os.cpu_count() or 1)
 
@@ -372,6 +372,28 @@ def init_dist(args):
     return world, rank, local
 
 
+_FULL_AFFINITY = None
+
+
+def numa_bind(args, world, local):
+    """N > 1, one process per GPU: keep the rank's pinned buffers and host threads next to its GPU."""
+    global _FULL_AFFINITY
+    if world > 1 and args.numa_bind:
+        from kpal_b200 import multigpu
+        previous = multigpu.bind_to_gpu_cpus(local)
+        if _FULL_AFFINITY is None:
+            _FULL_AFFINITY = previous
+
+
+def whole_host():
+    """Undo init_dist's binding (for the untimed oracle checks on rank 0)."""
+    if _FULL_AFFINITY is not None:
+        try:
+            os.sched_setaffinity(0, _FULL_AFFINITY)
+        except OSError:
+            pass
+
+
 def barrier_sync(world):
     import torch
     import torch.distributed as dist
@@ -395,6 +417,7 @@ def bench_count(args, world, rank, local):
     import torch.distributed as dist
     from kpal_b200 import _cabi
 
+    numa_bind(args, world, local)
     L = _cabi.load()
     _cabi.check(L.kpal_set_device(local))
     _cabi.check(L.kpal_set_option(b"count_path", args.count_path))
@@ -627,6 +650,7 @@ def bench_count(args, world, rank, local):
         dist.reduce(check, dst=0, op=dist.ReduceOp.SUM)
     if rank == 0:
         from oracle import c_oracle
+        whole_host()
         threads = host_threads()
         want = np.zeros(bins, dtype=np.int64)
         cpu_s = 0.0
@@ -785,6 +809,7 @@ def bench_matrix(args, world, rank, local):
     import torch.distributed as dist
     from kpal_b200 import _cabi, multigpu
 
+    numa_bind(args, world, local)
     L = _cabi.load()
     _cabi.check(L.kpal_set_device(local))
     dev = torch.device("cuda", local)
@@ -892,6 +917,7 @@ def bench_matrix(args, world, rank, local):
     parity = None
     if rank == 0:
         from oracle import c_oracle
+        whole_host()
         threads = host_threads()
         rng = np.random.default_rng(44)
         lead = min(64, n)
@@ -993,6 +1019,7 @@ def bench_matrix(args, world, rank, local):
         del x8
 
     # ---- end to end through the public entry points, host buffers in, host matrix out
+    numa_bind(args, world, local)
     e2e = None
     if n_e2e:
         del F, R, bitmap, out
@@ -1099,6 +1126,8 @@ def main():
                     help="count workload at N > 1: slices (default) = balance + narrow reduce-scatter + distributed "
                          "finalize over NVLink peer memory; fused / peer = u32 table all-to-all onto rank 0 (fused "
                          "into the one-window radix count / as push + collect kernels); nccl = dist.reduce")
+    ap.add_argument("--numa-bind", type=int, default=1, choices=[0, 1],
+                    help="N > 1: pin every rank to the CPUs next to its GPU (NVML ideal affinity)")
     ap.add_argument("--no-e2e", action="store_true", help="matrix workload: skip the host-buffer end-to-end leg")
     ap.add_argument("--no-gram", action="store_true",
                     help="matrix workload: skip the euclidean (tensor-core Gram form) measurement")

@@ -100,10 +100,22 @@ reduce_collect_kernel(const T *__restrict__ inbox, int rank, int world, uint64_t
 // 4^k bytes.  Inboxes are double-buffered by epoch parity: a rank can be at most one step
 // ahead of a peer (its collect of step s+1 needs the peer's push of step s+1, which the peer
 // issues after its own collect of step s).
+//
+// Order of the rows inside a sender's row set.  A row = the 64 counts of one (h, m).  When the
+// world is a power of two (<= 64) every slice is a whole range of h, nh = 64 / world values:
+// the rows are then kept TILE-MAJOR -- row (h, m) at position m * nh + (h - h_first) -- so that
+// the nh rows a tile sends to one owner are contiguous there (512 bytes at 8 ranks, 2 KB at 2)
+// and leave the sender as full 16-byte-per-lane peer stores.  Any other world: in index order
+// (position = row - first row of the slice), 64-byte pieces.
 struct SliceInbox {
     void *base[kMaxPeers];      // inbox of rank o (both parities), mapped on THIS device
     int rank, world;
 };
+__host__ __device__ inline int slice_log_nh(int world)      // log2(64 / world), or -1: not tile-major
+{
+    for (int s = 0; s <= 6; ++s) if (world == (1 << s)) return 6 - s;
+    return -1;
+}
 
 __host__ __device__ inline uint64_t slice64_begin(uint64_t bins, int o, int world)
 {
@@ -213,6 +225,7 @@ __global__ void __launch_bounds__(256, sizeof(CounterT) == 4 ? 3 : 1)
 slice_push_kernel(const CounterT *__restrict__ table, int k, const SliceInbox peers, int parity,
                   unsigned long long epoch, unsigned int *__restrict__ state)
 {
+    const int log_nh = slice_log_nh(peers.world);               // >= 0: tile-major row sets
     extern __shared__ __align__(16) unsigned char push_smem[];
     __shared__ uint32_t begin_row_s[kMaxPeers + 1];             // slice boundaries in 64-count rows
     __shared__ ulonglong2 dst_s[2][128];                        // per stage and row of the tile pair: where its bytes / its u32 go
@@ -234,10 +247,11 @@ slice_push_kernel(const CounterT *__restrict__ table, int k, const SliceInbox pe
     const uint32_t part_at = a0 * kPushRow + (((rc_index(hl, 26) >> 2) ^ (((a0 >> 3) & 1u) << 1)) << 2);
     bool big = false;
 
-    // start the fetch of tile pair c into a stage (and work out where its rows go)
-    auto fetch = [&](uint32_t c, int stage) {
+    // start the fetch of tile pair c into a stage (and work out where its rows go); returns its m
+    auto fetch = [&](uint32_t c, int stage) -> uint32_t {
+        uint32_t m = 0;
         if (c < pairs) {
-            const uint32_t m = canon_unrank(mid, c);
+            m = canon_unrank(mid, c);
             const uint32_t mr = mid_bits ? ((~rev2(m)) >> (32 - mid_bits)) : 0u;
             CounterT *A = tiles_s + stage * 2 * kTile, *B = A + kTile;
 #pragma unroll
@@ -251,30 +265,40 @@ slice_push_kernel(const CounterT *__restrict__ table, int k, const SliceInbox pe
             if (threadIdx.x < 128) {
                 // destination of row (h, tile): the owner's inbox, this sender's row set.  Rows are
                 // whole 64-count units and bins = 4^k: 32-bit arithmetic, no division
-                const uint32_t h = threadIdx.x & 63u, row = (h << mid_bits) | ((threadIdx.x >> 6) ? mr : m);
-                int o = int((row * uint32_t(peers.world)) >> hshift);
-                if (o + 1 < peers.world && begin_row_s[o + 1] <= row) ++o;     // boundaries are rounded DOWN to whole rows
-                const uint64_t at = uint64_t(peers.rank) * cap + (uint64_t(row - begin_row_s[o]) << 6);
+                const uint32_t h = threadIdx.x & 63u, mm = (threadIdx.x >> 6) ? mr : m, row = (h << mid_bits) | mm;
+                int o;
+                uint64_t at = uint64_t(peers.rank) * cap;
+                if (log_nh >= 0) {
+                    o = int(h >> log_nh);
+                    at += uint64_t((mm << log_nh) | (h & ((1u << log_nh) - 1u))) << 6;
+                } else {
+                    o = int((row * uint32_t(peers.world)) >> hshift);
+                    if (o + 1 < peers.world && begin_row_s[o + 1] <= row) ++o;     // boundaries are rounded DOWN to whole rows
+                    at += uint64_t(row - begin_row_s[o]) << 6;
+                }
                 unsigned char *inbox = static_cast<unsigned char *>(peers.base[o]) + par_off + 256;
                 dst_s[stage][threadIdx.x] = make_ulonglong2((unsigned long long)(inbox + at),
                                                             (unsigned long long)(inbox + uint64_t(peers.world) * cap + 4 * at));
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        return m;
     };
 
     __syncthreads();                                            // begin_row_s
-    fetch(blockIdx.x, 0);
+    uint32_t m_next = fetch(blockIdx.x, 0);
     int stage = 0;
     for (uint32_t c = blockIdx.x; c < pairs; c += gridDim.x, stage ^= 1) {
         __syncthreads();                                        // the other stage has been read (previous trip)
-        fetch(c + gridDim.x, stage ^ 1);
+        const uint32_t m = m_next;
+        m_next = fetch(c + gridDim.x, stage ^ 1);
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads();                                        // this stage has landed, for every thread
-        const uint32_t m = canon_unrank(mid, c);
         const uint32_t mr = mid_bits ? ((~rev2(m)) >> (32 - mid_bits)) : 0u;
         const bool two = m != mr;
         const CounterT *A = tiles_s + stage * 2 * kTile, *B = A + kTile;
+        const bool staged = !WIDE && log_nh >= 0;               // byte rows leave through a staging area
+        uint32_t bytes[2][4];                                   // [tile][t]: the four bytes of this thread's piece of row hl + 16 t
 #pragma unroll
         for (int tile = 0; tile < 2; ++tile) {
             if (tile && !two) break;
@@ -304,10 +328,33 @@ slice_push_kernel(const CounterT *__restrict__ table, int k, const SliceInbox pe
                         }
                     }
                 }
-                if constexpr (!WIDE)
-                    *(reinterpret_cast<uint32_t *>(dst.x) + l4) = out[0] | (out[1] << 8) | (out[2] << 16) | (out[3] << 24);
-                else
+                if constexpr (!WIDE) {
+                    bytes[tile][t] = out[0] | (out[1] << 8) | (out[2] << 16) | (out[3] << 24);
+                    if (!staged) *(reinterpret_cast<uint32_t *>(dst.x) + l4) = bytes[tile][t];
+                } else {
                     *reinterpret_cast<uint4 *>(wide) = make_uint4(out[0], out[1], out[2], out[3]);
+                }
+            }
+        }
+        if constexpr (!WIDE) {
+            if (staged) {
+                // the byte rows of the pair, [tile][h][64 B], over the tiles just consumed; then every
+                // thread sends 16 bytes: four lanes a row, the nh rows of an owner back to back
+                uint32_t *stg = reinterpret_cast<uint32_t *>(tiles_s + stage * 2 * kTile);
+                __syncthreads();                                // the tiles have been read
+#pragma unroll
+                for (int tile = 0; tile < 2; ++tile)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (!tile || two) stg[tile * 1024 + (hl + 16 * t) * 16 + l4] = bytes[tile][t];
+                __syncthreads();
+#pragma unroll
+                for (int tile = 0; tile < 2; ++tile) {
+                    if (tile && !two) break;
+                    const uint32_t h = threadIdx.x >> 2, q = threadIdx.x & 3u;
+                    const uint4 v = *reinterpret_cast<const uint4 *>(stg + tile * 1024 + h * 16 + 4 * q);
+                    *reinterpret_cast<uint4 *>(dst_s[stage][64 * tile + h].x + 16 * q) = v;
+                }
             }
         }
     }
@@ -325,7 +372,7 @@ __global__ void slice_signal_kernel(const SliceInbox peers, int parity, unsigned
 // signal >= 0: the first CTA first tells the peers that this rank's rows have landed (signal = the
 // wide_rows of its push, the kernel before this one on the stream).
 template <bool HOST_FORMS>
-__global__ void __launch_bounds__(256, HOST_FORMS ? 4 : 5)
+__global__ void __launch_bounds__(256, 4)
 slice_collect_kernel(const SliceInbox peers, int signal, uint64_t bins, int parity,
                      unsigned long long epoch, int64_t *__restrict__ out64, uint16_t *__restrict__ o16,
                      uint8_t *__restrict__ o8, unsigned int *__restrict__ flags)
@@ -361,7 +408,16 @@ slice_collect_kernel(const SliceInbox peers, int signal, uint64_t bins, int pari
     // lane 2p+1: 8p+2, 8p+3 then 8p+6, 8p+7).  Storing its own 32 bytes as two 16-byte pieces left
     // every 32-byte sector half written per instruction: twice the L1 -> L2 write sectors, which
     // bounded the kernel (ncu: l1tex2xbar write 54 % busy at 2.6 TB/s).  Called by whole warps.
-    auto emit = [&](uint64_t i, const unsigned long long *acc, bool valid) {
+    // position in a sender's row set -> offset in this rank's slice (tile-major row sets: SliceInbox)
+    const int log_nh = slice_log_nh(world);
+    const int hshift = 63 - __clzll((long long)bins) - 6;
+    auto slice_offset = [&](uint64_t i) -> uint64_t {
+        if (log_nh < 0) return i;
+        const uint64_t p = i >> 6;
+        return ((p & ((1ull << log_nh) - 1ull)) << hshift) | ((p >> log_nh) << 6) | (i & 63ull);
+    };
+    auto emit = [&](uint64_t at, const unsigned long long *acc, bool valid) {
+        const uint64_t i = slice_offset(at);
         const bool odd = threadIdx.x & 1u;
         const unsigned long long r0 = __shfl_xor_sync(0xffffffffu, odd ? acc[0] : acc[2], 1);
         const unsigned long long r1 = __shfl_xor_sync(0xffffffffu, odd ? acc[1] : acc[3], 1);
@@ -379,6 +435,23 @@ slice_collect_kernel(const SliceInbox peers, int signal, uint64_t bins, int pari
             }
             *reinterpret_cast<uint2 *>(o16 + i) = make_uint2(p16[0], p16[1]);
             if (o8) *reinterpret_cast<uint32_t *>(o8 + i) = p8;
+        }
+    };
+    // the same for sums still packed as 16-bit halves (lo: bins 0 and 2, hi: bins 1 and 3): one
+    // 32-bit exchange per chunk
+    auto emit_packed = [&](uint64_t at, uint32_t lo, uint32_t hi, bool valid) {
+        const uint64_t i = slice_offset(at);
+        const bool odd = threadIdx.x & 1u;
+        const uint32_t b01 = __byte_perm(lo, hi, 0x5410), b23 = __byte_perm(lo, hi, 0x7632);     // (bin0 | bin1 << 16), (bin2 | bin3 << 16)
+        const uint32_t r = __shfl_xor_sync(0xffffffffu, odd ? b01 : b23, 1);
+        if (!valid) return;
+        const uint32_t a = odd ? r : b01, b = odd ? b23 : r;
+        __stcs(reinterpret_cast<ulonglong2 *>(out64 + (odd ? i - 2 : i)), make_ulonglong2(a & 0xffffu, a >> 16));
+        __stcs(reinterpret_cast<ulonglong2 *>(out64 + (odd ? i + 2 : i + 4)), make_ulonglong2(b & 0xffffu, b >> 16));
+        if constexpr (HOST_FORMS) {
+            over8 |= ((lo | hi) & 0xff00ff00u) != 0u;
+            *reinterpret_cast<uint2 *>(o16 + i) = make_uint2(b01, b23);
+            if (o8) *reinterpret_cast<uint32_t *>(o8 + i) = __byte_perm(b01, b23, 0x6420);
         }
     };
     // Four neighbouring bins per thread and chunk: one 4-byte (narrow) or 16-byte (wide) load per
@@ -412,12 +485,19 @@ slice_collect_kernel(const SliceInbox peers, int signal, uint64_t bins, int pari
                     hi[u] += (w[u] >> 8) & 0x00ff00ffu;
                 }
             }
+            if (!__any_sync(0xffffffffu, esc != 0u)) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (w0 + stride * u < n) emit_packed(i0 + stride * u, lo[u], hi[u], i0 + stride * u < n);
+                continue;
+            }
+            // rare: replace every 255 by the value in the sender's wide row set
             unsigned long long acc[U][4];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 acc[u][0] = lo[u] & 0xffffu; acc[u][1] = hi[u] & 0xffffu; acc[u][2] = lo[u] >> 16; acc[u][3] = hi[u] >> 16;
             }
-            if (esc) {                      // rare: replace every 255 by the value in the sender's wide row set
+            if (esc) {
                 for (int s = 0; s < world; ++s)
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
@@ -533,7 +613,7 @@ int launch_slice_collect(int k, int rank, int world, void *const *inbox_ptrs, un
     const uint64_t bins = 1ull << (2 * k);
     const uint64_t n = slice64_begin(bins, rank + 1, world) - slice64_begin(bins, rank, world);
     // a few CTAs per SM, looping: every CTA waits for the signals once
-    const unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>((n / 16 + 255) / 256, uint64_t(sm_count()) * 5)));
+    const unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>((n / 16 + 255) / 256, uint64_t(sm_count()) * 4)));
     if (d_flags) KPAL_CUDA(cudaMemsetAsync(d_flags, 0, 8, stream));
     if (d_o16)
         slice_collect_kernel<true><<<grid, 256, 0, stream>>>(peers, signal, bins, int(epoch & 1ull), epoch, d_out64, d_o16, d_o8, d_flags);

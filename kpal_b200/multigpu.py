@@ -23,6 +23,30 @@ from . import _cabi
 
 
 # ------------------------------------------------------------------ sharding
+def bind_to_gpu_cpus(device_index):
+    """Pin the calling thread (and the threads it starts later: the library's host workers) to
+    the CPUs next to GPU `device_index` (NVML's ideal affinity: the GPU's NUMA node), so that a
+    rank's pinned buffers and its widening threads stay on the memory controller its PCIe link
+    hangs off.  One process per GPU on a two-socket host otherwise leaves that to chance.  Returns
+    the previous affinity (restore it with ``os.sched_setaffinity(0, previous)``) or None when
+    NVML or the call is unavailable -- it is an optimisation, never an error."""
+    import os
+    try:
+        import pynvml
+        previous = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        ideal = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        ideal &= previous
+        if not ideal:
+            return None
+        os.sched_setaffinity(0, ideal)
+        return previous
+    except Exception:
+        return None
+
+
 def balanced_ranges(sizes, parts):
     """Cut ``len(sizes)`` consecutive items into `parts` contiguous ranges of
     about equal total size.  Returns ``parts`` ``(begin, end)`` pairs covering
