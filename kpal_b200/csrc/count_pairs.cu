@@ -19,13 +19,15 @@
 //           (rank in the bucket's slot) + one 16-bit store; full 32-byte groups are flushed
 //           to the CTA's region of the bucket.  Half the shared-memory operations and half
 //           the staging bytes (1 B / window) of the one-window path.
-//   pass 2  pair_histogram_kernel<ROLE>   one CTA per bucket, run once per window of the pair:
-//           ROLE 1 (window 1 = C : R) histograms R into the bucket's contiguous table slice;
-//           ROLE 0 (window 0 = b0 : C : R >> 2) into four runs of 4^(k-6) bins.  Within a role
-//           every table bin belongs to exactly one CTA, so the slice is updated with plain
-//           16-byte read-modify-writes; the two roles touch the same bins from different
-//           CTAs, hence two launches, one after the other.  A histogram is 4^(k-5) counters
-//           (64 KB at k = 12): three CTAs per SM, whose zero / histogram / flush phases overlap.
+//   pass 2  pair_histogram_kernel    one CTA per (bucket, role), the role = which window of the pair:
+//           role 1 (window 1 = C : R) histograms R into the bucket's contiguous table slice;
+//           role 0 (window 0 = b0 : C : R >> 2) into four runs of 4^(k-6) bins.  A histogram is
+//           4^(k-5) 32-bit counters in shared memory (64 KB at k = 12): three CTAs per SM, whose
+//           zero / histogram / flush phases overlap.  The histogram is ADDED to the table by the
+//           TMA unit (cp.reduce.async.bulk ... add.u32, SASS UBLKRED): atomic at the L2, so the
+//           two roles (and the single-window REDs of pass 1) may touch the same bins from
+//           different CTAs in ONE launch.  64-bit tables (>= 2^32 bases) take the older form:
+//           one launch per role with plain 16-byte read-modify-writes.
 //
 // Slot or region overflow (skewed / repetitive sequence) falls back to REDs on the table for
 // both windows of the pair: exact for every input.
