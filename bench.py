@@ -432,6 +432,8 @@ def bench_count(args, world, rank, local):
     _cabi.check(L.kpal_set_option(b"narrow_d2h", args.narrow_d2h))
     _cabi.check(L.kpal_set_option(b"dma_share", args.dma_share))
     _cabi.check(L.kpal_set_option(b"fasta_split", args.fasta_split))
+    _cabi.check(L.kpal_set_option(b"fasta_hybrid", args.fasta_hybrid))
+    _cabi.check(L.kpal_set_option(b"fasta_hybrid_share", args.fasta_hybrid_share))
     dev = torch.device("cuda", local)
 
     # ---- this rank's shard of records (same size on every rank: weak scaling)
@@ -619,10 +621,16 @@ def bench_count(args, world, rank, local):
         e2e_step()
     barrier_sync(world)
     t0 = time.perf_counter()
+    h2d_sum, host_text_sum = 0, 0
+    up, packed_text = ctypes.c_uint64(), ctypes.c_uint64()
     for _ in range(args.steps):
         e2e_step()
+        L.kpal_last_upload(ctypes.byref(up), ctypes.byref(packed_text))     # (two loads; this rank's call)
+        h2d_sum += up.value
+        host_text_sum += packed_text.value
     barrier_sync(world)
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps, world)
+    h2d_mean, host_text_mean = h2d_sum / args.steps, host_text_sum / args.steps
 
     # ---- parity of what was just measured, against the ORACLE: the C port counts the
     # concatenation of every rank's shard (rank 0 rebuilds the shards of the other ranks from
@@ -750,10 +758,13 @@ def bench_count(args, world, rank, local):
                        if world > 1 else "1 GPU",
                        **({"reduce_note": reduce_note} if reduce_note else {})},
             "e2e": {"value": total_bases / 1e9 / e2e_s, "unit": "Gbases/s",
-                    "h2d_bytes_per_step": int(n_fasta * world),
+                    "h2d_bytes_per_step": int(h2d_mean * world),
+                    "text_bytes_per_step": int(n_fasta * world),
+                    "host_packed_text_frac": round(host_text_mean / n_fasta, 4),
                     "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": e2e_s * 1e3,
-                    "path": ("pinned FASTA bytes -> kpal_count_fasta (H2D of the raw text in chunks, GPU scan/pack, "
+                    "path": ("pinned FASTA bytes -> kpal_count_fasta (hybrid upload: the head of the text goes up raw and is packed by the GPU, "
+                             "while host threads pack the tail and only its 0.375 B/base cross the bus; "
                              "count + balance kernels, " if world == 1 else
                              "per rank: pinned FASTA bytes -> kpal_count_fasta_dev_table (H2D in chunks, GPU scan/pack, "
                              "count), kpal_dev_slice_push, kpal_dev_slice_collect_to_host (this rank's slice: "
@@ -1136,6 +1147,12 @@ def main():
                     help="e2e leg: 1 = the profile leaves the device as uint8 / uint16 (the narrowest that "
                          "holds every count) and host threads widen it (library default), 2 = uint16 only, "
                          "0 = plain int64 copy")
+    ap.add_argument("--fasta-hybrid", type=int, default=1,
+                    help="e2e leg: 1 = host threads pack segments from the end of the text while its head uploads raw "
+                         "(hybrid upload, cabi.cu fasta_hybrid_count), 0 = the whole text uploads raw, "
+                         "2..64 = at most that many host packers")
+    ap.add_argument("--fasta-hybrid-share", type=int, default=0,
+                    help="e2e leg, hybrid upload: percent of the text the host packs (0 = adapted from call to call)")
     ap.add_argument("--fasta-split", type=int, default=0, choices=[0, 1],
                     help="e2e leg: 1 = a large FASTA text is cut at a header line into two parts, the first counted "
                          "while the second is uploaded, 0 = one part (library default: the cut measured no gain)")

@@ -111,6 +111,35 @@ int kpal_fasta_scan(const char *fasta, uint64_t n_bytes, uint64_t *n_records,
 int kpal_fasta_pack(const char *fasta, uint64_t n_bytes, uint32_t *codes, uint32_t *valid,
                     uint64_t *rec_starts /* n_records+1 */, char *names /* name_bytes */);
 
+/*
+ * One SEGMENT of a FASTA text (text[begin, end), begin at a line start; bytes before
+ * the segment's first header line are skipped) packed into a slot of its own, same rules as kpal_fasta_pack (kpal/klib.py:111):
+ * codes / valid point at the slot's first words, cap_bases is the slot's length (a
+ * multiple of 64, >= end - begin); one invalid base is emitted at every header (the
+ * record separator) and the slot is invalid behind the emitted bases.  This is what
+ * idle host threads do to the tail of a large text while kpal_count_fasta uploads
+ * its head raw (hybrid upload); 32 bytes per step with AVX2 + BMI2, scalar otherwise.
+ */
+int kpal_fasta_pack_segment(const char *fasta, uint64_t n_bytes, uint64_t begin, uint64_t end,
+                            uint32_t *codes, uint32_t *valid, uint64_t cap_bases,
+                            uint64_t *n_bases_out);
+
+/*
+ * The whole text as a SLOTTED stream (csrc/slotted.h): cut at line starts into segments
+ * of about seg_bytes, each packed independently into a slot of its own, plus one 64-base
+ * junction record per cut holding the k - 1 windows that cross it.  Counting the windows
+ * of this stream gives Profile.from_fasta's counts (kpal/klib.py:97-112) for that k.  It
+ * is the layout kpal_count_fasta builds on the device when host threads pack the tail of
+ * a large text while its head uploads raw; this entry point does all of it on the host
+ * (tests, and callers that want to pack ahead of time).  codes / valid must hold
+ * kpal_packed_words(kpal_fasta_slotted_bases(n_bytes, seg_bytes)) words; *stream_bases_out
+ * receives the stream's length.  KPAL_EINVAL when the text has no header line within its
+ * first MB or lines above 64 KB (such a text cannot be cut).
+ */
+uint64_t kpal_fasta_slotted_bases(uint64_t n_bytes, uint64_t seg_bytes);
+int kpal_fasta_pack_slotted(const char *fasta, uint64_t n_bytes, int k, uint64_t seg_bytes,
+                            uint32_t *codes, uint32_t *valid, uint64_t *stream_bases_out);
+
 /* ------------------------------------------------------ counting: host API */
 
 /*
@@ -488,9 +517,21 @@ int kpal_dev_fasta_pack(const void *d_text, uint64_t n_bytes, uint32_t *d_codes,
  * host entry points: 1 = uint8 / uint16, 2 = uint16 only, 0 = int64),
  * "dma_share" (0..8 sixteenths of a narrow-copied profile that the copy engine
  * moves as int64 into a pinned destination; default 0), "fasta_chunks" (0 = auto
- * .. 32 chunks of the pipelined FASTA upload), and the tuning switches of the
+ * .. 32 chunks of the pipelined FASTA upload), "fasta_hybrid" (1 = host threads
+ * pack segments from the end of a text of >= 32 MB while its head uploads raw,
+ * 0 = the whole text uploads raw, 2..64 = at most that many host packers),
+ * "fasta_hybrid_share" (percent of the text the host packs; 0 = adapted from call
+ * to call to the measured host and bus rates), and the tuning switches of the
  * count path ("count_path", "radix_shape", "radix_payload_bits", "tiled_finalize"). */
 int kpal_set_option(const char *name, int value);
+
+/*
+ * The text upload of the last kpal_count_fasta / kpal_count_fasta_to_dev /
+ * kpal_count_fasta_dev_table call on this process: bytes that crossed the bus host ->
+ * device (raw text + packed segments) and how many text bytes the host threads packed
+ * themselves (hybrid upload; 0 when the whole text went up raw).  For reporting.
+ */
+void kpal_last_upload(uint64_t *h2d_bytes, uint64_t *host_packed_text_bytes);
 
 /* counters for bench.py's "gpu_launches": kernels launched by this library
  * in the calling process since load / since the last reset. */

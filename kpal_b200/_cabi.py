@@ -25,7 +25,7 @@ SYMBOLS = (
     "kpal_abi_version", "kpal_last_error", "kpal_device_count", "kpal_set_device",
     "kpal_host_alloc", "kpal_host_free", "kpal_dev_alloc", "kpal_dev_free",
     "kpal_memcpy_h2d", "kpal_memcpy_d2h", "kpal_dev_memset", "kpal_stream_sync",
-    "kpal_packed_words", "kpal_pack_sequences", "kpal_fasta_scan", "kpal_fasta_pack",
+    "kpal_packed_words", "kpal_pack_sequences", "kpal_fasta_scan", "kpal_fasta_pack", "kpal_fasta_pack_segment", "kpal_fasta_slotted_bases", "kpal_fasta_pack_slotted",
     "kpal_count_sequences", "kpal_count_fasta", "kpal_count_by_record", "kpal_balance",
     "kpal_distance_matrix", "kpal_pair_distance",
     "kpal_matrix_open", "kpal_matrix_push", "kpal_matrix_finish", "kpal_matrix_close",
@@ -43,7 +43,7 @@ SYMBOLS = (
     "kpal_distance_tile_elems", "kpal_dev_distance_tiles_packed", "kpal_dev_distance_unpack_tiles",
     "kpal_gram_row_stride", "kpal_dev_gram_prepare", "kpal_dev_gram_distances",
     "kpal_fasta_scratch_bytes", "kpal_dev_fasta_pack", "kpal_set_option",
-    "kpal_kernel_launches", "kpal_reset_kernel_launches",
+    "kpal_kernel_launches", "kpal_reset_kernel_launches", "kpal_last_upload",
 )
 
 _lib = None
@@ -89,6 +89,9 @@ def load():
     sig("kpal_pack_sequences", i32, vp, vp, u64, vp, vp, vp, pu64)
     sig("kpal_fasta_scan", i32, vp, u64, pu64, pu64, pu64)
     sig("kpal_fasta_pack", i32, vp, u64, vp, vp, vp, vp)
+    sig("kpal_fasta_pack_segment", i32, vp, u64, u64, u64, vp, vp, u64, pu64)
+    sig("kpal_fasta_slotted_bases", u64, u64, u64)
+    sig("kpal_fasta_pack_slotted", i32, vp, u64, i32, u64, vp, vp, pu64)
     sig("kpal_count_sequences", i32, vp, vp, u64, i32, i32, vp)
     sig("kpal_count_fasta", i32, vp, u64, i32, i32, vp)
     sig("kpal_count_by_record", i32, vp, vp, u64, vp, u64, u64, i32, i32, vp)
@@ -150,6 +153,7 @@ def load():
     sig("kpal_set_option", i32, c.c_char_p, i32)
     sig("kpal_kernel_launches", u64)
     sig("kpal_reset_kernel_launches", None)
+    sig("kpal_last_upload", None, pu64, pu64)
     _lib = L
     return L
 
@@ -279,6 +283,42 @@ def fasta_pack(text):
     check(L.kpal_fasta_pack(buf, len(text), ptr(codes), ptr(valid), ptr(rec_starts), names))
     name_list = names.raw[:name_bytes.value].split(b"\0")[:n_rec.value] if n_rec.value else []
     return codes, valid, rec_starts, [n.decode("latin-1") for n in name_list], n_bases.value
+
+
+def fasta_pack_segment(text, begin=0, end=None):
+    """Host-side pack of the records of text[begin:end] into a slot of its own (the unit
+    of the hybrid upload of kpal_count_fasta).  Returns (codes, valid, n_bases); the slot
+    holds len(segment) rounded up to 64 bases.  No GPU needed."""
+    L = load()
+    if isinstance(text, str):
+        text = text.encode("latin-1", "replace")
+    end = len(text) if end is None else end
+    cap = (end - begin + 63) // 64 * 64 + 64
+    codes = np.full(cap // 16, 0xdeadbeef, dtype=np.uint32)       # the call must define every word
+    valid = np.full(cap // 32, 0xdeadbeef, dtype=np.uint32)
+    n_bases = ctypes.c_uint64()
+    buf = ctypes.c_char_p(text) if text else None
+    check(L.kpal_fasta_pack_segment(buf, len(text), begin, end, ptr(codes), ptr(valid), cap,
+                                    ctypes.byref(n_bases)))
+    return codes, valid, n_bases.value
+
+
+def fasta_pack_slotted(text, k, seg_bytes):
+    """Host-side pack of a FASTA text as a slotted stream (segments of about seg_bytes cut at
+    line starts + junction records for window length k).  Returns (codes, valid, n_bases).
+    No GPU needed."""
+    L = load()
+    if isinstance(text, str):
+        text = text.encode("latin-1", "replace")
+    cap = L.kpal_fasta_slotted_bases(len(text), seg_bytes)
+    cw, vw = ctypes.c_uint64(), ctypes.c_uint64()
+    L.kpal_packed_words(cap, ctypes.byref(cw), ctypes.byref(vw))
+    codes = np.full(cw.value, 0xdeadbeef, dtype=np.uint32)
+    valid = np.full(vw.value, 0xdeadbeef, dtype=np.uint32)
+    n_bases = ctypes.c_uint64()
+    check(L.kpal_fasta_pack_slotted(ctypes.c_char_p(text), len(text), k, seg_bytes, ptr(codes), ptr(valid),
+                                    ctypes.byref(n_bases)))
+    return codes, valid, n_bases.value
 
 
 def pack_sequences(sequences):

@@ -4,11 +4,13 @@
 // the "dev" entry points are thin launch wrappers for callers that already
 // hold device memory (bench harness, multi-GPU driver in kpal_b200/multigpu.py).
 #include "common.cuh"
+#include "slotted.h"
 
 #include <algorithm>
 #include <chrono>
 #include <stdio.h>
 #include <mutex>
+#include <memory>
 #include <numeric>
 #include <thread>
 #include <string.h>
@@ -66,7 +68,10 @@ void set_pair_flush_every(int v);
 int launch_fasta_pack(const uint8_t *, uint64_t, uint32_t *, uint32_t *, void *, cudaStream_t);
 int launch_fasta_pack_begin(uint64_t, uint32_t *, uint32_t *, void *, cudaStream_t);
 int launch_fasta_pack_tiles(const uint8_t *, uint64_t, uint64_t, uint64_t, uint32_t *, uint32_t *, void *,
-                            cudaStream_t);
+                            cudaStream_t, uint64_t layout_bytes = 0);
+WidenHandle *pool_run_begin(void (*fn)(void *), void *arg);
+void pool_run_end(WidenHandle *h);
+unsigned widen_workers();
 uint64_t fasta_tile_bytes();
 uint64_t split_length(int k);
 uint64_t split_scratch_bytes(int k);
@@ -89,6 +94,9 @@ static thread_local char t_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_host_fasta{-1};       // -1: from the environment (KPAL_HOST_FASTA=1)
 static std::atomic<int> g_fasta_split{0};         // 1: a large FASTA text is cut in two parts, the first counted while the second uploads (fasta_gpu_count; measured: no gain yet, so off)
+static std::atomic<int> g_fasta_hybrid_share{0};  // percent of the text the host packs (0: adapted from call to call)
+static std::atomic<int> g_fasta_hybrid{1};        // 1: idle host threads pack segments from the end of a large text while its head uploads raw (fasta_hybrid_count)
+static std::atomic<uint64_t> g_last_h2d_bytes{0}, g_last_host_text_bytes{0};   // kpal_last_upload
 static std::atomic<int> g_fasta_chunks{0};      // 0 = automatic (one chunk per ~6 MB, at most 16), else 1 .. 32
 static std::atomic<int> g_dma_share{0};         // sixteenths of a narrow-copied profile the DMA engine moves as int64 (pinned destinations)
 static std::atomic<int> g_gram{1};              // 1: euclidean / cosine matrices take the tensor-core Gram form when the counts allow it
@@ -362,6 +370,14 @@ extern "C" int kpal_set_option(const char *name, int value)
         g_fasta_chunks.store(value); return KPAL_OK;
     }
     if (!strcmp(name, "fasta_split")) { g_fasta_split.store(value ? 1 : 0); return KPAL_OK; }
+    if (!strcmp(name, "fasta_hybrid")) {
+        if (value < 0 || value > 64) return bad_arg("fasta_hybrid must be 0 (off), 1 (on) or 2 .. 64 (on, that many host packers at most)");
+        g_fasta_hybrid.store(value); return KPAL_OK;
+    }
+    if (!strcmp(name, "fasta_hybrid_share")) {
+        if (value < 0 || value > 95) return bad_arg("fasta_hybrid_share must be 0 (adaptive) .. 95 percent of the text");
+        g_fasta_hybrid_share.store(value); return KPAL_OK;
+    }
     if (!strcmp(name, "exact_div")) { set_exact_div(value != 0); return KPAL_OK; }
     if (!strcmp(name, "gram")) { g_gram.store(value ? 1 : 0); return KPAL_OK; }
     if (!strcmp(name, "narrow_lists")) { g_narrow_lists.store(value ? 1 : 0); return KPAL_OK; }
@@ -402,6 +418,12 @@ extern "C" int kpal_set_option(const char *name, int value)
     }
     set_error("unknown option '%s'", name);
     return KPAL_EINVAL;
+}
+
+extern "C" void kpal_last_upload(uint64_t *h2d_bytes, uint64_t *host_packed_text_bytes)
+{
+    if (h2d_bytes) *h2d_bytes = g_last_h2d_bytes.load();
+    if (host_packed_text_bytes) *host_packed_text_bytes = g_last_host_text_bytes.load();
 }
 
 extern "C" uint64_t kpal_fasta_scratch_bytes(uint64_t n_bytes) { return fasta_scratch_bytes(n_bytes); }
@@ -770,6 +792,218 @@ static uint64_t fasta_split_point(const char *fasta, uint64_t n_bytes)
     return 0;
 }
 
+// ---------------------------------------------------------------- hybrid upload
+// The upload of the text is 60 % of a large kpal_count_fasta call and the host has nothing
+// to do meanwhile.  So the text is cut at header lines into segments of ~512 KB: the head of
+// the text goes to the device raw (chunked upload + device packer, as before) while the
+// pool's threads pack the segments of the tail (pack.cpp: fasta_pack_segment, 32 bytes per
+// step) into pinned staging, and only their 0.375 B/base cross the bus behind the raw text.
+// The packed stream is SLOTTED: segment j owns the bases [slot_j, slot_{j+1}) with
+// slot_j = align64(cut_j) + 64 j (a byte emits at most one base, so slot_j lies behind
+// everything the text before cut_j can emit), unused slot ends are invalid, and one count
+// launch takes the whole stream -- the count kernels already run over one position per text
+// byte (the device packer's upper bound).  The host's share of the text follows the measured
+// rates of the previous call (host packing vs. raw upload) so that the packers finish just
+// before the raw text has gone up; exact whatever the share.
+struct HybridState {
+    const unsigned char *text = nullptr;
+    uint64_t n_bytes = 0;
+    int k = 0;
+    SlottedPlan plan;
+    uint32_t *pcodes = nullptr, *pvalid = nullptr;    // pinned staging, laid out like the device stream from slot[first] on
+    uint64_t first = 0;                           // host segments [first, m)
+    std::atomic<uint64_t> next{0};
+    std::unique_ptr<std::atomic<unsigned char>[]> done;
+    std::atomic<uint64_t> host_bases{0};
+    std::atomic<unsigned> joined{0};
+    unsigned max_packers = 0;
+};
+
+static void hybrid_packer(void *arg)
+{
+    HybridState *h = static_cast<HybridState *>(arg);
+    if (h->joined.fetch_add(1) >= h->max_packers) return;
+    const uint64_t base = h->plan.slot[h->first];
+    for (;;) {
+        const uint64_t j = h->next.fetch_add(1, std::memory_order_relaxed);
+        if (j >= h->plan.m) return;
+        const uint64_t n = slotted_pack_segment(h->plan, h->text, h->n_bytes, j, h->first, h->k, h->pcodes, h->pvalid, base);
+        h->host_bases.fetch_add(n, std::memory_order_relaxed);
+        h->done[j].store(1, std::memory_order_release);
+    }
+}
+
+static unsigned hybrid_packers()
+{
+    const int opt = g_fasta_hybrid.load();
+    if (opt <= 0 || !fasta_segment_fast()) return 0;
+    unsigned n = widen_workers() - 1;               // the caller feeds the copy engine
+    if (opt > 1) n = std::min<unsigned>(n, unsigned(opt));
+    else {
+        // one process per GPU (torchrun): the ranks of a node share its cores
+        const char *e = getenv("LOCAL_WORLD_SIZE");
+        const unsigned ranks = e ? unsigned(std::max(1, atoi(e))) : 1u;
+        const unsigned hw = std::thread::hardware_concurrency();
+        if (ranks > 1 && hw) n = std::min(n, std::max(1u, hw / ranks));
+    }
+    return n;
+}
+
+// the host's share of the text, adapted from call to call (per process; under g_count_mutex)
+static double g_hybrid_share = 0.30;
+static cudaEvent_t g_hybrid_ev[2] = {};             // raw upload: start / done (timing events)
+static double g_hybrid_prev[3] = {0, 0, 0};         // previous call: host seconds, host text bytes, raw bytes
+
+static void hybrid_adapt()
+{
+    if (g_hybrid_prev[0] <= 0 || g_hybrid_prev[1] <= 0 || g_hybrid_prev[2] <= 0 || !g_hybrid_ev[0]) return;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_hybrid_ev[0], g_hybrid_ev[1]) != cudaSuccess || ms <= 0.f) { cudaGetLastError(); return; }
+    const double host_rate = g_hybrid_prev[1] / g_hybrid_prev[0], bus_rate = g_hybrid_prev[2] / (ms * 1e-3);
+    // The bus carries (1 - x) of the text raw and x of it packed (0.375 B/base, a little more
+    // with the slot ends and the shorter copies: 0.41); the packers should be done a little
+    // before the bus is:  x / host_rate = 0.93 ((1 - x) + 0.41 x) / bus_rate
+    const double x = 0.93 * host_rate / (bus_rate + 0.93 * 0.59 * host_rate);
+    g_hybrid_share = std::min(0.75, std::max(0.05, 0.3 * g_hybrid_share + 0.7 * x));
+    g_hybrid_prev[0] = 0;
+}
+
+// Returns KPAL_OK with *taken = false when the text is not one for the hybrid form.
+static int fasta_hybrid_count(CountWorkspace *w, const char *fasta, uint64_t n_bytes, int k,
+                              void *d_table, int bits, cudaStream_t st, unsigned *flags,
+                              uint64_t *n_bases, bool *taken)
+{
+    *taken = false;
+    const unsigned packers = hybrid_packers();
+    if (packers < 2 || n_bytes < (32ull << 20) || n_bytes >= (1ull << 32)) return KPAL_OK;
+    HybridState h;
+    if (!slotted_plan(fasta, n_bytes, 512u << 10, h.plan) || h.plan.m < 8) return KPAL_OK;
+    *taken = true;
+    hybrid_adapt();
+    const int forced = g_fasta_hybrid_share.load();
+    const double share = forced > 0 ? forced / 100.0 : g_hybrid_share;
+    const uint64_t m = h.plan.m;
+    const uint64_t first = std::min<uint64_t>(m - 1, std::max<uint64_t>(1, uint64_t(double(m) * (1.0 - share) + 0.5)));
+    h.text = reinterpret_cast<const unsigned char *>(fasta);
+    h.n_bytes = n_bytes;
+    h.k = k;
+    h.first = first;
+    h.next.store(first);
+    const uint64_t stream_bases = h.plan.stream_bases(first), host_base = h.plan.slot[first], raw_len = h.plan.cut[first];
+    uint64_t cw = 0, vw = 0, cw_max = 0, vw_max = 0;
+    kpal_packed_words(stream_bases, &cw, &vw);
+    kpal_packed_words(h.plan.stream_bases(0), &cw_max, &vw_max);
+    // (sized for any share: the share moves from call to call and a pinned reallocation costs milliseconds)
+    KPAL_CHECK(w->text.ensure(n_bytes + 32));
+    KPAL_CHECK(w->codes.ensure(cw_max * 4));
+    KPAL_CHECK(w->valid.ensure(vw_max * 4));
+    KPAL_CHECK(w->pcodes.ensure(cw_max * 4));
+    KPAL_CHECK(w->pvalid.ensure(vw_max * 4));
+    KPAL_CHECK(w->fscratch.ensure(fasta_scratch_bytes(n_bytes)));
+    KPAL_CHECK(w->pstatus.ensure(2 * sizeof(FastaStatus)));
+    FastaStatus *status = static_cast<FastaStatus *>(w->pstatus.p);
+    memset(status, 0, 2 * sizeof(FastaStatus));
+    if (!w->copy_stream) {
+        KPAL_CUDA(cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
+        for (auto &e : w->chunk_done) KPAL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    if (!g_hybrid_ev[0]) for (auto &e : g_hybrid_ev) KPAL_CUDA(cudaEventCreate(&e));
+    h.pcodes = static_cast<uint32_t *>(w->pcodes.p);
+    h.pvalid = static_cast<uint32_t *>(w->pvalid.p);
+    h.done.reset(new std::atomic<unsigned char>[m]);
+    for (uint64_t j = 0; j < m; ++j) h.done[j].store(0, std::memory_order_relaxed);
+    h.max_packers = packers;
+    uint8_t *d_text = w->text.as_bytes();
+    uint32_t *d_codes = static_cast<uint32_t *>(w->codes.p), *d_valid = static_cast<uint32_t *>(w->valid.p);
+    void *d_scratch = w->fscratch.p;
+    const uint64_t tile = fasta_tile_bytes();
+
+    const auto t_host0 = std::chrono::steady_clock::now();
+    WidenHandle *pool = pool_run_begin(hybrid_packer, &h);           // the packers start on the tail
+    int rc = KPAL_OK;
+    cudaError_t err = cudaSuccess;
+    auto fail = [&](cudaError_t e) { if (err == cudaSuccess) err = e; };
+    // zero the stream up to the host's part (the device packer ORs into it; the slots of the
+    // host's part are written whole by the copies) and the halo behind the stream
+    fail(cudaMemsetAsync(d_codes, 0, host_base / 4, st));
+    fail(cudaMemsetAsync(d_valid, 0, host_base / 8, st));
+    fail(cudaMemsetAsync(d_codes + stream_bases / 16, 0, (cw - stream_bases / 16) * 4, st));
+    fail(cudaMemsetAsync(d_valid + stream_bases / 32, 0, (vw - stream_bases / 32) * 4, st));
+    fail(cudaMemsetAsync(d_scratch, 0, sizeof(FastaStatus) + 16, st));
+    fail(cudaMemsetAsync(d_scratch, 0xff, sizeof(unsigned long long), st));      // first_header = ~0
+    g_trace.dev_mark("start", w->copy_stream);
+    fail(cudaEventRecord(g_hybrid_ev[0], w->copy_stream));
+    // the head: raw chunks on the copy stream, each packed as soon as it has landed
+    uint64_t n_chunks = std::min<uint64_t>(std::max<uint64_t>(raw_len / (6ull << 20), 1), 16);
+    if (g_fasta_chunks.load() > 0) n_chunks = std::min<uint64_t>(uint64_t(g_fasta_chunks.load()), 30);
+    const uint64_t chunk = ((raw_len + n_chunks - 1) / n_chunks + tile - 1) / tile * tile;
+    uint64_t event = 0;
+    for (uint64_t off = 0; off < raw_len && err == cudaSuccess && rc == KPAL_OK; off += chunk) {
+        const uint64_t len = std::min(chunk, raw_len - off);
+        fail(cudaMemcpyAsync(d_text + off, fasta + off, len, cudaMemcpyHostToDevice, w->copy_stream));
+        fail(cudaEventRecord(w->chunk_done[event], w->copy_stream));
+        fail(cudaStreamWaitEvent(st, w->chunk_done[event], 0));
+        ++event;
+        if (err == cudaSuccess)
+            rc = launch_fasta_pack_tiles(d_text, raw_len, off / tile, (off + len + tile - 1) / tile, d_codes, d_valid, d_scratch, st);
+    }
+    fail(cudaEventRecord(g_hybrid_ev[1], w->copy_stream));
+    g_trace.dev_mark("raw_h2d", w->copy_stream);
+    if (err == cudaSuccess && rc == KPAL_OK)
+        fail(cudaMemcpyAsync(status, d_scratch, sizeof(FastaStatus), cudaMemcpyDeviceToHost, st));
+    g_trace.mark("raw_queued");
+    // the tail: the finished segments go up in runs, in order, behind the raw text
+    uint64_t up = first;
+    double host_s = 0;
+    while (up < m) {
+        uint64_t r = up;
+        while (r < m && h.done[r].load(std::memory_order_acquire)) ++r;
+        if (r == m && host_s == 0) host_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_host0).count();
+        if (r - up >= 16 || (r == m && r > up)) {
+            // (the junction records lie behind the last slot and are complete with the last segment)
+            const uint64_t b0 = h.plan.slot[up], b1 = r == m ? stream_bases : h.plan.slot[r];
+            if (err == cudaSuccess) {
+                fail(cudaMemcpyAsync(d_codes + b0 / 16, h.pcodes + (b0 - host_base) / 16, (b1 - b0) / 4, cudaMemcpyHostToDevice, w->copy_stream));
+                fail(cudaMemcpyAsync(d_valid + b0 / 32, h.pvalid + (b0 - host_base) / 32, (b1 - b0) / 8, cudaMemcpyHostToDevice, w->copy_stream));
+            }
+            up = r;
+        } else {
+            std::this_thread::yield();
+        }
+    }
+    pool_run_end(pool);
+    g_trace.mark("host_packed");
+    if (err != cudaSuccess) {
+        set_error("hybrid FASTA upload failed: %s", cudaGetErrorString(err));
+        cudaGetLastError();
+        cudaStreamSynchronize(w->copy_stream);
+        cudaStreamSynchronize(st);
+        return KPAL_ECUDA;
+    }
+    if (rc != KPAL_OK) { cudaStreamSynchronize(w->copy_stream); cudaStreamSynchronize(st); return rc; }
+    KPAL_CUDA(cudaEventRecord(w->chunk_done[31], w->copy_stream));
+    g_trace.dev_mark("h2d", w->copy_stream);
+    // Two count launches into the one table: the device's part (it ends in >= 64 invalid bases, so no
+    // window of it reaches into the host's slots) is counted while the packed tail is still on the bus.
+    KPAL_CHECK(launch_count(d_codes, d_valid, host_base, k, d_table, bits, st));
+    KPAL_CUDA(cudaStreamWaitEvent(st, w->chunk_done[31], 0));
+    g_trace.dev_mark("packed", st);
+    KPAL_CHECK(launch_count(d_codes + host_base / 16, d_valid + host_base / 32, stream_bases - host_base, k, d_table, bits, st));
+    g_trace.dev_mark("counted", st);
+    g_trace.mark("count_queued");
+    g_hybrid_prev[0] = host_s; g_hybrid_prev[1] = double(n_bytes - raw_len); g_hybrid_prev[2] = double(raw_len);
+    g_last_h2d_bytes.store(raw_len + (stream_bases - host_base) / 8 * 3);
+    g_last_host_text_bytes.store(n_bytes - raw_len);
+    if (g_trace.on && g_trace.at + 48 <= sizeof g_trace.line)
+        g_trace.at += size_t(snprintf(g_trace.line + g_trace.at, sizeof g_trace.line - g_trace.at, " host_share_pct=%.0f",
+                                      100.0 * double(n_bytes - raw_len) / double(n_bytes)));
+    if (!flags) return KPAL_OK;
+    KPAL_CUDA(cudaStreamSynchronize(st));
+    *flags = status[0].flags;
+    if (n_bases) *n_bases = status[0].total_bases + h.host_bases.load();
+    return KPAL_OK;
+}
+
 // Raw FASTA bytes (host) -> device text -> GPU scan/pack -> windows accumulated
 // into d_table.  *flags gets bit 0 when the text holds bytes the GPU packer
 // does not handle (tabs & co on sequence lines): the caller then redoes the
@@ -791,6 +1025,13 @@ static int fasta_gpu_count(CountWorkspace *w, const char *fasta, uint64_t n_byte
                            void *d_table, int bits, cudaStream_t st, unsigned *flags,
                            uint64_t *n_bases)
 {
+    if (g_fasta_split.load() == 0) {
+        bool taken = false;
+        const int rc = fasta_hybrid_count(w, fasta, n_bytes, k, d_table, bits, st, flags, n_bases, &taken);
+        if (rc != KPAL_OK || taken) return rc;
+    }
+    g_last_h2d_bytes.store(n_bytes);
+    g_last_host_text_bytes.store(0);
     const uint64_t split = fasta_split_point(fasta, n_bytes);
     const uint64_t part_len[2] = {split ? split : n_bytes, split ? n_bytes - split : 0};
     const uint64_t text_off[2] = {0, (part_len[0] + 255) / 256 * 256};      // 16-byte loads need alignment

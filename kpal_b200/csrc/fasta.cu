@@ -335,11 +335,18 @@ uint64_t fasta_tile_bytes() { return kTileBytes; }
 // order on one stream; only bytes below tile1 * 4096 are read, so a range can run as soon
 // as its part of the text has arrived (the host-level entry points overlap the H2D copy of
 // chunk c+1 with the packing of chunk c this way).
+//
+// layout_bytes (0 = n_bytes): the text length the scratch arrays were laid out for, when
+// n_bytes -- the end of the text as the kernels see it -- is only settled with the last range
+// (hybrid upload: the device packs the head of the text up to wherever the host packers got).
 int launch_fasta_pack_tiles(const uint8_t *d_text, uint64_t n_bytes, uint64_t tile0, uint64_t tile1,
-                            uint32_t *d_codes, uint32_t *d_valid, void *d_scratch, cudaStream_t stream)
+                            uint32_t *d_codes, uint32_t *d_valid, void *d_scratch, cudaStream_t stream,
+                            uint64_t layout_bytes)
 {
-    const uint64_t tiles = (n_bytes + kTileBytes - 1) / kTileBytes;
-    if (tile1 > tiles) tile1 = tiles;
+    const uint64_t tiles_now = (n_bytes + kTileBytes - 1) / kTileBytes;
+    if (layout_bytes < n_bytes) layout_bytes = n_bytes;
+    const uint64_t tiles = (layout_bytes + kTileBytes - 1) / kTileBytes;
+    if (tile1 > tiles_now) tile1 = tiles_now;
     if (tile0 >= tile1) return KPAL_OK;
     if (tiles > 0x7fffffffull) return bad_arg("FASTA text too large for one launch");
     FastaScratch *sc = static_cast<FastaScratch *>(d_scratch);
@@ -368,7 +375,7 @@ int launch_fasta_pack(const uint8_t *d_text, uint64_t n_bytes, uint32_t *d_codes
                       void *d_scratch, cudaStream_t stream)
 {
     KPAL_CHECK(launch_fasta_pack_begin(n_bytes, d_codes, d_valid, d_scratch, stream));
-    return launch_fasta_pack_tiles(d_text, n_bytes, 0, ~0ull, d_codes, d_valid, d_scratch, stream);
+    return launch_fasta_pack_tiles(d_text, n_bytes, 0, ~0ull, d_codes, d_valid, d_scratch, stream, 0);
 }
 
 }  // namespace kpal

@@ -140,6 +140,9 @@ struct WidenJob {
     std::atomic<uint64_t> done{0};          // finished work items
     std::atomic<uint64_t> ready{0};         // elements that have landed in src
     std::atomic<int> abort{0};
+    // a job of another kind (the FASTA segment packers of cabi.cu): every worker calls it once
+    void (*custom)(void *) = nullptr;
+    void *custom_arg = nullptr;
 };
 
 class WidenPool {
@@ -209,6 +212,7 @@ private:
 
     static void work(WidenJob *job)
     {
+        if (job->custom) { job->custom(job->custom_arg); return; }
         for (;;) {
             const uint64_t item = job->next.fetch_add(1, std::memory_order_relaxed);
             if (item >= job->n_items) return;
@@ -273,6 +277,26 @@ void widen_end(WidenHandle *h, int abort)
 }
 
 unsigned widen_workers() { return WidenPool::get().workers() + 1; }
+
+// The same pool for another kind of work: fn(arg) runs once on every worker (begin) and on
+// the caller (end), which returns when all of them are back.  One job at a time, like the
+// widening: begin .. end holds the pool.
+WidenHandle *pool_run_begin(void (*fn)(void *), void *arg)
+{
+    g_widen_one_job.lock();
+    WidenHandle *h = new WidenHandle();
+    h->job.custom = fn;
+    h->job.custom_arg = arg;
+    WidenPool::get().start(&h->job);
+    return h;
+}
+
+void pool_run_end(WidenHandle *h)
+{
+    WidenPool::get().finish(&h->job);
+    delete h;
+    g_widen_one_job.unlock();
+}
 
 }  // namespace kpal
 

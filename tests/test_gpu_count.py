@@ -674,6 +674,72 @@ def test_large_fasta_is_counted_in_two_overlapped_parts():
         _set_option("fasta_chunks", 0)
 
 
+def test_hybrid_upload_of_a_large_fasta():
+    """A text of 32 MB or more is uploaded in hybrid form (cabi.cu fasta_hybrid_count): the
+    head raw, packed by the device, while host threads pack the segments of the tail
+    (pack.cpp, csrc/slotted.h) into slots of the same stream.  The host's share adapts to the
+    machine from call to call, so the test also forces it.  Same bits as the C oracle, and as
+    the plain upload."""
+    rng = np.random.default_rng(77)
+    n_reads, read_len = 240_000, 150
+    reads = random_reads(77, n_reads, read_len, p_n=0.002, p_lower=0.1)
+    reads[rng.random(reads.shape) < 0.0005] = ord(" ")              # blanks inside lines are dropped
+    extra = np.frombuffer(b" \r", dtype=np.uint8)[rng.integers(0, 2, n_reads)]      # 'ACGT \n' and 'ACGT\r\n' lines
+    header = np.frombuffer(b">r0000000 x\n", dtype=np.uint8)
+    rows = np.empty((n_reads, len(header) + read_len + 2), dtype=np.uint8)
+    rows[:, :len(header)] = header
+    for d in range(7):
+        rows[:, 8 - d] = ord("0") + (np.arange(n_reads) // 10 ** d) % 10
+    rows[:, len(header):-2] = reads
+    rows[:, -2] = extra
+    rows[:, -1] = ord("\n")
+    fasta = b"junk before the first header\nACGT\n" + rows.tobytes()
+    assert len(fasta) > (32 << 20)
+    body = rows[:, len(header):].reshape(-1)
+    body = body[(body != ord(" ")) & (body != ord("\r"))].tobytes()    # what the reader keeps, one read per line
+    want = {k: c_oracle.count_bytes(body, k, threads=c_oracle.max_threads()) for k in (6, 12)}
+    tricky = fasta.replace(b">r0097", b">r>>97").replace(b">r0200", b">r>>00")      # '>' inside header lines
+    tab_late = fasta[:-20] + b"\tAC\t\n" + fasta[-20:]             # tabs in the host's part: packed exactly there
+    keep = lambda line: line.replace(b" ", b"").replace(b"\r", b"")
+    body_tab = (rows[:-1, len(header):].reshape(-1)[(rows[:-1, len(header):].reshape(-1) != ord(" "))
+                                                     & (rows[:-1, len(header):].reshape(-1) != ord("\r"))].tobytes()
+                + keep(reads[-1, :132].tobytes()) + b"\tAC" + keep(reads[-1, 132:].tobytes()) + b"\n")   # the lines of a record join
+    tab_early = fasta[:5000] + fasta[5000:].replace(b"\n>", b"\t\n>", 1)    # a trailing tab in the device's part: whole-file fallback
+    genome = b">chr\n" + reads.tobytes() + b"\n>tail\nACGTACGTAC\n"      # no header lines to cut at
+    want_genome = c_oracle.count_bytes(reads.tobytes().replace(b" ", b"") + b"\nACGTACGTAC\n", 12, threads=c_oracle.max_threads())
+    # 70-column records far longer than a segment: every cut falls inside a record, the junction
+    # records (csrc/slotted.h) restore the windows that cross the cuts
+    flat = reads.reshape(-1)
+    half = (flat.size // 140) * 70
+    wrap = lambda seq: np.concatenate([seq.reshape(-1, 70), np.full((seq.size // 70, 1), 10, dtype=np.uint8)], axis=1).tobytes()
+    wrapped = b">chr1 first\n" + wrap(flat[:half]) + b">chr2\n" + wrap(flat[half:2 * half]) + b"ACGTTGCA"
+    unwrapped = flat[:half].tobytes().replace(b" ", b"") + b"\n" + flat[half:2 * half].tobytes().replace(b" ", b"") + b"ACGTTGCA\n"
+    try:
+        for hybrid, share in ((1, 0), (0, 0), (2, 0), (64, 10), (5, 50), (1, 90), (1, 1), (1, 0)):
+            _set_option("fasta_hybrid", hybrid)
+            _set_option("fasta_hybrid_share", share)         # percent of the text for the host (0: adaptive)
+            for k in (6, 12):
+                assert np.array_equal(_cabi.count_fasta(fasta, k), want[k]), (hybrid, share, k)
+            assert np.array_equal(_cabi.count_fasta(tricky, 12), want[12]), (hybrid, share)
+        _set_option("fasta_hybrid", 1)
+        assert np.array_equal(_cabi.count_fasta(fasta, 12, balance=True), ko.balance(want[12]))
+        assert np.array_equal(_cabi.count_fasta(tab_late, 12), c_oracle.count_bytes(body_tab, 12, threads=c_oracle.max_threads()))
+        assert np.array_equal(_cabi.count_fasta(tab_early, 6), want[6])
+        assert np.array_equal(_cabi.count_fasta(genome, 12), want_genome)
+        for k in (6, 12, 13):
+            want_wrapped = c_oracle.count_bytes(unwrapped, k, threads=c_oracle.max_threads())
+            for share in (0, 15, 80):
+                _set_option("fasta_hybrid_share", share)
+                assert np.array_equal(_cabi.count_fasta(wrapped, k), want_wrapped), (k, share)
+        _set_option("fasta_hybrid_share", 0)
+        # text handles go the same way
+        profile = klib.Profile.from_fasta(io.BytesIO(fasta), 6)
+        assert np.array_equal(profile.counts, want[6])
+    finally:
+        _set_option("fasta_hybrid", 1)
+        _set_option("fasta_hybrid_share", 0)
+
+
 def test_narrow_profile_copy_and_its_overflow_path():
     """From k = 10 on the host entry points move the profile over PCIe as uint8 or uint16
     (whichever holds every count) and widen it on the host (cabi.cu finalize_to_host).
