@@ -2,7 +2,7 @@
 # round 2: hybrid FASTA upload (host threads pack the tail of the text while the head uploads raw)
 mkdir -p gpurun_out
 nproc; grep -m1 "model name" /proc/cpuinfo
-timeout 900 python -m pytest tests/test_gpu_count.py -x -q -m gpu -k "hybrid or two_overlapped or chunked_upload or exotic or full_size or large_synthetic or agree" --tb=short 2>&1 | tail -8
+timeout 900 python -m pytest tests/test_gpu_count.py -x -q -m gpu -k "hybrid" --tb=short 2>&1 | tail -4
 run() {   # name, bench args
   KPAL_TRACE=1 timeout 300 python bench.py --workload count --steps 10 $2 > gpurun_out/r02_hyb_$1.json 2> gpurun_out/r02_hyb_$1.err
   python -c "
@@ -12,8 +12,9 @@ print('$1', 'value', round(d['value'],1), 'e2e', round(e['value'],2), round(e['m
   grep "kpal trace" gpurun_out/r02_hyb_$1.err | tail -${3:-2}
   grep -v "kpal trace" gpurun_out/r02_hyb_$1.err | tail -2
 }
-run adaptive "--fasta-hybrid 1 --steps 20" 3
-run off "--fasta-hybrid 0"
-run cfg5 "--config 5" 4
-run cfg5off "--config 5 --fasta-hybrid 0"
-run skewed "--composition skewed"
+run avx512 "--fasta-hybrid 1 --steps 20" 2
+KPAL_PACK_NO_AVX512=1 run avx2 "--fasta-hybrid 1 --steps 20" 2
+run cfg5_avx512 "--config 5" 2
+KPAL_PACK_NO_AVX512=1 run cfg5_avx2 "--config 5" 2
+run avx512b "--fasta-hybrid 1 --steps 20" 2
+KPAL_PACK_NO_AVX512=1 run avx2b "--fasta-hybrid 1 --steps 20" 2
