@@ -233,6 +233,18 @@ int      kpal_row_stats(const int64_t *rows, uint64_t n_rows, uint64_t n_cols, d
 uint64_t kpal_deflate_bound(uint64_t chunk_bytes);
 int      kpal_deflate_chunks(const void *data, uint64_t n_chunks, uint64_t chunk_bytes, int level,
                              void *out, uint64_t slot_bytes, uint32_t *sizes);
+/* The same container with a one-pass encoder for sparse data (a per-record count row is almost
+ * all zero bytes: zero runs as distance-1 matches in one dynamic-Huffman block with a code fixed
+ * in advance): valid zlib streams that inflate to the same bytes, ~20x faster than zlib on such
+ * rows; dense chunks go through zlib.  What klib.save_profiles / h5lite use. */
+int      kpal_deflate_chunks_sparse(const void *data, uint64_t n_chunks, uint64_t chunk_bytes, int level,
+                                    void *out, uint64_t slot_bytes, uint32_t *sizes);
+/* Straight to the packed form (no slot array): begin compresses (sparse != 0: the one-pass encoder
+ * where it applies) and reports sizes[c] and their total, finish copies the streams back to back
+ * into out (NULL: discard) and frees the job. */
+int      kpal_deflate_packed_begin(const void *data, uint64_t n_chunks, uint64_t chunk_bytes, int level,
+                                   int sparse, uint32_t *sizes, void **handle_out, uint64_t *total_out);
+int      kpal_deflate_packed_finish(void *handle, void *out);
 /* the streams packed back to back into out (NULL: only their total size, which is returned) */
 uint64_t kpal_compact_slots(const void *slots, uint64_t slot_bytes, const uint32_t *sizes,
                             uint64_t n_chunks, void *out);

@@ -30,7 +30,7 @@ SYMBOLS = (
     "kpal_distance_matrix", "kpal_pair_distance",
     "kpal_matrix_open", "kpal_matrix_push", "kpal_matrix_finish", "kpal_matrix_close",
     "kpal_format_matrix", "kpal_widen_u16", "kpal_widen_u8", "kpal_pair_distance_positive",
-    "kpal_row_stats", "kpal_deflate_bound", "kpal_deflate_chunks", "kpal_compact_slots",
+    "kpal_row_stats", "kpal_deflate_bound", "kpal_deflate_chunks", "kpal_deflate_chunks_sparse", "kpal_deflate_packed_begin", "kpal_deflate_packed_finish", "kpal_compact_slots",
     "kpal_split_length", "kpal_split", "kpal_show_balance",
     "kpal_ipc_export", "kpal_ipc_open", "kpal_ipc_close", "kpal_peer_inbox_bytes",
     "kpal_dev_reduce_push", "kpal_dev_reduce_collect", "kpal_dev_count_packed_push",
@@ -109,6 +109,9 @@ def load():
     sig("kpal_row_stats", i32, vp, u64, u64, vp)
     sig("kpal_deflate_bound", u64, u64)
     sig("kpal_deflate_chunks", i32, vp, u64, u64, i32, vp, u64, vp)
+    sig("kpal_deflate_chunks_sparse", i32, vp, u64, u64, i32, vp, u64, vp)
+    sig("kpal_deflate_packed_begin", i32, vp, u64, u64, i32, i32, vp, c.POINTER(vp), pu64)
+    sig("kpal_deflate_packed_finish", i32, vp, vp)
     sig("kpal_compact_slots", u64, vp, u64, vp, u64, vp)
     sig("kpal_split_length", u64, i32)
     sig("kpal_split", i32, vp, i32, vp, vp)
@@ -338,12 +341,19 @@ def pack_sequences(sequences):
     return codes, valid, rec_starts, n_bases.value
 
 
-def count_by_record(codes, valid, n_bases, rec_starts, first, n, k, balance=False):
-    """Dense [n][4**k] int64 rows for records [first, first+n)."""
+def count_by_record(codes, valid, n_bases, rec_starts, first, n, k, balance=False, out=None):
+    """Dense [n][4**k] int64 rows for records [first, first+n).  `out`: a C-contiguous int64
+    array with room for the rows, reused by the caller from batch to batch (a fresh 256 MB
+    array per batch costs more in page faults than the GPU call it receives)."""
     _check_k(k)
     L = load()
     require_gpu()
-    out = np.empty((n, 4 ** k), dtype=np.int64)
+    if out is None:
+        out = np.empty((n, 4 ** k), dtype=np.int64)
+    else:
+        if out.dtype != np.int64 or not out.flags.c_contiguous or out.size < n * 4 ** k:
+            raise ValueError("out must be a C-contiguous int64 array of at least n * 4**k elements")
+        out = out.reshape(-1)[:n * 4 ** k].reshape(n, 4 ** k)
     check(L.kpal_count_by_record(ptr(codes), ptr(valid), int(n_bases), ptr(rec_starts), int(first),
                                  int(n), int(k), int(bool(balance)), ptr(out)))
     return out
@@ -446,10 +456,12 @@ def row_stats(rows):
     return out
 
 
-def deflate_chunks(data, chunk_bytes, level):
+def deflate_chunks(data, chunk_bytes, level, sparse=False):
     """zlib streams of the equal-sized chunks of `data` (a C-contiguous array whose size is a
     multiple of `chunk_bytes`): ``(buffer, slot_bytes, sizes)`` -- chunk ``c`` is
-    ``buffer[c * slot_bytes : c * slot_bytes + sizes[c]]``.  Host, multi-threaded."""
+    ``buffer[c * slot_bytes : c * slot_bytes + sizes[c]]``.  Host, multi-threaded.
+    `sparse`: the one-pass encoder for mostly-zero data (valid zlib streams, not the bytes
+    zlib itself would write)."""
     L = load()
     raw = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
     if chunk_bytes < 1 or raw.size % chunk_bytes:
@@ -458,18 +470,25 @@ def deflate_chunks(data, chunk_bytes, level):
     slot = int(L.kpal_deflate_bound(chunk_bytes))
     buffer = np.empty(n_chunks * slot, dtype=np.uint8)
     sizes = np.empty(n_chunks, dtype=np.uint32)
-    check(L.kpal_deflate_chunks(ptr(raw), n_chunks, int(chunk_bytes), int(level), ptr(buffer), slot, ptr(sizes)))
+    call = L.kpal_deflate_chunks_sparse if sparse else L.kpal_deflate_chunks
+    check(call(ptr(raw), n_chunks, int(chunk_bytes), int(level), ptr(buffer), slot, ptr(sizes)))
     return buffer, slot, sizes
 
 
-def deflate_chunks_packed(data, chunk_bytes, level):
+def deflate_chunks_packed(data, chunk_bytes, level, sparse=False):
     """The same streams back to back: ``(blob, sizes)`` (chunk ``c`` starts at
     ``sizes[:c].sum()``)."""
-    buffer, slot, sizes = deflate_chunks(data, chunk_bytes, level)
     L = load()
-    total = int(L.kpal_compact_slots(ptr(buffer), slot, ptr(sizes), sizes.size, None))
-    blob = np.empty(total, dtype=np.uint8)
-    L.kpal_compact_slots(ptr(buffer), slot, ptr(sizes), sizes.size, ptr(blob))
+    raw = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+    if chunk_bytes < 1 or raw.size % chunk_bytes:
+        raise ValueError("data must be whole chunks")
+    n_chunks = raw.size // chunk_bytes
+    sizes = np.empty(n_chunks, dtype=np.uint32)
+    handle, total = ctypes.c_void_p(), ctypes.c_uint64()
+    check(L.kpal_deflate_packed_begin(ptr(raw), n_chunks, int(chunk_bytes), int(level), 1 if sparse else 0,
+                                      ptr(sizes), ctypes.byref(handle), ctypes.byref(total)))
+    blob = np.empty(total.value, dtype=np.uint8)
+    check(L.kpal_deflate_packed_finish(handle, ptr(blob)))
     return blob, sizes
 
 

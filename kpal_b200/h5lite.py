@@ -565,7 +565,7 @@ class Group(_Node):
                     dataset.attrs[key] = values[i]
             return
         per = m // chunk
-        blob, sizes = native.deflate_chunks_packed(rows, chunk * rows.dtype.itemsize, level)
+        blob, sizes = native.deflate_chunks_packed(rows, chunk * rows.dtype.itemsize, level, sparse=True)
         self._file._drain(0)                                    # keep the file in creation order
         base = self._file._append(blob)
         ends = np.cumsum(sizes, dtype=np.uint64)

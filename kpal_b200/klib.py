@@ -129,16 +129,43 @@ class Profile(object):
         The same profiles as :meth:`from_fasta_by_record`, a device batch at a time: a
         generator of ``(names, rows)`` with `rows` the dense ``[n][4**length]`` int64 counts of
         `n` consecutive records.  What ``kpal count --by-record`` feeds to
-        :func:`save_profiles` (no Profile object, no row copy per record).
+        :func:`save_profiles` (no Profile object, no row copy per record).  `rows` lives in one
+        of two reused buffers: it is valid until the next batch is asked for (copy it to keep it).
         """
         _cabi._check_k(length)
         prefix = prefix + '_' if prefix else ''
         codes, valid, rec_starts, names, n_bases = _cabi.fasta_pack(_read_text(handle))
         n_records = len(names)
         batch = max(1, cls._BY_RECORD_BATCH_BYTES // (8 * 4 ** length))
-        for first in range(0, n_records, batch):
+        starts = list(range(0, n_records, batch))
+        if not starts:
+            return
+        # Two row buffers, reused: the device counts batch b + 1 (on a helper thread; the C call
+        # releases the GIL) while the caller works on batch b.  `rows` is only valid until the
+        # next batch is asked for.
+        import threading
+        buffers = [np.empty((min(batch, n_records), 4 ** length), dtype=np.int64) for _ in range(min(2, len(starts)))]
+        result = [None, None]
+
+        def count(slot, first):
             n = min(batch, n_records - first)
-            rows = _cabi.count_by_record(codes, valid, n_bases, rec_starts, first, n, length)
+            try:
+                result[slot] = _cabi.count_by_record(codes, valid, n_bases, rec_starts, first, n, length,
+                                                     out=buffers[slot])
+            except BaseException as error:      # handed to the consumer
+                result[slot] = error
+
+        worker = threading.Thread(target=count, args=(0, starts[0]))
+        worker.start()
+        for b, first in enumerate(starts):
+            worker.join()
+            rows = result[b % 2]
+            if isinstance(rows, BaseException):
+                raise rows
+            if b + 1 < len(starts):
+                worker = threading.Thread(target=count, args=((b + 1) % 2, starts[b + 1]))
+                worker.start()
+            n = rows.shape[0]
             yield [prefix + (names[first + i] or str(first + i + 1)) for i in range(n)], rows
 
     @classmethod

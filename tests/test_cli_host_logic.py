@@ -43,14 +43,19 @@ class _SessionDouble(object):
 
 @pytest.fixture
 def gpu_double(monkeypatch):
-    def by_record(codes, valid, n_bases, rec_starts, first, n, k, balance=False):
+    def by_record(codes, valid, n_bases, rec_starts, first, n, k, balance=False, out=None):
         stream = unpack(codes, valid, n_bases)
         rows = []
         for r in range(first, first + n):
             seq = ''.join('ACGTN'[c] for c in stream[int(rec_starts[r]):int(rec_starts[r + 1]) - 1])
             counts = ko.count_sequences([seq], k)
             rows.append(ko.balance(counts) if balance else counts)
-        return np.array(rows, dtype=np.int64).reshape(n, 4 ** k)
+        rows = np.array(rows, dtype=np.int64).reshape(n, 4 ** k)
+        if out is not None:                      # the reused batch buffer of Profile.record_batches
+            view = out.reshape(-1)[:n * 4 ** k].reshape(n, 4 ** k)
+            view[:] = rows
+            return view
+        return rows
 
     def count_fasta(text, k, balance=False, out=None):
         counts = ko.count_fasta(text if isinstance(text, str) else text.decode('latin-1'), k)

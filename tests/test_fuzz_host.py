@@ -234,3 +234,60 @@ def test_slotted_stream_wrapped_genome():
                         if run >= k:
                             exp[index] = exp.get(index, 0) + 1
                 assert got == exp, (k, seg)
+
+
+# ---- the one-pass deflate encoder for sparse rows (csrc/rowops.cpp: sparse_deflate) ----
+def _inflate_all(blob, sizes):
+    import zlib
+    out, at = [], 0
+    for size in sizes:
+        out.append(zlib.decompress(bytes(blob[at:at + size])))
+        at += int(size)
+    assert at == blob.size
+    return out
+
+
+@settings(max_examples=300, **COMMON)
+@given(st.integers(1, 3000), st.integers(0, 2 ** 32 - 1), st.floats(0.0, 0.4), st.integers(1, 4))
+def test_sparse_deflate_streams_inflate_to_the_data(n, seed, density, chunks):
+    rng = np.random.default_rng(seed)
+    data = (rng.integers(0, 256, n * chunks) * (rng.random(n * chunks) < density)).astype(np.uint8)
+    for slotted in (False, True):
+        if slotted:
+            buffer, slot, sizes = _cabi.deflate_chunks(data, n, 4, sparse=True)
+            streams = [bytes(buffer[c * slot:c * slot + sizes[c]]) for c in range(chunks)]
+            import zlib
+            got = [zlib.decompress(s) for s in streams]
+        else:
+            got = _inflate_all(*_cabi.deflate_chunks_packed(data, n, 4, sparse=True))
+        assert got == [data[c * n:(c + 1) * n].tobytes() for c in range(chunks)]
+
+
+def test_sparse_deflate_on_count_rows_and_run_lengths():
+    rng = np.random.default_rng(9)
+    rows = np.zeros((6, 4 ** 8), dtype=np.int64)
+    for r in range(1, 6):
+        np.add.at(rows[r], rng.integers(0, 4 ** 8, 200 * r), 1)
+    rows[5, 17] = 2 ** 40 + 5                      # several non-zero bytes in one count
+    rows[4, :300] = -1                             # 0xff bytes
+    blob, sizes = _cabi.deflate_chunks_packed(rows, 65536, 4, sparse=True)
+    raw = rows.view(np.uint8).reshape(-1)
+    assert _inflate_all(blob, sizes) == [raw[c * 65536:(c + 1) * 65536].tobytes() for c in range(sizes.size)]
+    assert sizes[:8].max() < 150                   # an all-zero 64 KiB chunk: 2 bits per 258 bytes
+    # every zero-run length around the match lengths of deflate (3 .. 258) and their multiples
+    for run in list(range(0, 12)) + [255, 256, 257, 258, 259, 260, 261, 515, 516, 517, 518, 519, 1031, 1032, 1033]:
+        for lead in (0, 1, 9):
+            data = np.concatenate([np.full(lead, 7, np.uint8), np.zeros(run, np.uint8), np.full(2, 9, np.uint8)])
+            assert _inflate_all(*_cabi.deflate_chunks_packed(data, data.size, 4, sparse=True)) == [data.tobytes()]
+
+
+def test_row_stats_of_sparse_rows_take_the_median_shortcut_exactly():
+    rng = np.random.default_rng(10)
+    for cols, hits in ((4 ** 8, 993), (4 ** 6, 2047), (4 ** 6, 2048), (4 ** 6, 2049), (4 ** 6, 4000), (4 ** 3 + 1, 31), (4 ** 3 + 1, 33)):
+        rows = np.zeros((5, cols), dtype=np.int64)
+        for r in range(5):
+            rows[r, rng.choice(cols, hits, replace=False)] = rng.integers(1, 50, hits)
+        stats = _cabi.row_stats(rows)
+        for r, x in enumerate(rows):
+            want = (float(x.sum()), float(np.count_nonzero(x)), x.mean(), np.median(x), x.std())
+            assert tuple(stats[r]) == want, (cols, hits, r)
