@@ -60,6 +60,8 @@ const char *kpal_last_error(void);
 int         kpal_device_count(void);
 /* bind the calling thread's library context to `device` (default 0) */
 int         kpal_set_device(int device);
+/* the calling thread's device (-1 without one); a helper thread passes it to kpal_set_device */
+int         kpal_get_device(void);
 /* pinned (page-locked) host memory for fast H2D/D2H; caller frees */
 void       *kpal_host_alloc(size_t bytes);
 void        kpal_host_free(void *p);
@@ -245,6 +247,11 @@ int      kpal_deflate_chunks_sparse(const void *data, uint64_t n_chunks, uint64_
 int      kpal_deflate_packed_begin(const void *data, uint64_t n_chunks, uint64_t chunk_bytes, int level,
                                    int sparse, uint32_t *sizes, void **handle_out, uint64_t *total_out);
 int      kpal_deflate_packed_finish(void *handle, void *out);
+/* kpal_row_stats and the packed streams of the rows' chunks (chunk_bytes divides a row) in one
+ * pass over the rows; finish with kpal_deflate_packed_finish. */
+int      kpal_rows_stats_deflate_begin(const int64_t *rows, uint64_t n_rows, uint64_t n_cols, uint64_t chunk_bytes,
+                                       int level, int sparse, double *stats_out, uint32_t *sizes,
+                                       void **handle_out, uint64_t *total_out);
 /* the streams packed back to back into out (NULL: only their total size, which is returned) */
 uint64_t kpal_compact_slots(const void *slots, uint64_t slot_bytes, const uint32_t *sizes,
                             uint64_t n_chunks, void *out);

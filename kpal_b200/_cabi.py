@@ -22,7 +22,7 @@ MAX_K = 15
 
 #: every symbol include/kpal_b200.h declares (checked by tests/test_cabi.py)
 SYMBOLS = (
-    "kpal_abi_version", "kpal_last_error", "kpal_device_count", "kpal_set_device",
+    "kpal_abi_version", "kpal_last_error", "kpal_device_count", "kpal_set_device", "kpal_get_device",
     "kpal_host_alloc", "kpal_host_free", "kpal_dev_alloc", "kpal_dev_free",
     "kpal_memcpy_h2d", "kpal_memcpy_d2h", "kpal_dev_memset", "kpal_stream_sync",
     "kpal_packed_words", "kpal_pack_sequences", "kpal_fasta_scan", "kpal_fasta_pack", "kpal_fasta_pack_segment", "kpal_fasta_slotted_bases", "kpal_fasta_pack_slotted",
@@ -30,7 +30,7 @@ SYMBOLS = (
     "kpal_distance_matrix", "kpal_pair_distance",
     "kpal_matrix_open", "kpal_matrix_push", "kpal_matrix_finish", "kpal_matrix_close",
     "kpal_format_matrix", "kpal_widen_u16", "kpal_widen_u8", "kpal_pair_distance_positive",
-    "kpal_row_stats", "kpal_deflate_bound", "kpal_deflate_chunks", "kpal_deflate_chunks_sparse", "kpal_deflate_packed_begin", "kpal_deflate_packed_finish", "kpal_compact_slots",
+    "kpal_row_stats", "kpal_deflate_bound", "kpal_deflate_chunks", "kpal_deflate_chunks_sparse", "kpal_deflate_packed_begin", "kpal_deflate_packed_finish", "kpal_rows_stats_deflate_begin", "kpal_compact_slots",
     "kpal_split_length", "kpal_split", "kpal_show_balance",
     "kpal_ipc_export", "kpal_ipc_open", "kpal_ipc_close", "kpal_peer_inbox_bytes",
     "kpal_dev_reduce_push", "kpal_dev_reduce_collect", "kpal_dev_count_packed_push",
@@ -77,6 +77,7 @@ def load():
     sig("kpal_last_error", c.c_char_p)
     sig("kpal_device_count", i32)
     sig("kpal_set_device", i32, i32)
+    sig("kpal_get_device", i32)
     sig("kpal_host_alloc", vp, c.c_size_t)
     sig("kpal_host_free", None, vp)
     sig("kpal_dev_alloc", vp, c.c_size_t)
@@ -112,6 +113,7 @@ def load():
     sig("kpal_deflate_chunks_sparse", i32, vp, u64, u64, i32, vp, u64, vp)
     sig("kpal_deflate_packed_begin", i32, vp, u64, u64, i32, i32, vp, c.POINTER(vp), pu64)
     sig("kpal_deflate_packed_finish", i32, vp, vp)
+    sig("kpal_rows_stats_deflate_begin", i32, vp, u64, u64, u64, i32, i32, vp, vp, c.POINTER(vp), pu64)
     sig("kpal_compact_slots", u64, vp, u64, vp, u64, vp)
     sig("kpal_split_length", u64, i32)
     sig("kpal_split", i32, vp, i32, vp, vp)
@@ -490,6 +492,24 @@ def deflate_chunks_packed(data, chunk_bytes, level, sparse=False):
     blob = np.empty(total.value, dtype=np.uint8)
     check(L.kpal_deflate_packed_finish(handle, ptr(blob)))
     return blob, sizes
+
+
+def rows_stats_deflate(rows, chunk_bytes, level, sparse=True):
+    """``row_stats(rows)`` and ``deflate_chunks_packed(rows, chunk_bytes, level, sparse)`` in one
+    pass over the C-contiguous int64 `rows`: ``(stats, blob, sizes)``."""
+    L = load()
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    n, m = rows.shape
+    if chunk_bytes < 1 or (m * 8) % chunk_bytes:
+        raise ValueError("chunk_bytes must divide a row")
+    stats = np.empty((n, 5), dtype=np.float64)
+    sizes = np.empty(n * (m * 8 // chunk_bytes), dtype=np.uint32)
+    handle, total = ctypes.c_void_p(), ctypes.c_uint64()
+    check(L.kpal_rows_stats_deflate_begin(ptr(rows), n, m, int(chunk_bytes), int(level), 1 if sparse else 0,
+                                          ptr(stats), ptr(sizes), ctypes.byref(handle), ctypes.byref(total)))
+    blob = np.empty(total.value, dtype=np.uint8)
+    check(L.kpal_deflate_packed_finish(handle, ptr(blob)))
+    return stats, blob, sizes
 
 
 def format_matrix(values, precision):

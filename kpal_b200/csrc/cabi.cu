@@ -315,6 +315,13 @@ extern "C" int kpal_set_device(int device)
     return KPAL_OK;
 }
 
+extern "C" int kpal_get_device(void)
+{
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return dev;
+}
+
 extern "C" void *kpal_host_alloc(size_t bytes)
 {
     void *p = nullptr;

@@ -101,33 +101,34 @@ static double pairwise_sq(const int64_t *x, double mean, size_t n)
     return pairwise_sq(x, mean, n2) + pairwise_sq(x + n2, mean, n - n2);
 }
 
+static void one_row_stats(const int64_t *x, uint64_t n_cols, double *out)
+{
+    int64_t total = 0, lowest = 0;
+    uint64_t non_zero = 0;
+    for (uint64_t i = 0; i < n_cols; ++i) { total += x[i]; non_zero += x[i] != 0; lowest = std::min(lowest, x[i]); }
+    const double mean = double(total) / double(n_cols);
+    const double var = pairwise_sq(x, mean, n_cols) / double(n_cols);
+    // median: mean of the two middle order statistics (one for an odd length), as np.median.
+    // Counts are not negative: when more than half of them are zero, so are the middle ones.
+    const uint64_t mid = n_cols / 2;
+    double median = 0.0;
+    if (lowest < 0 || n_cols - non_zero < mid + 1) {
+        std::vector<int64_t> copy(x, x + n_cols);
+        std::nth_element(copy.begin(), copy.begin() + mid, copy.end());
+        median = double(copy[mid]);
+        if (n_cols % 2 == 0) {
+            const int64_t below = *std::max_element(copy.begin(), copy.begin() + mid);
+            median = (double(below) + double(copy[mid])) / 2.0;        // np.mean of the two: add, then divide
+        }
+    }
+    out[0] = double(total); out[1] = double(non_zero); out[2] = mean; out[3] = median; out[4] = sqrt(var);
+}
+
 extern "C" int kpal_row_stats(const int64_t *rows, uint64_t n_rows, uint64_t n_cols, double *stats_out)
 {
     if ((!rows || !stats_out) && n_rows) return KPAL_EINVAL;
     if (n_cols == 0) return KPAL_EINVAL;
-    parallel_for(n_rows, [&](uint64_t r) {
-        const int64_t *x = rows + r * n_cols;
-        int64_t total = 0, lowest = 0;
-        uint64_t non_zero = 0;
-        for (uint64_t i = 0; i < n_cols; ++i) { total += x[i]; non_zero += x[i] != 0; lowest = std::min(lowest, x[i]); }
-        const double mean = double(total) / double(n_cols);
-        const double var = pairwise_sq(x, mean, n_cols) / double(n_cols);
-        // median: mean of the two middle order statistics (one for an odd length), as np.median.
-        // Counts are not negative: when more than half of them are zero, so are the middle ones.
-        const uint64_t mid = n_cols / 2;
-        double median = 0.0;
-        if (lowest < 0 || n_cols - non_zero < mid + 1) {
-            std::vector<int64_t> copy(x, x + n_cols);
-            std::nth_element(copy.begin(), copy.begin() + mid, copy.end());
-            median = double(copy[mid]);
-            if (n_cols % 2 == 0) {
-                const int64_t below = *std::max_element(copy.begin(), copy.begin() + mid);
-                median = (double(below) + double(copy[mid])) / 2.0;        // np.mean of the two: add, then divide
-            }
-        }
-        double *out = stats_out + r * 5;
-        out[0] = double(total); out[1] = double(non_zero); out[2] = mean; out[3] = median; out[4] = sqrt(var);
-    });
+    parallel_for(n_rows, [&](uint64_t r) { one_row_stats(rows + r * n_cols, n_cols, stats_out + r * 5); });
     return KPAL_OK;
 }
 
@@ -362,13 +363,35 @@ struct PackedJob {
 };
 }  // namespace
 
+static int deflate_packed(const void *data, uint64_t n_chunks, uint64_t chunk_bytes, int level, int sparse,
+                          uint32_t *sizes, void **handle_out, uint64_t *total_out, uint64_t per, uint64_t n_cols,
+                          double *stats_out);
+
 extern "C" int kpal_deflate_packed_begin(const void *data, uint64_t n_chunks, uint64_t chunk_bytes, int level,
                                          int sparse, uint32_t *sizes, void **handle_out, uint64_t *total_out)
+{
+    return deflate_packed(data, n_chunks, chunk_bytes, level, sparse, sizes, handle_out, total_out, 32, 0, nullptr);
+}
+
+// The rows of a --by-record batch in ONE pass: a work item is a row -- its statistics (as
+// kpal_row_stats) and then the streams of its chunks, while the row is still in the core's cache.
+extern "C" int kpal_rows_stats_deflate_begin(const int64_t *rows, uint64_t n_rows, uint64_t n_cols, uint64_t chunk_bytes,
+                                             int level, int sparse, double *stats_out, uint32_t *sizes,
+                                             void **handle_out, uint64_t *total_out)
+{
+    if (!stats_out || n_cols == 0 || chunk_bytes == 0 || (n_cols * 8) % chunk_bytes) return KPAL_EINVAL;
+    const uint64_t per = n_cols * 8 / chunk_bytes;
+    return deflate_packed(rows, n_rows * per, chunk_bytes, level, sparse, sizes, handle_out, total_out, per, n_cols, stats_out);
+}
+
+static int deflate_packed(const void *data, uint64_t n_chunks, uint64_t chunk_bytes, int level, int sparse,
+                          uint32_t *sizes, void **handle_out, uint64_t *total_out, uint64_t per, uint64_t n_cols,
+                          double *stats_out)
 {
     if (!handle_out || !total_out || ((!data || !sizes) && n_chunks)) return KPAL_EINVAL;
     if (level < 0 || level > 9 || chunk_bytes == 0 || chunk_bytes >= (1ull << 31)) return KPAL_EINVAL;
     const uint64_t bound = compressBound(uLong(chunk_bytes));
-    const uint64_t per = 32, items = (n_chunks + per - 1) / per;
+    const uint64_t items = (n_chunks + per - 1) / per;
     const unsigned n_threads = worker_count(items);
     PackedJob *job = new PackedJob();
     job->arena.resize(n_threads);
@@ -381,6 +404,7 @@ extern "C" int kpal_deflate_packed_begin(const void *data, uint64_t n_chunks, ui
         std::vector<unsigned char> &arena = job->arena[t];
         std::vector<unsigned char> scratch(bound);
         for (uint64_t item; (item = next.fetch_add(1)) < items;) {
+            if (stats_out) one_row_stats(static_cast<const int64_t *>(data) + item * n_cols, n_cols, stats_out + item * 5);
             for (uint64_t c = item * per; c < std::min(n_chunks, (item + 1) * per); ++c) {
                 const unsigned char *src = static_cast<const unsigned char *>(data) + c * chunk_bytes;
                 uint64_t len = (sparse && level > 0) ? sparse_deflate(src, chunk_bytes, scratch.data(), bound) : 0;

@@ -529,14 +529,27 @@ class Group(_Node):
         parent._children[name] = dataset
         return dataset
 
-    def create_datasets(self, names, rows, compression_opts=None, attrs=None):
+    def bulk_layout(self, rows, compression_opts=None):
+        """``(chunk_elements, gzip_level)`` with which :meth:`create_datasets` stores the rows in
+        bulk, or None when it would take the general path -- for callers that deflate the chunks
+        themselves (``klib.save_profiles``: statistics and streams in one pass over the rows)."""
+        if rows.ndim != 2 or rows.dtype.kind not in 'iuf' or not rows.shape[0] or not rows.shape[1]:
+            return None
+        m = rows.shape[1]
+        chunk = _guess_chunk((m,), rows.dtype.itemsize)[0]
+        if m % chunk or m // chunk > 2 * CHUNK_K:
+            return None
+        return chunk, GZIP_LEVEL if compression_opts is None else int(compression_opts)
+
+    def create_datasets(self, names, rows, compression_opts=None, attrs=None, streams=None):
         """
         ``create_dataset(name, data=row, dtype=rows.dtype, compression='gzip')`` for every row
         of the C-contiguous 2-D array `rows`, plus ``dataset.attrs[key] = values[i]`` for every
         ``key: values`` of `attrs` (arrays of one int64 / float64 scalar per row) -- the bulk
         form behind ``klib.save_profiles``.  Same file content as the loop; the chunks of all
         rows are deflated by the native library on all host threads (``kpal_deflate_chunks``)
-        and written with one call, the metadata is laid out in bulk on ``close()``.
+        and written with one call, the metadata is laid out in bulk on ``close()``.  `streams`
+        = ``(blob, sizes)``: the chunks already deflated by the caller (layout: :meth:`bulk_layout`).
         (h5lite extension: h5py has no such call.)
         """
         self._file._require_writable()
@@ -565,7 +578,12 @@ class Group(_Node):
                     dataset.attrs[key] = values[i]
             return
         per = m // chunk
-        blob, sizes = native.deflate_chunks_packed(rows, chunk * rows.dtype.itemsize, level, sparse=True)
+        if streams is not None:             # the zlib streams of the rows' chunks, back to back, and their sizes
+            blob, sizes = streams
+            if sizes.size != n * per or int(sizes.sum()) != blob.size:
+                raise ValueError('streams do not match the rows')
+        else:
+            blob, sizes = native.deflate_chunks_packed(rows, chunk * rows.dtype.itemsize, level, sparse=True)
         self._file._drain(0)                                    # keep the file in creation order
         base = self._file._append(blob)
         ends = np.cumsum(sizes, dtype=np.uint64)

@@ -143,30 +143,26 @@ class Profile(object):
         # Two row buffers, reused: the device counts batch b + 1 (on a helper thread; the C call
         # releases the GIL) while the caller works on batch b.  `rows` is only valid until the
         # next batch is asked for.
-        import threading
+        from concurrent.futures import ThreadPoolExecutor
         buffers = [np.empty((min(batch, n_records), 4 ** length), dtype=np.int64) for _ in range(min(2, len(starts)))]
-        result = [None, None]
+
+        device = _cabi.load().kpal_get_device()         # the helper thread works on the caller's device
 
         def count(slot, first):
             n = min(batch, n_records - first)
-            try:
-                result[slot] = _cabi.count_by_record(codes, valid, n_bases, rec_starts, first, n, length,
-                                                     out=buffers[slot])
-            except BaseException as error:      # handed to the consumer
-                result[slot] = error
+            if device >= 0:
+                _cabi.check(_cabi.load().kpal_set_device(device))
+            return _cabi.count_by_record(codes, valid, n_bases, rec_starts, first, n, length, out=buffers[slot])
 
-        worker = threading.Thread(target=count, args=(0, starts[0]))
-        worker.start()
-        for b, first in enumerate(starts):
-            worker.join()
-            rows = result[b % 2]
-            if isinstance(rows, BaseException):
-                raise rows
-            if b + 1 < len(starts):
-                worker = threading.Thread(target=count, args=((b + 1) % 2, starts[b + 1]))
-                worker.start()
-            n = rows.shape[0]
-            yield [prefix + (names[first + i] or str(first + i + 1)) for i in range(n)], rows
+        # ONE helper thread for all batches: a thread's first CUDA call costs milliseconds
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            pending = pool.submit(count, 0, starts[0])
+            for b, first in enumerate(starts):
+                rows = pending.result()
+                if b + 1 < len(starts):
+                    pending = pool.submit(count, (b + 1) % 2, starts[b + 1])
+                n = rows.shape[0]
+                yield [prefix + (names[first + i] or str(first + i + 1)) for i in range(n)], rows
 
     @classmethod
     def from_sequences(cls, sequences, length, name=None):
@@ -330,9 +326,15 @@ def save_profiles(handle, names, rows):
         for name, row in zip(names, rows):
             Profile(row, name=name).save(handle)
         return
-    stats = _cabi.row_stats(rows)
+    layout = group.bulk_layout(rows) if hasattr(group, 'bulk_layout') else None
+    streams = None
+    if layout:      # statistics and the chunks' zlib streams in one pass over the rows
+        stats, blob, sizes = _cabi.rows_stats_deflate(rows, layout[0] * 8, layout[1])
+        streams = (blob, sizes)
+    else:
+        stats = _cabi.row_stats(rows)
     length = int(math.log(rows.shape[1], 4))
-    group.create_datasets(list(names), rows, attrs={
+    group.create_datasets(list(names), rows, streams=streams, attrs={
         'length': np.full(len(names), length, dtype=np.int64),
         'total': stats[:, 0].astype(np.int64), 'non_zero': stats[:, 1].astype(np.int64),
         'mean': stats[:, 2].copy(), 'median': stats[:, 3].copy(), 'std': stats[:, 4].copy()})
