@@ -848,16 +848,17 @@ static unsigned hybrid_packers()
     unsigned n = widen_workers() - 1;               // the caller feeds the copy engine
     if (opt > 1) n = std::min<unsigned>(n, unsigned(opt));
     else {
-        // One process per GPU (torchrun): the ranks of a node share its cores.  With fewer than 8
-        // cores per rank the packers take from the copy engines what they save them (measured, 8
-        // ranks on 32 vCPUs: 6.39 ms per call with 4 packers each, 6.05 ms without; 2 ranks on 24
-        // vCPUs: 2.97 vs 3.37 ms), so the text then goes up raw.
+        // One process per GPU (torchrun): the ranks of a node share its cores.  With few cores per
+        // rank the packers take from the copy engines what they save them (measured, 8 ranks on 32
+        // vCPUs: 6.39 ms per call with 4 packers each, 6.05 ms without; 2 ranks on 24 vCPUs: 2.97
+        // vs 3.37 ms), so below 12 cores per rank -- the smallest share measured to pay -- the text
+        // goes up raw.
         const char *e = getenv("LOCAL_WORLD_SIZE");
         const unsigned ranks = e ? unsigned(std::max(1, atoi(e))) : 1u;
         const long online = sysconf(_SC_NPROCESSORS_ONLN);      // (not the affinity mask: a rank may be bound to its GPU's node)
         const unsigned hw = online > 0 ? unsigned(online) : std::thread::hardware_concurrency();
         if (ranks > 1 && hw) {
-            if (hw / ranks < 8) return 0;
+            if (hw / ranks < 12) return 0;
             n = std::min(n, hw / ranks);
         }
     }
