@@ -825,6 +825,8 @@ struct HybridState {
     std::atomic<uint64_t> host_bases{0};
     std::atomic<unsigned> joined{0};
     unsigned max_packers = 0;
+    std::atomic<uint64_t> busy_ns{0};             // summed over the packers that got a segment
+    std::atomic<unsigned> active{0};
 };
 
 static void hybrid_packer(void *arg)
@@ -832,12 +834,19 @@ static void hybrid_packer(void *arg)
     HybridState *h = static_cast<HybridState *>(arg);
     if (h->joined.fetch_add(1) >= h->max_packers) return;
     const uint64_t base = h->plan.slot[h->first];
+    const auto t0 = std::chrono::steady_clock::now();
+    bool worked = false;
     for (;;) {
         const uint64_t j = h->next.fetch_add(1, std::memory_order_relaxed);
-        if (j >= h->plan.m) return;
+        if (j >= h->plan.m) break;
+        worked = true;
         const uint64_t n = slotted_pack_segment(h->plan, h->text, h->n_bytes, j, h->first, h->k, h->pcodes, h->pvalid, base);
         h->host_bases.fetch_add(n, std::memory_order_relaxed);
         h->done[j].store(1, std::memory_order_release);
+    }
+    if (worked) {       // the packing rate proper (no wake-up latency): what the next call's share is computed from
+        h->busy_ns.fetch_add(uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count()));
+        h->active.fetch_add(1);
     }
 }
 
@@ -866,7 +875,7 @@ static unsigned hybrid_packers()
 }
 
 // the host's share of the text, adapted from call to call (per process; under g_count_mutex)
-static double g_hybrid_share = 0.30;
+static double g_hybrid_share = 0.45;
 static cudaEvent_t g_hybrid_ev[2] = {};             // raw upload: start / done (timing events)
 static double g_hybrid_prev[3] = {0, 0, 0};         // previous call: host seconds, host text bytes, raw bytes
 
@@ -967,6 +976,9 @@ static int fasta_hybrid_count(CountWorkspace *w, const char *fasta, uint64_t n_b
     g_trace.dev_mark("raw_h2d", w->copy_stream);
     if (err == cudaSuccess && rc == KPAL_OK)
         fail(cudaMemcpyAsync(status, d_scratch, sizeof(FastaStatus), cudaMemcpyDeviceToHost, st));
+    // The device's part is counted as soon as it is packed, i.e. while the packed tail is still on
+    // the bus: it ends in >= 64 invalid bases, so no window of it reaches into the host's slots.
+    if (err == cudaSuccess && rc == KPAL_OK) rc = launch_count(d_codes, d_valid, host_base, k, d_table, bits, st);
     g_trace.mark("raw_queued");
     // the tail: the finished segments go up in runs, in order, behind the raw text
     uint64_t up = first;
@@ -999,14 +1011,13 @@ static int fasta_hybrid_count(CountWorkspace *w, const char *fasta, uint64_t n_b
     if (rc != KPAL_OK) { cudaStreamSynchronize(w->copy_stream); cudaStreamSynchronize(st); return rc; }
     KPAL_CUDA(cudaEventRecord(w->chunk_done[31], w->copy_stream));
     g_trace.dev_mark("h2d", w->copy_stream);
-    // Two count launches into the one table: the device's part (it ends in >= 64 invalid bases, so no
-    // window of it reaches into the host's slots) is counted while the packed tail is still on the bus.
-    KPAL_CHECK(launch_count(d_codes, d_valid, host_base, k, d_table, bits, st));
+    // the second count launch into the same table: the host's slots and the junction records
     KPAL_CUDA(cudaStreamWaitEvent(st, w->chunk_done[31], 0));
     g_trace.dev_mark("packed", st);
     KPAL_CHECK(launch_count(d_codes + host_base / 16, d_valid + host_base / 32, stream_bases - host_base, k, d_table, bits, st));
     g_trace.dev_mark("counted", st);
     g_trace.mark("count_queued");
+    if (h.active.load()) host_s = double(h.busy_ns.load()) * 1e-9 / double(h.active.load());
     g_hybrid_prev[0] = host_s; g_hybrid_prev[1] = double(n_bytes - raw_len); g_hybrid_prev[2] = double(raw_len);
     g_last_h2d_bytes.store(raw_len + (stream_bases - host_base) / 8 * 3);
     g_last_host_text_bytes.store(n_bytes - raw_len);

@@ -12,9 +12,7 @@ print('$1', 'value', round(d['value'],1), 'e2e', round(e['value'],2), round(e['m
   grep "kpal trace" gpurun_out/r02_hyb_$1.err | tail -${3:-2}
   grep -v "kpal trace" gpurun_out/r02_hyb_$1.err | tail -2
 }
-run avx512 "--fasta-hybrid 1 --steps 20" 2
-KPAL_PACK_NO_AVX512=1 run avx2 "--fasta-hybrid 1 --steps 20" 2
-run cfg5_avx512 "--config 5" 2
-KPAL_PACK_NO_AVX512=1 run cfg5_avx2 "--config 5" 2
-run avx512b "--fasta-hybrid 1 --steps 20" 2
-KPAL_PACK_NO_AVX512=1 run avx2b "--fasta-hybrid 1 --steps 20" 2
+run early20 "--fasta-hybrid 1 --steps 20" 3
+run early10 "--fasta-hybrid 1" 2
+run cfg5early "--config 5" 2
+run skewed_early "--composition skewed" 2
