@@ -234,6 +234,11 @@ __device__ __forceinline__ double add_term(double acc, double n, double den)
 // behind the fp64 pipe (4.55 T/s measured against 18 T fp64 instructions/s: one reciprocal per 5
 // fp64 instructions is 80 % of its rate).  Denominators are >= 1 / S_B > 0 and their product is
 // far inside the double range.
+#ifndef KPAL_DD_UNROLL
+#define KPAL_DD_UNROLL 2                 // element pairs of the inner loop unrolled (tuning: make variant DEFS=-DKPAL_DD_UNROLL=..)
+#endif
+#define KPAL_PRAGMA_(x) _Pragma(#x)
+#define KPAL_UNROLL(n) KPAL_PRAGMA_(unroll n)
 #ifndef KPAL_PAIR_RCP
 #define KPAL_PAIR_RCP 1
 #endif
@@ -405,7 +410,7 @@ distance_tile_kernel(const TileArgs a)
         mbar_wait(smem_u32(&bars[s]), ph);
         const unsigned char *sA = smem + s * STAGE_BYTES + ti * ROW_BYTES;
         const unsigned char *sB = smem + s * STAGE_BYTES + A_BYTES + tj * ROW_BYTES;
-#pragma unroll 2
+        KPAL_UNROLL(KPAL_DD_UNROLL)
         for (int dd = 0; dd < DC / 2; ++dd) {
             double2 av[RI], bf[RJ], bp[RJ];
 #pragma unroll
