@@ -202,6 +202,7 @@ struct CountWorkspace {
     int device = -1;
     GrowDev codes, valid, table, counts, text, fscratch, counts16, counts8, overflow, rows16[2], wide_flag;
     GrowDev list8, list16;                       // side lists of the narrow profile copy: (index, value) of the large counts
+    GrowDev br_codes, br_valid, br_starts;       // by-record: the packed chunks and record starts of the call
     GrowPin pcodes, pvalid, pstatus, pnarrow, pflag, prows16[2], plist;
     cudaEvent_t rows_done[2] = {};               // by-record: a batch of uint16 rows has landed
     cudaStream_t copy_stream = nullptr;          // H2D of the FASTA text, chunk by chunk
@@ -1308,21 +1309,26 @@ extern "C" int kpal_count_by_record(const uint32_t *codes, const uint32_t *valid
         rs[r] = rec_starts[first + r] - c0 * 64;
         if (r) longest = std::max(longest, rs[r] - rs[r - 1]);
     }
-    DevBuf d_codes, d_valid, d_rs, d_rows;
-    KPAL_CHECK(d_codes.alloc((c1 - c0) * 16));
-    KPAL_CHECK(d_valid.alloc((c1 - c0) * 8));
-    KPAL_CHECK(d_rs.alloc((n + 1) * 8));
+    // (device buffers from the grow-only workspace: a cudaMalloc / cudaFree pair per buffer and call
+    // costs more than the kernel when a --by-record run makes hundreds of calls)
+    std::lock_guard<std::mutex> lock(g_count_mutex);
+    CountWorkspace *w;
+    KPAL_CHECK(get_count_ws(&w));
+    KPAL_CHECK(w->br_codes.ensure((c1 - c0) * 16));
+    KPAL_CHECK(w->br_valid.ensure((c1 - c0) * 8));
+    KPAL_CHECK(w->br_starts.ensure((n + 1) * 8));
+    struct Ref { void *p; uint32_t *u32() const { return static_cast<uint32_t *>(p); } uint64_t *u64() const { return static_cast<uint64_t *>(p); } };
+    const Ref d_codes{w->br_codes.p}, d_valid{w->br_valid.p}, d_rs{w->br_starts.p};
+    DevBuf d_rows;
     cudaStream_t st = 0;
     KPAL_CUDA(cudaMemcpyAsync(d_codes.p, codes + c0 * 4, (c1 - c0) * 16, cudaMemcpyHostToDevice, st));
     KPAL_CUDA(cudaMemcpyAsync(d_valid.p, valid + c0 * 2, (c1 - c0) * 8, cudaMemcpyHostToDevice, st));
     KPAL_CUDA(cudaMemcpyAsync(d_rs.p, rs.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
 
     if (g_narrow_d2h.load() && k >= 2 && longest < (balance ? 32768ull : 65536ull)) {
-        std::lock_guard<std::mutex> lock(g_count_mutex);
-        CountWorkspace *w;
-        KPAL_CHECK(get_count_ws(&w));
-        // batches of ~128 MB of uint16 rows (1 GB of int64 on the host side)
-        const uint64_t batch = std::max<uint64_t>(1, std::min<uint64_t>(n, (128ull << 20) / (bins * 2)));
+        // Batches of ~16 MB of uint16 rows (128 MB of int64 on the host side), at most 128 MB: several
+        // per call, so that the copy of batch b + 1 runs while the host threads widen batch b.
+        const uint64_t batch = std::max<uint64_t>(1, std::min<uint64_t>(n, (16ull << 20) / (bins * 2)));
         for (int i = 0; i < 2; ++i) {
             KPAL_CHECK(w->rows16[i].ensure(batch * bins * 2));
             KPAL_CHECK(w->prows16[i].ensure(batch * bins * 2));
@@ -1332,7 +1338,7 @@ extern "C" int kpal_count_by_record(const uint32_t *codes, const uint32_t *valid
         auto enqueue = [&](uint64_t b) -> int {
             const uint64_t r = b * batch, m = std::min(batch, n - r);
             uint16_t *d = static_cast<uint16_t *>(w->rows16[b & 1].p);
-            KPAL_CHECK(launch_by_record_u16(d_codes.as<uint32_t>(), d_valid.as<uint32_t>(), d_rs.as<uint64_t>(),
+            KPAL_CHECK(launch_by_record_u16(d_codes.u32(), d_valid.u32(), d_rs.u64(),
                                             r, m, k, balance, d, st));
             KPAL_CUDA(cudaMemcpyAsync(w->prows16[b & 1].p, d, m * bins * 2, cudaMemcpyDeviceToHost, st));
             KPAL_CUDA(cudaEventRecord(w->rows_done[b & 1], st));
@@ -1363,7 +1369,7 @@ extern "C" int kpal_count_by_record(const uint32_t *codes, const uint32_t *valid
     KPAL_CHECK(d_rows.alloc(batch * bins * 8));
     for (uint64_t r = 0; r < n; r += batch) {
         const uint64_t m = std::min(batch, n - r);
-        KPAL_CHECK(launch_by_record(d_codes.as<uint32_t>(), d_valid.as<uint32_t>(), d_rs.as<uint64_t>(),
+        KPAL_CHECK(launch_by_record(d_codes.u32(), d_valid.u32(), d_rs.u64(),
                                     r, m, k, balance, d_rows.as<int64_t>(), st));
         KPAL_CUDA(cudaMemcpyAsync(rows_out + r * bins, d_rows.p, m * bins * 8, cudaMemcpyDeviceToHost, st));
         KPAL_CUDA(cudaStreamSynchronize(st));
