@@ -203,6 +203,10 @@ struct CountWorkspace {
     GrowDev codes, valid, table, counts, text, fscratch, counts16, counts8, overflow, rows16[2], wide_flag;
     GrowDev list8, list16;                       // side lists of the narrow profile copy: (index, value) of the large counts
     GrowDev br_codes, br_valid, br_starts;       // by-record: the packed chunks and record starts of the call
+    // hybrid upload (fasta_hybrid_count): the host's share of the text, adapted from call to call on this device
+    double hybrid_share = 0.45;
+    cudaEvent_t hybrid_ev[2] = {};               // raw upload: start / done (timing events)
+    double hybrid_prev[3] = {0, 0, 0};           // previous call: packers' seconds, host text bytes, raw bytes
     GrowPin pcodes, pvalid, pstatus, pnarrow, pflag, prows16[2], plist;
     cudaEvent_t rows_done[2] = {};               // by-record: a batch of uint16 rows has landed
     cudaStream_t copy_stream = nullptr;          // H2D of the FASTA text, chunk by chunk
@@ -875,23 +879,19 @@ static unsigned hybrid_packers()
     return n;
 }
 
-// the host's share of the text, adapted from call to call (per process; under g_count_mutex)
-static double g_hybrid_share = 0.45;
-static cudaEvent_t g_hybrid_ev[2] = {};             // raw upload: start / done (timing events)
-static double g_hybrid_prev[3] = {0, 0, 0};         // previous call: host seconds, host text bytes, raw bytes
-
-static void hybrid_adapt()
+// The host's share of the text for the next call on this device, from the rates of the previous one.
+static void hybrid_adapt(CountWorkspace *w)
 {
-    if (g_hybrid_prev[0] <= 0 || g_hybrid_prev[1] <= 0 || g_hybrid_prev[2] <= 0 || !g_hybrid_ev[0]) return;
+    if (w->hybrid_prev[0] <= 0 || w->hybrid_prev[1] <= 0 || w->hybrid_prev[2] <= 0 || !w->hybrid_ev[0]) return;
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, g_hybrid_ev[0], g_hybrid_ev[1]) != cudaSuccess || ms <= 0.f) { cudaGetLastError(); return; }
-    const double host_rate = g_hybrid_prev[1] / g_hybrid_prev[0], bus_rate = g_hybrid_prev[2] / (ms * 1e-3);
+    if (cudaEventElapsedTime(&ms, w->hybrid_ev[0], w->hybrid_ev[1]) != cudaSuccess || ms <= 0.f) { cudaGetLastError(); return; }
+    const double host_rate = w->hybrid_prev[1] / w->hybrid_prev[0], bus_rate = w->hybrid_prev[2] / (ms * 1e-3);
     // The bus carries (1 - x) of the text raw and x of it packed (0.375 B/base, a little more
     // with the slot ends and the shorter copies: 0.41); the packers should be done a little
     // before the bus is:  x / host_rate = 0.93 ((1 - x) + 0.41 x) / bus_rate
     const double x = 0.93 * host_rate / (bus_rate + 0.93 * 0.59 * host_rate);
-    g_hybrid_share = std::min(0.75, std::max(0.05, 0.3 * g_hybrid_share + 0.7 * x));
-    g_hybrid_prev[0] = 0;
+    w->hybrid_share = std::min(0.75, std::max(0.05, 0.3 * w->hybrid_share + 0.7 * x));
+    w->hybrid_prev[0] = 0;
 }
 
 // Returns KPAL_OK with *taken = false when the text is not one for the hybrid form.
@@ -905,9 +905,9 @@ static int fasta_hybrid_count(CountWorkspace *w, const char *fasta, uint64_t n_b
     HybridState h;
     if (!slotted_plan(fasta, n_bytes, 512u << 10, h.plan) || h.plan.m < 8) return KPAL_OK;
     *taken = true;
-    hybrid_adapt();
+    hybrid_adapt(w);
     const int forced = g_fasta_hybrid_share.load();
-    const double share = forced > 0 ? forced / 100.0 : g_hybrid_share;
+    const double share = forced > 0 ? forced / 100.0 : w->hybrid_share;
     const uint64_t m = h.plan.m;
     const uint64_t first = std::min<uint64_t>(m - 1, std::max<uint64_t>(1, uint64_t(double(m) * (1.0 - share) + 0.5)));
     h.text = reinterpret_cast<const unsigned char *>(fasta);
@@ -933,7 +933,7 @@ static int fasta_hybrid_count(CountWorkspace *w, const char *fasta, uint64_t n_b
         KPAL_CUDA(cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
         for (auto &e : w->chunk_done) KPAL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    if (!g_hybrid_ev[0]) for (auto &e : g_hybrid_ev) KPAL_CUDA(cudaEventCreate(&e));
+    if (!w->hybrid_ev[0]) for (auto &e : w->hybrid_ev) KPAL_CUDA(cudaEventCreate(&e));
     h.pcodes = static_cast<uint32_t *>(w->pcodes.p);
     h.pvalid = static_cast<uint32_t *>(w->pvalid.p);
     h.done.reset(new std::atomic<unsigned char>[m]);
@@ -958,7 +958,7 @@ static int fasta_hybrid_count(CountWorkspace *w, const char *fasta, uint64_t n_b
     fail(cudaMemsetAsync(d_scratch, 0, sizeof(FastaStatus) + 16, st));
     fail(cudaMemsetAsync(d_scratch, 0xff, sizeof(unsigned long long), st));      // first_header = ~0
     g_trace.dev_mark("start", w->copy_stream);
-    fail(cudaEventRecord(g_hybrid_ev[0], w->copy_stream));
+    fail(cudaEventRecord(w->hybrid_ev[0], w->copy_stream));
     // the head: raw chunks on the copy stream, each packed as soon as it has landed
     uint64_t n_chunks = std::min<uint64_t>(std::max<uint64_t>(raw_len / (6ull << 20), 1), 16);
     if (g_fasta_chunks.load() > 0) n_chunks = std::min<uint64_t>(uint64_t(g_fasta_chunks.load()), 30);
@@ -973,7 +973,7 @@ static int fasta_hybrid_count(CountWorkspace *w, const char *fasta, uint64_t n_b
         if (err == cudaSuccess)
             rc = launch_fasta_pack_tiles(d_text, raw_len, off / tile, (off + len + tile - 1) / tile, d_codes, d_valid, d_scratch, st);
     }
-    fail(cudaEventRecord(g_hybrid_ev[1], w->copy_stream));
+    fail(cudaEventRecord(w->hybrid_ev[1], w->copy_stream));
     g_trace.dev_mark("raw_h2d", w->copy_stream);
     if (err == cudaSuccess && rc == KPAL_OK)
         fail(cudaMemcpyAsync(status, d_scratch, sizeof(FastaStatus), cudaMemcpyDeviceToHost, st));
@@ -1019,7 +1019,7 @@ static int fasta_hybrid_count(CountWorkspace *w, const char *fasta, uint64_t n_b
     g_trace.dev_mark("counted", st);
     g_trace.mark("count_queued");
     if (h.active.load()) host_s = double(h.busy_ns.load()) * 1e-9 / double(h.active.load());
-    g_hybrid_prev[0] = host_s; g_hybrid_prev[1] = double(n_bytes - raw_len); g_hybrid_prev[2] = double(raw_len);
+    w->hybrid_prev[0] = host_s; w->hybrid_prev[1] = double(n_bytes - raw_len); w->hybrid_prev[2] = double(raw_len);
     g_last_h2d_bytes.store(raw_len + (stream_bases - host_base) / 8 * 3);
     g_last_host_text_bytes.store(n_bytes - raw_len);
     if (g_trace.on && g_trace.at + 48 <= sizeof g_trace.line)
