@@ -347,12 +347,43 @@ def run_reference(args):
                 "e2e": {"value": value, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
 
+    def python_leg():
+        """The UNMODIFIED reference's own pure-Python counting loop (kpal/klib.py:135-170 + balance,
+        285-298), when its sources travelled with the repo (baseline/_ref: `pip install --no-deps
+        --target baseline/_ref` of the reference, see __graft_entry__.build): one core, a bounded
+        sample of the same reads, and its counts compared with the C port's on that sample."""
+        try:
+            from oracle import ref_loader
+            if not ref_loader.available():
+                return {"unavailable": "baseline/_ref (offline install of the reference) is not present"}
+            klib = ref_loader.load()[0]
+            k = args.k or K_COUNT
+            reads = synthetic_reads(1000)[:20000]                       # 3 Mbp of the config-2 reads
+            sequences = [row.tobytes().decode("ascii") for row in reads]
+            t0 = time.perf_counter()
+            profile = klib.Profile.from_sequences(sequences, k)
+            t1 = time.perf_counter()
+            profile.balance()                                           # a Python loop over the 4^k bins
+            t2 = time.perf_counter()
+            port = c_oracle.balance(c_oracle.count_bytes(np.insert(reads, READ_LEN, ord("\n"), axis=1).reshape(-1), k,
+                                                         threads=threads))
+            return {"value": reads.size / 1e9 / (t1 - t0), "unit": "Gbases/s", "cores": 1,
+                    "count_seconds": t1 - t0, "balance_seconds": t2 - t1,
+                    "sample": "first 20000 reads (3 Mbp) of the config-2 input, k=%d: kpal.klib.Profile.from_sequences "
+                              "of the unmodified reference (value = its counting loop alone), then Profile.balance "
+                              "(independent of the input size)" % k,
+                    "counts_equal_c_port": bool(np.array_equal(np.asarray(profile.counts), port))}
+        except Exception as error:          # never fail the arm over the optional leg
+            return {"unavailable": "%s: %s" % (type(error).__name__, error)}
+
     if args.workload == "matrix":
         out = matrix_leg()
     else:
         out = count_leg()
         if args.workload == "all":
             out["matrix"] = matrix_leg()
+        if args.config == 2 and args.composition == "uniform":
+            out["reference_python"] = python_leg()
     print(json.dumps(out))
 
 

@@ -13,8 +13,11 @@ None of them carries hot-path arithmetic, so tiny stand-in modules are put in
 ``sys.modules`` *before* the import.  ``Bio.SeqIO.parse`` is served by the
 oracle's own FASTA reader (documented Biopython FastaIterator behaviour).
 
-Nothing in the product package (``kpal_b200``) may import this module, and it
-must never be used on the GPU box: ``/root/reference`` does not exist there.
+Nothing in the product package (``kpal_b200``) may import this module.
+``/root/reference`` does not exist on the GPU box; the offline install of the
+reference in ``baseline/_ref`` (git-ignored, it travels with the snapshot) does,
+and ``bench.py --impl reference`` uses it there to time the reference's own
+Python beside the C port.  The ``-m gpu`` tests and ``smoke()`` never do.
 """
 import builtins
 import contextlib
