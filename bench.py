@@ -17,16 +17,20 @@ A step = one pass of the hot path over the whole batch:
           kernel), timed with CUDA events on the launching stream, L2 flushed
           between steps (untimed), max over ranks;
   e2e   : the same job through the host-buffer C ABI (kpal_count_fasta): pinned
-          FASTA bytes -> H2D in chunks -> GPU scan/pack -> count kernels ->
-          [table sum] -> narrow (uint8 / uint16) D2H of the profile, widened to
-          int64 by host threads; wall clock around the call with device syncs.
+          FASTA bytes -> hybrid upload (the head of the text raw, scanned / packed
+          by the GPU; the tail packed by idle host threads, 0.375 B/base over the
+          bus) -> count kernels -> [table sum] -> narrow (uint8 / uint16) D2H of
+          the profile, widened to int64 by host threads; wall clock around the
+          call with device syncs.  h2d_bytes_per_step = the bytes that crossed
+          the bus (kpal_last_upload), text_bytes_per_step = the FASTA bytes.
 
 Multi-GPU (weak scaling): every rank counts its own shard of records (same
-size per rank), the 4^k u32 tables are summed onto rank 0 -- over NVLink peer
-memory fused into the count's histogram pass at 2 GPUs, with an NCCL reduce
-from 4 GPUs on (`--reduce auto`, chosen by measurement) -- and finalised
-(widen + balance) once.  `--config 5`: one GPU's shard of BASELINE configs[4]
-(k=13 genome-like records).
+size per rank); `--reduce auto` = `slices`: every rank balances its table and
+stores it, one byte per bin, into the slice owners' inboxes over NVLink peer
+memory, every owner sums its slice (multigpu.SliceReducer; no NCCL call on
+the data path), the profile stays sharded by slice.  `--reduce fused|peer|nccl`:
+the round-1 forms (u32 tables summed onto rank 0).  `--config 5`: one GPU's
+shard of BASELINE configs[4] (k=13 genome-like records).
 
 Matrix workload: BASELINE.json configs[3], the 4096-profile k=10 scaled multiset distance
 matrix (profile-pairs/s), with its own small step count (<= 2).  At N > 1 (strong scaling)
@@ -38,8 +42,9 @@ finished tiles are gathered on rank 0 as compact tile arrays (kpal_b200/multigpu
 GPU's shard of configs[4] (k=13; the full 3 Gbp job at --gpus 8).
 
 `--impl reference`: the CPU baseline -- the oracle's C port of the reference
-algorithm on all host threads (the reference itself is pure Python and cannot
-run on the GPU box; BASELINE.md has its measured 1-core figures).
+algorithm on all host threads (`value`), plus `reference_python`: the unmodified
+reference's own pure-Python loop on one core and a bounded sample, when its
+offline install (baseline/_ref) is present.
 """
 import argparse
 import ctypes
